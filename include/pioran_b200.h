@@ -1,0 +1,126 @@
+/*
+ * pioran_b200.h — C ABI of libpioran_b200.so, the B200 (sm_100a) backend of Pioran.jl's likelihood hot path.
+ *
+ * The reference (mlefkir/Pioran.jl, pure Julia) has no FFI of its own; its operator boundary for this path is
+ * Julia dispatch on  log_likelihood(cov, τ, y, σ2; solver::Symbol)  (src/celerite_solver.jl:262-294), selected by
+ * the `solver` field of ScalableGP (src/scalable_GP.jl:24-40,162-166).  Each entry point below names the reference
+ * function it stands in for; INTEGRATION.md shows the `ccall` stubs a Pioran maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in any signature (streams are passed as void*).
+ *   - every function returns 0 on success or a negative PIORAN_E* code; it never throws or aborts.
+ *     pioran_last_error() returns a thread-local, NUL-terminated description of the last failure.
+ *   - logL values that are NaN/±Inf are data (a non-positive-definite θ), not errors — like the reference, which
+ *     takes log|D_n| (src/celerite_solver.jl:140) and never checks definiteness on the celerite path.
+ *   - pointers are HOST memory unless the function name ends in `_dev`; the caller owns every buffer and the
+ *     library keeps no pointer after return.  A context is bound to one CUDA device; one context per thread.
+ *   - all floating point is IEEE double (FP64); there is no CPU fallback: with no usable GPU every call fails
+ *     with PIORAN_ECUDA.
+ */
+#ifndef PIORAN_B200_H
+#define PIORAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIORAN_OK 0
+#define PIORAN_EINVAL (-1)  /* bad argument (message in pioran_last_error)            */
+#define PIORAN_ECUDA (-2)   /* CUDA runtime / driver failure, or no sm_100 device     */
+#define PIORAN_ENOMEM (-3)  /* host or device allocation failed                       */
+#define PIORAN_ESINGULAR (-4) /* spectral matrix of approx() is singular              */
+#define PIORAN_EUNSUPPORTED (-5) /* shape outside the compiled kernel set             */
+
+/* Tonari.jl PSD models usable on the fused path (formulas pinned by reference test/test_psd.jl:6,12). */
+#define PIORAN_PSD_SBPL 0 /* SingleBendingPowerLaw(α₁, f₁, α₂)            — 3 parameters */
+#define PIORAN_PSD_DBPL 1 /* DoubleBendingPowerLaw(α₁, f₁, α₂, f₂, α₃)    — 5 parameters */
+
+/* basis_function of approx (src/psd.jl:214) */
+#define PIORAN_BASIS_SHO 0
+#define PIORAN_BASIS_DRWCELERITE 1
+
+typedef struct pioran_ctx pioran_ctx;
+
+/* Parameters of  approx(psd_model, f_min, f_max, n_components, norm, S_low, S_high; is_integrated_power,
+ * basis_function)  (src/psd.jl:214) that do not vary inside a batch. */
+typedef struct pioran_approx_spec {
+    int32_t psd_model;           /* PIORAN_PSD_*                                  */
+    int32_t n_components;        /* J                                             */
+    int32_t basis;               /* PIORAN_BASIS_*                                */
+    int32_t is_integrated_power; /* 1 (reference default) or 0                    */
+    double f_min, f_max;         /* frequency range of the time series            */
+    double S_low, S_high;        /* reference defaults 20, 20                     */
+} pioran_approx_spec;
+
+const char *pioran_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+int pioran_version(void);
+
+/* ---- context & resident time series -------------------------------------------------------------------- */
+/* Binds a context to CUDA device `device` (must be compute capability 10.x).  Creates one stream. */
+int pioran_ctx_create(int device, pioran_ctx **out);
+int pioran_ctx_destroy(pioran_ctx *ctx);
+/* Use an external stream (e.g. torch's current stream, passed as its cudaStream_t cast to void*) for all
+ * subsequent launches of this context; NULL restores the context's own stream. */
+int pioran_ctx_set_stream(pioran_ctx *ctx, void *cuda_stream);
+int pioran_ctx_synchronize(pioran_ctx *ctx);
+/* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t pioran_ctx_launch_count(pioran_ctx *ctx);
+
+/* Uploads one time series (τ, y, σ²) — the (x, Y, diag Σy) of logpdf(f(t, σ²), y), src/scalable_GP.jl:162-166 —
+ * and keeps it resident.  t must be strictly increasing.  A sampler uploads once and evaluates ~1e5 times. */
+int pioran_series_upload(pioran_ctx *ctx, int64_t N, const double *t, const double *y, const double *s2,
+                         int *series_id);
+int pioran_series_free(pioran_ctx *ctx, int series_id);
+int pioran_series_length(pioran_ctx *ctx, int series_id, int64_t *N);
+
+/* ---- K1: approx (src/psd.jl:214-289) --------------------------------------------------------------------- */
+/* theta: [B × (n_psd_par + 1)] row-major = psd parameters…, norm.  Outputs a,b,c,d: [B × Jt] row-major with
+ * Jt = J (SHO) or 2J (DRWCelerite: J celerite terms followed by J DRW terms, src/psd.jl:264-275). */
+int pioran_approx_coeffs(pioran_ctx *ctx, const pioran_approx_spec *spec, int B, const double *theta,
+                         double *a, double *b, double *c, double *d);
+
+/* ---- K2: celerite log-likelihood ------------------------------------------------------------------------ */
+/* Drop-in for  logl(a, b, c, d, τ, y, σ2)  (src/celerite_solver.jl:312-334) over a batch of B coefficient sets,
+ * [B × Jt] row-major each.  mu/nu: per-set constant mean and variance scale (y−μ, ν·σ²; NULL → 0 / 1), the two
+ * θ-dependent scalars of the samplers' likelihoods (examples/ultranest/single_pl.jl:70-73).
+ * y_batch: NULL, or [B × N] per-set data vectors replacing the resident y (custom mean functions, log-shift
+ * transforms); s2_batch likewise for σ².  logl_out: [B]. */
+int pioran_celerite_logl(pioran_ctx *ctx, int series_id, int B, int Jt,
+                         const double *a, const double *b, const double *c, const double *d,
+                         const double *mu, const double *nu,
+                         const double *y_batch, const double *s2_batch, double *logl_out);
+
+/* Fused  approx(...) + logpdf(ScalableGP(μ, 𝓡)(t, ν·σ²), y)  for B parameter vectors on each of S resident series.
+ * specs: [S] (f_min/f_max differ per series; J, basis, model must agree).  theta: [B × (n_psd_par+3)] row-major =
+ * psd parameters…, norm, ν, μ — shared by all series when theta_per_series == 0, else [S × B × (n_psd_par+3)].
+ * y_batch: NULL or [S × B × Nmax]-free form is not supported here (use pioran_celerite_logl).  logl_out: [S × B]. */
+int pioran_approx_logl(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,
+                       int B, const double *theta, int theta_per_series, double *logl_out);
+
+/* Same as pioran_approx_logl with θ and the result resident in device memory; asynchronous on the context's
+ * stream (no host synchronisation).  theta_dev: [S or 1][B][n_psd_par+3]; logl_dev: [S × B]. */
+int pioran_approx_logl_dev(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,
+                           int B, const double *theta_dev, int theta_per_series, double *logl_dev);
+
+/* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
+/* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
+int pioran_celerite_logl_scan(pioran_ctx *ctx, int series_id, int B, int Jt,
+                              const double *a, const double *b, const double *c, const double *d,
+                              const double *mu, const double *nu, double *logl_out);
+
+/* ---- K4: dense cross-check ------------------------------------------------------------------------------- */
+/* Drop-in for  log_likelihood_direct(cov, t, y, σ²)  (src/direct_solver.jl:6-21) with the kernel of
+ * src/Celerite.jl:42-44 summed over terms.  Returns +NLL like the reference (tests negate it,
+ * test/test_likelihood.jl:54).  info_out[i] = 0, or k>0 when the leading minor of order k is not positive
+ * definite (the reference throws PosDefException; here nll_out[i] = NaN). */
+int pioran_direct_logl(pioran_ctx *ctx, int series_id, int B, int Jt,
+                       const double *a, const double *b, const double *c, const double *d,
+                       const double *mu, const double *nu, double *nll_out, int *info_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIORAN_B200_H */

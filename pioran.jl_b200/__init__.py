@@ -1,0 +1,11 @@
+"""pioran.jl_b200 — B200 (sm_100a) backend of Pioran.jl's celerite likelihood path.
+
+The directory name carries a dot, so import it through the repo-root shim:  `import pioran_b200`.
+Contents: csrc/ (CUDA kernels + C ABI, built into libpioran_b200.so), backend.py (ctypes handle),
+api.py (mirror of the reference's Julia interface), build.py (nvcc recipe)."""
+from . import _lib, backend, build  # noqa: F401
+from .api import (BatchedLikelihood, Celerite, CustomMean, DoubleBendingPowerLaw, Exp, ScalableGP, SHO,  # noqa: F401
+                  SingleBendingPowerLaw, SumOfCelerite, approx, celerite_coefs, log_likelihood,
+                  log_likelihood_direct, logpdf)
+from .backend import Context, get_context, make_spec  # noqa: F401
+from ._lib import ApproxSpec, PioranError  # noqa: F401

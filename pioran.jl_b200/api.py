@@ -1,0 +1,229 @@
+"""Host-side mirror of the Pioran.jl interface for the likelihood path — same names, argument meaning and error
+behaviour as the reference, with the arithmetic done by libpioran_b200's CUDA kernels.
+
+    𝓟  = SingleBendingPowerLaw(α₁, f₁, α₂)
+    𝓡  = approx(𝓟, f_min, f_max, 20, variance, basis_function="SHO")     # src/psd.jl:214
+    f  = ScalableGP(μ, 𝓡)                                                 # src/scalable_GP.jl:36
+    ℓ  = logpdf(f(t, σ²), y)                                              # src/scalable_GP.jl:162-166
+
+Batched entry for samplers that evaluate many parameter vectors at once (ultranest `vectorized=True`):
+    like = BatchedLikelihood(t, y, σ², psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO")
+    ℓ    = like(Θ)        # Θ rows = [psd parameters…, variance, ν, μ]  (examples/ultranest/single_pl.jl:67)
+"""
+import numpy as np
+
+from . import backend
+from .backend import get_context, make_spec
+
+
+# ----------------------------------------------------------------------------------------------- PSD models
+class PowerSpectralDensity:
+    """Tonari.jl's abstract type (src/Pioran.jl:15,20)."""
+    model_name = None
+
+    def params(self):
+        raise NotImplementedError
+
+
+class SingleBendingPowerLaw(PowerSpectralDensity):
+    """𝓟(f) = (f/f₁)^(−α₁) / (1 + (f/f₁)^(α₂−α₁))   (test/test_psd.jl:6)"""
+    model_name = "SingleBendingPowerLaw"
+
+    def __init__(self, α1, f1, α2):
+        self.α1, self.f1, self.α2 = float(α1), float(f1), float(α2)
+
+    def params(self):
+        return [self.α1, self.f1, self.α2]
+
+
+class DoubleBendingPowerLaw(PowerSpectralDensity):
+    """𝓟(f) = (f/f₁)^(−α₁) / (1 + (f/f₁)^(α₂−α₁)) / (1 + (f/f₂)^(α₃−α₂))   (test/test_psd.jl:12)"""
+    model_name = "DoubleBendingPowerLaw"
+
+    def __init__(self, α1, f1, α2, f2, α3):
+        self.α1, self.f1, self.α2, self.f2, self.α3 = map(float, (α1, f1, α2, f2, α3))
+
+    def params(self):
+        return [self.α1, self.f1, self.α2, self.f2, self.α3]
+
+
+# ----------------------------------------------------------------------------------------------- ACVF types
+class SemiSeparable:
+    """src/acvf.jl: abstract semi-separable covariance."""
+
+
+class Celerite(SemiSeparable):
+    """Celerite(a, b, c, d): k(τ) = exp(−cτ)(a cos dτ + b sin dτ)   (src/Celerite.jl:20-44)"""
+
+    def __init__(self, a, b, c, d):
+        self.a, self.b, self.c, self.d = float(a), float(b), float(c), float(d)
+
+
+class SHO(Celerite):
+    """SHO(A, ω₀, Q=1/√2)  → (A, A, ω₀/√2, ω₀/√2)   (src/SHO.jl)"""
+
+    def __init__(self, A, ω0):
+        super().__init__(A, A, ω0 / np.sqrt(2.0), ω0 / np.sqrt(2.0))
+
+
+class Exp(Celerite):
+    """Exp(A, α) → (A, 0, α, 0)   (src/Exp.jl)"""
+
+    def __init__(self, A, α):
+        super().__init__(A, 0.0, α, 0.0)
+
+
+class SumOfCelerite(SemiSeparable):
+    """Container of the coefficient vectors (src/acvf.jl:35-53).  `+` of terms concatenates."""
+
+    def __init__(self, a, b, c, d, _fused=None):
+        self.a, self.b, self.c, self.d = (np.asarray(x, dtype=np.float64).ravel().copy() for x in (a, b, c, d))
+        if not (self.a.shape == self.b.shape == self.c.shape == self.d.shape):
+            raise ValueError("a, b, c, d must have the same length")
+        self._fused = _fused  # (spec, psd parameters, norm) when produced by approx(): enables the fused kernel
+
+    def __call__(self, t1, t2):
+        """Kernel value (src/acvf.jl:138-140); host arithmetic on J numbers, used by tests like `𝓡(0,0) ≈ va`."""
+        τ = abs(t1 - t2)
+        return float(np.sum(np.exp(-self.c * τ) * (self.a * np.cos(self.d * τ) + self.b * np.sin(self.d * τ))))
+
+    def __add__(self, other):
+        o = celerite_coefs(other)
+        return SumOfCelerite(*(np.concatenate([x, y]) for x, y in zip(celerite_coefs(self), o)))
+
+
+def celerite_coefs(cov):
+    """(a, b, c, d) vectors of a covariance (src/acvf.jl:119-127, src/Celerite.jl:33-39)."""
+    if isinstance(cov, SumOfCelerite):
+        return cov.a, cov.b, cov.c, cov.d
+    if isinstance(cov, Celerite):
+        return (np.array([cov.a]), np.array([cov.b]), np.array([cov.c]), np.array([cov.d]))
+    raise TypeError(f"no celerite coefficients for {type(cov).__name__}")
+
+
+# ----------------------------------------------------------------------------------------------- approx
+def approx(psd_model, f_min, f_max, n_components=20, norm=1.0, S_low=20.0, S_high=20.0, *, is_integrated_power=True,
+           basis_function="SHO", ctx=None):
+    """approx(psd_model, f_min, f_max, n_components, norm, S_low, S_high; is_integrated_power, basis_function)
+    (src/psd.jl:214-289) → SumOfCelerite.  Runs the K1 kernel."""
+    if not isinstance(psd_model, PowerSpectralDensity):
+        raise TypeError("psd_model must be a PowerSpectralDensity")
+    ctx = ctx or get_context()
+    spec = make_spec(psd_model.model_name, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
+    theta = np.array([psd_model.params() + [float(norm)]])
+    a, b, c, d = ctx.approx_coeffs(spec, theta)
+    return SumOfCelerite(a[0], b[0], c[0], d[0], _fused=(spec, psd_model.params(), float(norm)))
+
+
+# ----------------------------------------------------------------------------------------------- GP API
+class CustomMean:
+    """AbstractGPs.CustomMean: a callable evaluated on the time vector (test/test_mean.jl)."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def __call__(self, t):
+        return np.asarray(self.f(np.asarray(t, dtype=np.float64)), dtype=np.float64)
+
+
+_SOLVERS = ("celerite", "celerite_gpu", "direct")
+
+
+class ScalableGP:
+    """ScalableGP(μ, 𝓡[, solver])  (src/scalable_GP.jl:24-40).  μ: number or CustomMean."""
+
+    def __init__(self, *args, solver="celerite"):
+        if len(args) == 1:
+            mean, kernel = 0.0, args[0]
+        elif len(args) == 2:
+            mean, kernel = args
+        elif len(args) == 3:
+            mean, kernel, solver = args
+        else:
+            raise TypeError("ScalableGP(kernel) | ScalableGP(μ, kernel) | ScalableGP(μ, kernel, solver)")
+        if not isinstance(kernel, SemiSeparable):
+            raise TypeError("kernel must be a SemiSeparable covariance")
+        self.mean, self.kernel, self.solver = mean, kernel, str(solver).lstrip(":")
+
+    def __call__(self, t, σ2):
+        """f(t, σ²) → finite-dimensional projection (AbstractGPs.FiniteGP with Diagonal(σ²))."""
+        t = np.asarray(t, dtype=np.float64)
+        σ2 = np.broadcast_to(np.asarray(σ2, dtype=np.float64), t.shape).copy()
+        return FiniteScalableGP(self, t, σ2)
+
+
+class FiniteScalableGP:
+    def __init__(self, f, x, σ2):
+        self.f, self.x, self.σ2 = f, x, σ2
+
+    def mean_vector(self):
+        m = self.f.mean
+        return m(self.x) if callable(m) else np.full(self.x.shape, float(m))
+
+
+def log_likelihood(cov, τ, y, σ2, *, solver="celerite", ctx=None):
+    """log_likelihood(cov, τ, y, σ2; solver)  (src/celerite_solver.jl:262-294).
+    `celerite` and `celerite_gpu` both run the B200 kernel (there is no CPU path in this package)."""
+    solver = str(solver).lstrip(":")
+    if solver not in ("celerite", "celerite_gpu"):
+        raise ValueError(f"solver {solver} not recognised, use either :celerite or :celerite_gpu")
+    ctx = ctx or get_context()
+    a, b, c, d = celerite_coefs(cov)
+    ser = ctx.upload_series(τ, y, σ2)
+    try:
+        return float(ctx.celerite_logl(ser, a, b, c, d)[0])
+    finally:
+        ser.free()
+
+
+def log_likelihood_direct(cov, t, y, σ2, *, ctx=None):
+    """log_likelihood_direct(cov, t, y, σ²)  (src/direct_solver.jl:6-21): returns +NLL; raises like the
+    reference's PosDefException when the covariance is not positive definite."""
+    ctx = ctx or get_context()
+    a, b, c, d = celerite_coefs(cov)
+    ser = ctx.upload_series(t, y, σ2)
+    try:
+        nll, info = ctx.direct_logl(ser, a, b, c, d)
+    finally:
+        ser.free()
+    if info[0] != 0:
+        raise np.linalg.LinAlgError(f"PosDefException: matrix is not positive definite; leading minor {int(info[0])}")
+    return float(nll[0])
+
+
+def logpdf(fx, Y, *, ctx=None):
+    """logpdf(f(t, σ²), Y)  (src/scalable_GP.jl:162-166)."""
+    if not isinstance(fx, FiniteScalableGP):
+        raise TypeError("logpdf expects ScalableGP(...)(t, σ²)")
+    y = np.asarray(Y, dtype=np.float64) - fx.mean_vector()
+    if fx.f.solver == "direct":
+        return -log_likelihood_direct(fx.f.kernel, fx.x, y, fx.σ2, ctx=ctx)
+    return log_likelihood(fx.f.kernel, fx.x, y, fx.σ2, solver=fx.f.solver, ctx=ctx)
+
+
+# ----------------------------------------------------------------------------------------------- batched entry
+class BatchedLikelihood:
+    """Vectorised log-likelihood of the samplers' model (examples/ultranest/single_pl.jl:65-93):
+        Θ row = [psd parameters…, variance, ν, μ]  →  logpdf(ScalableGP(μ, approx(𝓟, f_min, f_max, J, variance))(t, ν·σ²), y)
+    The series (and its trig/exp table) is uploaded once; each call runs K1 + K2 on the whole batch."""
+
+    def __init__(self, t, y, σ2, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
+                 f_min=None, f_max=None, S_low=20.0, S_high=20.0, is_integrated_power=True, ctx=None):
+        self.ctx = ctx or get_context()
+        t = np.asarray(t, dtype=np.float64)
+        if f_min is None:
+            f_min = 1.0 / (t[-1] - t[0])             # examples/ultranest/single_pl.jl:48
+        if f_max is None:
+            f_max = 1.0 / np.min(np.diff(t)) / 2.0
+        if isinstance(psd_model, type):
+            psd_model = psd_model.model_name
+        self.spec = make_spec(psd_model, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
+        self.series = self.ctx.upload_series(t, y, σ2)
+        self.n_par = backend.N_PSD_PAR[self.spec.psd_model] + 3
+
+    def __call__(self, theta):
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        return self.ctx.approx_logl(self.series, self.spec, theta)[0]
+
+    def close(self):
+        self.series.free()

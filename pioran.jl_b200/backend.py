@@ -1,0 +1,186 @@
+"""Thin Python handle on a libpioran_b200 context (one CUDA device).  numpy in, numpy out; every call runs
+the sm_100a kernels through the C ABI of include/pioran_b200.h."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import ApproxSpec, check
+
+PSD_MODELS = {"SingleBendingPowerLaw": 0, "DoubleBendingPowerLaw": 1}
+N_PSD_PAR = {0: 3, 1: 5}
+BASES = {"SHO": 0, "DRWCelerite": 1}
+
+_dp = C.POINTER(C.c_double)
+
+
+def _f64(x, shape=None):
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def make_spec(psd_model, f_min, f_max, n_components=20, S_low=20.0, S_high=20.0, is_integrated_power=True,
+              basis_function="SHO"):
+    if basis_function not in BASES:
+        # same failure mode as src/psd.jl:285
+        raise ValueError(f"Basis function {basis_function} not implemented")
+    model = PSD_MODELS[psd_model] if isinstance(psd_model, str) else int(psd_model)
+    return ApproxSpec(model, int(n_components), BASES[basis_function], int(bool(is_integrated_power)), float(f_min),
+                      float(f_max), float(S_low), float(S_high))
+
+
+class Series:
+    def __init__(self, ctx, sid, N):
+        self.ctx, self.id, self.N = ctx, sid, N
+
+    def free(self):
+        if self.id is not None:
+            check(self.ctx.lib.pioran_series_free(self.ctx.h, self.id))
+            self.id = None
+
+
+class Context:
+    """pioran_ctx bound to one device."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        check(self.lib.pioran_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pioran_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def set_stream(self, cuda_stream_ptr):
+        check(self.lib.pioran_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        check(self.lib.pioran_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pioran_ctx_launch_count(self.h))
+
+    def upload_series(self, t, y, s2):
+        t, y, s2 = _f64(t), _f64(y), _f64(s2)
+        if not (t.ndim == 1 and t.shape == y.shape == s2.shape):
+            raise ValueError("t, y, s2 must be 1-D arrays of equal length")
+        sid = C.c_int(-1)
+        check(self.lib.pioran_series_upload(self.h, t.shape[0], _p(t), _p(y), _p(s2), C.byref(sid)))
+        return Series(self, sid.value, t.shape[0])
+
+    # -- K1
+    def approx_coeffs(self, spec, theta):
+        """theta [B × (n_psd_par+1)] → (a, b, c, d) each [B × Jt]  (src/psd.jl:214-289)."""
+        theta = np.atleast_2d(_f64(theta))
+        npar = N_PSD_PAR[spec.psd_model]
+        if theta.shape[1] != npar + 1:
+            raise ValueError(f"theta must have {npar + 1} columns (psd parameters, norm)")
+        B = theta.shape[0]
+        Jt = spec.n_components * (1 if spec.basis == 0 else 2)
+        out = [np.empty((B, Jt)) for _ in range(4)]
+        check(self.lib.pioran_approx_coeffs(self.h, C.byref(spec), B, _p(theta), *[_p(o) for o in out]))
+        return tuple(out)
+
+    # -- K2 generic
+    def celerite_logl(self, series, a, b, c, d, mu=None, nu=None, y_batch=None, s2_batch=None):
+        """Batched logl(a,b,c,d,τ,y,σ2) (src/celerite_solver.jl:312-334); coefficient arrays [B × Jt]."""
+        a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
+        B, Jt = a.shape
+        for x in (b, c, d):
+            if x.shape != (B, Jt):
+                raise ValueError("a, b, c, d must have the same shape")
+        mu = _f64(mu, (B,)) if mu is not None else None
+        nu = _f64(nu, (B,)) if nu is not None else None
+        yb = _f64(y_batch, (B, series.N)) if y_batch is not None else None
+        sb = _f64(s2_batch, (B, series.N)) if s2_batch is not None else None
+        out = np.empty(B)
+        check(self.lib.pioran_celerite_logl(self.h, series.id, B, Jt, _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu),
+                                            _p(yb), _p(sb), _p(out)))
+        return out
+
+    # -- fused approx + logpdf
+    def approx_logl(self, series_list, specs, theta, theta_per_series=False):
+        """theta rows = [psd parameters…, norm, ν, μ].  Returns logL [S × B]."""
+        if isinstance(series_list, Series):
+            series_list, specs = [series_list], [specs]
+        S = len(series_list)
+        npar = N_PSD_PAR[specs[0].psd_model]
+        theta = _f64(theta)
+        if theta_per_series:
+            if theta.ndim != 3 or theta.shape[0] != S or theta.shape[2] != npar + 3:
+                raise ValueError(f"theta must be [S, B, {npar + 3}]")
+            B = theta.shape[1]
+        else:
+            theta = np.atleast_2d(theta)
+            if theta.shape[1] != npar + 3:
+                raise ValueError(f"theta must have {npar + 3} columns (psd parameters, norm, ν, μ)")
+            B = theta.shape[0]
+        ids = (C.c_int * S)(*[s.id for s in series_list])
+        sp = (ApproxSpec * S)(*specs)
+        out = np.empty((S, B))
+        check(self.lib.pioran_approx_logl(self.h, S, ids, sp, B, _p(theta), int(theta_per_series), _p(out)))
+        return out
+
+    def approx_logl_dev(self, series_list, specs, B, theta_ptr, out_ptr, theta_per_series=False):
+        """Device-resident variant: raw device pointers (ints), asynchronous on the context's stream."""
+        S = len(series_list)
+        ids = (C.c_int * S)(*[s.id for s in series_list])
+        sp = (ApproxSpec * S)(*specs)
+        check(self.lib.pioran_approx_logl_dev(self.h, S, ids, sp, int(B), C.c_void_p(theta_ptr), int(theta_per_series),
+                                              C.c_void_p(out_ptr)))
+
+    # -- K3
+    def celerite_logl_scan(self, series, a, b, c, d, mu=None, nu=None):
+        a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
+        B, Jt = a.shape
+        mu = _f64(mu, (B,)) if mu is not None else None
+        nu = _f64(nu, (B,)) if nu is not None else None
+        out = np.empty(B)
+        check(self.lib.pioran_celerite_logl_scan(self.h, series.id, B, Jt, _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu),
+                                                 _p(out)))
+        return out
+
+    # -- K4
+    def direct_logl(self, series, a, b, c, d, mu=None, nu=None):
+        """Batched log_likelihood_direct (src/direct_solver.jl:6-21): returns (+NLL [B], info [B])."""
+        a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
+        B, Jt = a.shape
+        mu = _f64(mu, (B,)) if mu is not None else None
+        nu = _f64(nu, (B,)) if nu is not None else None
+        out = np.empty(B)
+        info = np.zeros(B, dtype=np.int32)
+        check(self.lib.pioran_direct_logl(self.h, series.id, B, Jt, _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu),
+                                          _p(out), info.ctypes.data_as(C.POINTER(C.c_int))))
+        return out, info
+
+
+_default = {}
+
+
+def get_context(device=None):
+    """Process-wide context per device (created on first use)."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

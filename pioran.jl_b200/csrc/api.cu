@@ -1,0 +1,634 @@
+// api.cu — C ABI of libpioran_b200.so (include/pioran_b200.h): contexts, resident series, launch logic.
+// No CPU fallback anywhere: every entry point either runs the sm_100a kernels or fails with an error code.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/pioran_b200.h"
+#include "approx.cuh"
+#include "celerite.cuh"
+#include "common.cuh"
+#include "dense.cuh"
+#include "scan.cuh"
+#include "table.cuh"
+
+using namespace pioran;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? PIORAN_ENOMEM : PIORAN_ECUDA, "%s failed: %s",  \
+                        #expr, cudaGetErrorString(e__));                                                   \
+    } while (0)
+
+extern "C" const char* pioran_last_error(void) { return g_err.c_str(); }
+extern "C" int pioran_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------ context
+namespace {
+
+struct DevBuf {  // grow-only device workspace
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes, (size_t)4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(PIORAN_ENOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cap = want;
+        return 0;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+using TableKey = std::tuple<int, int, double, double>;  // basis, J, f0, fM
+struct Table { double* d = nullptr; int rpad = 0; int64_t npad = 0; };
+
+struct Series {
+    int64_t N = 0;
+    double *t = nullptr, *y = nullptr, *s2 = nullptr;
+    std::map<TableKey, Table> tables;
+};
+
+using PlanKey = std::tuple<int, int, int, int, double, double, double, double>;
+
+}  // namespace
+
+struct pioran_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    std::vector<Series*> series;
+    std::map<PlanKey, ApproxPlan*> plans;  // device pointers
+    DevBuf theta, amp, suma, out, work, coef, rows, misc;
+    std::mutex mu;
+};
+
+static int bs_for_rank(int R) {
+    int bs = (R + G - 1) / G;
+    if (bs < 4) bs = 4;
+    return bs;
+}
+
+extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
+    if (!out) return fail(PIORAN_EINVAL, "out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PIORAN_ECUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(PIORAN_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PIORAN_ECUDA, "device %d is sm_%d%d; libpioran_b200 carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    pioran_ctx* c = new (std::nothrow) pioran_ctx();
+    if (!c) return fail(PIORAN_ENOMEM, "out of host memory");
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(PIORAN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+    c->stream = c->own;
+    *out = c;
+    return PIORAN_OK;
+}
+
+static void free_series(Series* s) {
+    if (!s) return;
+    cudaFree(s->t); cudaFree(s->y); cudaFree(s->s2);
+    for (auto& kv : s->tables) cudaFree(kv.second.d);
+    delete s;
+}
+
+extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
+    if (!c) return PIORAN_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (Series* s : c->series) free_series(s);
+    for (auto& kv : c->plans) cudaFree(kv.second);
+    c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
+    c->coef.release(); c->rows.release(); c->misc.release();
+    if (c->own) cudaStreamDestroy(c->own);
+    delete c;
+    return PIORAN_OK;
+}
+
+extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+    return PIORAN_OK;
+}
+extern "C" int pioran_ctx_synchronize(pioran_ctx* c) {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int pioran_series_upload(pioran_ctx* c, int64_t N, const double* t, const double* y, const double* s2,
+                                    int* series_id) {
+    if (!c || !t || !y || !s2 || !series_id) return fail(PIORAN_EINVAL, "NULL argument");
+    if (N < 1) return fail(PIORAN_EINVAL, "N must be >= 1 (got %lld)", (long long)N);
+    for (int64_t n = 1; n < N; n++)
+        if (!(t[n] > t[n - 1])) return fail(PIORAN_EINVAL, "t must be strictly increasing (t[%lld] <= t[%lld])", (long long)n, (long long)(n - 1));
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = new (std::nothrow) Series();
+    if (!s) return fail(PIORAN_ENOMEM, "out of host memory");
+    s->N = N;
+    const size_t bytes = sizeof(double) * (size_t)N;
+    if (cudaMalloc(&s->t, bytes) != cudaSuccess || cudaMalloc(&s->y, bytes) != cudaSuccess ||
+        cudaMalloc(&s->s2, bytes) != cudaSuccess) {
+        free_series(s);
+        return fail(PIORAN_ENOMEM, "cudaMalloc of a %lld-point series failed", (long long)N);
+    }
+    cudaMemcpyAsync(s->t, t, bytes, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(s->y, y, bytes, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(s->s2, s2, bytes, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { free_series(s); return fail(PIORAN_ECUDA, "series upload failed: %s", cudaGetErrorString(e)); }
+    int id = -1;
+    for (size_t k = 0; k < c->series.size(); k++)
+        if (!c->series[k]) { id = (int)k; break; }
+    if (id < 0) { c->series.push_back(nullptr); id = (int)c->series.size() - 1; }
+    c->series[id] = s;
+    *series_id = id;
+    return PIORAN_OK;
+}
+
+static Series* get_series(pioran_ctx* c, int id) {
+    if (id < 0 || id >= (int)c->series.size()) return nullptr;
+    return c->series[id];
+}
+
+extern "C" int pioran_series_free(pioran_ctx* c, int id) {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    Series* s = get_series(c, id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_series(s);
+    c->series[id] = nullptr;
+    return PIORAN_OK;
+}
+
+extern "C" int pioran_series_length(pioran_ctx* c, int id, int64_t* N) {
+    if (!c || !N) return fail(PIORAN_EINVAL, "NULL argument");
+    Series* s = get_series(c, id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
+    *N = s->N;
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ approx plan
+static int n_psd_par_of(int model) { return model == PIORAN_PSD_SBPL ? 3 : model == PIORAN_PSD_DBPL ? 5 : -1; }
+
+static int check_spec(const pioran_approx_spec& sp) {
+    if (n_psd_par_of(sp.psd_model) < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", sp.psd_model);
+    if (sp.basis != PIORAN_BASIS_SHO && sp.basis != PIORAN_BASIS_DRWCELERITE)
+        return fail(PIORAN_EINVAL, "unknown basis %d (src/psd.jl:285 errors likewise)", sp.basis);
+    if (sp.n_components < 2 || sp.n_components > MAXJ)
+        return fail(PIORAN_EINVAL, "n_components must be in [2,%d] (got %d)", MAXJ, sp.n_components);
+    if (!(sp.f_min > 0) || !(sp.f_max > sp.f_min) || !(sp.S_low > 0) || !(sp.S_high > 0))
+        return fail(PIORAN_EINVAL, "need 0 < f_min < f_max and positive S_low, S_high");
+    return 0;
+}
+
+// Builds (or fetches) the device plan: grid (src/psd.jl:81-83), spectral matrix (:86-97), LU with partial pivoting.
+static int get_plan(pioran_ctx* c, const pioran_approx_spec& sp, ApproxPlan** out) {
+    PlanKey key{sp.psd_model, sp.n_components, sp.basis, sp.is_integrated_power, sp.f_min, sp.f_max, sp.S_low, sp.S_high};
+    auto it = c->plans.find(key);
+    if (it != c->plans.end()) { *out = it->second; return 0; }
+    static thread_local ApproxPlan hp;
+    std::memset(&hp, 0, sizeof hp);
+    const int J = sp.n_components;
+    const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
+    for (int j = 0; j < J; j++) hp.fj[j] = f0 * std::pow(fM / f0, (double)j / (double)(J - 1));
+    double* A = hp.lu;
+    for (int j = 0; j < J; j++)
+        for (int k = 0; k < J; k++) {
+            const double r = hp.fj[j] / hp.fj[k], r2 = r * r;
+            A[j + k * J] = 1.0 / (1.0 + (sp.basis == PIORAN_BASIS_SHO ? r2 * r2 : r2 * r2 * r2));
+        }
+    for (int k = 0; k < J; k++) {  // right-looking LU, partial pivoting
+        int p = k;
+        double best = std::fabs(A[k + k * J]);
+        for (int r = k + 1; r < J; r++)
+            if (std::fabs(A[r + k * J]) > best) { best = std::fabs(A[r + k * J]); p = r; }
+        if (best == 0.0) return fail(PIORAN_ESINGULAR, "spectral matrix is singular at column %d", k);
+        hp.piv[k] = p;
+        if (p != k)
+            for (int col = 0; col < J; col++) std::swap(A[k + col * J], A[p + col * J]);
+        const double inv = 1.0 / A[k + k * J];
+        for (int r = k + 1; r < J; r++) A[r + k * J] *= inv;
+        for (int col = k + 1; col < J; col++) {
+            const double akc = A[k + col * J];
+            for (int r = k + 1; r < J; r++) A[r + col * J] -= A[r + k * J] * akc;
+        }
+    }
+    hp.J = J; hp.basis = sp.basis; hp.model = sp.psd_model; hp.n_psd_par = n_psd_par_of(sp.psd_model);
+    hp.is_integrated_power = sp.is_integrated_power ? 1 : 0;
+    hp.f_min = sp.f_min; hp.f_max = sp.f_max;
+    ApproxPlan* dp = nullptr;
+    CUDA_TRY(cudaMalloc(&dp, sizeof(ApproxPlan)));
+    cudaError_t e = cudaMemcpyAsync(dp, &hp, sizeof(ApproxPlan), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // hp is reused by the next call
+    if (e != cudaSuccess) { cudaFree(dp); return fail(PIORAN_ECUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+    c->plans[key] = dp;
+    *out = dp;
+    return 0;
+}
+
+static int rank_of(int basis, int J) { return basis == PIORAN_BASIS_SHO ? 2 * J : 3 * J; }
+
+// Row descriptors of the shared table for a spec (rows: cos/sin pairs of the J complex terms, then — DRWCelerite
+// only — the J real terms).  Coefficient formulas: src/psd.jl:250 (c = d = √2 π f) and :266-271 (c = π f, d = √3 c; 2c).
+static void make_rows(const pioran_approx_spec& sp, int RP, std::vector<RowDesc>& rows) {
+    const int J = sp.n_components;
+    const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
+    rows.assign(RP, RowDesc{0, 0, 0, ROW_PAD, 0});
+    for (int j = 0; j < J; j++) {
+        const double fj = f0 * std::pow(fM / f0, (double)j / (double)(J - 1));
+        if (sp.basis == PIORAN_BASIS_SHO) {
+            const double cj = std::sqrt(2.0) * M_PI * fj;
+            rows[2 * j] = RowDesc{cj, cj, 1.0, ROW_COS, j};
+            rows[2 * j + 1] = RowDesc{cj, cj, 1.0, ROW_SIN, j};
+        } else {
+            const double cj = M_PI * fj, dj = std::sqrt(3.0) * cj;
+            rows[2 * j] = RowDesc{cj, dj, std::sqrt(3.0), ROW_COS, j};
+            rows[2 * j + 1] = RowDesc{cj, dj, std::sqrt(3.0), ROW_SIN, j};
+            rows[2 * J + j] = RowDesc{2.0 * cj, 0.0, 0.0, ROW_REAL, j};
+        }
+    }
+}
+
+static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out) {
+    const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
+    TableKey key{sp.basis, sp.n_components, f0, fM};
+    auto it = s->tables.find(key);
+    if (it != s->tables.end()) { *out = it->second; return 0; }
+    const int R = rank_of(sp.basis, sp.n_components);
+    const int BS = bs_for_rank(R);
+    if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8 (n_components too large for this build)", R, BS);
+    const int RP = G * BS;
+    std::vector<RowDesc> rows;
+    make_rows(sp, RP, rows);
+    int rc = c->rows.ensure(sizeof(RowDesc) * RP);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->rows.p, rows.data(), sizeof(RowDesc) * RP, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // rows is a local
+    Table tb;
+    tb.rpad = RP;
+    tb.npad = ((s->N + CHUNK_STEPS - 1) / CHUNK_STEPS) * CHUNK_STEPS;
+    const size_t bytes = sizeof(double) * (size_t)tb.npad * table_step_doubles(RP);
+    CUDA_TRY(cudaMalloc(&tb.d, bytes));
+    const int64_t total = tb.npad * RP;
+    const int tpb = 256;
+    table_build_kernel<<<(unsigned)((total + tpb - 1) / tpb), tpb, 0, c->stream>>>(tb.d, s->t, s->y, s->s2, s->N, tb.npad,
+                                                                                 c->rows.as<RowDesc>(), RP);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    s->tables[key] = tb;
+    *out = tb;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 launchers
+template <int BS> struct KCfg { static constexpr int NW = (BS <= 5) ? 12 : (BS == 6) ? 10 : 8; };
+
+template <int BS>
+static size_t shared_smem_bytes() {
+    constexpr int RP = G * BS, SD = table_step_doubles(RP);
+    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)KCfg<BS>::NW * 2 * RP) + 2 * sizeof(uint64_t);
+}
+template <int BS>
+static size_t generic_smem_bytes(int Jt) {
+    constexpr int RP = G * BS, SD = table_step_doubles(RP);
+    return sizeof(double) * (size_t)KCfg<BS>::NW * ((size_t)GCH * SD + 2 * RP + (size_t)(GCH + 2) * Jt);
+}
+
+template <int BS>
+static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    auto kern = celerite_shared_kernel<BS, KCfg<BS>::NW>;
+    const size_t smem = shared_smem_bytes<BS>();
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int BS>
+static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
+    const size_t smem = generic_smem_bytes<BS>(args.Jt);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int nw_for_bs(int BS) { return BS <= 5 ? 12 : BS == 6 ? 10 : 8; }
+
+static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+    switch (BS) {
+        case 4: return launch_shared<4>(c, a, nitems);
+        case 5: return launch_shared<5>(c, a, nitems);
+        case 6: return launch_shared<6>(c, a, nitems);
+        case 7: return launch_shared<7>(c, a, nitems);
+        case 8: return launch_shared<8>(c, a, nitems);
+    }
+    return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
+}
+static int dispatch_generic(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+    switch (BS) {
+        case 4: return launch_generic<4>(c, a, nitems);
+        case 5: return launch_generic<5>(c, a, nitems);
+        case 6: return launch_generic<6>(c, a, nitems);
+        case 7: return launch_generic<7>(c, a, nitems);
+        case 8: return launch_generic<8>(c, a, nitems);
+    }
+    return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
+}
+
+// Splits S series × B parameter vectors into CTA work items of at most NW vectors, sized so that the number of
+// items is close to a multiple of the SM count (one CTA per SM is resident), longest series first.
+struct ItemPlan { std::vector<WorkItem> items; };
+static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* tabs, int B, int NW, bool theta_per_series,
+                       ItemPlan& ip) {
+    const long long E = (long long)S * B;
+    int tpi = (int)std::min<long long>(NW, std::max<long long>(1, (E + c->num_sms - 1) / c->num_sms));
+    long long items = 0;
+    for (int s = 0; s < S; s++) items += (B + tpi - 1) / tpi;
+    const long long waves = (items + c->num_sms - 1) / c->num_sms;
+    const long long target = waves * c->num_sms;
+    tpi = (int)std::min<long long>(NW, std::max<long long>(1, (E + target - 1) / target));
+    std::vector<int> order(S);
+    for (int s = 0; s < S; s++) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ser[x]->N > ser[y]->N; });
+    ip.items.clear();
+    for (int s : order) {
+        const int nit = (B + tpi - 1) / tpi;
+        for (int k = 0; k < nit; k++) {
+            const int beg = (int)((long long)B * k / nit), end = (int)((long long)B * (k + 1) / nit);
+            WorkItem w;
+            w.table = tabs ? tabs[s].d : nullptr;
+            w.t = ser[s]->t; w.y = ser[s]->y; w.s2 = ser[s]->s2;
+            w.N = ser[s]->N;
+            w.theta_begin = s * B + beg;
+            w.par_begin = (theta_per_series ? s * B : 0) + beg;
+            w.count = end - beg;
+            w.out_begin = s * B + beg;
+            ip.items.push_back(w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1 entry
+extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spec, int B, const double* theta,
+                                    double* a, double* b, double* cc, double* d) {
+    if (!c || !spec || !theta || !a || !b || !cc || !d) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    int rc = check_spec(*spec);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    ApproxPlan* plan;
+    if ((rc = get_plan(c, *spec, &plan))) return rc;
+    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 1;
+    const int Jt = spec->basis == PIORAN_BASIS_SHO ? spec->n_components : 2 * spec->n_components;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * ts))) return rc;
+    if ((rc = c->coef.ensure(sizeof(double) * (size_t)B * Jt * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * (size_t)B * ts, cudaMemcpyHostToDevice, c->stream));
+    double* da = c->coef.as<double>();
+    const size_t n = (size_t)B * Jt;
+    approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, c->theta.as<double>(), ts, da, da + n, da + 2 * n,
+                                                         da + 3 * n, nullptr, 0, nullptr);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(a, da, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(b, da + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(cc, da + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d, da + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused entry
+static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs, int B,
+                                  const double* theta_dev, int theta_per_series, double* logl_dev) {
+    int rc;
+    if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
+    if ((long long)S * B > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "S*B too large");
+    std::vector<Series*> ser(S);
+    std::vector<Table> tabs(S);
+    for (int s = 0; s < S; s++) {
+        if ((rc = check_spec(specs[s]))) return rc;
+        if (specs[s].psd_model != specs[0].psd_model || specs[s].basis != specs[0].basis ||
+            specs[s].n_components != specs[0].n_components)
+            return fail(PIORAN_EINVAL, "all specs of one call must share psd_model, basis and n_components");
+        ser[s] = get_series(c, series_ids[s]);
+        if (!ser[s]) return fail(PIORAN_EINVAL, "unknown series id %d", series_ids[s]);
+    }
+    const int npar = n_psd_par_of(specs[0].psd_model), ts = npar + 3;
+    const int R = rank_of(specs[0].basis, specs[0].n_components);
+    const int BS = bs_for_rank(R);
+    if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
+    const int RP = G * BS;
+    for (int s = 0; s < S; s++)
+        if ((rc = get_table(c, ser[s], specs[s], &tabs[s]))) return rc;
+    // K1: amplitudes for every (series, θ)
+    if ((rc = c->amp.ensure(sizeof(double) * (size_t)S * B * RP))) return rc;
+    if ((rc = c->suma.ensure(sizeof(double) * (size_t)S * B))) return rc;
+    for (int s = 0; s < S; s++) {
+        ApproxPlan* plan;
+        if ((rc = get_plan(c, specs[s], &plan))) return rc;
+        const double* th = theta_dev + (theta_per_series ? (size_t)s * B * ts : 0);
+        approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, th, ts, nullptr, nullptr, nullptr, nullptr,
+                                                             c->amp.as<double>() + (size_t)s * B * RP, RP,
+                                                             c->suma.as<double>() + (size_t)s * B);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    // K2
+    ItemPlan ip;
+    plan_items(c, S, ser.data(), tabs.data(), B, nw_for_bs(BS), theta_per_series != 0, ip);
+    if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // ip.items is a local; a few µs, before the kernel starts
+    BatchArgs args{};
+    args.work = c->work.as<WorkItem>();
+    args.amp = c->amp.as<double>();
+    args.suma = c->suma.as<double>();
+    args.mu = theta_dev + npar + 2;
+    args.nu = theta_dev + npar + 1;
+    args.pstride = ts;
+    args.out = logl_dev;
+    return dispatch_shared(c, BS, args, (int)ip.items.size());
+}
+
+extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
+                                      int B, const double* theta_dev, int theta_per_series, double* logl_dev) {
+    if (!c || !series_ids || !specs || !theta_dev || !logl_dev) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return approx_logl_dev_locked(c, S, series_ids, specs, B, theta_dev, theta_per_series, logl_dev);
+}
+
+extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs, int B,
+                                  const double* theta, int theta_per_series, double* logl_out) {
+    if (!c || !series_ids || !specs || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int npar = n_psd_par_of(specs[0].psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", specs[0].psd_model);
+    const int ts = npar + 3;
+    const size_t nth = (size_t)(theta_per_series ? S : 1) * B * ts;
+    int rc;
+    if ((rc = c->theta.ensure(sizeof(double) * nth))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)S * B))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = approx_logl_dev_locked(c, S, series_ids, specs, B, c->theta.as<double>(), theta_per_series,
+                                     c->out.as<double>())))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)S * B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ generic entry
+// Uploads [B×Jt] coefficient arrays and per-θ scalars; returns device pointers inside ctx workspaces.
+struct GenericInputs { double *a, *b, *c, *d, *mu, *nu, *yb, *sb; };
+static int upload_generic(pioran_ctx* c, int B, int Jt, int64_t N, const double* a, const double* b, const double* cc,
+                          const double* d, const double* mu, const double* nu, const double* y_batch,
+                          const double* s2_batch, GenericInputs& gi) {
+    int rc;
+    const size_t n = (size_t)B * Jt;
+    if ((rc = c->coef.ensure(sizeof(double) * (4 * n + 2 * (size_t)B)))) return rc;
+    double* base = c->coef.as<double>();
+    gi.a = base; gi.b = base + n; gi.c = base + 2 * n; gi.d = base + 3 * n;
+    gi.mu = mu ? base + 4 * n : nullptr;
+    gi.nu = nu ? base + 4 * n + B : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(gi.a, a, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(gi.b, b, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(gi.c, cc, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(gi.d, d, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    if (mu) CUDA_TRY(cudaMemcpyAsync(gi.mu, mu, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    if (nu) CUDA_TRY(cudaMemcpyAsync(gi.nu, nu, sizeof(double) * B, cudaMemcpyHostToDevice, c->stream));
+    gi.yb = gi.sb = nullptr;
+    const size_t ny = (size_t)B * N;
+    if (y_batch || s2_batch) {
+        if ((rc = c->misc.ensure(sizeof(double) * 2 * ny))) return rc;
+        if (y_batch) {
+            gi.yb = c->misc.as<double>();
+            CUDA_TRY(cudaMemcpyAsync(gi.yb, y_batch, sizeof(double) * ny, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (s2_batch) {
+            gi.sb = c->misc.as<double>() + ny;
+            CUDA_TRY(cudaMemcpyAsync(gi.sb, s2_batch, sizeof(double) * ny, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    return 0;
+}
+
+extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                    const double* cc, const double* d, const double* mu, const double* nu,
+                                    const double* y_batch, const double* s2_batch, double* logl_out) {
+    if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    // rank reduction: a term that is real (b = d = 0) for every set of the batch needs one row, not two
+    std::vector<int> term_row(Jt + 1);
+    int R = 0;
+    for (int m = 0; m < Jt; m++) {
+        bool real = true;
+        for (int i = 0; i < B && real; i++) real = (b[(size_t)i * Jt + m] == 0.0 && d[(size_t)i * Jt + m] == 0.0);
+        term_row[m] = real ? -(R + 1) : R;  // negative → real term at row R
+        R += real ? 1 : 2;
+    }
+    const int BS = bs_for_rank(R);
+    if (BS > 8)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) needs block size %d > 8; this build supports rank <= 64", R, Jt, BS);
+    int rc;
+    GenericInputs gi;
+    if ((rc = upload_generic(c, B, Jt, s->N, a, b, cc, d, mu, nu, y_batch, s2_batch, gi))) return rc;
+    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->rows.p, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
+    ItemPlan ip;
+    Series* sp = s;
+    plan_items(c, 1, &sp, nullptr, B, nw_for_bs(BS), false, ip);
+    if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    BatchArgs args{};
+    args.work = c->work.as<WorkItem>();
+    args.a = gi.a; args.b = gi.b; args.c = gi.c; args.d = gi.d;
+    args.Jt = Jt;
+    args.term_row = c->rows.as<int>();
+    args.R = R;
+    args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
+    args.y_batch = gi.yb; args.s2_batch = gi.sb; args.ystride = s->N;
+    args.out = c->out.as<double>();
+    if ((rc = dispatch_generic(c, BS, args, (int)ip.items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 / K4 entries
+extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                         const double* cc, const double* d, const double* mu, const double* nu,
+                                         double* logl_out) {
+    if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    return scan_logl_host(c->stream, c->num_sms, &c->launches, s->N, s->t, s->y, s->s2, B, Jt, a, b, cc, d, mu, nu,
+                          logl_out, fail);
+}
+
+extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                  const double* cc, const double* d, const double* mu, const double* nu,
+                                  double* nll_out, int* info_out) {
+    if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    return dense_logl_host(c->stream, &c->launches, s->N, s->t, s->y, s->s2, B, Jt, a, b, cc, d, mu, nu, nll_out,
+                           info_out, fail);
+}

@@ -1,0 +1,447 @@
+// celerite.cuh — K2: batched celerite factorisation + solve + log-determinant (FP64, sm_100a).
+//
+// Replaces  logl(a,b,c,d,τ,y,σ2)  = init_semi_separable! + solve_prec!  of the reference
+// (src/celerite_solver.jl:12-100, 115-158, 312-334) for a batch of parameter vectors.
+//
+// Algorithm (forward-only fused sweep).  With A_n = Σa + ν σ²_n and the amplitude-scaled state
+// T = diag(amp) S diag(amp)  (S is the reference's S_n matrix, celerite_solver.jl:69-90):
+//     T   ← (φ_n φ_nᵀ) ∘ (T + q_{n-1} w_{n-1}ᵀ)            q = D·w
+//     p   = T Ũ_n ;  D_n = A_n − Ũ_nᵀ p                     (celerite_solver.jl:92)
+//     q_n = amp∘V_n − p ;  w_n = q_n / D_n                   (W of the paper, celerite_solver.jl:95-98)
+//     g   ← φ_n ∘ (g + w_{n-1} z_{n-1}) ;  z_n = (y_n − μ) − Ũ_nᵀ g      (celerite_solver.jl:132-142)
+//     logL = −½ Σ log|D_n| − ½ Σ z_n²/D_n − (N/2) log 2π     (y'K⁻¹y = Σ z_n²/D_n, celerite_solver.jl:333)
+// No U/W/φ matrices are materialised and there is no backward pass.
+//
+// Mapping.  One warp per (parameter vector, series).  The symmetric R_pad×R_pad state (R_pad = 8·BS) is cut
+// into an 8×8 grid of BS×BS blocks.  Lane l = (i = l>>2, o = l&3) keeps in registers
+//     o = 1,2,3 : the full off-diagonal block (I = i, K = (i+o) mod 8);
+//     o = 0     : a composite block — strict lower triangle of the diagonal block (i,i) and, in the upper
+//                 triangle, its half of the distance-4 block {i, i^4};
+// the 8·BS true diagonal entries live with the row owners (lane (i,o) owns rows i·BS+o and i·BS+o+4).
+// Every lane therefore runs the same BS×BS instruction stream (no divergence) with 4 FP64 issue slots per
+// stored entry: 1 DMUL + 1 DFMA (rank-1 update and decay) + 2 DFMA (symmetric matrix-vector product).
+// The per-entry decay product φ_j φ_k is never formed: the state is stored with one factor pending,
+// alternately on the row side (odd steps) and the column side (even steps), and the pending factor is folded
+// into the vectors (UH = φ∘Ũ, KAP = φ_n∘φ_{n−1} in the series table).
+// Cross-lane traffic per step: BS+ceil(BS/2)+ceil(BS/4) 64-bit shuffles for the matvec reduce-scatter, one
+// 2-value butterfly all-reduce for (ŨᵀTŨ, Ũᵀg), and 2 shared-memory vectors (q, w) per warp.
+//
+// θ-independent per-step vectors (Ũ, φ∘Ũ, φφ', φ, V, y, σ²) come from the series table (table.cuh), staged
+// chunk-wise into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) and shared by all warps of a
+// CTA; in generic mode (explicit per-θ c,d) each warp builds its own chunk with sincos/exp.
+#pragma once
+#include "common.cuh"
+
+namespace pioran {
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// 1-D TMA bulk copy global → shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Per-lane persistent state of one (θ, series) evaluation.
+template <int BS>
+struct LaneState {
+    double M[BS][BS];   // block of the (pending-scaled) state matrix
+    double sjj[2];      // true diagonal entries of the owned rows
+    double g[2];        // forward-substitution vector of the owned rows
+    double amp[2];      // row amplitudes of the owned rows
+    double chi2, logacc, dkeep, dfirst;
+};
+
+// One time step.  ODD: the step index n is odd → the state leaves the step with the row factor pending.
+//   T      : this step's table record in shared memory
+//   qs, ws : per-warp scratch vectors (q and w of the previous step, one of them pre-multiplied by φ_n)
+template <int BS, bool ODD>
+__device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* __restrict__ T, double* __restrict__ qs,
+                                              double* __restrict__ ws, const int rowI, const int colA, const int colB,
+                                              const int o, const double dmask, const int src_lane, const int j0,
+                                              const int j1, const bool valid1, const double yn, const double s2n,
+                                              const double suma, const double mu, const double nu, const int64_t n,
+                                              const int lane) {
+    constexpr int RP = G * BS;
+    // ---- row-side operands of block-row I
+    double qrow[BS], qdia[BS], urow[BS], xrow[BS];
+#pragma unroll
+    for (int r = 0; r < BS; r++) {
+        qrow[r] = qs[rowI + r];
+        urow[r] = T[(ODD ? F_UH : F_UT) * RP + rowI + r];   // weight of the column partial sums
+        xrow[r] = T[(ODD ? F_PHI : F_KAP) * RP + rowI + r]; // ODD: post-scale of row sums; EVEN: decay of row r
+        qdia[r] = qrow[r] * dmask;
+    }
+    double rowpart[BS], xout[BS], selfa[BS];
+#pragma unroll
+    for (int r = 0; r < BS; r++) rowpart[r] = 0.0;
+
+    // ---- block phase: rank-1 update + decay + symmetric matvec, column by column
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+        const double wA = ws[colA + c], wB = ws[colB + c];
+        const double uA = T[(ODD ? F_UT : F_UH) * RP + colA + c], uB = T[(ODD ? F_UT : F_UH) * RP + colB + c];
+        const double zA = T[(ODD ? F_KAP : F_PHI) * RP + colA + c], zB = T[(ODD ? F_KAP : F_PHI) * RP + colB + c];
+        double cA = 0.0, cB = 0.0;
+#pragma unroll
+        for (int r = 0; r < BS; r++) {
+            const bool useA = r > c;  // compile-time after unrolling
+            const double w = useA ? wA : wB;
+            const double u = useA ? uA : uB;
+            const double qr = (r == c) ? qdia[r] : qrow[r];
+            double m;
+            if (ODD) m = fma(useA ? zA : zB, st.M[r][c], qr * w);  // κ_c·M + q_r·(φ_c w_c)
+            else     m = fma(xrow[r], st.M[r][c], qr * w);         // κ_r·M + (φ_r q_r)·w_c
+            st.M[r][c] = m;
+            rowpart[r] = fma(m, u, rowpart[r]);
+            if (useA) cA = fma(m, urow[r], cA);
+            else      cB = fma(m, urow[r], cB);
+        }
+        if (!ODD) { cA *= zA; cB *= zB; }  // column factor pending → apply φ_c to the column sums
+        xout[c] = cB + (o ? cA : 0.0);
+        selfa[c] = o ? 0.0 : cA;
+    }
+
+    // ---- matvec reduction: rotate column sums to the owning block-row, then reduce-scatter over the 4 lanes
+    double tot[BS];
+#pragma unroll
+    for (int c = 0; c < BS; c++) {
+        const double yv = __shfl_sync(FULL, xout[c], src_lane);
+        if (ODD) tot[c] = fma(xrow[c], rowpart[c], yv) + selfa[c];
+        else     tot[c] = (rowpart[c] + yv) + selfa[c];
+    }
+    const bool bit0 = (o & 1) != 0, bit1 = (o & 2) != 0;
+    double e[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        if (2 * m < BS) {
+            const double lo = tot[(2 * m < BS) ? 2 * m : 0];
+            const double hi = (2 * m + 1 < BS) ? tot[(2 * m + 1 < BS) ? 2 * m + 1 : 0] : 0.0;
+            const double recv = __shfl_xor_sync(FULL, bit0 ? lo : hi, 1);
+            e[m] = (bit0 ? hi : lo) + recv;
+        } else {
+            e[m] = 0.0;
+        }
+    }
+    double f0, f1 = 0.0;
+    {
+        const double recv = __shfl_xor_sync(FULL, bit1 ? e[0] : e[1], 2);
+        f0 = (bit1 ? e[1] : e[0]) + recv;
+    }
+    if (BS > 4) {
+        const double recv = __shfl_xor_sync(FULL, bit1 ? e[2] : e[3], 2);
+        f1 = (bit1 ? e[3] : e[2]) + recv;
+    }
+
+    // ---- owner phase: rows j0 (and j1)
+    const double ut0 = T[F_UT * RP + j0], ut1 = T[F_UT * RP + j1];
+    const double v0 = T[F_V * RP + j0], v1 = T[F_V * RP + j1];
+    const double pn0 = T[F_PHN * RP + j0], pn1 = T[F_PHN * RP + j1];
+    const double p0 = fma(st.sjj[0], ut0, f0);
+    const double p1 = fma(st.sjj[1], ut1, f1);
+    double spart = fma(ut1, p1, ut0 * p0);
+    double upart = fma(ut1, st.g[1], ut0 * st.g[0]);
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        spart += __shfl_xor_sync(FULL, spart, sft);
+        upart += __shfl_xor_sync(FULL, upart, sft);
+    }
+    const double An = fma(nu, s2n, suma);
+    const double D = An - spart;              // celerite_solver.jl:92
+    const double rD = 1.0 / D;
+    const double z = (yn - mu) - upart;       // celerite_solver.jl:141
+    st.chi2 = fma(z * z, rD, st.chi2);
+    // log|D_n| (celerite_solver.jl:140; no abs on the first pivot, :126): lane n%32 keeps D_n, one log per 32 steps
+    if (n == 0) st.dfirst = D;
+    else if ((int)(n & 31) == lane) st.dkeep = D;
+    if ((n & 31) == 31) { st.logacc += log(fabs(st.dkeep)); st.dkeep = 1.0; }
+
+    const double q0 = fma(st.amp[0], v0, -p0), q1 = fma(st.amp[1], v1, -p1);
+    const double w0 = q0 * rD, w1 = q1 * rD;
+    st.g[0] = pn0 * fma(w0, z, st.g[0]);
+    st.g[1] = pn1 * fma(w1, z, st.g[1]);
+    st.sjj[0] = (pn0 * pn0) * fma(q0, w0, st.sjj[0]);   // celerite_solver.jl:85
+    st.sjj[1] = (pn1 * pn1) * fma(q1, w1, st.sjj[1]);
+    __syncwarp();
+    // the NEXT step is odd iff this one is even: odd steps consume (q, φ∘w), even steps (φ∘q, w)
+    if (!ODD) {
+        qs[j0] = q0; ws[j0] = pn0 * w0;
+        if (valid1) { qs[j1] = q1; ws[j1] = pn1 * w1; }
+    } else {
+        qs[j0] = pn0 * q0; ws[j0] = w0;
+        if (valid1) { qs[j1] = pn1 * q1; ws[j1] = w1; }
+    }
+    __syncwarp();
+}
+
+// Per-θ inputs of the batched kernel.
+struct BatchArgs {
+    const WorkItem* work;
+    // shared-table mode: row amplitudes [nθ × R_pad] and Σa [nθ]
+    const double* amp;
+    const double* suma;
+    // generic mode: celerite coefficients [nθ × Jt]
+    const double* a; const double* b; const double* c; const double* d;
+    int Jt;
+    const int* term_row;    // generic mode: first row of term m (≥0: complex, 2 rows; <0: real term at row −v−1)
+    int R;                  // generic mode: number of live rows
+    const double* mu;       // [nθ] (stride pstride) or nullptr
+    const double* nu;       // [nθ] (stride pstride) or nullptr
+    int pstride;
+    const double* y_batch;  // [nθ × ystride] or nullptr
+    const double* s2_batch; // [nθ × ystride] or nullptr
+    int64_t ystride;
+    double* out;            // logL
+};
+
+template <int BS>
+__device__ __forceinline__ void lane_init(LaneState<BS>& st) {
+#pragma unroll
+    for (int r = 0; r < BS; r++)
+#pragma unroll
+        for (int c = 0; c < BS; c++) st.M[r][c] = 0.0;
+    st.sjj[0] = st.sjj[1] = 0.0;
+    st.g[0] = st.g[1] = 0.0;
+    st.chi2 = 0.0; st.logacc = 0.0; st.dkeep = 1.0; st.dfirst = 1.0;
+}
+
+template <int BS>
+__device__ __forceinline__ double lane_finish(LaneState<BS>& st, int64_t N, int lane) {
+    // flush the log|D| ring: steps since the last multiple of 32
+    const int rem = (int)(N & 31);
+    if (rem != 0 && lane < rem) st.logacc += log(fabs(st.dkeep));
+    double la = st.logacc;
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) la += __shfl_xor_sync(FULL, la, sft);
+    const double logdet = log(st.dfirst) + la;
+    // celerite_solver.jl:333
+    return -logdet / 2 - (double)N * 1.8378770664093453 / 2 - st.chi2 / 2;
+}
+
+// ------------------------------------------------------------------------------------------- shared-table kernel
+// grid = number of work items; block = NW warps; each warp one θ of the item's series.
+// dynamic smem: 2 stages × CHUNK_STEPS × SD doubles | NW × 2·R_pad scratch | 2 mbarriers
+template <int BS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const BatchArgs args) {
+    constexpr int RP = G * BS, SD = table_step_doubles(RP), STAGE = CHUNK_STEPS * SD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    double* scratch = stages + 2 * STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 2 * RP);
+
+    const WorkItem wk = args.work[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t N = wk.N;
+    const int64_t nchunks = (N + CHUNK_STEPS - 1) / CHUNK_STEPS;
+    constexpr uint32_t STAGE_BYTES = STAGE * sizeof(double);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2 && k < nchunks; k++) {
+            mbar_arrive_expect_tx(&bars[k], STAGE_BYTES);
+            tma_load_1d(stages + k * STAGE, wk.table + (size_t)k * STAGE, STAGE_BYTES, &bars[k]);
+        }
+    }
+
+    const bool active = warp < wk.count;
+    const int th = wk.theta_begin + (active ? warp : 0);
+    const int i = lane >> 2, o = lane & 3;
+    const int rowI = i * BS;
+    const int colA = ((i + o) & 7) * BS;
+    const int colB = (o == 0) ? ((i ^ 4) * BS) : colA;
+    const double dmask = (o == 0 && i >= 4) ? 0.0 : 1.0;
+    const int src_lane = (((i - (o ? o : 4)) & 7) << 2) | o;
+    const int j0 = rowI + o;
+    const bool valid1 = (o + 4) < BS;
+    const int j1 = valid1 ? j0 + 4 : j0;
+
+    LaneState<BS> st;
+    lane_init(st);
+    st.amp[0] = args.amp[(size_t)th * RP + j0];
+    st.amp[1] = valid1 ? args.amp[(size_t)th * RP + j1] : 0.0;
+    const double suma = args.suma[th];
+    const size_t pi = (size_t)wk.par_begin + (active ? warp : 0);
+    const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
+    const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
+    const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : nullptr;
+    const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : nullptr;
+
+    double* qs = scratch + warp * 2 * RP;
+    double* ws = qs + RP;
+    for (int k = lane; k < 2 * RP; k += 32) qs[k] = 0.0;
+    __syncwarp();
+
+    for (int64_t k = 0; k < nchunks; k++) {
+        const int sidx = (int)(k & 1);
+        mbar_wait(&bars[sidx], (uint32_t)((k >> 1) & 1));
+        const double* stage = stages + sidx * STAGE;
+        const int64_t nbeg = k * CHUNK_STEPS;
+        const int nsteps = (int)((N - nbeg) < CHUNK_STEPS ? (N - nbeg) : CHUNK_STEPS);
+        if (active) {
+            for (int s = 0; s < nsteps; s += 2) {
+                const double* T0 = stage + s * SD;
+                const int64_t n = nbeg + s;
+                double yn = yb ? yb[n] : T0[6 * RP + 0];
+                double s2n = sb ? sb[n] : T0[6 * RP + 1];
+                celerite_step<BS, false>(st, T0, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yn, s2n,
+                                         suma, mu, nu, n, lane);
+                if (s + 1 < nsteps) {
+                    const double* T1 = T0 + SD;
+                    yn = yb ? yb[n + 1] : T1[6 * RP + 0];
+                    s2n = sb ? sb[n + 1] : T1[6 * RP + 1];
+                    celerite_step<BS, true>(st, T1, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yn,
+                                            s2n, suma, mu, nu, n + 1, lane);
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with this stage → refill it with chunk k+2
+        if (threadIdx.x == 0 && k + 2 < nchunks) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
+            tma_load_1d(stages + sidx * STAGE, wk.table + (size_t)(k + 2) * STAGE, STAGE_BYTES, &bars[sidx]);
+        }
+    }
+    if (active) {
+        const double res = lane_finish(st, N, lane);
+        if (lane == 0) args.out[wk.out_begin + warp] = res;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- generic kernel
+// Explicit per-θ (a,b,c,d): every term gets a cos-row and a sin-row (R = 2·Jt, like the reference), the warp
+// computes its own table chunk (GCH steps) with sincos/exp — celerite_solver.jl:51-64 — then runs the same steps.
+constexpr int GCH = 4;
+
+template <int BS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const BatchArgs args) {
+    constexpr int RP = G * BS, SD = table_step_doubles(RP);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // per warp: GCH·SD table | 2·RP scratch | (GCH+2)·Jt φ side array
+    const int Jt = args.Jt;
+    const int per_warp = GCH * SD + 2 * RP + (GCH + 2) * Jt;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
+    double* tab = base;
+    double* qs = base + GCH * SD;
+    double* ws = qs + RP;
+    double* phs = ws + RP;
+
+    const WorkItem wk = args.work[blockIdx.x];
+    if (warp >= wk.count) return;
+    const int th = wk.theta_begin + warp;
+    const int64_t N = wk.N;
+    const double* ca = args.a + (size_t)th * Jt;
+    const double* cb = args.b + (size_t)th * Jt;
+    const double* cc = args.c + (size_t)th * Jt;
+    const double* cd = args.d + (size_t)th * Jt;
+
+    const int i = lane >> 2, o = lane & 3;
+    const int rowI = i * BS;
+    const int colA = ((i + o) & 7) * BS;
+    const int colB = (o == 0) ? ((i ^ 4) * BS) : colA;
+    const double dmask = (o == 0 && i >= 4) ? 0.0 : 1.0;
+    const int src_lane = (((i - (o ? o : 4)) & 7) << 2) | o;
+    const int j0 = rowI + o;
+    const bool valid1 = (o + 4) < BS;
+    const int j1 = valid1 ? j0 + 4 : j0;
+    const int R = args.R;
+    const int* term_row = args.term_row;
+
+    LaneState<BS> st;
+    lane_init(st);
+    st.amp[0] = (j0 < R) ? 1.0 : 0.0;
+    st.amp[1] = (valid1 && j1 < R) ? 1.0 : 0.0;
+    double suma = 0.0;
+    for (int m = 0; m < Jt; m++) suma += ca[m];   // celerite_solver.jl:21
+    const size_t pi = (size_t)wk.par_begin + warp;
+    const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
+    const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
+    const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : wk.y;
+    const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : wk.s2;
+
+    for (int k = lane; k < 2 * RP; k += 32) qs[k] = 0.0;
+    // zero the padded rows of the table once (rows ≥ R never change)
+    for (int k = lane; k < GCH * SD; k += 32) tab[k] = 0.0;
+    __syncwarp();
+
+    for (int64_t nbeg = 0; nbeg < N; nbeg += GCH) {
+        const int nsteps = (int)((N - nbeg) < GCH ? (N - nbeg) : GCH);
+        // pass 1: φ for steps nbeg-1 … nbeg+GCH  (φ_0 = 0, φ_N = 0)
+        for (int idx = lane; idx < (GCH + 2) * Jt; idx += 32) {
+            const int s = idx / Jt, m = idx - s * Jt;
+            const int64_t n = nbeg - 1 + s;
+            double ph = 0.0;
+            if (n >= 1 && n < N) ph = exp(-cc[m] * (wk.t[n] - wk.t[n - 1]));
+            phs[idx] = ph;
+        }
+        __syncwarp();
+        // pass 2: rows
+        for (int idx = lane; idx < nsteps * Jt; idx += 32) {
+            const int s = idx / Jt, m = idx - s * Jt;
+            const int64_t n = nbeg + s;
+            const double php = phs[s * Jt + m], ph = phs[(s + 1) * Jt + m], phn = phs[(s + 2) * Jt + m];
+            double* Tn = tab + s * SD;
+            const int tr = term_row[m];
+            if (tr < 0) {  // real term (b = d = 0): U = a, V = 1; the sin-row is identically zero and is dropped
+                const int r0 = -tr - 1;
+                Tn[F_UT * RP + r0] = ca[m];       Tn[F_UH * RP + r0] = ph * ca[m];
+                Tn[F_KAP * RP + r0] = ph * php;   Tn[F_PHI * RP + r0] = ph;
+                Tn[F_V * RP + r0] = 1.0;          Tn[F_PHN * RP + r0] = phn;
+            } else {
+                double si, co;
+                sincos(cd[m] * wk.t[n], &si, &co);
+                const double u0 = ca[m] * co + cb[m] * si;   // celerite_solver.jl:60
+                const double u1 = ca[m] * si - cb[m] * co;   // celerite_solver.jl:59
+                const int r0 = tr, r1 = tr + 1;
+                Tn[F_UT * RP + r0] = u0;        Tn[F_UT * RP + r1] = u1;
+                Tn[F_UH * RP + r0] = ph * u0;   Tn[F_UH * RP + r1] = ph * u1;
+                Tn[F_KAP * RP + r0] = ph * php; Tn[F_KAP * RP + r1] = ph * php;
+                Tn[F_PHI * RP + r0] = ph;       Tn[F_PHI * RP + r1] = ph;
+                Tn[F_V * RP + r0] = co;         Tn[F_V * RP + r1] = si;
+                Tn[F_PHN * RP + r0] = phn;      Tn[F_PHN * RP + r1] = phn;
+            }
+        }
+        __syncwarp();
+        for (int s = 0; s < nsteps; s += 2) {
+            const double* T0 = tab + s * SD;
+            const int64_t n = nbeg + s;
+            celerite_step<BS, false>(st, T0, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yb[n], sb[n],
+                                     suma, mu, nu, n, lane);
+            if (s + 1 < nsteps)
+                celerite_step<BS, true>(st, T0 + SD, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1,
+                                        yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane);
+        }
+        __syncwarp();
+    }
+    const double res = lane_finish(st, N, lane);
+    if (lane == 0) args.out[wk.out_begin + warp] = res;
+}
+
+}  // namespace pioran

@@ -1,0 +1,54 @@
+// common.cuh — shared definitions of the B200 celerite backend (device + host).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pioran {
+
+// ---------------------------------------------------------------------------------------------------------
+// Row layout.  A sum of celerite terms is turned into R "rows" (the rank of the semiseparable part):
+//   complex term (b≠0 or d≠0) → 2 rows (cos-row, sin-row);  real term (b=d=0) → 1 row.
+// The reference always uses 2 rows per term (src/celerite_solver.jl:20, R = 2J) and carries identically-zero
+// rows for real terms; dropping them changes no arithmetic result.
+// Rows are grouped into G = 8 blocks of BS rows: R_pad = 8·BS ≥ R, padded rows are all-zero.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int G = 8;
+
+enum RowKind : int { ROW_COS = 0, ROW_SIN = 1, ROW_REAL = 2, ROW_PAD = 3 };
+
+// θ-independent description of one row (shared-table mode): which celerite term, which component.
+struct RowDesc {
+    double c;      // decay rate of the term
+    double d;      // angular frequency of the term
+    double ratio;  // b/a of the term (SHO: 1, DRWCelerite celerite part: √3, real terms: 0)
+    int kind;      // RowKind
+    int term;      // index of the amplitude this row scales with
+};
+
+// Per-step record of the series table (doubles).  Six row vectors of R_pad entries then 8 scalars.
+//   UT  : Ũ_n            (U_n = amp ∘ Ũ_n;  src/celerite_solver.jl:59-60 with a factored out)
+//   UH  : φ_n ∘ Ũ_n
+//   KAP : φ_n ∘ φ_{n-1}
+//   PHI : φ_n = exp(-c (t_n - t_{n-1}))   (φ_0 = 0;  src/celerite_solver.jl:54-57)
+//   V   : cos/sin(d t_n) (or 1 for real rows;  src/celerite_solver.jl:62-63)
+//   PHN : φ_{n+1}        (0 at the last step)
+//   scalars: [0] y_n  [1] σ²_n  [2] t_n
+__host__ __device__ constexpr int table_step_doubles(int rpad) { return 6 * rpad + 8; }
+enum TableField : int { F_UT = 0, F_UH = 1, F_KAP = 2, F_PHI = 3, F_V = 4, F_PHN = 5 };
+
+constexpr int CHUNK_STEPS = 16;  // steps per TMA stage
+
+// One unit of work of the batched kernel: `count` parameter vectors of one series.
+struct WorkItem {
+    const double* table;   // series table (shared mode) or nullptr (generic mode)
+    const double* t;       // series arrays (device)
+    const double* y;
+    const double* s2;
+    int64_t N;
+    int theta_begin;       // first row of the per-(series,θ) arrays (amp, Σa) handled by this CTA
+    int par_begin;         // first row of the per-θ scalar arrays (μ, ν, y_batch) handled by this CTA
+    int count;             // number of θ (≤ warps per CTA)
+    int out_begin;         // first index of logl_out
+};
+
+}  // namespace pioran
