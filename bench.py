@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — celerite logpdf evaluations / second at N=1 000, J=20 (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 10 --warmup 3
+    python bench.py --impl reference ...          # CPU restatement of the reference algorithm on the host cores
+
+A "step" is one pass of the hot path — fused approx (K1) + batched celerite factor/solve/logdet (K2) — over one batch
+of B parameter vectors per GPU against one resident time series.  The batch is sharded over the ranks with no
+data-path collective; one NCCL all-gather returns the logL vector to every rank and is inside the
+timed region.  `value` is measured with θ resident in HBM (device entry point of the C ABI); `e2e` goes through the
+host entry point of the C ABI with pinned host buffers (H2D of θ and D2H of logL inside the timed region).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import workloads as wl  # noqa: E402
+
+METRIC = "celerite logpdf evals/sec at N=1k,J=20"
+UNIT = "evals/s"
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_peak_microbench.json")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--basis", default="DRWCelerite", choices=["SHO", "DRWCelerite"])
+    ap.add_argument("--N", type=int, default=1000, help="series length")
+    ap.add_argument("--J", type=int, default=20, help="n_components of approx")
+    ap.add_argument("--B", type=int, default=65536, help="parameter vectors per GPU per step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (SHO headline, config C2)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons of one GPU, sampled every 200 ms while running."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fp64_peak_tflops():
+    """FP64 FMA peak of this pool's B200, measured by tools/fp64_peak.cu (MEASURED_PEAKS.json holds no FP64 figure)."""
+    try:
+        with open(FP64_PEAK_FILE) as f:
+            d = json.load(f)
+        return float(d["dfma_tflops_sustained"]), "measured: tools/fp64_peak.cu DFMA microbenchmark (profiles/r01_fp64_peak_microbench.json)"
+    except Exception:
+        return 37.0, "fallback: nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"
+
+
+def build_workload(N, J, basis, B, seed_series, seed_theta):
+    t, y, s2, f_min, f_max = wl.make_series(N, seed_series)
+    theta = wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), seed_theta, alpha2_max=4.0 if basis == "SHO" else 6.0)
+    return t, y, s2, f_min, f_max, theta
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_leg(t, y, s2, f_min, f_max, J, basis, theta, target_s, steps=1, warmup=0):
+    """Times the CPU restatement of the reference algorithm (oracle/pioran_oracle.c: approx + logl exactly as
+    src/psd.jl:214-289 and src/celerite_solver.jl:12-158 do them, U/V/ϕ materialised, forward + backward pass) with
+    OpenMP over θ on all host cores.  Each step evaluates a bounded sample of the workload's θ."""
+    from oracle import oracle as orc
+    cores = orc.max_threads()
+    per_round = 1e9
+    for _ in range(3):                                       # first call pays library load + thread start-up
+        t0 = time.perf_counter()
+        orc.approx_logl_batch("SBPL", theta[:cores], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        per_round = min(per_round, max(time.perf_counter() - t0, 1e-4))   # one eval per thread
+    n = int(max(1, min(len(theta) // cores, round(target_s / per_round)))) * cores
+    for _ in range(warmup):
+        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} of the step's parameter vectors per step x {steps} step(s), {dt:.1f} s, OpenMP over theta on "
+                      f"{cores} threads; C restatement of Pioran.jl approx+logl (Julia is not installed on this image)"}, dt / steps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    R = wl.rank_of(args.basis, args.J)
+    t, y, s2, f_min, f_max, theta = build_workload(args.N, args.J, args.basis, min(args.B, 8192), 1234, 42)
+    # each step ≈ 60 s / (steps + warmup) of CPU work so the whole run ends within a few minutes
+    target = max(1.0, 60.0 / max(1, args.steps + args.warmup))
+    cb, per_step = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, target, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, R), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, R):
+    return {"workload": f"headline: {args.B} parameter vectors per GPU x one irregular series of N={args.N}, "
+                        f"approx(SingleBendingPowerLaw, J={args.J}, {args.basis}) -> celerite rank R={R}",
+            "N": args.N, "J": args.J, "basis": args.basis, "B_per_gpu": args.B, "rank": R,
+            "l2": "flushed (256 MiB memset) between timed steps", "parallelism": f"theta-sharded x{args.gpus}, one all-gather of logL"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def time_steps(torch, fn, steps, warmup, flush, dist_on):
+    """W untimed + K timed steps; each timed step has its own CUDA-event pair on the launching stream, with an L2
+    flush between steps (outside the event pairs).  Returns seconds for the K steps on this rank."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_on:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+
+def measure(torch, ctx, pb, t, y, s2, f_min, f_max, J, basis, theta, steps, warmup, flush, world, rank, want_e2e=True):
+    """Returns dict with device-resident and end-to-end timings of one workload on this rank."""
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+    B = theta.shape[0]
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+    ser = ctx.upload_series(t, y, s2)
+    th_dev = torch.from_numpy(theta).cuda()
+    out_dev = torch.empty(B, dtype=torch.float64, device="cuda")
+    gathered = torch.empty(B * world, dtype=torch.float64, device="cuda") if dist_on else None
+    k2_ms = []
+
+    def step_dev():
+        ctx.approx_logl_dev([ser], [spec], B, th_dev.data_ptr(), out_dev.data_ptr())
+        if dist_on:
+            dist.all_gather_into_tensor(gathered, out_dev)
+
+    sec = time_steps(torch, step_dev, steps, warmup, flush, dist_on)
+    n0 = ctx.launch_count
+    step_dev()
+    launches = (ctx.launch_count - n0) * steps   # library kernels per step (K1 + K2) x timed steps
+    # dominant kernel alone (events inside the library around the K2 launch), a few extra launches after the timed region
+    for _ in range(3):
+        flush.zero_()
+        ctx.approx_logl_dev([ser], [spec], B, th_dev.data_ptr(), out_dev.data_ptr())
+        k2_ms.append(ctx.last_kernel_ms())
+    res = {"sec": sec, "launches": launches, "k2_ms": float(np.mean(k2_ms)), "out": out_dev.cpu().numpy()}
+
+    if want_e2e:
+        th_pin = torch.from_numpy(theta).pin_memory()
+        out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
+        th_np, out_np = th_pin.numpy(), out_pin.numpy()
+        import ctypes as C
+        from pioran_b200._lib import ApproxSpec, check
+        ids = (C.c_int * 1)(ser.id)
+        sp = (ApproxSpec * 1)(spec)
+        dp = C.POINTER(C.c_double)
+        g_in = torch.empty(B * world, dtype=torch.float64).pin_memory() if dist_on else None
+
+        def step_host():
+            # the call a sampler makes: host θ in, host logL out (H2D + K1 + K2 + D2H + sync inside)
+            check(ctx.lib.pioran_approx_logl(ctx.h, 1, ids, sp, B, th_np.ctypes.data_as(dp), 0, out_np.ctypes.data_as(dp)))
+            if dist_on:
+                dist.all_gather_into_tensor(gathered, out_dev.copy_(out_pin, non_blocking=True))
+                g_in.copy_(gathered, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        for _ in range(warmup):
+            step_host()
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_host()
+        torch.cuda.synchronize()
+        res["e2e_sec"] = time.perf_counter() - t0
+        res["h2d"] = theta.nbytes
+        res["d2h"] = out_np.nbytes * (world if dist_on else 1)
+        assert np.array_equal(out_np, res["out"], equal_nan=True), "host and device entry points disagree"
+    ser.free()
+    return res
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 backend has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import pioran_b200 as pb
+    ctx = pb.Context(local_rank)
+    # one explicit stream carries the library's launches, torch's copies/collectives and the CUDA events below
+    # (torch's default stream is the legacy NULL stream, which the C ABI reads as "use the context's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    R = wl.rank_of(args.basis, args.J)
+
+    # every rank builds the same series; θ shards are disjoint slices of one seeded global batch
+    t, y, s2, f_min, f_max, theta_all = build_workload(args.N, args.J, args.basis, args.B * world, 1234, 42)
+    theta = np.ascontiguousarray(theta_all[rank * args.B:(rank + 1) * args.B])
+
+    with ClockSampler(local_rank) as clk:
+        m = measure(torch, ctx, pb, t, y, s2, f_min, f_max, args.J, args.basis, theta, args.steps, args.warmup, flush,
+                    world, rank)
+    clocks = clk.summary()
+
+    def maxred(x):
+        if not dist_on:
+            return x
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    sec = maxred(m["sec"])
+    e2e_sec = maxred(m["e2e_sec"])
+    k2_ms = maxred(m["k2_ms"])
+    evals_per_step = args.B * world
+    value = evals_per_step * args.steps / sec
+    peak, peak_src = fp64_peak_tflops()
+    flops_launch = float(args.B) * args.N * wl.flops_per_step(R)
+    achieved = flops_launch / (k2_ms * 1e-3) / 1e12
+    finite = float(np.isfinite(m["out"]).mean())
+
+    extra = {}
+    if not args.no_extra and world == 1:
+        # secondary workloads, fewer steps: the other basis at the headline shape, and BASELINE config C2
+        other = "SHO" if args.basis == "DRWCelerite" else "DRWCelerite"
+        for name, N2, basis2, B2 in ((f"headline_{other}", args.N, other, args.B), ("C2_4096theta_N10000_DRWCelerite", 10000, "DRWCelerite", 4096)):
+            R2 = wl.rank_of(basis2, args.J)
+            t2, y2, s22, fm2, fx2, th2 = build_workload(N2, args.J, basis2, B2, 1234 if N2 == args.N else 1235, 42)
+            m2 = measure(torch, ctx, pb, t2, y2, s22, fm2, fx2, args.J, basis2, th2, max(3, args.steps // 2), 3, flush, 1, 0)
+            fl = float(B2) * N2 * wl.flops_per_step(R2)
+            extra[name] = {"evals_per_s": B2 * max(3, args.steps // 2) / m2["sec"],
+                           "e2e_evals_per_s": B2 * max(3, args.steps // 2) / m2["e2e_sec"],
+                           "k2_ms": m2["k2_ms"], "rank": R2, "fp64_tflops": fl / (m2["k2_ms"] * 1e-3) / 1e12,
+                           "fp64_frac": fl / (m2["k2_ms"] * 1e-3) / 1e12 / peak,
+                           "finite_frac": float(np.isfinite(m2["out"]).mean())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, 15.0)
+        # spot parity of the timed batch against the same CPU code (full parity lives in tests/)
+        from oracle import oracle as orc
+        ref = orc.approx_logl_batch("SBPL", theta[:64], f_min, f_max, args.J, t, y, s2, basis=args.basis, nthreads=0)
+        ok = np.isfinite(ref)
+        cpu["parity_max_rel_64"] = float(np.max(np.abs(m["out"][:64][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))))
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, R),
+                "e2e": {"value": evals_per_step * args.steps / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": m["h2d"],
+                        "d2h_bytes_per_step": m["d2h"],
+                        "note": "pioran_approx_logl (C ABI, host pointers, pinned): H2D theta + K1 + K2 + D2H logL"
+                                + (" + NCCL all-gather + D2H of the gathered vector" if dist_on else "") + " per step; series resident (uploaded once per sampler run)"},
+                "gpu_launches": int(m["launches"]),
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
+                             "flops_per_launch": flops_launch,
+                             "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d)", "peak_source": peak_src,
+                             "note": "FP64-pipe bound: the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},
+                "cpu_baseline": cpu, "clocks": clocks, "finite_frac": finite, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # launched without torchrun: re-exec under torch.distributed.run
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port)] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,9 @@ int pioran_ctx_set_stream(pioran_ctx *ctx, void *cuda_stream);
 int pioran_ctx_synchronize(pioran_ctx *ctx);
 /* Number of CUDA kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t pioran_ctx_launch_count(pioran_ctx *ctx);
+/* Device time (ms, CUDA events on the context's stream) of the most recent main-kernel launch — the batched
+ * celerite kernel K2, the scan K3 or the dense K4.  Waits for that launch to finish. */
+int pioran_ctx_last_kernel_ms(pioran_ctx *ctx, double *ms);
 
 /* Uploads one time series (τ, y, σ²) — the (x, Y, diag Σy) of logpdf(f(t, σ²), y), src/scalable_GP.jl:162-166 —
  * and keeps it resident.  t must be strictly increasing.  A sampler uploads once and evaluates ~1e5 times. */

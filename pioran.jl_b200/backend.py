@@ -80,6 +80,12 @@ class Context:
     def launch_count(self):
         return int(self.lib.pioran_ctx_launch_count(self.h))
 
+    def last_kernel_ms(self):
+        """Device time of the most recent K2/K3/K4 launch (CUDA events inside the library)."""
+        ms = C.c_double(0.0)
+        check(self.lib.pioran_ctx_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def upload_series(self, t, y, s2):
         t, y, s2 = _f64(t), _f64(y), _f64(s2)
         if not (t.ndim == 1 and t.shape == y.shape == s2.shape):

@@ -84,6 +84,13 @@ struct pioran_ctx {
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
     DevBuf theta, amp, suma, out, work, coef, rows, misc;
+    // device time of the most recent main-kernel launch (K2/K3/K4), for bench.py's roofline line
+    cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
+    bool ev_valid = false;
+    // the work-item list of the last fused call, kept on the device while the call shape repeats (a sampler
+    // evaluates the same series × batch-size shape ~1e5 times)
+    std::vector<int64_t> work_key;
+    int work_items = 0;
     std::mutex mu;
 };
 
@@ -93,6 +100,7 @@ static int bs_for_rank(int R) {
     return bs;
 }
 
+extern "C" int pioran_ctx_destroy(pioran_ctx* c);
 extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
     if (!out) return fail(PIORAN_EINVAL, "out is NULL");
     int ndev = 0;
@@ -114,6 +122,10 @@ extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
     e = cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(PIORAN_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
     c->stream = c->own;
+    if (cudaEventCreate(&c->ev_beg) != cudaSuccess || cudaEventCreate(&c->ev_end) != cudaSuccess) {
+        pioran_ctx_destroy(c);
+        return fail(PIORAN_ECUDA, "cudaEventCreate failed");
+    }
     *out = c;
     return PIORAN_OK;
 }
@@ -133,6 +145,8 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
     for (auto& kv : c->plans) cudaFree(kv.second);
     c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
     c->coef.release(); c->rows.release(); c->misc.release();
+    if (c->ev_beg) cudaEventDestroy(c->ev_beg);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
     return PIORAN_OK;
@@ -150,6 +164,16 @@ extern "C" int pioran_ctx_synchronize(pioran_ctx* c) {
     return PIORAN_OK;
 }
 extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) { return c ? c->launches : 0; }
+extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) {
+    if (!c || !ms) return fail(PIORAN_EINVAL, "NULL argument");
+    if (!c->ev_valid) return fail(PIORAN_EINVAL, "no main kernel has been launched on this context yet");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev_end));
+    float f = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&f, c->ev_beg, c->ev_end));
+    *ms = (double)f;
+    return PIORAN_OK;
+}
 
 extern "C" int pioran_series_upload(pioran_ctx* c, int64_t N, const double* t, const double* y, const double* s2,
                                     int* series_id) {
@@ -297,7 +321,7 @@ static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Tab
     const int R = rank_of(sp.basis, sp.n_components);
     const int BS = bs_for_rank(R);
     if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8 (n_components too large for this build)", R, BS);
-    const int RP = G * BS;
+    const int RP = G * BS;            // logical rows; the table stores them in the padded layout of rps_of(BS)
     std::vector<RowDesc> rows;
     make_rows(sp, RP, rows);
     int rc = c->rows.ensure(sizeof(RowDesc) * RP);
@@ -307,12 +331,12 @@ static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Tab
     Table tb;
     tb.rpad = RP;
     tb.npad = ((s->N + CHUNK_STEPS - 1) / CHUNK_STEPS) * CHUNK_STEPS;
-    const size_t bytes = sizeof(double) * (size_t)tb.npad * table_step_doubles(RP);
+    const size_t bytes = sizeof(double) * (size_t)tb.npad * table_step_doubles(rps_of(BS));
     CUDA_TRY(cudaMalloc(&tb.d, bytes));
-    const int64_t total = tb.npad * RP;
+    const int64_t total = tb.npad * rps_of(BS);
     const int tpb = 256;
     table_build_kernel<<<(unsigned)((total + tpb - 1) / tpb), tpb, 0, c->stream>>>(tb.d, s->t, s->y, s->s2, s->N, tb.npad,
-                                                                                 c->rows.as<RowDesc>(), RP);
+                                                                                 c->rows.as<RowDesc>(), BS);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     s->tables[key] = tb;
@@ -325,13 +349,13 @@ template <int BS> struct KCfg { static constexpr int NW = (BS <= 5) ? 12 : (BS =
 
 template <int BS>
 static size_t shared_smem_bytes() {
-    constexpr int RP = G * BS, SD = table_step_doubles(RP);
-    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)KCfg<BS>::NW * 2 * RP) + 2 * sizeof(uint64_t);
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)KCfg<BS>::NW * 2 * RPS) + 2 * sizeof(uint64_t);
 }
 template <int BS>
 static size_t generic_smem_bytes(int Jt) {
-    constexpr int RP = G * BS, SD = table_step_doubles(RP);
-    return sizeof(double) * (size_t)KCfg<BS>::NW * ((size_t)GCH * SD + 2 * RP + (size_t)(GCH + 2) * Jt);
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    return sizeof(double) * (size_t)KCfg<BS>::NW * ((size_t)GCH * SD + 2 * RPS + (size_t)(((GCH + 2) * Jt + 1) & ~1));
 }
 
 template <int BS>
@@ -339,7 +363,10 @@ static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_shared_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = shared_smem_bytes<BS>();
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -349,7 +376,10 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = generic_smem_bytes<BS>(args.Jt);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -477,12 +507,22 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     }
     CUDA_TRY(cudaGetLastError());
     // K2
-    ItemPlan ip;
-    plan_items(c, S, ser.data(), tabs.data(), B, nw_for_bs(BS), theta_per_series != 0, ip);
-    if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
-                             c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));  // ip.items is a local; a few µs, before the kernel starts
+    std::vector<int64_t> key;
+    key.reserve(4 + 3 * (size_t)S);
+    key.push_back(S); key.push_back(B); key.push_back(BS); key.push_back(theta_per_series != 0);
+    for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
+    if (key != c->work_key) {
+        ItemPlan ip;
+        plan_items(c, S, ser.data(), tabs.data(), B, nw_for_bs(BS), theta_per_series != 0, ip);
+        c->work_key.clear();
+        if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                                 c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // ip.items is a local; only when the call shape changes
+        c->work_key = key;
+        c->work_items = (int)ip.items.size();
+    }
+    const int nitems = c->work_items;
     BatchArgs args{};
     args.work = c->work.as<WorkItem>();
     args.amp = c->amp.as<double>();
@@ -491,7 +531,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     args.nu = theta_dev + npar + 1;
     args.pstride = ts;
     args.out = logl_dev;
-    return dispatch_shared(c, BS, args, (int)ip.items.size());
+    return dispatch_shared(c, BS, args, nitems);
 }
 
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
@@ -589,6 +629,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     ItemPlan ip;
     Series* sp = s;
     plan_items(c, 1, &sp, nullptr, B, nw_for_bs(BS), false, ip);
+    c->work_key.clear();  // the work buffer is shared with the fused path's cached plan
     if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
                              c->stream));

@@ -74,63 +74,154 @@ struct LaneState {
     double chi2, logacc, dkeep, dfirst;
 };
 
+// Lane → block mapping (constant over the sweep); offsets are in the padded vector layout (common.cuh).
+struct LaneMap {
+    int rowI, colA, colB;  // padded offsets of block-row I and of the column blocks of the A / B parts
+    int j0, j1;            // padded offsets of the two owned rows
+    int src_lane;          // lane whose column sums belong to my block-row
+    int o;
+    bool valid1, hi;       // second owned row exists; lane ≥ 16
+    bool dzero;            // this lane's copy of the distance-4 block diagonal is the masked one
+};
+template <int BS>
+__device__ __forceinline__ LaneMap make_lane_map(int lane) {
+    constexpr int BSP = bsp_of(BS);
+    LaneMap lm;
+    const int i = lane >> 2, o = lane & 3;
+    lm.o = o;
+    lm.rowI = i * BSP;
+    lm.colA = ((i + o) & 7) * BSP;
+    lm.colB = (o == 0) ? ((i ^ 4) * BSP) : lm.colA;
+    lm.dzero = (o == 0 && i >= 4);
+    lm.src_lane = (((i - (o ? o : 4)) & 7) << 2) | o;
+    lm.j0 = lm.rowI + o;
+    lm.valid1 = (o + 4) < BS;
+    lm.j1 = lm.valid1 ? lm.j0 + 4 : lm.j0;
+    lm.hi = lane >= 16;
+    return lm;
+}
+
+// BS consecutive doubles from a 16-byte aligned shared-memory address: 128-bit loads, one 64-bit tail when BS is odd.
+template <int BS>
+__device__ __forceinline__ void load_slice(double (&dst)[BS], const double* __restrict__ p) {
+#pragma unroll
+    for (int r = 0; r + 1 < BS; r += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(p + r);
+        dst[r] = v.x; dst[r + 1] = v.y;
+    }
+    if (BS & 1) dst[BS - 1] = p[BS - 1];
+}
+
+// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H, ≥ 20 bits) + two Newton steps.  x = 0, ±Inf, NaN give non-finite
+// results, which the likelihood treats as data (a θ whose covariance is not positive definite).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // One time step.  ODD: the step index n is odd → the state leaves the step with the row factor pending.
-//   T      : this step's table record in shared memory
+//   T      : this step's table record in shared memory (padded vectors)
 //   qs, ws : per-warp scratch vectors (q and w of the previous step, one of them pre-multiplied by φ_n)
 template <int BS, bool ODD>
 __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* __restrict__ T, double* __restrict__ qs,
-                                              double* __restrict__ ws, const int rowI, const int colA, const int colB,
-                                              const int o, const double dmask, const int src_lane, const int j0,
-                                              const int j1, const bool valid1, const double yn, const double s2n,
-                                              const double suma, const double mu, const double nu, const int64_t n,
-                                              const int lane) {
-    constexpr int RP = G * BS;
+                                              double* __restrict__ ws, const LaneMap& lm, const double yn,
+                                              const double s2n, const double suma, const double mu, const double nu,
+                                              const int64_t n, const int lane) {
+    constexpr int RP = rps_of(BS);
+    const int o = lm.o;
     // ---- row-side operands of block-row I
-    double qrow[BS], qdia[BS], urow[BS], xrow[BS];
-#pragma unroll
-    for (int r = 0; r < BS; r++) {
-        qrow[r] = qs[rowI + r];
-        urow[r] = T[(ODD ? F_UH : F_UT) * RP + rowI + r];   // weight of the column partial sums
-        xrow[r] = T[(ODD ? F_PHI : F_KAP) * RP + rowI + r]; // ODD: post-scale of row sums; EVEN: decay of row r
-        qdia[r] = qrow[r] * dmask;
-    }
-    double rowpart[BS], xout[BS], selfa[BS];
+    double qrow[BS], urow[BS], xrow[BS];
+    load_slice<BS>(qrow, qs + lm.rowI);
+    load_slice<BS>(urow, T + (ODD ? F_UH : F_UT) * RP + lm.rowI);    // weight of the column partial sums
+    load_slice<BS>(xrow, T + (ODD ? F_PHI : F_KAP) * RP + lm.rowI);  // ODD: post-scale of row sums; EVEN: decay of row r
+    double prow[BS];                                                  // EVEN: φ of my rows = post-scale of column sums
+    if (!ODD) load_slice<BS>(prow, T + F_PHI * RP + lm.rowI);
+    double rowpart[BS], acc[BS];
 #pragma unroll
     for (int r = 0; r < BS; r++) rowpart[r] = 0.0;
 
-    // ---- block phase: rank-1 update + decay + symmetric matvec, column by column
+    // ---- block phase: rank-1 update + decay + symmetric matvec, two columns per pass (128-bit operand loads)
+    const double* wsA = ws + lm.colA;
+    const double* wsB = ws + lm.colB;
+    const double* uAp = T + (ODD ? F_UT : F_UH) * RP + lm.colA;
+    const double* uBp = T + (ODD ? F_UT : F_UH) * RP + lm.colB;
+    const double* zAp = T + F_KAP * RP + lm.colA;   // ODD only: decay of column c
+    const double* zBp = T + F_KAP * RP + lm.colB;
 #pragma unroll
-    for (int c = 0; c < BS; c++) {
-        const double wA = ws[colA + c], wB = ws[colB + c];
-        const double uA = T[(ODD ? F_UT : F_UH) * RP + colA + c], uB = T[(ODD ? F_UT : F_UH) * RP + colB + c];
-        const double zA = T[(ODD ? F_KAP : F_PHI) * RP + colA + c], zB = T[(ODD ? F_KAP : F_PHI) * RP + colB + c];
-        double cA = 0.0, cB = 0.0;
-#pragma unroll
-        for (int r = 0; r < BS; r++) {
-            const bool useA = r > c;  // compile-time after unrolling
-            const double w = useA ? wA : wB;
-            const double u = useA ? uA : uB;
-            const double qr = (r == c) ? qdia[r] : qrow[r];
-            double m;
-            if (ODD) m = fma(useA ? zA : zB, st.M[r][c], qr * w);  // κ_c·M + q_r·(φ_c w_c)
-            else     m = fma(xrow[r], st.M[r][c], qr * w);         // κ_r·M + (φ_r q_r)·w_c
-            st.M[r][c] = m;
-            rowpart[r] = fma(m, u, rowpart[r]);
-            if (useA) cA = fma(m, urow[r], cA);
-            else      cB = fma(m, urow[r], cB);
+    for (int c0 = 0; c0 < BS; c0 += 2) {
+        double wA2[2], wB2[2], uA2[2], uB2[2], zA2[2] = {0.0, 0.0}, zB2[2] = {0.0, 0.0};
+        if (c0 + 1 < BS) {
+            const double2 a0 = *reinterpret_cast<const double2*>(wsA + c0), a1 = *reinterpret_cast<const double2*>(wsB + c0);
+            const double2 a2 = *reinterpret_cast<const double2*>(uAp + c0), a3 = *reinterpret_cast<const double2*>(uBp + c0);
+            wA2[0] = a0.x; wA2[1] = a0.y; wB2[0] = a1.x; wB2[1] = a1.y;
+            uA2[0] = a2.x; uA2[1] = a2.y; uB2[0] = a3.x; uB2[1] = a3.y;
+            if (ODD) {
+                const double2 a4 = *reinterpret_cast<const double2*>(zAp + c0), a5 = *reinterpret_cast<const double2*>(zBp + c0);
+                zA2[0] = a4.x; zA2[1] = a4.y; zB2[0] = a5.x; zB2[1] = a5.y;
+            }
+        } else {
+            wA2[0] = wsA[c0]; wB2[0] = wsB[c0]; uA2[0] = uAp[c0]; uB2[0] = uBp[c0];
+            if (ODD) { zA2[0] = zAp[c0]; zB2[0] = zBp[c0]; }
+            wA2[1] = wB2[1] = uA2[1] = uB2[1] = 0.0;
         }
-        if (!ODD) { cA *= zA; cB *= zB; }  // column factor pending → apply φ_c to the column sums
-        xout[c] = cB + (o ? cA : 0.0);
-        selfa[c] = o ? 0.0 : cA;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = c0 + cc;
+            if (c < BS) {
+                const double wA = wA2[cc], wB = wB2[cc], uA = uA2[cc], uB = uB2[cc], zA = zA2[cc], zB = zB2[cc];
+                double cA = 0.0, cB = 0.0;
+#pragma unroll
+                for (int r = 0; r < BS; r++) {
+                    const bool useA = r > c;  // compile-time after unrolling
+                    const double w = useA ? wA : wB;
+                    const double u = useA ? uA : uB;
+                    const double qr = (r == c) ? (lm.dzero ? 0.0 : qrow[r]) : qrow[r];
+                    double m;
+                    if (ODD) m = fma(useA ? zA : zB, st.M[r][c], qr * w);  // κ_c·M + q_r·(φ_c w_c)
+                    else     m = fma(xrow[r], st.M[r][c], qr * w);         // κ_r·M + (φ_r q_r)·w_c
+                    st.M[r][c] = m;
+                    rowpart[r] = fma(m, u, rowpart[r]);
+                    if (useA) cA = fma(m, urow[r], cA);
+                    else      cB = fma(m, urow[r], cB);
+                }
+                // column sums go to the lane that owns block-row K; the diagonal-block part (o = 0) stays here.
+                // EVEN steps: the column factor φ_c is still pending — the receiver applies it (prow) in `tot`.
+                const double yv = __shfl_sync(FULL, cB + (o ? cA : 0.0), lm.src_lane);
+                acc[c] = yv + (o ? 0.0 : cA);
+            }
+        }
     }
 
-    // ---- matvec reduction: rotate column sums to the owning block-row, then reduce-scatter over the 4 lanes
+    // ---- ŨᵀTŨ from the block-level partial sums (each stored entry is off-diagonal and counts twice), so the
+    //      all-reduce below does not wait for the reduce-scatter of p
+    const double ut0 = T[F_UT * RP + lm.j0], ut1 = T[F_UT * RP + lm.j1];
+    double sblk = 0.0;
+#pragma unroll
+    for (int r = 0; r < BS; r++) sblk = fma(urow[r], rowpart[r], sblk);
+    double spart = fma(st.sjj[1] * ut1, ut1, fma(st.sjj[0] * ut0, ut0, sblk + sblk));
+    double upart = fma(ut1, st.g[1], ut0 * st.g[0]);
+    // all-reduce of (spart, upart) in 6 exchanges: halves swap roles first, so each half reduces one value
+    {
+        const double recv = __shfl_xor_sync(FULL, lm.hi ? spart : upart, 16);
+        double keep = (lm.hi ? upart : spart) + recv;
+#pragma unroll
+        for (int sft = 8; sft >= 1; sft >>= 1) keep += __shfl_xor_sync(FULL, keep, sft);
+        const double other = __shfl_xor_sync(FULL, keep, 16);
+        spart = lm.hi ? other : keep;
+        upart = lm.hi ? keep : other;
+    }
+
+    // ---- matvec reduction: reduce-scatter of the BS row sums over the 4 lanes of the block-row
     double tot[BS];
 #pragma unroll
     for (int c = 0; c < BS; c++) {
-        const double yv = __shfl_sync(FULL, xout[c], src_lane);
-        if (ODD) tot[c] = fma(xrow[c], rowpart[c], yv) + selfa[c];
-        else     tot[c] = (rowpart[c] + yv) + selfa[c];
+        if (ODD) tot[c] = fma(xrow[c], rowpart[c], acc[c]);
+        else     tot[c] = fma(prow[c], acc[c], rowpart[c]);
     }
     const bool bit0 = (o & 1) != 0, bit1 = (o & 2) != 0;
     double e[4];
@@ -156,21 +247,13 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     }
 
     // ---- owner phase: rows j0 (and j1)
-    const double ut0 = T[F_UT * RP + j0], ut1 = T[F_UT * RP + j1];
-    const double v0 = T[F_V * RP + j0], v1 = T[F_V * RP + j1];
-    const double pn0 = T[F_PHN * RP + j0], pn1 = T[F_PHN * RP + j1];
+    const double v0 = T[F_V * RP + lm.j0], v1 = T[F_V * RP + lm.j1];
+    const double pn0 = T[F_PHN * RP + lm.j0], pn1 = T[F_PHN * RP + lm.j1];
     const double p0 = fma(st.sjj[0], ut0, f0);
     const double p1 = fma(st.sjj[1], ut1, f1);
-    double spart = fma(ut1, p1, ut0 * p0);
-    double upart = fma(ut1, st.g[1], ut0 * st.g[0]);
-#pragma unroll
-    for (int sft = 16; sft >= 1; sft >>= 1) {
-        spart += __shfl_xor_sync(FULL, spart, sft);
-        upart += __shfl_xor_sync(FULL, upart, sft);
-    }
     const double An = fma(nu, s2n, suma);
     const double D = An - spart;              // celerite_solver.jl:92
-    const double rD = 1.0 / D;
+    const double rD = fast_rcp(D);
     const double z = (yn - mu) - upart;       // celerite_solver.jl:141
     st.chi2 = fma(z * z, rD, st.chi2);
     // log|D_n| (celerite_solver.jl:140; no abs on the first pivot, :126): lane n%32 keeps D_n, one log per 32 steps
@@ -187,11 +270,11 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     __syncwarp();
     // the NEXT step is odd iff this one is even: odd steps consume (q, φ∘w), even steps (φ∘q, w)
     if (!ODD) {
-        qs[j0] = q0; ws[j0] = pn0 * w0;
-        if (valid1) { qs[j1] = q1; ws[j1] = pn1 * w1; }
+        qs[lm.j0] = q0; ws[lm.j0] = pn0 * w0;
+        if (lm.valid1) { qs[lm.j1] = q1; ws[lm.j1] = pn1 * w1; }
     } else {
-        qs[j0] = pn0 * q0; ws[j0] = w0;
-        if (valid1) { qs[j1] = pn1 * q1; ws[j1] = w1; }
+        qs[lm.j0] = pn0 * q0; ws[lm.j0] = w0;
+        if (lm.valid1) { qs[lm.j1] = pn1 * q1; ws[lm.j1] = w1; }
     }
     __syncwarp();
 }
@@ -242,14 +325,16 @@ __device__ __forceinline__ double lane_finish(LaneState<BS>& st, int64_t N, int 
 
 // ------------------------------------------------------------------------------------------- shared-table kernel
 // grid = number of work items; block = NW warps; each warp one θ of the item's series.
-// dynamic smem: 2 stages × CHUNK_STEPS × SD doubles | NW × 2·R_pad scratch | 2 mbarriers
+// dynamic smem: 2 stages × CHUNK_STEPS × SD doubles | NW × 2·RPS scratch | 2 mbarriers
+// Every warp runs the full sweep (warps beyond the item's count redo its last θ and skip the store): the hot loop
+// then has no lane-dependent control flow and the shuffles compile to plain SHFL (no WARPSYNC.COLLECTIVE).
 template <int BS, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const BatchArgs args) {
-    constexpr int RP = G * BS, SD = table_step_doubles(RP), STAGE = CHUNK_STEPS * SD;
+    constexpr int RP = G * BS, RPS = rps_of(BS), SD = table_step_doubles(RPS), STAGE = CHUNK_STEPS * SD;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     double* scratch = stages + 2 * STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 2 * RP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 2 * RPS);
 
     const WorkItem wk = args.work[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -271,31 +356,25 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
     }
 
     const bool active = warp < wk.count;
-    const int th = wk.theta_begin + (active ? warp : 0);
+    const int slot = active ? warp : wk.count - 1;
+    const int th = wk.theta_begin + slot;
+    const LaneMap lm = make_lane_map<BS>(lane);
     const int i = lane >> 2, o = lane & 3;
-    const int rowI = i * BS;
-    const int colA = ((i + o) & 7) * BS;
-    const int colB = (o == 0) ? ((i ^ 4) * BS) : colA;
-    const double dmask = (o == 0 && i >= 4) ? 0.0 : 1.0;
-    const int src_lane = (((i - (o ? o : 4)) & 7) << 2) | o;
-    const int j0 = rowI + o;
-    const bool valid1 = (o + 4) < BS;
-    const int j1 = valid1 ? j0 + 4 : j0;
 
     LaneState<BS> st;
     lane_init(st);
-    st.amp[0] = args.amp[(size_t)th * RP + j0];
-    st.amp[1] = valid1 ? args.amp[(size_t)th * RP + j1] : 0.0;
+    st.amp[0] = args.amp[(size_t)th * RP + i * BS + o];
+    st.amp[1] = lm.valid1 ? args.amp[(size_t)th * RP + i * BS + o + 4] : 0.0;
     const double suma = args.suma[th];
-    const size_t pi = (size_t)wk.par_begin + (active ? warp : 0);
+    const size_t pi = (size_t)wk.par_begin + slot;
     const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
     const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
     const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : nullptr;
     const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : nullptr;
 
-    double* qs = scratch + warp * 2 * RP;
-    double* ws = qs + RP;
-    for (int k = lane; k < 2 * RP; k += 32) qs[k] = 0.0;
+    double* qs = scratch + warp * 2 * RPS;
+    double* ws = qs + RPS;
+    for (int k = lane; k < 2 * RPS; k += 32) qs[k] = 0.0;
     __syncwarp();
 
     for (int64_t k = 0; k < nchunks; k++) {
@@ -304,21 +383,17 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
         const double* stage = stages + sidx * STAGE;
         const int64_t nbeg = k * CHUNK_STEPS;
         const int nsteps = (int)((N - nbeg) < CHUNK_STEPS ? (N - nbeg) : CHUNK_STEPS);
-        if (active) {
-            for (int s = 0; s < nsteps; s += 2) {
-                const double* T0 = stage + s * SD;
-                const int64_t n = nbeg + s;
-                double yn = yb ? yb[n] : T0[6 * RP + 0];
-                double s2n = sb ? sb[n] : T0[6 * RP + 1];
-                celerite_step<BS, false>(st, T0, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yn, s2n,
-                                         suma, mu, nu, n, lane);
-                if (s + 1 < nsteps) {
-                    const double* T1 = T0 + SD;
-                    yn = yb ? yb[n + 1] : T1[6 * RP + 0];
-                    s2n = sb ? sb[n + 1] : T1[6 * RP + 1];
-                    celerite_step<BS, true>(st, T1, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yn,
-                                            s2n, suma, mu, nu, n + 1, lane);
-                }
+        for (int s = 0; s < nsteps; s += 2) {
+            const double* T0 = stage + s * SD;
+            const int64_t n = nbeg + s;
+            double yn = yb ? yb[n] : T0[6 * RPS + 0];
+            double s2n = sb ? sb[n] : T0[6 * RPS + 1];
+            celerite_step<BS, false>(st, T0, qs, ws, lm, yn, s2n, suma, mu, nu, n, lane);
+            if (s + 1 < nsteps) {
+                const double* T1 = T0 + SD;
+                yn = yb ? yb[n + 1] : T1[6 * RPS + 0];
+                s2n = sb ? sb[n + 1] : T1[6 * RPS + 1];
+                celerite_step<BS, true>(st, T1, qs, ws, lm, yn, s2n, suma, mu, nu, n + 1, lane);
             }
         }
         __syncthreads();  // every warp is done with this stage → refill it with chunk k+2
@@ -328,10 +403,8 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
             tma_load_1d(stages + sidx * STAGE, wk.table + (size_t)(k + 2) * STAGE, STAGE_BYTES, &bars[sidx]);
         }
     }
-    if (active) {
-        const double res = lane_finish(st, N, lane);
-        if (lane == 0) args.out[wk.out_begin + warp] = res;
-    }
+    const double res = lane_finish(st, N, lane);
+    if (active && lane == 0) args.out[wk.out_begin + warp] = res;
 }
 
 // ------------------------------------------------------------------------------------------- generic kernel
@@ -341,53 +414,47 @@ constexpr int GCH = 4;
 
 template <int BS, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const BatchArgs args) {
-    constexpr int RP = G * BS, SD = table_step_doubles(RP);
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // per warp: GCH·SD table | 2·RP scratch | (GCH+2)·Jt φ side array
+    // per warp: GCH·SD table | 2·RPS scratch | (GCH+2)·Jt φ side array (rounded up to an even count: 16-byte alignment)
     const int Jt = args.Jt;
-    const int per_warp = GCH * SD + 2 * RP + (GCH + 2) * Jt;
+    const int per_warp = GCH * SD + 2 * RPS + (((GCH + 2) * Jt + 1) & ~1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* base = reinterpret_cast<double*>(smem_raw) + (size_t)warp * per_warp;
     double* tab = base;
     double* qs = base + GCH * SD;
-    double* ws = qs + RP;
-    double* phs = ws + RP;
+    double* ws = qs + RPS;
+    double* phs = ws + RPS;
 
     const WorkItem wk = args.work[blockIdx.x];
-    if (warp >= wk.count) return;
-    const int th = wk.theta_begin + warp;
+    const bool active = warp < wk.count;
+    const int slot = active ? warp : wk.count - 1;
+    const int th = wk.theta_begin + slot;
     const int64_t N = wk.N;
     const double* ca = args.a + (size_t)th * Jt;
     const double* cb = args.b + (size_t)th * Jt;
     const double* cc = args.c + (size_t)th * Jt;
     const double* cd = args.d + (size_t)th * Jt;
 
+    const LaneMap lm = make_lane_map<BS>(lane);
     const int i = lane >> 2, o = lane & 3;
-    const int rowI = i * BS;
-    const int colA = ((i + o) & 7) * BS;
-    const int colB = (o == 0) ? ((i ^ 4) * BS) : colA;
-    const double dmask = (o == 0 && i >= 4) ? 0.0 : 1.0;
-    const int src_lane = (((i - (o ? o : 4)) & 7) << 2) | o;
-    const int j0 = rowI + o;
-    const bool valid1 = (o + 4) < BS;
-    const int j1 = valid1 ? j0 + 4 : j0;
     const int R = args.R;
     const int* term_row = args.term_row;
 
     LaneState<BS> st;
     lane_init(st);
-    st.amp[0] = (j0 < R) ? 1.0 : 0.0;
-    st.amp[1] = (valid1 && j1 < R) ? 1.0 : 0.0;
+    st.amp[0] = (i * BS + o < R) ? 1.0 : 0.0;
+    st.amp[1] = (lm.valid1 && i * BS + o + 4 < R) ? 1.0 : 0.0;
     double suma = 0.0;
     for (int m = 0; m < Jt; m++) suma += ca[m];   // celerite_solver.jl:21
-    const size_t pi = (size_t)wk.par_begin + warp;
+    const size_t pi = (size_t)wk.par_begin + slot;
     const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
     const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
     const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : wk.y;
     const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : wk.s2;
 
-    for (int k = lane; k < 2 * RP; k += 32) qs[k] = 0.0;
-    // zero the padded rows of the table once (rows ≥ R never change)
+    for (int k = lane; k < 2 * RPS; k += 32) qs[k] = 0.0;
+    // zero the table once: padded slots and rows ≥ R never change
     for (int k = lane; k < GCH * SD; k += 32) tab[k] = 0.0;
     __syncwarp();
 
@@ -410,38 +477,36 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
             double* Tn = tab + s * SD;
             const int tr = term_row[m];
             if (tr < 0) {  // real term (b = d = 0): U = a, V = 1; the sin-row is identically zero and is dropped
-                const int r0 = -tr - 1;
-                Tn[F_UT * RP + r0] = ca[m];       Tn[F_UH * RP + r0] = ph * ca[m];
-                Tn[F_KAP * RP + r0] = ph * php;   Tn[F_PHI * RP + r0] = ph;
-                Tn[F_V * RP + r0] = 1.0;          Tn[F_PHN * RP + r0] = phn;
+                const int r0 = pad_index(-tr - 1, BS);
+                Tn[F_UT * RPS + r0] = ca[m];       Tn[F_UH * RPS + r0] = ph * ca[m];
+                Tn[F_KAP * RPS + r0] = ph * php;   Tn[F_PHI * RPS + r0] = ph;
+                Tn[F_V * RPS + r0] = 1.0;          Tn[F_PHN * RPS + r0] = phn;
             } else {
                 double si, co;
                 sincos(cd[m] * wk.t[n], &si, &co);
                 const double u0 = ca[m] * co + cb[m] * si;   // celerite_solver.jl:60
                 const double u1 = ca[m] * si - cb[m] * co;   // celerite_solver.jl:59
-                const int r0 = tr, r1 = tr + 1;
-                Tn[F_UT * RP + r0] = u0;        Tn[F_UT * RP + r1] = u1;
-                Tn[F_UH * RP + r0] = ph * u0;   Tn[F_UH * RP + r1] = ph * u1;
-                Tn[F_KAP * RP + r0] = ph * php; Tn[F_KAP * RP + r1] = ph * php;
-                Tn[F_PHI * RP + r0] = ph;       Tn[F_PHI * RP + r1] = ph;
-                Tn[F_V * RP + r0] = co;         Tn[F_V * RP + r1] = si;
-                Tn[F_PHN * RP + r0] = phn;      Tn[F_PHN * RP + r1] = phn;
+                const int r0 = pad_index(tr, BS), r1 = pad_index(tr + 1, BS);
+                Tn[F_UT * RPS + r0] = u0;        Tn[F_UT * RPS + r1] = u1;
+                Tn[F_UH * RPS + r0] = ph * u0;   Tn[F_UH * RPS + r1] = ph * u1;
+                Tn[F_KAP * RPS + r0] = ph * php; Tn[F_KAP * RPS + r1] = ph * php;
+                Tn[F_PHI * RPS + r0] = ph;       Tn[F_PHI * RPS + r1] = ph;
+                Tn[F_V * RPS + r0] = co;         Tn[F_V * RPS + r1] = si;
+                Tn[F_PHN * RPS + r0] = phn;      Tn[F_PHN * RPS + r1] = phn;
             }
         }
         __syncwarp();
         for (int s = 0; s < nsteps; s += 2) {
             const double* T0 = tab + s * SD;
             const int64_t n = nbeg + s;
-            celerite_step<BS, false>(st, T0, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1, yb[n], sb[n],
-                                     suma, mu, nu, n, lane);
+            celerite_step<BS, false>(st, T0, qs, ws, lm, yb[n], sb[n], suma, mu, nu, n, lane);
             if (s + 1 < nsteps)
-                celerite_step<BS, true>(st, T0 + SD, qs, ws, rowI, colA, colB, o, dmask, src_lane, j0, j1, valid1,
-                                        yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane);
+                celerite_step<BS, true>(st, T0 + SD, qs, ws, lm, yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane);
         }
         __syncwarp();
     }
     const double res = lane_finish(st, N, lane);
-    if (lane == 0) args.out[wk.out_begin + warp] = res;
+    if (active && lane == 0) args.out[wk.out_begin + warp] = res;
 }
 
 }  // namespace pioran

@@ -25,7 +25,16 @@ struct RowDesc {
     int term;      // index of the amplitude this row scales with
 };
 
-// Per-step record of the series table (doubles).  Six row vectors of R_pad entries then 8 scalars.
+// Shared-memory layout of a row vector: block g (BS rows) starts at g·BSP doubles with BSP even and
+// BSP/2 odd, so that (i) every block starts 16-byte aligned (128-bit shared loads) and (ii) the 8 block starts fall
+// into 8 different 16-byte bank groups — a warp reading "its" block (8 distinct blocks, 4 lanes each) is
+// conflict-free.  (BS = 8 unpadded: stride 64 B → 4-way bank conflict on every load, measured in
+// profiles/r01_k2_bs8_before_padding.txt.)
+__host__ __device__ constexpr int bsp_of(int bs) { return bs <= 6 ? 6 : 10; }
+__host__ __device__ constexpr int rps_of(int bs) { return G * bsp_of(bs); }
+__host__ __device__ constexpr int pad_index(int j, int bs) { return (j / bs) * bsp_of(bs) + (j % bs); }
+
+// Per-step record of the series table (doubles).  Six row vectors of RPS = 8·BSP entries (padded layout) then 8 scalars.
 //   UT  : Ũ_n            (U_n = amp ∘ Ũ_n;  src/celerite_solver.jl:59-60 with a factored out)
 //   UH  : φ_n ∘ Ũ_n
 //   KAP : φ_n ∘ φ_{n-1}
@@ -33,7 +42,7 @@ struct RowDesc {
 //   V   : cos/sin(d t_n) (or 1 for real rows;  src/celerite_solver.jl:62-63)
 //   PHN : φ_{n+1}        (0 at the last step)
 //   scalars: [0] y_n  [1] σ²_n  [2] t_n
-__host__ __device__ constexpr int table_step_doubles(int rpad) { return 6 * rpad + 8; }
+__host__ __device__ constexpr int table_step_doubles(int rps) { return 6 * rps + 8; }
 enum TableField : int { F_UT = 0, F_UH = 1, F_KAP = 2, F_PHI = 3, F_V = 4, F_PHN = 5 };
 
 constexpr int CHUNK_STEPS = 16;  // steps per TMA stage

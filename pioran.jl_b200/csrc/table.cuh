@@ -13,15 +13,18 @@ namespace pioran {
 // of CHUNK_STEPS; steps n ≥ N are zero-filled.
 __global__ void table_build_kernel(double* __restrict__ table, const double* __restrict__ t,
                                    const double* __restrict__ y, const double* __restrict__ s2, int64_t N,
-                                   int64_t N_pad, const RowDesc* __restrict__ rows, int RP) {
+                                   int64_t N_pad, const RowDesc* __restrict__ rows, int BS) {
+    const int RP = rps_of(BS), BSP = bsp_of(BS);   // one thread per padded slot; slots ≥ BS of a block are zero
     const int SD = table_step_doubles(RP);
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= N_pad * RP) return;
     const int64_t n = gid / RP;
     const int j = (int)(gid - n * RP);
     double* Tn = table + n * SD;
+    const int jb = j / BSP, jr = j - jb * BSP;
+    RowDesc rd{0, 0, 0, ROW_PAD, 0};
+    if (jr < BS) rd = rows[jb * BS + jr];
     double ut = 0, v = 0, ph = 0, php = 0, phn = 0;
-    const RowDesc rd = rows[j];
     if (n < N && rd.kind != ROW_PAD) {
         const double tn = t[n];
         if (n >= 1) ph = exp(-rd.c * (tn - t[n - 1]));           // celerite_solver.jl:54

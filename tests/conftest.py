@@ -20,6 +20,28 @@ def rel_err(x, ref):
     return np.abs(x - ref) / np.maximum(1.0, np.abs(ref))
 
 
+def assert_parity(got, want, theta, ld_fn, tol=1e-9, slack=4.0):
+    """Parity bar of BASELINE.json (≤ 1e-9 relative on logL, FP64) made conditioning-aware: a row may exceed `tol`
+    only if the reference algorithm's own FP64 answer `want` is itself farther than tol/slack from the 80-bit
+    evaluation of the same recursion (ld_fn(row) → long double twin in the oracle), and then the GPU value must lie
+    within slack × that distance of the 80-bit value.  SURVEY §7 "parity on ill-conditioned θ": at steep PSD slopes
+    the cancellation D_n = Σa + σ²_n − UᵀSU (src/celerite_solver.jl:92) loses ~7 digits in any operation order."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    r = rel_err(got, want)
+    bad = np.flatnonzero(~(r <= tol))
+    report = []
+    for i in bad:
+        if not np.isfinite(want[i]):
+            assert not np.isfinite(got[i]), f"row {i}: reference non-finite, GPU {got[i]}"
+            continue
+        ld = float(ld_fn(theta[i]))
+        e_ref, e_gpu = float(rel_err(want[i], ld)), float(rel_err(got[i], ld))
+        report.append((int(i), float(r[i]), e_ref, e_gpu))
+        assert e_ref > tol / slack and e_gpu <= slack * e_ref, (
+            f"row {i}: |gpu-ref| {r[i]:.3e} > {tol:g}; vs 80-bit: ref {e_ref:.3e}, gpu {e_gpu:.3e}")
+    return report
+
+
 class GoldenRun:
     """One shipped ultranest run of the reference: the series it used and the (θ, logL) pairs it produced."""
 
@@ -65,54 +87,16 @@ def periodic_mean(t, row):
     return A * np.sin(2 * np.pi * t / T0 + phi) + mu
 
 
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import workloads as _wl  # noqa: E402
+
+
 def synthetic_series(N, seed, theta0=(0.82, 0.01, 3.3), variance=1.0, basis="SHO", J=20):
-    """SURVEY §8d generator: gaps 0.05+Exp(1), σ~U(0.01,0.05); y = GP draw at θ₀ (state-space sampling of the
-    celerite model, equivalent in distribution to Pioran.sim, src/celerite_solver.jl:515-549) + N(0,σ²)."""
-    from oracle import oracle as orc
-    rng = np.random.default_rng(seed)
-    t = np.cumsum(0.05 + rng.exponential(1.0, N))
-    t -= t[0]
-    sig = rng.uniform(0.01, 0.05, N)
-    f_min, f_max = 1.0 / (t[-1] - t[0]), 1.0 / np.min(np.diff(t)) / 2.0
-    a, b, c, d = orc.approx("SBPL", theta0, f_min, f_max, J, variance, basis=basis)
-    y = np.zeros(N)
-    for aj, bj, cj, dj in zip(a, b, c, d):
-        # complex term: x = (x1,x2) with stationary covariance [[a,-b],[-b,a]]... sample through the exact
-        # discretised OU-rotation; for simplicity draw each term as a stationary complex AR(1) with the right ACVF
-        if aj <= 0:
-            continue
-        rr = min(abs(bj) / aj, 1.0) if aj > 0 else 0.0
-        s = np.sign(bj) if bj != 0 else 1.0
-        # P∞ = [[a, -b],[-b, a]] has eigenvalues a∓b ≥ 0 when |b| ≤ a
-        P = np.array([[aj, -s * rr * aj], [-s * rr * aj, aj]])
-        w, V = np.linalg.eigh(P)
-        Lc = V @ np.diag(np.sqrt(np.clip(w, 0, None)))
-        x = Lc @ rng.normal(size=2)
-        y[0] += x[0]
-        for n in range(1, N):
-            dt = t[n] - t[n - 1]
-            e = np.exp(-cj * dt)
-            co, si = np.cos(dj * dt), np.sin(dj * dt)
-            F = e * np.array([[co, -si], [si, co]])
-            Q = P - F @ P @ F.T
-            Q = 0.5 * (Q + Q.T)
-            wq, Vq = np.linalg.eigh(Q)
-            x = F @ x + Vq @ (np.sqrt(np.clip(wq, 0, None)) * rng.normal(size=2))
-            y[n] += x[0]
-    y += sig * rng.normal(size=N)
-    return t, y, sig ** 2, f_min, f_max
+    """SURVEY §8d generator (tools/workloads.py — the same inputs bench.py uses): gaps 0.05+Exp(1), σ~U(0.01,0.05),
+    y = celerite GP draw at θ₀ + N(0,σ²).  → t, y, σ², f_min, f_max"""
+    return _wl.make_series(N, seed, theta0, variance, J)
 
 
 def prior_theta(B, f_min, f_max, ybar, ysd, seed, alpha2_max=4.0):
     """Prior transform of examples/ultranest/single_pl.jl:96-104 on a seeded unit cube."""
-    rng = np.random.default_rng(seed)
-    u = rng.uniform(size=(B, 6))
-    f0, fM = f_min / 20.0, f_max * 20.0
-    a1 = 1.5 * u[:, 0]
-    f1 = np.exp(np.log(4 * f0) + u[:, 1] * (np.log(fM / 4) - np.log(4 * f0)))
-    a2 = a1 + u[:, 2] * (alpha2_max - a1)
-    from scipy import stats
-    var = stats.lognorm(s=np.sqrt(2.0), scale=np.exp(-3.0)).ppf(u[:, 3])
-    nu = stats.gamma(a=2, scale=0.5).ppf(u[:, 4])
-    mu = stats.norm(loc=ybar, scale=5 * ysd).ppf(u[:, 5])
-    return np.column_stack([a1, f1, a2, var, nu, mu])
+    return _wl.prior_theta(B, f_min, f_max, ybar, ysd, seed, alpha2_max)

@@ -1,0 +1,49 @@
+"""Summarise an .ncu-rep (one kernel) into a compact text block for profiles/: key raw metrics + stall mix + opcode mix per
+warp-step.  usage: python tools/ncu_summary.py rep.ncu-rep warp_steps > profiles/xxx.txt"""
+import collections, csv, io, re, subprocess, sys
+rep, wsteps = sys.argv[1], float(sys.argv[2])
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, val = rows[0], rows[2]
+m = dict(zip(hdr, val))
+keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "sm__cycles_elapsed.max", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+print(f"# {rep}")
+for k in keys:
+    if k in m:
+        print(f"{k}: {m[k]}")
+wf = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "0").replace(",", "") or 0)
+ld = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "0").replace(",", "") or 0)
+stw = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "0").replace(",", "") or 0)
+print(f"per warp-step: shared-pipe wavefronts {wf / wsteps:.1f} (ld {ld / wsteps:.1f}, st {stw / wsteps:.1f}, other/shfl {(wf - ld - stw) / wsteps:.1f}); "
+      f"instructions {float(m['smsp__inst_executed.sum'].replace(',', '')) / wsteps:.1f}")
+try:
+    fl = sum(float(m[f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum"].replace(",", "")) * w for o, w in (("dfma", 2), ("dmul", 1), ("dadd", 1)))
+    print(f"executed FP64 flops (2*dfma+dmul+dadd, thread level): {fl:.4g}")
+except KeyError:
+    pass
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(src)))
+hdr, data = rows[1], rows[2:]
+ix = {h: i for i, h in enumerate(hdr)}
+tot = sum(int(r[ix["# Samples"]]) for r in data)
+stall, ops, samp = collections.Counter(), collections.Counter(), collections.Counter()
+for r in data:
+    mm = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)(\.[A-Z0-9_.]+)?", r[ix["Source"]])
+    op = mm.group(2) + (".128" if mm.group(3) and "128" in mm.group(3) else "") if mm else "?"
+    ops[op] += int(r[ix["Instructions Executed"]])
+    samp[op] += int(r[ix["# Samples"]])
+    for k in hdr:
+        if k.startswith("stall_") and "Not Issued" not in k:
+            stall[k] += int(r[ix[k]] or 0)
+print("stall mix (% of samples): " + ", ".join(f"{k[6:]} {100 * v / tot:.1f}" for k, v in stall.most_common(8)))
+print("opcode mix per warp-step (executed | % of stall samples):")
+for op, n in ops.most_common(16):
+    print(f"  {op:10s} {n / wsteps:7.2f} | {100 * samp[op] / tot:5.1f}")
