@@ -110,6 +110,10 @@ int pioran_approx_logl_dev(pioran_ctx *ctx, int S, const int *series_ids, const 
 
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
+/* Number of time-axis chunks per parameter vector used by pioran_celerite_logl_scan (0 = automatic: two per SM, at
+ * least 64 steps each).  The result does not depend on it beyond rounding; tests use it to exercise the scan on short
+ * series. */
+int pioran_ctx_set_scan_chunks(pioran_ctx *ctx, int chunks);
 int pioran_celerite_logl_scan(pioran_ctx *ctx, int series_id, int B, int Jt,
                               const double *a, const double *b, const double *c, const double *d,
                               const double *mu, const double *nu, double *logl_out);

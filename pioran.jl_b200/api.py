@@ -67,10 +67,10 @@ class SHO(Celerite):
 
 
 class Exp(Celerite):
-    """Exp(A, α) → (A, 0, α, 0)   (src/Exp.jl)"""
+    """Exp(A, α): k(τ) = A/2·exp(−ατ) → (A/2, 0, α, 0)   (src/Exp.jl:22-34; test/test_covariancefunctions.jl:44-47)"""
 
     def __init__(self, A, α):
-        super().__init__(A, 0.0, α, 0.0)
+        super().__init__(A / 2.0, 0.0, α, 0.0)
 
 
 class SumOfCelerite(SemiSeparable):

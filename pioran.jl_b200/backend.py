@@ -156,6 +156,10 @@ class Context:
                                               C.c_void_p(out_ptr)))
 
     # -- K3
+    def set_scan_chunks(self, chunks):
+        """Chunks of the time axis per parameter vector in celerite_logl_scan (0 = automatic)."""
+        check(self.lib.pioran_ctx_set_scan_chunks(self.h, int(chunks)))
+
     def celerite_logl_scan(self, series, a, b, c, d, mu=None, nu=None):
         a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
         B, Jt = a.shape

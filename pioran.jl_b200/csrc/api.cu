@@ -91,8 +91,11 @@ struct pioran_ctx {
     // evaluates the same series × batch-size shape ~1e5 times)
     std::vector<int64_t> work_key;
     int work_items = 0;
+    int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     std::mutex mu;
 };
+
+static int make_term_rows(int B, int Jt, const double* b, const double* d, std::vector<int>& term_row);
 
 static int bs_for_rank(int R) {
     int bs = (R + G - 1) / G;
@@ -363,7 +366,7 @@ static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_shared_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = shared_smem_bytes<BS>();
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEventRecord(c->ev_beg, c->stream);
+    if (c->ev_beg) cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -376,7 +379,7 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = generic_smem_bytes<BS>(args.Jt);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaEventRecord(c->ev_beg, c->stream);
+    if (c->ev_beg) cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -435,6 +438,7 @@ static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* ta
             w.par_begin = (theta_per_series ? s * B : 0) + beg;
             w.count = end - beg;
             w.out_begin = s * B + beg;
+            w.n_begin = 0; w.n_end = ser[s]->N; w.init = nullptr; w.part = nullptr;
             ip.items.push_back(w);
         }
     }
@@ -608,15 +612,8 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    // rank reduction: a term that is real (b = d = 0) for every set of the batch needs one row, not two
-    std::vector<int> term_row(Jt + 1);
-    int R = 0;
-    for (int m = 0; m < Jt; m++) {
-        bool real = true;
-        for (int i = 0; i < B && real; i++) real = (b[(size_t)i * Jt + m] == 0.0 && d[(size_t)i * Jt + m] == 0.0);
-        term_row[m] = real ? -(R + 1) : R;  // negative → real term at row R
-        R += real ? 1 : 2;
-    }
+    std::vector<int> term_row;
+    const int R = make_term_rows(B, Jt, b, d, term_row);
     const int BS = bs_for_rank(R);
     if (BS > 8)
         return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) needs block size %d > 8; this build supports rank <= 64", R, Jt, BS);
@@ -650,26 +647,182 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
 }
 
 // ------------------------------------------------------------------------------------------------ K3 / K4 entries
+// Rank reduction shared by the generic and the scan entry: a term that is real (b = d = 0) for every coefficient set of
+// the batch needs one row, not two.  term_row[m] ≥ 0: complex term at rows (v, v+1); < 0: real term at row −v−1.
+static int make_term_rows(int B, int Jt, const double* b, const double* d, std::vector<int>& term_row) {
+    term_row.assign(Jt + 1, 0);
+    int R = 0;
+    for (int m = 0; m < Jt; m++) {
+        bool real = true;
+        for (int i = 0; i < B && real; i++) real = (b[(size_t)i * Jt + m] == 0.0 && d[(size_t)i * Jt + m] == 0.0);
+        term_row[m] = real ? -(R + 1) : R;
+        R += real ? 1 : 2;
+    }
+    return R;
+}
+
+extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
+    c->scan_chunks = chunks;
+    return PIORAN_OK;
+}
+
 extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                          const double* cc, const double* d, const double* mu, const double* nu,
                                          double* logl_out) {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    return scan_logl_host(c->stream, c->num_sms, &c->launches, s->N, s->t, s->y, s->s2, B, Jt, a, b, cc, d, mu, nu,
-                          logl_out, fail);
+    std::vector<int> term_row;
+    const int R = make_term_rows(B, Jt, b, d, term_row);
+    const int BS = bs_for_rank(R);
+    if (BS > 8 || R > SR)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
+    const int64_t N = s->N;
+    // chunking: enough chunks to give every SM two re-filter warps, at least 64 steps per chunk
+    int P = c->scan_chunks > 0 ? c->scan_chunks : 2 * c->num_sms;
+    P = (int)std::max<int64_t>(1, std::min<int64_t>(P, N / 64));
+    int G2 = (int)std::ceil(std::sqrt((double)P));
+    int G1 = (P + G2 - 1) / G2;
+    std::vector<int64_t> bounds(P + 1);
+    for (int k = 0; k <= P; k++) bounds[k] = (int64_t)((__int128)N * k / P);
+
+    int rc;
+    GenericInputs gi;
+    if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, gi))) return rc;
+    const int NW = nw_for_bs(BS);
+    const size_t nch = (size_t)B * P;
+    const size_t nitems = (nch + NW - 1) / NW * NW;
+    // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out
+    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch + 1);
+    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B)))) return rc;
+    double* elems = c->misc.as<double>();
+    double* pref = elems + n_el;
+    double* gstate = pref + n_el;
+    double* cstate = gstate + n_gs;
+    double* parts = cstate + n_cs;
+    double* out = parts + n_pt;
+    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
+    int64_t* bounds_dev = c->rows.as<int64_t>();
+    int* term_row_dev = reinterpret_cast<int*>(bounds_dev + P + 2);
+    CUDA_TRY(cudaMemcpyAsync(bounds_dev, bounds.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(term_row_dev, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+    std::vector<WorkItem> items(nitems);
+    for (size_t k = 0; k < nitems; k++) {
+        const size_t q = std::min(k, nch - 1);
+        const int th = (int)(q / P), ch = (int)(q % P);
+        WorkItem& w = items[k];
+        w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = N;
+        w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
+        w.n_begin = bounds[ch]; w.n_end = bounds[ch + 1];
+        w.init = ch == 0 ? nullptr : cstate + q * SSTATE;
+        w.part = k < nch ? parts + 2 * q : parts + 2 * nch;   // padding warps write to the dummy pair
+    }
+    c->work_key.clear();
+    if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // bounds, term_row, items are locals
+
+    cudaEventRecord(c->ev_beg, c->stream);
+    ScanArgs sa{};
+    sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = bounds_dev;
+    sa.a = gi.a; sa.b = gi.b; sa.c = gi.c; sa.d = gi.d; sa.Jt = Jt; sa.term_row = term_row_dev;
+    sa.mu = gi.mu; sa.nu = gi.nu; sa.elems = elems;
+    scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
+    c->launches++;
+    if (P > 1) {
+        CUDA_TRY(cudaFuncSetAttribute(scan_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(scan_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(elems, pref, P, G2);
+        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(pref, gstate, P, G2, G1);
+        scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(pref, gstate, cstate, P, G2, G1);
+        c->launches += 3;
+    }
+    CUDA_TRY(cudaGetLastError());
+    BatchArgs args{};
+    args.work = c->work.as<WorkItem>();
+    args.a = gi.a; args.b = gi.b; args.c = gi.c; args.d = gi.d;
+    args.Jt = Jt; args.term_row = term_row_dev; args.R = R;
+    args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
+    args.out = out;
+    args.per_warp_items = 1;
+    cudaEvent_t keep_beg = c->ev_beg;   // dispatch_generic re-records the events; K3 reports the whole pipeline
+    c->ev_beg = nullptr;
+    rc = dispatch_generic(c, BS, args, (int)(nitems / NW));
+    c->ev_beg = keep_beg;
+    if (rc) return rc;
+    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(parts, P, B, N, out);
+    c->launches++;
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(logl_out, out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
 }
 
 extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                   const double* cc, const double* d, const double* mu, const double* nu,
                                   double* nll_out, int* info_out) {
     if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    return dense_logl_host(c->stream, &c->launches, s->N, s->t, s->y, s->s2, B, Jt, a, b, cc, d, mu, nu, nll_out,
-                           info_out, fail);
+    const int64_t N = s->N;
+    const int nblk = (int)((N + 1 + DNB - 1) / DNB);        // +1: the augmented (y − μ)ᵀ row
+    const int64_t ld = (int64_t)nblk * DNB;
+    const size_t per = sizeof(double) * (size_t)ld * (size_t)ld;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::min<size_t>(free_b / 2 + c->misc.cap, (size_t)32 << 30);
+    if (per > budget)
+        return fail(PIORAN_ENOMEM, "dense path needs %zu bytes per parameter vector at N = %lld (free: %zu); use the celerite entry",
+                    per, (long long)N, free_b);
+    const int chunk = (int)std::min<size_t>((size_t)B, budget / per);
+    int rc;
+    GenericInputs gi;
+    if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, gi))) return rc;
+    if ((rc = c->misc.ensure(per * (size_t)chunk))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * 3 * (size_t)chunk + sizeof(int) * (size_t)chunk))) return rc;
+    double* A = c->misc.as<double>();
+    double* acc = c->out.as<double>();
+    double* nll = acc + 2 * (size_t)chunk;
+    int* info = reinterpret_cast<int*>(nll + chunk);
+    const int ntri = nblk * (nblk + 1) / 2;
+    const size_t fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB);
+    if (fill_smem > 48 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
+    cudaEventRecord(c->ev_beg, c->stream);
+    for (int th0 = 0; th0 < B; th0 += chunk) {
+        const int nb = std::min(chunk, B - th0);
+        CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)chunk + sizeof(int) * (size_t)chunk, c->stream));
+        dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
+                                                                         gi.d, gi.mu, gi.nu, th0);
+        c->launches++;
+        for (int kb = 0; kb < nblk; kb++) {
+            dense_potrf_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, N, kb, acc, info);
+            c->launches++;
+            const int m = nblk - kb - 1;
+            if (m > 0) {
+                dense_trsm_kernel<<<dim3(m, nb), DNB, 0, c->stream>>>(A, ld, kb);
+                dense_syrk_kernel<<<dim3(m * (m + 1) / 2, nb), 256, 0, c->stream>>>(A, ld, kb);
+                c->launches += 2;
+            }
+        }
+        dense_finish_kernel<<<(nb + 127) / 128, 128, 0, c->stream>>>(acc, info, N, nb, nll);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(nll_out + th0, nll, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
+        if (info_out) CUDA_TRY(cudaMemcpyAsync(info_out + th0, info, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // the workspace is reused by the next chunk
+    }
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    return PIORAN_OK;
 }

@@ -297,6 +297,7 @@ struct BatchArgs {
     const double* s2_batch; // [nθ × ystride] or nullptr
     int64_t ystride;
     double* out;            // logL
+    int per_warp_items;     // generic kernel: warp w of CTA b takes work item b·NW + w (K3 pass 3)
 };
 
 template <int BS>
@@ -310,15 +311,18 @@ __device__ __forceinline__ void lane_init(LaneState<BS>& st) {
     st.chi2 = 0.0; st.logacc = 0.0; st.dkeep = 1.0; st.dfirst = 1.0;
 }
 
+// Σ log|D_n| over the steps this warp swept (log D_1 without abs, celerite_solver.jl:126).
 template <int BS>
-__device__ __forceinline__ double lane_finish(LaneState<BS>& st, int64_t N, int lane) {
-    // flush the log|D| ring: steps since the last multiple of 32
-    const int rem = (int)(N & 31);
-    if (rem != 0 && lane < rem) st.logacc += log(fabs(st.dkeep));
-    double la = st.logacc;
+__device__ __forceinline__ double lane_logdet(LaneState<BS>& st) {
+    // flush the log|D| ring: lanes without a pending pivot hold 1.0 (log 1 = 0)
+    double la = st.logacc + log(fabs(st.dkeep));
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) la += __shfl_xor_sync(FULL, la, sft);
-    const double logdet = log(st.dfirst) + la;
+    return log(st.dfirst) + la;
+}
+template <int BS>
+__device__ __forceinline__ double lane_finish(LaneState<BS>& st, int64_t N, int lane) {
+    const double logdet = lane_logdet(st);
     // celerite_solver.jl:333
     return -logdet / 2 - (double)N * 1.8378770664093453 / 2 - st.chi2 / 2;
 }
@@ -426,11 +430,12 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     double* ws = qs + RPS;
     double* phs = ws + RPS;
 
-    const WorkItem wk = args.work[blockIdx.x];
-    const bool active = warp < wk.count;
-    const int slot = active ? warp : wk.count - 1;
+    const WorkItem wk = args.work[args.per_warp_items ? blockIdx.x * NW + warp : blockIdx.x];
+    const bool active = args.per_warp_items ? true : warp < wk.count;
+    const int slot = args.per_warp_items ? 0 : (active ? warp : wk.count - 1);
     const int th = wk.theta_begin + slot;
     const int64_t N = wk.N;
+    const int64_t n0 = wk.n_begin, n1 = wk.n_end;
     const double* ca = args.a + (size_t)th * Jt;
     const double* cb = args.b + (size_t)th * Jt;
     const double* cc = args.c + (size_t)th * Jt;
@@ -457,15 +462,37 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     // zero the table once: padded slots and rows ≥ R never change
     for (int k = lane; k < GCH * SD; k += 32) tab[k] = 0.0;
     __syncwarp();
+    if (wk.init) {
+        // K3 pass 3: inject the state entering step n0 (already decayed to t_n0).  The first local step is an EVEN
+        // step with φ_n0 = φ_n0−1 := 1 below, so the blocks hold the true values with no factor pending.
+        constexpr int RL = SCAN_LD;
+        const double* S0 = wk.init;
+        const int rI = i * BS, cA = ((i + o) & 7) * BS, cB = (o == 0) ? ((i ^ 4) * BS) : cA;
+#pragma unroll
+        for (int r = 0; r < BS; r++)
+#pragma unroll
+            for (int c = 0; c < BS; c++) {
+                double v = S0[(size_t)(rI + r) * RL + ((r > c) ? cA : cB) + c];
+                if (r == c && lm.dzero) v = 0.0;     // the masked copy of the distance-4 diagonal
+                st.M[r][c] = v;
+            }
+        st.sjj[0] = S0[(size_t)(rI + o) * RL + rI + o];
+        st.g[0] = S0[(size_t)RL * RL + rI + o];
+        if (lm.valid1) {
+            st.sjj[1] = S0[(size_t)(rI + o + 4) * RL + rI + o + 4];
+            st.g[1] = S0[(size_t)RL * RL + rI + o + 4];
+        }
+    }
 
-    for (int64_t nbeg = 0; nbeg < N; nbeg += GCH) {
-        const int nsteps = (int)((N - nbeg) < GCH ? (N - nbeg) : GCH);
-        // pass 1: φ for steps nbeg-1 … nbeg+GCH  (φ_0 = 0, φ_N = 0)
+    for (int64_t nbeg = n0; nbeg < n1; nbeg += GCH) {
+        const int nsteps = (int)((n1 - nbeg) < GCH ? (n1 - nbeg) : GCH);
+        // pass 1: φ for steps nbeg-1 … nbeg+GCH  (φ_0 = 0, φ_N = 0; chunk start of K3: φ := 1 up to step n0)
         for (int idx = lane; idx < (GCH + 2) * Jt; idx += 32) {
             const int s = idx / Jt, m = idx - s * Jt;
             const int64_t n = nbeg - 1 + s;
             double ph = 0.0;
             if (n >= 1 && n < N) ph = exp(-cc[m] * (wk.t[n] - wk.t[n - 1]));
+            if (wk.init && n <= n0) ph = 1.0;
             phs[idx] = ph;
         }
         __syncwarp();
@@ -505,8 +532,13 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
         }
         __syncwarp();
     }
-    const double res = lane_finish(st, N, lane);
-    if (active && lane == 0) args.out[wk.out_begin + warp] = res;
+    if (wk.part) {
+        const double logdet = lane_logdet(st);
+        if (lane == 0) { wk.part[0] = logdet; wk.part[1] = st.chi2; }
+    } else {
+        const double res = lane_finish(st, N, lane);
+        if (active && lane == 0) args.out[wk.out_begin + warp] = res;
+    }
 }
 
 }  // namespace pioran

@@ -46,8 +46,10 @@ __host__ __device__ constexpr int table_step_doubles(int rps) { return 6 * rps +
 enum TableField : int { F_UT = 0, F_UH = 1, F_KAP = 2, F_PHI = 3, F_V = 4, F_PHN = 5 };
 
 constexpr int CHUNK_STEPS = 16;  // steps per TMA stage
+constexpr int SCAN_LD = 64;      // leading dimension of the K3 state matrices (rank ≤ 64)
 
-// One unit of work of the batched kernel: `count` parameter vectors of one series.
+// One unit of work of the batched kernels: `count` parameter vectors of one series (or, for the chunked re-filter of
+// the long-series path K3, one parameter vector on the step range [n_begin, n_end) starting from a given state).
 struct WorkItem {
     const double* table;   // series table (shared mode) or nullptr (generic mode)
     const double* t;       // series arrays (device)
@@ -58,6 +60,12 @@ struct WorkItem {
     int par_begin;         // first row of the per-θ scalar arrays (μ, ν, y_batch) handled by this CTA
     int count;             // number of θ (≤ warps per CTA)
     int out_begin;         // first index of logl_out
+    // K3 pass 3 (generic kernel, one work item per warp): sweep steps [n_begin, n_end) only, starting from the state
+    // `init` = S (SCAN_LD×SCAN_LD row-major over the logical rows) followed by g (SCAN_LD) entering step n_begin, and write the
+    // partial sums (Σ log|D_n|, Σ z_n²/D_n) to `part` instead of a log-likelihood.  init == nullptr: whole series.
+    int64_t n_begin, n_end;
+    const double* init;
+    double* part;
 };
 
 }  // namespace pioran

@@ -1,0 +1,94 @@
+"""GPU tests of K3 — the parallel-in-time (chunked associative scan) evaluation of the celerite log-likelihood for long
+single series — through the C ABI: same value as logl(a,b,c,d,τ,y,σ2) (src/celerite_solver.jl:312-334) computed by the
+sequential kernel K2 and by the CPU oracle."""
+import time
+
+import numpy as np
+import pytest
+
+from conftest import rel_err, synthetic_series
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import pioran_b200
+    return pioran_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(pb):
+    c = pb.get_context(0)
+    yield c
+    c.set_scan_chunks(0)
+
+
+@pytest.mark.parametrize("basis,J", [("SHO", 20), ("DRWCelerite", 20), ("SHO", 30), ("SHO", 8)])
+def test_scan_equals_sequential_and_oracle(pb, ctx, basis, J):
+    t, y, s2, f_min, f_max = synthetic_series(3000, seed=11)
+    a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, J, 1.0, basis=basis)
+    want = orc.celerite_logl(a, b, c, d, t, y, s2)
+    ser = ctx.upload_series(t, y, s2)
+    seq = ctx.celerite_logl(ser, a, b, c, d)[0]
+    assert rel_err(seq, want) <= TOL
+    for chunks in (1, 2, 3, 7, 16, 37):
+        ctx.set_scan_chunks(chunks)
+        got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
+        assert rel_err(got, want) <= TOL, (chunks, got, want)
+        assert rel_err(got, seq) <= 1e-11, (chunks, got, seq)
+    ser.free()
+
+
+def test_scan_batch_with_mean_and_variance_scale(pb, ctx):
+    t, y, s2, f_min, f_max = synthetic_series(2500, seed=12)
+    rng = np.random.default_rng(0)
+    B = 3
+    th = np.array([[0.5, 0.02, 2.8], [0.82, 0.01, 3.3], [1.1, 0.2, 3.9]])
+    co = [orc.approx("SBPL", th[i], f_min, f_max, 20, [0.5, 1.0, 2.0][i]) for i in range(B)]
+    a, b, c, d = (np.stack([x[k] for x in co]) for k in range(4))
+    mu = rng.normal(0, 0.2, B); nu = rng.uniform(0.5, 2.0, B)
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_scan_chunks(12)
+    got = ctx.celerite_logl_scan(ser, a, b, c, d, mu=mu, nu=nu)
+    want = orc.celerite_logl_batch(a, b, c, d, t, y, s2, mu=mu, nu=nu, nthreads=0)
+    assert rel_err(got, want).max() <= TOL
+    ser.free()
+
+
+def test_scan_short_series_falls_back_to_one_chunk(pb, ctx):
+    t, y, s2, f_min, f_max = synthetic_series(50, seed=13)
+    a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, 20, 1.0)
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_scan_chunks(0)
+    assert rel_err(ctx.celerite_logl_scan(ser, a, b, c, d)[0], orc.celerite_logl(a, b, c, d, t, y, s2)) <= TOL
+    ser.free()
+
+
+def test_config_c4_long_series_n1e6_j30(pb, ctx):
+    """BASELINE configs[3]: N = 1e6, J = 30 (SHO, rank 60), parallel associative scan vs the sequential sweep."""
+    import workloads as wl
+    N = 1_000_000
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=4)
+    a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, 30, float(np.var(y)))
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_scan_chunks(0)
+    got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]          # warm-up (buffers)
+    t0 = time.perf_counter()
+    got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
+    wall_scan, dev_scan = time.perf_counter() - t0, ctx.last_kernel_ms()
+    t0 = time.perf_counter()
+    seq = ctx.celerite_logl(ser, a, b, c, d)[0]
+    wall_seq = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want = orc.celerite_logl(a, b, c, d, t, y, s2)
+    wall_cpu = time.perf_counter() - t0
+    print(f"\nC4 N=1e6 R=60: scan {dev_scan:.2f} ms device ({wall_scan * 1e3:.1f} ms wall), sequential GPU sweep "
+          f"{wall_seq * 1e3:.0f} ms, CPU restatement {wall_cpu:.1f} s; logL {got:.6f}; "
+          f"rel(scan, seq) {rel_err(got, seq):.2e}, rel(scan, cpu) {rel_err(got, want):.2e}")
+    assert np.isfinite(got)
+    assert rel_err(got, seq) <= TOL
+    assert rel_err(got, want) <= TOL
+    ser.free()

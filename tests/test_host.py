@@ -85,7 +85,7 @@ def test_acvf_types():
     """(a,b,c,d) conventions of the kernel types (test/test_covariancefunctions.jl, test/test_acvf.jl)."""
     pb = _build()
     e = pb.Exp(2.0, 0.5)
-    assert pb.celerite_coefs(e) == (np.array([2.0]), np.array([0.0]), np.array([0.5]), np.array([0.0]))
+    assert pb.celerite_coefs(e) == (np.array([1.0]), np.array([0.0]), np.array([0.5]), np.array([0.0]))  # a = A/2 (src/Exp.jl:30)
     s = pb.SHO(1.5, 2.0)
     a, b, c, d = pb.celerite_coefs(s)
     assert a[0] == b[0] == 1.5 and c[0] == d[0] == 2.0 / np.sqrt(2)

@@ -101,3 +101,28 @@ def flops_per_step(R):
 
 def rank_of(basis, J):
     return 2 * J if basis == "SHO" else 3 * J
+
+
+def make_series_fast(N, seed, taus=(3.0, 60.0, 2000.0), amps=(0.4, 0.7, 1.0)):
+    """Long irregular series for the N ~ 1e6 configuration (C4) without the O(N·R²) GP draw: y = sum of three
+    Ornstein–Uhlenbeck processes (red-noise-like, exact irregular-step recurrence) + white noise.
+    → t, y, σ², f_min, f_max"""
+    rng = np.random.default_rng(seed)
+    dt = 0.05 + rng.exponential(1.0, N)
+    t = np.cumsum(dt)
+    t -= t[0]
+    sig = rng.uniform(0.01, 0.05, N)
+    y = sig * rng.normal(size=N)
+    for tau, amp in zip(taus, amps):
+        e = np.exp(-dt / tau)
+        drive = amp * np.sqrt(1.0 - e * e) * rng.normal(size=N)
+        x = np.empty(N)
+        acc = amp * rng.normal()
+        el, dl = e.tolist(), drive.tolist()
+        out = [0.0] * N
+        for n in range(N):
+            acc = el[n] * acc + dl[n]
+            out[n] = acc
+        y += np.asarray(out)
+    f_min, f_max = 1.0 / (t[-1] - t[0]), 1.0 / np.min(np.diff(t)) / 2.0
+    return t, y, sig ** 2, f_min, f_max
