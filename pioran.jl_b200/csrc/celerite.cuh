@@ -127,18 +127,22 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // One time step.  ODD: the step index n is odd → the state leaves the step with the row factor pending.
 //   T      : this step's table record in shared memory (padded vectors)
 //   qs, ws : per-warp scratch vectors (q and w of the previous step, one of them pre-multiplied by φ_n)
-template <int BS, bool ODD>
+//   PRE    : the state is kept PRE-DECAYED — the decay factor of the coming step (κ_c of an odd step, κ_r of an even
+//            step, read from the next record Tnext) is applied at the END of a step, where it is independent of the
+//            reductions still in flight, instead of inside the rank-1 update at the start of the next one.  Same FP64
+//            count (DMUL κ·m + DFMA q·w+m instead of DMUL q·w + DFMA κ·m+qw), shorter critical path.
+template <int BS, bool ODD, bool PRE = false>
 __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* __restrict__ T, double* __restrict__ qs,
                                               double* __restrict__ ws, const LaneMap& lm, const double yn,
                                               const double s2n, const double suma, const double mu, const double nu,
-                                              const int64_t n, const int lane) {
+                                              const int64_t n, const int lane, const double* __restrict__ Tnext = nullptr) {
     constexpr int RP = rps_of(BS);
     const int o = lm.o;
     // ---- row-side operands of block-row I
     double qrow[BS], urow[BS], xrow[BS];
     load_slice<BS>(qrow, qs + lm.rowI);
     load_slice<BS>(urow, T + (ODD ? F_UH : F_UT) * RP + lm.rowI);    // weight of the column partial sums
-    load_slice<BS>(xrow, T + (ODD ? F_PHI : F_KAP) * RP + lm.rowI);  // ODD: post-scale of row sums; EVEN: decay of row r
+    if (ODD || !PRE) load_slice<BS>(xrow, T + (ODD ? F_PHI : F_KAP) * RP + lm.rowI);  // ODD: post-scale of row sums; EVEN: decay of row r
     double prow[BS];                                                  // EVEN: φ of my rows = post-scale of column sums
     if (!ODD) load_slice<BS>(prow, T + F_PHI * RP + lm.rowI);
     double rowpart[BS], acc[BS];
@@ -160,13 +164,13 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
             const double2 a2 = *reinterpret_cast<const double2*>(uAp + c0), a3 = *reinterpret_cast<const double2*>(uBp + c0);
             wA2[0] = a0.x; wA2[1] = a0.y; wB2[0] = a1.x; wB2[1] = a1.y;
             uA2[0] = a2.x; uA2[1] = a2.y; uB2[0] = a3.x; uB2[1] = a3.y;
-            if (ODD) {
+            if (ODD && !PRE) {
                 const double2 a4 = *reinterpret_cast<const double2*>(zAp + c0), a5 = *reinterpret_cast<const double2*>(zBp + c0);
                 zA2[0] = a4.x; zA2[1] = a4.y; zB2[0] = a5.x; zB2[1] = a5.y;
             }
         } else {
             wA2[0] = wsA[c0]; wB2[0] = wsB[c0]; uA2[0] = uAp[c0]; uB2[0] = uBp[c0];
-            if (ODD) { zA2[0] = zAp[c0]; zB2[0] = zBp[c0]; }
+            if (ODD && !PRE) { zA2[0] = zAp[c0]; zB2[0] = zBp[c0]; }
             wA2[1] = wB2[1] = uA2[1] = uB2[1] = 0.0;
         }
 #pragma unroll
@@ -182,8 +186,9 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
                     const double u = useA ? uA : uB;
                     const double qr = (r == c) ? (lm.dzero ? 0.0 : qrow[r]) : qrow[r];
                     double m;
-                    if (ODD) m = fma(useA ? zA : zB, st.M[r][c], qr * w);  // κ_c·M + q_r·(φ_c w_c)
-                    else     m = fma(xrow[r], st.M[r][c], qr * w);         // κ_r·M + (φ_r q_r)·w_c
+                    if (PRE)      m = fma(qr, w, st.M[r][c]);                   // the decay is already in M
+                    else if (ODD) m = fma(useA ? zA : zB, st.M[r][c], qr * w);  // κ_c·M + q_r·(φ_c w_c)
+                    else          m = fma(xrow[r], st.M[r][c], qr * w);         // κ_r·M + (φ_r q_r)·w_c
                     st.M[r][c] = m;
                     rowpart[r] = fma(m, u, rowpart[r]);
                     if (useA) cA = fma(m, urow[r], cA);
@@ -200,9 +205,13 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     // ---- ŨᵀTŨ from the block-level partial sums (each stored entry is off-diagonal and counts twice), so the
     //      all-reduce below does not wait for the reduce-scatter of p
     const double ut0 = T[F_UT * RP + lm.j0], ut1 = T[F_UT * RP + lm.j1];
-    double sblk = 0.0;
+    double sblk = 0.0, sblk2 = 0.0;   // two chains: the sum is on the critical path to D_n
 #pragma unroll
-    for (int r = 0; r < BS; r++) sblk = fma(urow[r], rowpart[r], sblk);
+    for (int r = 0; r < BS; r += 2) {
+        sblk = fma(urow[r], rowpart[r], sblk);
+        if (r + 1 < BS) sblk2 = fma(urow[r + 1], rowpart[r + 1], sblk2);
+    }
+    sblk += sblk2;
     double spart = fma(st.sjj[1] * ut1, ut1, fma(st.sjj[0] * ut0, ut0, sblk + sblk));
     double upart = fma(ut1, st.g[1], ut0 * st.g[0]);
     // all-reduce of (spart, upart) in 6 exchanges: halves swap roles first, so each half reduces one value
@@ -214,6 +223,28 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
         const double other = __shfl_xor_sync(FULL, keep, 16);
         spart = lm.hi ? other : keep;
         upart = lm.hi ? keep : other;
+    }
+
+    // ---- PRE: decay of the coming step, independent of everything above that is still in flight
+    if (PRE) {
+        if (!ODD) {   // next step is odd: column factors κ_c(n+1)
+            const double* nA = Tnext + F_KAP * RP + lm.colA;
+            const double* nB = Tnext + F_KAP * RP + lm.colB;
+            double zA[BS], zB[BS];
+            load_slice<BS>(zA, nA);
+            load_slice<BS>(zB, nB);
+#pragma unroll
+            for (int c = 0; c < BS; c++)
+#pragma unroll
+                for (int r = 0; r < BS; r++) st.M[r][c] *= (r > c) ? zA[c] : zB[c];
+        } else {      // next step is even: row factors κ_r(n+1)
+            double xn[BS];
+            load_slice<BS>(xn, Tnext + F_KAP * RP + lm.rowI);
+#pragma unroll
+            for (int r = 0; r < BS; r++)
+#pragma unroll
+                for (int c = 0; c < BS; c++) st.M[r][c] *= xn[r];
+        }
     }
 
     // ---- matvec reduction: reduce-scatter of the BS row sums over the 4 lanes of the block-row
@@ -381,23 +412,30 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
     for (int k = lane; k < 2 * RPS; k += 32) qs[k] = 0.0;
     __syncwarp();
 
+    mbar_wait(&bars[0], 0);
     for (int64_t k = 0; k < nchunks; k++) {
         const int sidx = (int)(k & 1);
-        mbar_wait(&bars[sidx], (uint32_t)((k >> 1) & 1));
         const double* stage = stages + sidx * STAGE;
+        const double* nstage = stages + (sidx ^ 1) * STAGE;     // chunk k+1 (read by the last step's look-ahead)
+        const bool has_next = k + 1 < nchunks;
         const int64_t nbeg = k * CHUNK_STEPS;
         const int nsteps = (int)((N - nbeg) < CHUNK_STEPS ? (N - nbeg) : CHUNK_STEPS);
         for (int s = 0; s < nsteps; s += 2) {
             const double* T0 = stage + s * SD;
+            const double* T1 = T0 + SD;
             const int64_t n = nbeg + s;
+            // chunk k+1 was requested a whole chunk ago; its arrival is checked right before the first read
+            if (has_next && s + 2 >= nsteps) mbar_wait(&bars[sidx ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
             double yn = yb ? yb[n] : T0[6 * RPS + 0];
             double s2n = sb ? sb[n] : T0[6 * RPS + 1];
-            celerite_step<BS, false>(st, T0, qs, ws, lm, yn, s2n, suma, mu, nu, n, lane);
+            // look-ahead record: the next step's, or (end of the series) this one — its factors are then never used
+            const double* Ta = (s + 1 < nsteps) ? T1 : (has_next ? nstage : T0);
+            celerite_step<BS, false, true>(st, T0, qs, ws, lm, yn, s2n, suma, mu, nu, n, lane, Ta);
             if (s + 1 < nsteps) {
-                const double* T1 = T0 + SD;
                 yn = yb ? yb[n + 1] : T1[6 * RPS + 0];
                 s2n = sb ? sb[n + 1] : T1[6 * RPS + 1];
-                celerite_step<BS, true>(st, T1, qs, ws, lm, yn, s2n, suma, mu, nu, n + 1, lane);
+                const double* Tb = (s + 2 < nsteps) ? T1 + SD : (has_next ? nstage : T1);
+                celerite_step<BS, true, true>(st, T1, qs, ws, lm, yn, s2n, suma, mu, nu, n + 1, lane, Tb);
             }
         }
         __syncthreads();  // every warp is done with this stage → refill it with chunk k+2
