@@ -366,7 +366,7 @@ static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_shared_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = shared_smem_bytes<BS>();
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (c->ev_beg) cudaEventRecord(c->ev_beg, c->stream);
+    cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -379,7 +379,7 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
     const size_t smem = generic_smem_bytes<BS>(args.Jt);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (c->ev_beg) cudaEventRecord(c->ev_beg, c->stream);
+    cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -388,6 +388,30 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     return 0;
 }
 static int nw_for_bs(int BS) { return BS <= 5 ? 12 : BS == 6 ? 10 : 8; }
+
+// K3 pass 3: the generic kernel in its chunked variant, 2 warps per CTA so that a few hundred chunks cover every SM.
+constexpr int CHUNK_NW = 2;
+template <int BS>
+static int launch_chunked(pioran_ctx* c, const BatchArgs& args, int nctas) {
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    auto kern = celerite_generic_kernel<BS, CHUNK_NW, true>;
+    const size_t smem = sizeof(double) * (size_t)CHUNK_NW * ((size_t)GCH * SD + 2 * RPS + (size_t)(((GCH + 2) * args.Jt + 1) & ~1));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nctas, CHUNK_NW * 32, smem, c->stream>>>(args);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int dispatch_chunked(pioran_ctx* c, int BS, const BatchArgs& a, int nctas) {
+    switch (BS) {
+        case 4: return launch_chunked<4>(c, a, nctas);
+        case 5: return launch_chunked<5>(c, a, nctas);
+        case 6: return launch_chunked<6>(c, a, nctas);
+        case 7: return launch_chunked<7>(c, a, nctas);
+        case 8: return launch_chunked<8>(c, a, nctas);
+    }
+    return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
+}
 
 static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
     switch (BS) {
@@ -694,7 +718,7 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
     int rc;
     GenericInputs gi;
     if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, gi))) return rc;
-    const int NW = nw_for_bs(BS);
+    const int NW = CHUNK_NW;
     const size_t nch = (size_t)B * P;
     const size_t nitems = (nch + NW - 1) / NW * NW;
     // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out
@@ -750,12 +774,7 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
     args.Jt = Jt; args.term_row = term_row_dev; args.R = R;
     args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
     args.out = out;
-    args.per_warp_items = 1;
-    cudaEvent_t keep_beg = c->ev_beg;   // dispatch_generic re-records the events; K3 reports the whole pipeline
-    c->ev_beg = nullptr;
-    rc = dispatch_generic(c, BS, args, (int)(nitems / NW));
-    c->ev_beg = keep_beg;
-    if (rc) return rc;
+    if ((rc = dispatch_chunked(c, BS, args, (int)(nitems / NW)))) return rc;
     scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(parts, P, B, N, out);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);

@@ -328,7 +328,6 @@ struct BatchArgs {
     const double* s2_batch; // [nθ × ystride] or nullptr
     int64_t ystride;
     double* out;            // logL
-    int per_warp_items;     // generic kernel: warp w of CTA b takes work item b·NW + w (K3 pass 3)
 };
 
 template <int BS>
@@ -454,7 +453,8 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
 // computes its own table chunk (GCH steps) with sincos/exp — celerite_solver.jl:51-64 — then runs the same steps.
 constexpr int GCH = 4;
 
-template <int BS, int NW>
+// CHUNKED = true is the K3 pass-3 variant: one work item per warp, a step range and an injected initial state.
+template <int BS, int NW, bool CHUNKED = false>
 __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const BatchArgs args) {
     constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -468,12 +468,13 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     double* ws = qs + RPS;
     double* phs = ws + RPS;
 
-    const WorkItem wk = args.work[args.per_warp_items ? blockIdx.x * NW + warp : blockIdx.x];
-    const bool active = args.per_warp_items ? true : warp < wk.count;
-    const int slot = args.per_warp_items ? 0 : (active ? warp : wk.count - 1);
+    const WorkItem wk = args.work[CHUNKED ? blockIdx.x * NW + warp : blockIdx.x];
+    const bool active = CHUNKED ? true : warp < wk.count;
+    const int slot = CHUNKED ? 0 : (active ? warp : wk.count - 1);
     const int th = wk.theta_begin + slot;
     const int64_t N = wk.N;
-    const int64_t n0 = wk.n_begin, n1 = wk.n_end;
+    const int64_t n0 = CHUNKED ? wk.n_begin : 0, n1 = CHUNKED ? wk.n_end : N;
+    const double* const init = CHUNKED ? wk.init : nullptr;
     const double* ca = args.a + (size_t)th * Jt;
     const double* cb = args.b + (size_t)th * Jt;
     const double* cc = args.c + (size_t)th * Jt;
@@ -500,11 +501,11 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     // zero the table once: padded slots and rows ≥ R never change
     for (int k = lane; k < GCH * SD; k += 32) tab[k] = 0.0;
     __syncwarp();
-    if (wk.init) {
+    if (CHUNKED && init) {
         // K3 pass 3: inject the state entering step n0 (already decayed to t_n0).  The first local step is an EVEN
         // step with φ_n0 = φ_n0−1 := 1 below, so the blocks hold the true values with no factor pending.
         constexpr int RL = SCAN_LD;
-        const double* S0 = wk.init;
+        const double* S0 = init;
         const int rI = i * BS, cA = ((i + o) & 7) * BS, cB = (o == 0) ? ((i ^ 4) * BS) : cA;
 #pragma unroll
         for (int r = 0; r < BS; r++)
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
             const int64_t n = nbeg - 1 + s;
             double ph = 0.0;
             if (n >= 1 && n < N) ph = exp(-cc[m] * (wk.t[n] - wk.t[n - 1]));
-            if (wk.init && n <= n0) ph = 1.0;
+            if (CHUNKED && init && n <= n0) ph = 1.0;
             phs[idx] = ph;
         }
         __syncwarp();
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
                 Tn[F_V * RPS + r0] = 1.0;          Tn[F_PHN * RPS + r0] = phn;
             } else {
                 double si, co;
-                sincos(cd[m] * wk.t[n], &si, &co);
+                sincos_large(cd[m] * wk.t[n], &si, &co);
                 const double u0 = ca[m] * co + cb[m] * si;   // celerite_solver.jl:60
                 const double u1 = ca[m] * si - cb[m] * co;   // celerite_solver.jl:59
                 const int r0 = pad_index(tr, BS), r1 = pad_index(tr + 1, BS);
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
         }
         __syncwarp();
     }
-    if (wk.part) {
+    if (CHUNKED) {
         const double logdet = lane_logdet(st);
         if (lane == 0) { wk.part[0] = logdet; wk.part[1] = st.chi2; }
     } else {

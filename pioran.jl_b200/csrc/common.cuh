@@ -68,4 +68,24 @@ struct WorkItem {
     double* part;
 };
 
+// sin and cos of a large FP64 argument.  The celerite rows take cos/sin(d_j·t_n) at ABSOLUTE times
+// (src/celerite_solver.jl:52-53): arguments reach 1e5…1e9 rad, where CUDA's sincos() leaves its fast path (|x| > 105 615)
+// for a Payne–Hanek reduction that costs an order of magnitude more.  Here: k = rint(x·2/π), three-constant Cody–Waite
+// reduction with FMAs (π/2 split into 53+53+53 bits: absolute error of the reduced angle ≤ ~4e-16 for |x| < 2^31), then
+// sincos() of |r| ≤ π/4 (fast path) and the quadrant fix-up.  Absolute accuracy of the results ≈ 5e-16 — what the
+// covariance entries need; beyond 2^31 rad the library routine is used.
+__device__ __forceinline__ void sincos_large(double x, double* s, double* c) {
+    if (!(fabs(x) < 2147483648.0)) { sincos(x, s, c); return; }
+    const double k = rint(x * 0.63661977236758138);                 // 2/π
+    double r = fma(-k, 1.5707963267948966, x);                      // π/2 = P1 + P2 + P3
+    r = fma(-k, 6.123233995736766e-17, r);
+    r = fma(-k, -1.4973849048591698e-33, r);
+    double sr, cr;
+    sincos(r, &sr, &cr);
+    const int q = (int)(long long)k & 3;
+    const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
+
 }  // namespace pioran

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256, 1) scan_fold_kernel(const ScanArgs args) 
                 Us[s][r0] = ca[m]; Vs[s][r0] = 1.0; Ps[s][r0] = ph;
             } else {
                 double si, co;
-                sincos(cd[m] * tn, &si, &co);
+                sincos_large(cd[m] * tn, &si, &co);
                 Us[s][tr] = ca[m] * co + cb[m] * si;  Us[s][tr + 1] = ca[m] * si - cb[m] * co;
                 Vs[s][tr] = co;                       Vs[s][tr + 1] = si;
                 Ps[s][tr] = ph;                       Ps[s][tr + 1] = ph;
@@ -120,14 +120,18 @@ __global__ void __launch_bounds__(256, 1) scan_fold_kernel(const ScanArgs args) 
                 for (int r = 0; r < 4; r++) acc = fma(A[r][c], urow[r], acc);
                 atp[c] = acc;
             }
-            // rows: the 16 threads of one ty are 16 consecutive lanes → shuffle reduction
-#pragma unroll
-            for (int sft = 8; sft >= 1; sft >>= 1)
-#pragma unroll
-                for (int r = 0; r < 4; r++) cup[r] += __shfl_xor_sync(0xffffffffu, cup[r], sft);
-            if (tx == 0) {
-#pragma unroll
-                for (int r = 0; r < 4; r++) cu_s[4 * ty + r] = cup[r];
+            // rows: the 16 threads of one ty are 16 consecutive lanes → reduce-scatter (4 values → 2 → 1) + 2 rounds
+            {
+                const bool h8 = (tx & 8) != 0, h4 = (tx & 4) != 0;
+                const double r0 = __shfl_xor_sync(0xffffffffu, h8 ? cup[0] : cup[2], 8);
+                const double r1 = __shfl_xor_sync(0xffffffffu, h8 ? cup[1] : cup[3], 8);
+                const double e0 = (h8 ? cup[2] : cup[0]) + r0;     // h8 = 0 keeps rows 0,1; h8 = 1 keeps rows 2,3
+                const double e1 = (h8 ? cup[3] : cup[1]) + r1;
+                const double r2 = __shfl_xor_sync(0xffffffffu, h4 ? e0 : e1, 4);
+                double f = (h4 ? e1 : e0) + r2;                    // row 2·h8 + h4
+                f += __shfl_xor_sync(0xffffffffu, f, 2);
+                f += __shfl_xor_sync(0xffffffffu, f, 1);
+                if ((tx & 3) == 0) cu_s[4 * ty + 2 * (h8 ? 1 : 0) + (h4 ? 1 : 0)] = f;
             }
             *reinterpret_cast<double2*>(&part[ty][4 * tx]) = make_double2(atp[0], atp[1]);
             *reinterpret_cast<double2*>(&part[ty][4 * tx + 2]) = make_double2(atp[2], atp[3]);
@@ -136,9 +140,10 @@ __global__ void __launch_bounds__(256, 1) scan_fold_kernel(const ScanArgs args) 
             // ---- phase B (warps 0-1): D̂, ẑ, w, 𝒜ᵀu;  b, η updates
             if (tid < SR) {
                 const int j = tid;
-                double at = 0.0;
+                double at0 = 0.0, at1 = 0.0, at2 = 0.0, at3 = 0.0;
 #pragma unroll
-                for (int q = 0; q < 16; q++) at += part[q][j];
+                for (int q = 0; q < 16; q += 4) { at0 += part[q][j]; at1 += part[q + 1][j]; at2 += part[q + 2][j]; at3 += part[q + 3][j]; }
+                const double at = (at0 + at1) + (at2 + at3);
                 const double u = Us[s][j], v = Vs[s][j], cu = cu_s[j], bj = b_s[j];
                 double s1 = u * cu, s2v = u * bj;
 #pragma unroll
@@ -151,11 +156,13 @@ __global__ void __launch_bounds__(256, 1) scan_fold_kernel(const ScanArgs args) 
                 asm volatile("bar.sync 1, 64;");
                 const double den = An_s[s] - (red_s[0] + red_s[2]);       // celerite_solver.jl:92 on the chunk-local C
                 const double z = yn_s[s] - (red_s[1] + red_s[3]);         // celerite_solver.jl:141 on the chunk-local b
-                const double w = (v - cu) / den;
+                const double rden = 1.0 / den;
+                const double w = (v - cu) * rden;
                 const double ph = Ps[s][j];
-                w_s[j] = w; dw_s[j] = den * w; atu_s[j] = at; atus_s[j] = at / den;
+                const double ats = at * rden;
+                w_s[j] = w; dw_s[j] = v - cu; atu_s[j] = at; atus_s[j] = ats;
                 b_s[j] = ph * fma(w, z, bj);
-                eta_s[j] = eta_s[j] - at * (z / den);
+                eta_s[j] = fma(-ats, z, eta_s[j]);
             }
             __syncthreads();
 

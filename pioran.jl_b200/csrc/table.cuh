@@ -34,7 +34,7 @@ __global__ void table_build_kernel(double* __restrict__ table, const double* __r
             ut = 1.0; v = 1.0;                                   // d = 0: cos = 1, the sin-row vanishes
         } else {
             double si, co;
-            sincos(rd.d * tn, &si, &co);                         // celerite_solver.jl:52-53 (absolute time)
+            sincos_large(rd.d * tn, &si, &co);                         // celerite_solver.jl:52-53 (absolute time)
             if (rd.kind == ROW_COS) { ut = fma(rd.ratio, si, co); v = co; }    // (a·co + b·si)/a
             else                    { ut = fma(-rd.ratio, co, si); v = si; }   // (a·si − b·co)/a
         }

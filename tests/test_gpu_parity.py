@@ -268,3 +268,32 @@ def test_config_c2_full_size_subset_vs_oracle(pb, ctx):
     assert_parity(got[idx], want, th[idx], _ld_twin("SBPL", f_min, f_max, 20, "DRWCelerite", t, y, s2), TOL)
     perm = np.random.default_rng(2).permutation(4096)
     assert np.array_equal(like(th[perm]), got[perm], equal_nan=True)
+
+
+def test_config_c3_multi_source_full_size(pb, ctx):
+    """BASELINE configs[2] at full size on one GPU: 512 light curves (N ≈ 2 000, ragged) × 400 parameter vectors each,
+    SHO J = 20 — one fused call over all series (per-series θ and f_min/f_max).  A seeded subset is checked against the
+    oracle; single-series calls must reproduce the batched values bit for bit (work-item independence)."""
+    import workloads as wl
+    rng = np.random.default_rng(2000)
+    S, B = 512, 400
+    lengths = np.clip(np.rint(rng.normal(2000, 300, S)), 1000, 3000).astype(int)
+    series, specs, thetas, raw = [], [], [], []
+    for s in range(S):
+        t, y, s2, f_min, f_max = wl.make_series_fast(int(lengths[s]), seed=2000 + s)
+        raw.append((t, y, s2, f_min, f_max))
+        series.append(ctx.upload_series(t, y, s2))
+        specs.append(pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20))
+        thetas.append(prior_theta(B, f_min, f_max, y.mean(), y.std(), seed=5000 + s))
+    theta = np.stack(thetas)
+    got = ctx.approx_logl(series, specs, theta, theta_per_series=True)
+    assert got.shape == (S, B) and np.isfinite(got).mean() > 0.99
+    for s in rng.choice(S, 6, replace=False):
+        t, y, s2, f_min, f_max = raw[s]
+        idx = rng.choice(B, 4, replace=False)
+        want = orc.approx_logl_batch("SBPL", theta[s, idx], f_min, f_max, 20, t, y, s2, nthreads=0)
+        assert_parity(got[s, idx], want, theta[s, idx], _ld_twin("SBPL", f_min, f_max, 20, "SHO", t, y, s2), TOL)
+        single = ctx.approx_logl(series[s], specs[s], theta[s])[0]
+        assert np.array_equal(single, got[s], equal_nan=True)
+    for ser in series:
+        ser.free()
