@@ -348,12 +348,18 @@ static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Tab
 }
 
 // ------------------------------------------------------------------------------------------------ K2 launchers
-template <int BS> struct KCfg { static constexpr int NW = (BS <= 5) ? 12 : (BS == 6) ? 10 : 8; };
+#ifndef PIORAN_NW_SMALL
+#define PIORAN_NW_SMALL 12   // warps per CTA for block sizes <= 5 (register budget 168/thread)
+#endif
+#ifndef PIORAN_NW_LARGE
+#define PIORAN_NW_LARGE 8    // block sizes 7, 8 (register budget 255/thread)
+#endif
+template <int BS> struct KCfg { static constexpr int NW = (BS <= 5) ? PIORAN_NW_SMALL : (BS == 6) ? 10 : PIORAN_NW_LARGE; };
 
 template <int BS>
 static size_t shared_smem_bytes() {
     constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
-    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)KCfg<BS>::NW * 2 * RPS) + 2 * sizeof(uint64_t);
+    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)KCfg<BS>::NW * 2 * RPS) + 2 * sizeof(uint64_t) + 16;
 }
 template <int BS>
 static size_t generic_smem_bytes(int Jt) {
@@ -387,7 +393,7 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-static int nw_for_bs(int BS) { return BS <= 5 ? 12 : BS == 6 ? 10 : 8; }
+static int nw_for_bs(int BS) { return BS <= 5 ? PIORAN_NW_SMALL : BS == 6 ? 10 : PIORAN_NW_LARGE; }
 
 // K3 pass 3: the generic kernel in its chunked variant, 2 warps per CTA so that a few hundred chunks cover every SM.
 constexpr int CHUNK_NW = 2;

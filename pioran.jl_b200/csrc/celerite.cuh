@@ -32,6 +32,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef PIORAN_ABLATE
+#define PIORAN_ABLATE 0   // timing experiments only (tools/ablate.sh): non-zero values remove one cost and break the results
+#endif
+
 namespace pioran {
 
 // ------------------------------------------------------------------------------------------- PTX helpers
@@ -160,8 +164,13 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     for (int c0 = 0; c0 < BS; c0 += 2) {
         double wA2[2], wB2[2], uA2[2], uB2[2], zA2[2] = {0.0, 0.0}, zB2[2] = {0.0, 0.0};
         if (c0 + 1 < BS) {
+#if PIORAN_ABLATE == 1
+            const double2 a0 = *reinterpret_cast<const double2*>(wsA + c0), a1 = a0;
+            const double2 a2 = *reinterpret_cast<const double2*>(uAp + c0), a3 = a2;
+#else
             const double2 a0 = *reinterpret_cast<const double2*>(wsA + c0), a1 = *reinterpret_cast<const double2*>(wsB + c0);
             const double2 a2 = *reinterpret_cast<const double2*>(uAp + c0), a3 = *reinterpret_cast<const double2*>(uBp + c0);
+#endif
             wA2[0] = a0.x; wA2[1] = a0.y; wB2[0] = a1.x; wB2[1] = a1.y;
             uA2[0] = a2.x; uA2[1] = a2.y; uB2[0] = a3.x; uB2[1] = a3.y;
             if (ODD && !PRE) {
@@ -196,8 +205,12 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
                 }
                 // column sums go to the lane that owns block-row K; the diagonal-block part (o = 0) stays here.
                 // EVEN steps: the column factor φ_c is still pending — the receiver applies it (prow) in `tot`.
+#if PIORAN_ABLATE == 3
+                acc[c] = cB + cA;
+#else
                 const double yv = __shfl_sync(FULL, cB + (o ? cA : 0.0), lm.src_lane);
                 acc[c] = yv + (o ? 0.0 : cA);
+#endif
             }
         }
     }
@@ -215,6 +228,7 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     double spart = fma(st.sjj[1] * ut1, ut1, fma(st.sjj[0] * ut0, ut0, sblk + sblk));
     double upart = fma(ut1, st.g[1], ut0 * st.g[0]);
     // all-reduce of (spart, upart) in 6 exchanges: halves swap roles first, so each half reduces one value
+#if PIORAN_ABLATE != 2
     {
         const double recv = __shfl_xor_sync(FULL, lm.hi ? spart : upart, 16);
         double keep = (lm.hi ? upart : spart) + recv;
@@ -224,6 +238,7 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
         spart = lm.hi ? other : keep;
         upart = lm.hi ? keep : other;
     }
+#endif
 
     // ---- PRE: decay of the coming step, independent of everything above that is still in flight
     if (PRE) {
@@ -232,7 +247,12 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
             const double* nB = Tnext + F_KAP * RP + lm.colB;
             double zA[BS], zB[BS];
             load_slice<BS>(zA, nA);
+#if PIORAN_ABLATE == 1
+#pragma unroll
+            for (int c = 0; c < BS; c++) zB[c] = zA[c];
+#else
             load_slice<BS>(zB, nB);
+#endif
 #pragma unroll
             for (int c = 0; c < BS; c++)
 #pragma unroll
@@ -254,6 +274,11 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
         if (ODD) tot[c] = fma(xrow[c], rowpart[c], acc[c]);
         else     tot[c] = fma(prow[c], acc[c], rowpart[c]);
     }
+#if PIORAN_ABLATE == 4
+    double f0 = 0.0, f1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < BS; c++) { if (c & 1) f1 += tot[c]; else f0 += tot[c]; }
+#else
     const bool bit0 = (o & 1) != 0, bit1 = (o & 2) != 0;
     double e[4];
 #pragma unroll
@@ -276,6 +301,7 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
         const double recv = __shfl_xor_sync(FULL, bit1 ? e[2] : e[3], 2);
         f1 = (bit1 ? e[3] : e[2]) + recv;
     }
+#endif
 
     // ---- owner phase: rows j0 (and j1)
     const double v0 = T[F_V * RP + lm.j0], v1 = T[F_V * RP + lm.j1];
@@ -359,7 +385,7 @@ __device__ __forceinline__ double lane_finish(LaneState<BS>& st, int64_t N, int 
 
 // ------------------------------------------------------------------------------------------- shared-table kernel
 // grid = number of work items; block = NW warps; each warp one θ of the item's series.
-// dynamic smem: 2 stages × CHUNK_STEPS × SD doubles | NW × 2·RPS scratch | 2 mbarriers
+// dynamic smem: 2 stages × CHUNK_STEPS × SD doubles | NW × 2·RPS scratch | 2 mbarriers | 2 stage counters
 // Every warp runs the full sweep (warps beyond the item's count redo its last θ and skip the store): the hot loop
 // then has no lane-dependent control flow and the shuffles compile to plain SHFL (no WARPSYNC.COLLECTIVE).
 template <int BS, int NW>
@@ -369,6 +395,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
     double* stages = reinterpret_cast<double*>(smem_raw);
     double* scratch = stages + 2 * STAGE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 2 * RPS);
+    int* done = reinterpret_cast<int*>(bars + 2);     // per stage: number of warps that have finished reading it
 
     const WorkItem wk = args.work[blockIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,6 +406,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+        done[0] = done[1] = 0;
         fence_mbar_init();
     }
     __syncthreads();
@@ -437,11 +465,17 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
                 celerite_step<BS, true, true>(st, T1, qs, ws, lm, yn, s2n, suma, mu, nu, n + 1, lane, Tb);
             }
         }
-        __syncthreads();  // every warp is done with this stage → refill it with chunk k+2
-        if (threadIdx.x == 0 && k + 2 < nchunks) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
-            tma_load_1d(stages + sidx * STAGE, wk.table + (size_t)(k + 2) * STAGE, STAGE_BYTES, &bars[sidx]);
+        // Stage hand-back without a CTA barrier: every warp counts itself out of the stage and the LAST one refills it with
+        // chunk k+2, so no warp waits for its siblings unless it is a whole chunk ahead of them.
+        __syncwarp();
+        if (lane == 0 && k + 2 < nchunks) {
+            __threadfence_block();
+            if (atomicAdd(&done[sidx], 1) == NW - 1) {
+                done[sidx] = 0;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
+                tma_load_1d(stages + sidx * STAGE, wk.table + (size_t)(k + 2) * STAGE, STAGE_BYTES, &bars[sidx]);
+            }
         }
     }
     const double res = lane_finish(st, N, lane);
