@@ -111,6 +111,18 @@ def fp64_peak_tflops():
         return 37.0, "fallback: nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"
 
 
+def k2_traffic_bytes(basis, B, N):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch of this shape, from the committed `ncu --set full`
+    capture (profiles/r01_k2_traffic.json, written by tools/ncu_summary.py); None when no capture matches the shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")) as f:
+            d = json.load(f)
+        e = d.get(f"{basis}_B{B}_N{N}")
+        return float(e["dram_bytes"]) if e else None
+    except Exception:
+        return None
+
+
 def build_workload(N, J, basis, B, seed_series, seed_theta):
     t, y, s2, f_min, f_max = wl.make_series(N, seed_series)
     theta = wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), seed_theta, alpha2_max=4.0 if basis == "SHO" else 6.0)
@@ -334,7 +346,7 @@ def run_b200(args, rank, world, local_rank):
                                 + (" + NCCL all-gather + D2H of the gathered vector" if dist_on else "") + " per step; series resident (uploaded once per sampler run)"},
                 "gpu_launches": int(m["launches"]),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
+                             "traffic": k2_traffic_bytes(args.basis, args.B, args.N), "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
                              "flops_per_launch": flops_launch,
                              "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d)", "peak_source": peak_src,
                              "note": "FP64-pipe bound: the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},

@@ -51,6 +51,12 @@ def _load():
     lib.orc_celerite_logl_batch.restype = None
     lib.orc_celerite_logl_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp,
                                             _dp, C.c_int]
+    for name in ("orc_celerite_predict", "orc_direct_predict"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_int64, _dp, C.c_int64, _dp, _dp, _dp, _dp]
+    lib.orc_celerite_simulate.restype = C.c_int
+    lib.orc_celerite_simulate.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp]
     lib.orc_max_threads.restype = C.c_int
     return lib
 
@@ -151,6 +157,36 @@ def celerite_logl_batch(a, b, c, d, t, y, s2, mu=None, nu=None, nthreads=1):
     out = np.empty(B)
     lib().orc_celerite_logl_batch(B, Jt, _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu), len(t), _p(t), _p(y), _p(s2), _p(out),
                                   nthreads)
+    return out
+
+
+def celerite_predict(a, b, c, d, tau, t, y, s2):
+    """pred(a, b, c, d, τ, t, y, σ²) — src/celerite_solver.jl:376-483 (posterior mean at ascending τ)."""
+    a, b, c, d, tau, t, y, s2 = map(_arr, (a, b, c, d, tau, t, y, s2))
+    out = np.empty(len(tau))
+    rc = lib().orc_celerite_predict(len(a), _p(a), _p(b), _p(c), _p(d), len(tau), _p(tau), len(t), _p(t), _p(y), _p(s2), _p(out))
+    if rc:
+        raise MemoryError("orc_celerite_predict")
+    return out
+
+
+def direct_predict(a, b, c, d, tau, t, y, s2):
+    """predict_direct (mean) — src/direct_solver.jl:74-119."""
+    a, b, c, d, tau, t, y, s2 = map(_arr, (a, b, c, d, tau, t, y, s2))
+    out = np.empty(len(tau))
+    rc = lib().orc_direct_predict(len(a), _p(a), _p(b), _p(c), _p(d), len(tau), _p(tau), len(t), _p(t), _p(y), _p(s2), _p(out))
+    if rc:
+        raise ArithmeticError("orc_direct_predict: matrix not positive definite" if rc == 1 else "allocation failed")
+    return out
+
+
+def celerite_simulate(a, b, c, d, t, s2, q):
+    """sim(rng, a, b, c, d, τ, σ²) with the normal draws q supplied — src/celerite_solver.jl:515-549."""
+    a, b, c, d, t, s2, q = map(_arr, (a, b, c, d, t, s2, q))
+    out = np.empty(len(t))
+    rc = lib().orc_celerite_simulate(len(a), _p(a), _p(b), _p(c), _p(d), len(t), _p(t), _p(s2), _p(q), _p(out))
+    if rc:
+        raise MemoryError("orc_celerite_simulate")
     return out
 
 

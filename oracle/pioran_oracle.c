@@ -403,6 +403,270 @@ done:
     return res;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Widening rows: posterior mean `pred` and GP draw `sim`.
+ * Both start from the factorisation of init_semi_separable! (:12-100); ss_factor below repeats that part of
+ * orc_celerite_logl verbatim (U, W = V/D, ϕ, D materialised) and ss_solve repeats solve_prec! (:115-158). */
+static void ss_factor(int Jt, const double *a, const double *b, const double *c, const double *d, int64_t N,
+                      const double *t, const double *s2, double *U, double *V, double *phi, double *D, double *S)
+{
+    const int R = 2 * Jt;
+    double suma = 0.0;
+    for (int j = 0; j < Jt; j++) suma += a[j];
+    memset(S, 0, sizeof(double) * (size_t)R * R);
+    D[0] = suma + s2[0];
+    {
+        double buff = 1.0 / D[0], t1 = t[0];
+        for (int j = 0; j < Jt; j++) {
+            double co = cos(d[j] * t1), si = sin(d[j] * t1);
+            V[2 * j + 1] = si * buff; V[2 * j] = co * buff;
+            U[2 * j + 1] = a[j] * si - b[j] * co; U[2 * j] = a[j] * co + b[j] * si;
+        }
+    }
+    for (int64_t n = 1; n < N; n++) {
+        double s = 0.0, tn = t[n], dt = tn - t[n - 1];
+        double *Un = U + (size_t)R * n, *Vn = V + (size_t)R * n, *Vp = V + (size_t)R * (n - 1);
+        double *ph = phi + (size_t)R * (n - 1);
+        for (int j = 0; j < Jt; j++) {
+            double co = cos(d[j] * tn), si = sin(d[j] * tn), ec = exp(-c[j] * dt);
+            ph[2 * j + 1] = ec; ph[2 * j] = ec;
+            Un[2 * j + 1] = a[j] * si - b[j] * co; Un[2 * j] = a[j] * co + b[j] * si;
+            Vn[2 * j + 1] = si; Vn[2 * j] = co;
+        }
+        for (int j = 0; j < R; j++) {
+            double uj = Un[j], phj = ph[j], vn = Vp[j], dn = D[n - 1] * vn, vnj = Vn[j];
+            for (int k = 0; k < j; k++) {
+                double uk = Un[k];
+                double r = phj * ph[k] * (S[j + (size_t)k * R] + dn * Vp[k]);
+                S[j + (size_t)k * R] = r;
+                double v = uj * r;
+                Vn[k] -= v; vnj -= uk * r; s += 2 * v * uk;
+            }
+            S[j + (size_t)j * R] = phj * phj * (S[j + (size_t)j * R] + dn * vn);
+            double r = S[j + (size_t)j * R] * uj;
+            s += r * uj;
+            Vn[j] = vnj - r;
+        }
+        double dn = suma + s2[n] - s;
+        D[n] = dn;
+        for (int j = 0; j < R; j++) Vn[j] /= dn;
+    }
+}
+/* solve_prec! (:115-158): z ← K⁻¹ y */
+static void ss_solve(int R, int64_t N, const double *y, const double *U, const double *W, const double *D,
+                     const double *phi, double *z, double *f, double *g)
+{
+    memset(f, 0, sizeof(double) * R); memset(g, 0, sizeof(double) * R);
+    z[0] = y[0];
+    for (int64_t n = 1; n < N; n++) {
+        double s = 0.0, zp = z[n - 1];
+        const double *Wp = W + (size_t)R * (n - 1), *ph = phi + (size_t)R * (n - 1), *Un = U + (size_t)R * n;
+        for (int j = 0; j < R; j++) { f[j] = (f[j] + Wp[j] * zp) * ph[j]; s += Un[j] * f[j]; }
+        z[n] = y[n] - s;
+    }
+    z[N - 1] /= D[N - 1];
+    for (int64_t n = N - 2; n >= 0; n--) {
+        double s = 0.0, zn = z[n + 1];
+        const double *Un1 = U + (size_t)R * (n + 1), *ph = phi + (size_t)R * n, *Wn = W + (size_t)R * n;
+        for (int j = 0; j < R; j++) { g[j] = (g[j] + Un1[j] * zn) * ph[j]; s += Wn[j] * g[j]; }
+        z[n] = z[n] / D[n] - s;
+    }
+}
+
+/* src/celerite_solver.jl:376-483 `pred`: posterior mean at the (ascending) points tau given (t, y, σ²), with the
+ * reference's own index bookkeeping (start / stop / n₀ = searchsortedfirst(t, τ) − 1).  Indices below are 1-based
+ * like the Julia source; arrays are read with [n − 1].  Returns 0, or −1 on allocation failure. */
+int orc_celerite_predict(int Jt, const double *a, const double *b, const double *c, const double *d, int64_t M,
+                         const double *tau, int64_t N, const double *t, const double *y, const double *s2, double *mu_out)
+{
+    const int R = 2 * Jt;
+    double *S = (double *)malloc(sizeof(double) * (size_t)R * R);
+    double *phi = (double *)malloc(sizeof(double) * (size_t)R * (N > 1 ? N - 1 : 1));
+    double *U = (double *)malloc(sizeof(double) * (size_t)R * N);
+    double *V = (double *)malloc(sizeof(double) * (size_t)R * N);
+    double *D = (double *)malloc(sizeof(double) * N);
+    double *z = (double *)malloc(sizeof(double) * N);
+    double *f = (double *)malloc(sizeof(double) * R), *g = (double *)malloc(sizeof(double) * R);
+    double *Q = (double *)calloc(R, sizeof(double)), *Sv = (double *)calloc(R, sizeof(double));
+    int64_t *n0L = (int64_t *)malloc(sizeof(int64_t) * (M > 0 ? M : 1));
+    int rc = -1;
+    if (!S || !phi || !U || !V || !D || !z || !f || !g || !Q || !Sv || !n0L) goto done;
+    ss_factor(Jt, a, b, c, d, N, t, s2, U, V, phi, D, S);
+    ss_solve(R, N, y, U, V, D, phi, z, f, g);
+    for (int64_t m = 0; m < M; m++) { /* :395 searchsortedfirst(t, τ) − 1 = number of t_n < τ */
+        int64_t lo = 0, hi = N;
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (t[mid] < tau[m]) lo = mid + 1; else hi = mid; }
+        n0L[m] = lo;
+        mu_out[m] = 0.0;
+    }
+    /* forward pass :400-435 */
+    {
+        int64_t start = 1;
+        for (int64_t m = 0; m < M; m++) {
+            const int64_t n0 = n0L[m];
+            const double tm = tau[m];
+            for (int64_t n = start; n <= n0 - 1; n++) {
+                start += 1;
+                double tn = t[n - 1], tn1 = t[n], zn = z[n - 1];
+                for (int j = 0; j < Jt; j++) {
+                    double e = exp(-c[j] * (tn1 - tn));
+                    Q[2 * j] = (Q[2 * j] + zn * cos(d[j] * tn)) * e;
+                    Q[2 * j + 1] = (Q[2 * j + 1] + zn * sin(d[j] * tn)) * e;
+                }
+            }
+            if (start >= n0 && n0 != 0) {
+                double tn = t[n0 - 1], zn = z[n0 - 1];
+                double tn1 = (n0 == N) ? t[n0 - 1] : t[n0];
+                for (int j = 0; j < Jt; j++) {
+                    double e = exp(-c[j] * (tm - tn));
+                    Sv[2 * j + 1] = (Q[2 * j + 1] + zn * sin(d[j] * tn)) * e * (a[j] * sin(d[j] * tm) - b[j] * cos(d[j] * tm));
+                    Sv[2 * j] = (Q[2 * j] + zn * cos(d[j] * tn)) * e * (a[j] * cos(d[j] * tm) + b[j] * sin(d[j] * tm));
+                }
+                if (start + 1 == n0) {
+                    start += 1;
+                    for (int j = 0; j < Jt; j++) {
+                        double e = exp(-c[j] * (tn1 - tn));
+                        Q[2 * j] = (Q[2 * j] + zn * cos(d[j] * tn)) * e;
+                        Q[2 * j + 1] = (Q[2 * j + 1] + zn * sin(d[j] * tn)) * e;
+                    }
+                }
+            }
+            double sum = 0.0;
+            for (int j = 0; j < R; j++) sum += Sv[j];
+            mu_out[m] = sum;
+        }
+    }
+    memset(Q, 0, sizeof(double) * R);
+    /* backward pass :439-480 */
+    {
+        int64_t stop = N;
+        for (int64_t m = M - 1; m >= 0; m--) {
+            const int64_t n0 = n0L[m];
+            if (n0 == N) continue;
+            const double tm = tau[m];
+            const int64_t stop_cur = stop;
+            for (int64_t n = stop_cur; n >= n0 + 2; n--) {
+                stop -= 1;
+                double tn = t[n - 1], tnm = t[n - 2], zn = z[n - 1];
+                for (int j = 0; j < Jt; j++) {
+                    double e = exp(-c[j] * (tn - tnm));
+                    Q[2 * j] = (Q[2 * j] + zn * (a[j] * cos(d[j] * tn) + b[j] * sin(d[j] * tn))) * e;
+                    Q[2 * j + 1] = (Q[2 * j + 1] + zn * (a[j] * sin(d[j] * tn) - b[j] * cos(d[j] * tn))) * e;
+                }
+            }
+            const int64_t n = n0 + 1;
+            double zn = z[n - 1], tn = t[n - 1];
+            double tnm = (n == 1) ? t[0] : t[n - 2];
+            for (int j = 0; j < Jt; j++) {
+                double e = exp(-c[j] * (tn - tm));
+                Sv[2 * j] = (Q[2 * j] + zn * (a[j] * cos(d[j] * tn) + b[j] * sin(d[j] * tn))) * e * cos(d[j] * tm);
+                Sv[2 * j + 1] = (Q[2 * j + 1] + zn * (a[j] * sin(d[j] * tn) - b[j] * cos(d[j] * tn))) * e * sin(d[j] * tm);
+            }
+            const int64_t k = (m != 0) ? m : 1;   /* 0-based: the Julia k = m (m ≠ 1) else 2 */
+            if (stop_cur == n0 + 1 && M > 1 && n0L[k] != n0L[k - 1]) {
+                stop -= 1;
+                for (int j = 0; j < Jt; j++) {
+                    double e = exp(-c[j] * (tn - tnm));
+                    Q[2 * j] = (Q[2 * j] + zn * (a[j] * cos(d[j] * tn) + b[j] * sin(d[j] * tn))) * e;
+                    Q[2 * j + 1] = (Q[2 * j + 1] + zn * (a[j] * sin(d[j] * tn) - b[j] * cos(d[j] * tn))) * e;
+                }
+            }
+            double sum = 0.0;
+            for (int j = 0; j < R; j++) sum += Sv[j];
+            mu_out[m] += sum;
+        }
+    }
+    rc = 0;
+done:
+    free(S); free(phi); free(U); free(V); free(D); free(z); free(f); free(g); free(Q); free(Sv); free(n0L);
+    return rc;
+}
+
+/* src/celerite_solver.jl:515-549 `sim`: y = L q for standard-normal q (the caller supplies q; Julia's randn stream
+ * cannot be reproduced).  NaN where a pivot is negative (the reference raises DomainError in sqrt). */
+int orc_celerite_simulate(int Jt, const double *a, const double *b, const double *c, const double *d, int64_t N,
+                          const double *t, const double *s2, const double *q, double *y_sim)
+{
+    const int R = 2 * Jt;
+    double *S = (double *)malloc(sizeof(double) * (size_t)R * R);
+    double *phi = (double *)malloc(sizeof(double) * (size_t)R * (N > 1 ? N - 1 : 1));
+    double *U = (double *)malloc(sizeof(double) * (size_t)R * N);
+    double *V = (double *)malloc(sizeof(double) * (size_t)R * N);
+    double *D = (double *)malloc(sizeof(double) * N);
+    double *f = (double *)calloc(R, sizeof(double)), *g = (double *)calloc(R, sizeof(double));
+    int rc = -1;
+    if (!S || !phi || !U || !V || !D || !f || !g) goto done;
+    ss_factor(Jt, a, b, c, d, N, t, s2, U, V, phi, D, S);
+    for (int64_t n = 0; n < N; n++) y_sim[n] = 0.0;
+    y_sim[0] = sqrt(D[0]) * q[0];
+    for (int64_t n = 1; n < N; n++) { /* :538-546 */
+        const double *ph = phi + (size_t)R * (n - 1), *Wp = V + (size_t)R * (n - 1), *Un = U + (size_t)R * n;
+        for (int j = 0; j < R; j++) {
+            f[j] = ph[j] * (g[j] + Wp[j] * sqrt(D[n - 1]) * q[n - 1]);
+            y_sim[n] += Un[j] * f[j];
+        }
+        for (int j = 0; j < R; j++) g[j] = f[j];
+        y_sim[n] += sqrt(D[n]) * q[n];
+    }
+    rc = 0;
+done:
+    free(S); free(phi); free(U); free(V); free(D); free(f); free(g);
+    return rc;
+}
+
+/* src/direct_solver.jl:74-119 predict_direct (mean only): K_τ0 (K0 + diag σ²)⁻¹ y by Cholesky.  The reference's own
+ * tests pin pred against it (test/test_prediction.jl:49-58, test/test_predict_celerite.jl). */
+int orc_direct_predict(int Jt, const double *a, const double *b, const double *c, const double *d, int64_t M,
+                       const double *tau, int64_t N, const double *t, const double *y, const double *s2, double *mu_out)
+{
+    double *K = (double *)malloc(sizeof(double) * (size_t)N * N);
+    double *z = (double *)malloc(sizeof(double) * N);
+    int rc = -1;
+    if (!K || !z) goto done;
+    for (int64_t i = 0; i < N; i++)
+        for (int64_t j = 0; j <= i; j++) {
+            double dt = fabs(t[i] - t[j]), k = 0.0;
+            for (int m = 0; m < Jt; m++) k += exp(-c[m] * dt) * (a[m] * cos(d[m] * dt) + b[m] * sin(d[m] * dt));
+            if (i == j) k += s2[i];
+            K[i + (size_t)j * N] = k;
+        }
+    for (int64_t j = 0; j < N; j++) {
+        double djj = K[j + (size_t)j * N];
+        for (int64_t k = 0; k < j; k++) djj -= K[j + (size_t)k * N] * K[j + (size_t)k * N];
+        if (!(djj > 0.0)) { rc = 1; goto done; }
+        djj = sqrt(djj);
+        K[j + (size_t)j * N] = djj;
+        for (int64_t i = j + 1; i < N; i++) {
+            double v = K[i + (size_t)j * N];
+            for (int64_t k = 0; k < j; k++) v -= K[i + (size_t)k * N] * K[j + (size_t)k * N];
+            K[i + (size_t)j * N] = v / djj;
+        }
+    }
+    for (int64_t i = 0; i < N; i++) {             /* L z' = y */
+        double v = y[i];
+        for (int64_t k = 0; k < i; k++) v -= K[i + (size_t)k * N] * z[k];
+        z[i] = v / K[i + (size_t)i * N];
+    }
+    for (int64_t i = N - 1; i >= 0; i--) {        /* Lᵀ z = z' */
+        double v = z[i];
+        for (int64_t k = i + 1; k < N; k++) v -= K[k + (size_t)i * N] * z[k];
+        z[i] = v / K[i + (size_t)i * N];
+    }
+    for (int64_t m = 0; m < M; m++) {
+        double acc = 0.0;
+        for (int64_t n = 0; n < N; n++) {
+            double dt = fabs(tau[m] - t[n]), k = 0.0;
+            for (int jj = 0; jj < Jt; jj++) k += exp(-c[jj] * dt) * (a[jj] * cos(d[jj] * dt) + b[jj] * sin(d[jj] * dt));
+            acc += k * z[n];
+        }
+        mu_out[m] = acc;
+    }
+    rc = 0;
+done:
+    free(K); free(z);
+    return rc;
+}
+
 /* Batched driver = what a sampler does per parameter vector (examples/ultranest/single_pl.jl:65-93):
  * θ row = [psd params…, norm, ν, μ]; σ² = ν·s2_base; y' = y − μ (src/scalable_GP.jl:162-166); approx; logl.
  * OpenMP over θ when nthreads > 1 (the reference itself is one Julia thread per process; its users run one

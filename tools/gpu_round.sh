@@ -18,7 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
     python bench.py --steps 2 --warmup 1 --no-extra --no-cpu > gpurun_out/ncu_launches.log 2>&1
 fi
 ncu --set full --clock-control none --import-source on -k regex:celerite_shared -s 2 -c 1 -f -o gpurun_out/prof_k2_drw \
-    python bench.py --steps 2 --warmup 1 --no-extra --no-cpu --B 16384 > gpurun_out/ncu_full_drw.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-extra --no-cpu > gpurun_out/ncu_full_drw.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:celerite_shared -s 2 -c 1 -f -o gpurun_out/prof_k2_sho \
-    python bench.py --steps 2 --warmup 1 --no-extra --no-cpu --B 16384 --basis SHO > gpurun_out/ncu_full_sho.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-extra --no-cpu --basis SHO > gpurun_out/ncu_full_sho.log 2>&1
 ls -la gpurun_out

@@ -4,8 +4,9 @@ import collections, csv, io, re, subprocess, sys
 rep, wsteps = sys.argv[1], float(sys.argv[2])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, val = rows[0], rows[2]
+hdr, unit_row, val = rows[0], rows[1], rows[2]
 m = dict(zip(hdr, val))
+hdr_units = dict(zip(hdr, unit_row))
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "sm__cycles_elapsed.max", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -47,3 +48,20 @@ print("stall mix (% of samples): " + ", ".join(f"{k[6:]} {100 * v / tot:.1f}" fo
 print("opcode mix per warp-step (executed | % of stall samples):")
 for op, n in ops.most_common(16):
     print(f"  {op:10s} {n / wsteps:7.2f} | {100 * samp[op] / tot:5.1f}")
+
+# optional third argument: key under which the DRAM traffic of this launch is recorded in profiles/r01_k2_traffic.json
+if len(sys.argv) > 3:
+    import json, os
+    def num(k):
+        v, u = m.get(k, "0").replace(",", ""), hdr_units.get(k, "")
+        f = float(v or 0)
+        return f * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_k2_traffic.json")
+    try:
+        d = json.load(open(path))
+    except Exception:
+        d = {}
+    d[sys.argv[3]] = {"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                      "dram_bytes_read": num("dram__bytes_read.sum"), "dram_bytes_write": num("dram__bytes_write.sum"),
+                      "kernel_ms_under_ncu": float(m["gpu__time_duration.sum"].replace(",", "")), "source": os.path.basename(rep)}
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
