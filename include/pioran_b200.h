@@ -127,6 +127,22 @@ int pioran_direct_logl(pioran_ctx *ctx, int series_id, int B, int Jt,
                        const double *a, const double *b, const double *c, const double *d,
                        const double *mu, const double *nu, double *nll_out, int *info_out);
 
+/* ---- widening rows: posterior mean and GP draws ------------------------------------------ */
+/* Batched drop-in for  predict(cov, τ, t, y, σ²) = pred(a, b, c, d, τ, t, y, σ²)  (src/celerite_solver.jl:348-483), the
+ * routine behind  mean(posterior(f(t, σ²), y), τ)  (src/scalable_GP.jl:61-67, 84-85): for each of the B coefficient sets
+ * the posterior mean  mu_i + K(τ, t) (K(t, t) + diag(nu_i σ²))⁻¹ (y − mu_i)  at the M ascending points tau.
+ * mean_out is [B × M] row-major; mu/nu as in pioran_celerite_logl (NULL → 0 / 1). */
+int pioran_celerite_predict(pioran_ctx *ctx, int series_id, int B, int Jt,
+                            const double *a, const double *b, const double *c, const double *d,
+                            const double *mu, const double *nu, int64_t M, const double *tau, double *mean_out);
+/* Batched drop-in for  simulate(rng, cov, t, σ²) = sim(rng, a, b, c, d, t, σ²)  (src/celerite_solver.jl:497-549), behind
+ * rand(f(t, σ²))  (src/scalable_GP.jl:133-155): y_i = L_i q_i with L_i the celerite factor of K_i + diag(nu_i σ²) on the
+ * series' times.  The standard-normal draws q [B × N] are the caller's (Julia's randn stream cannot be reproduced on
+ * the device); y_out is [B × N].  A non-positive pivot gives NaN from that step on (the reference raises DomainError). */
+int pioran_celerite_simulate(pioran_ctx *ctx, int series_id, int B, int Jt,
+                             const double *a, const double *b, const double *c, const double *d,
+                             const double *nu, const double *q, double *y_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,6 @@ api.py (mirror of the reference's Julia interface), build.py (nvcc recipe)."""
 from . import _lib, backend, build, parallel  # noqa: F401
 from .api import (BatchedLikelihood, Celerite, CustomMean, DoubleBendingPowerLaw, Exp, ScalableGP, SHO,  # noqa: F401
                   SingleBendingPowerLaw, SumOfCelerite, approx, celerite_coefs, log_likelihood,
-                  log_likelihood_direct, logpdf)
+                  log_likelihood_direct, logpdf, mean, posterior, predict, rand, simulate, PosteriorGP)
 from .backend import Context, get_context, make_spec  # noqa: F401
 from ._lib import ApproxSpec, PioranError  # noqa: F401

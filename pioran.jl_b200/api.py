@@ -201,6 +201,69 @@ def logpdf(fx, Y, *, ctx=None):
     return log_likelihood(fx.f.kernel, fx.x, y, fx.σ2, solver=fx.f.solver, ctx=ctx)
 
 
+# ----------------------------------------------------------------------------------------------- posterior, draws
+class PosteriorGP:
+    """posterior(f(t, σ²), y)  (src/scalable_GP.jl:44-54): holds the finite GP and the data; mean(fp, τ) runs the batched
+    `pred` kernel (src/celerite_solver.jl:376-483)."""
+
+    def __init__(self, fx, y):
+        if not isinstance(fx, FiniteScalableGP):
+            raise TypeError("posterior expects ScalableGP(...)(t, σ²)")
+        self.f, self.y = fx, np.asarray(y, dtype=np.float64)
+
+
+def posterior(fx, y):
+    return PosteriorGP(fx, y)
+
+
+def predict(cov, τ, t, y, σ2, *, ctx=None):
+    """predict(cov, τ, t, y, σ²)  (src/celerite_solver.jl:348-374): posterior mean of the zero-mean GP at ascending τ."""
+    ctx = ctx or get_context()
+    a, b, c, d = celerite_coefs(cov)
+    ser = ctx.upload_series(t, y, σ2)
+    try:
+        return ctx.celerite_predict(ser, a, b, c, d, τ)[0]
+    finally:
+        ser.free()
+
+
+def mean(fp, τ=None, *, ctx=None):
+    """mean(fp[, τ])  (src/scalable_GP.jl:61-67, 84-85): predict on y − m(t), plus m(τ)."""
+    if not isinstance(fp, PosteriorGP):
+        raise TypeError("mean expects posterior(f(t, σ²), y)")
+    fx = fp.f
+    τ = fx.x if τ is None else np.asarray(τ, dtype=np.float64)
+    m = fx.f.mean
+    mτ = m(τ) if callable(m) else np.full(τ.shape, float(m))
+    return predict(fx.f.kernel, τ, fx.x, fp.y - fx.mean_vector(), fx.σ2, ctx=ctx) + mτ
+
+
+def simulate(cov, τ, σ2, q, *, ctx=None):
+    """simulate(rng, cov, τ, σ²)  (src/celerite_solver.jl:497-549) with the standard-normal draws q supplied by the caller
+    (q = randn(rng, N) in the reference)."""
+    ctx = ctx or get_context()
+    a, b, c, d = celerite_coefs(cov)
+    τ = np.asarray(τ, dtype=np.float64)
+    ser = ctx.upload_series(τ, np.zeros_like(τ), σ2)
+    try:
+        return ctx.celerite_simulate(ser, a, b, c, d, np.asarray(q, dtype=np.float64).reshape(1, -1))[0]
+    finally:
+        ser.free()
+
+
+def rand(fx, q, t=None, *, ctx=None):
+    """rand(rng, f(t, σ²)[, t'])  (src/scalable_GP.jl:133-155): one realisation on the GP's own times with its noise
+    variances, or on other times t' without noise; the mean function is added."""
+    if not isinstance(fx, FiniteScalableGP):
+        raise TypeError("rand expects ScalableGP(...)(t, σ²)")
+    m = fx.f.mean
+    if t is None:
+        return simulate(fx.f.kernel, fx.x, fx.σ2, q, ctx=ctx) + fx.mean_vector()
+    t = np.asarray(t, dtype=np.float64)
+    mt = m(t) if callable(m) else np.full(t.shape, float(m))
+    return simulate(fx.f.kernel, t, np.zeros_like(t), q, ctx=ctx) + mt
+
+
 # ----------------------------------------------------------------------------------------------- batched entry
 class BatchedLikelihood:
     """Vectorised log-likelihood of the samplers' model (examples/ultranest/single_pl.jl:65-93):

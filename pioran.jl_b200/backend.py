@@ -184,6 +184,31 @@ class Context:
         return out, info
 
 
+    # -- widening rows: posterior mean and draws
+    def celerite_predict(self, series, a, b, c, d, tau, mu=None, nu=None):
+        """Batched pred(a,b,c,d,τ,t,y,σ²) (src/celerite_solver.jl:376-483): posterior mean [B × M] at ascending τ."""
+        a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
+        B, Jt = a.shape
+        tau = _f64(tau)
+        mu = _f64(mu, (B,)) if mu is not None else None
+        nu = _f64(nu, (B,)) if nu is not None else None
+        out = np.empty((B, tau.shape[0]))
+        check(self.lib.pioran_celerite_predict(self.h, series.id, B, Jt, _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu),
+                                               tau.shape[0], _p(tau), _p(out)))
+        return out
+
+    def celerite_simulate(self, series, a, b, c, d, q, nu=None):
+        """Batched sim(rng,a,b,c,d,t,σ²) (src/celerite_solver.jl:515-549) with the normal draws q [B × N] supplied."""
+        a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
+        B, Jt = a.shape
+        q = _f64(q, (B, series.N))
+        nu = _f64(nu, (B,)) if nu is not None else None
+        out = np.empty((B, series.N))
+        check(self.lib.pioran_celerite_simulate(self.h, series.id, B, Jt, _p(a), _p(b), _p(c), _p(d), _p(nu), _p(q),
+                                                _p(out)))
+        return out
+
+
 _default = {}
 
 

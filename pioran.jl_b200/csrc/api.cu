@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "dense.cuh"
 #include "scan.cuh"
+#include "posterior.cuh"
 #include "table.cuh"
 
 using namespace pioran;
@@ -83,7 +84,7 @@ struct pioran_ctx {
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
-    DevBuf theta, amp, suma, out, work, coef, rows, misc;
+    DevBuf theta, amp, suma, out, work, coef, rows, misc, post;
     // device time of the most recent main-kernel launch (K2/K3/K4), for bench.py's roofline line
     cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
     bool ev_valid = false;
@@ -147,7 +148,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
     for (Series* s : c->series) free_series(s);
     for (auto& kv : c->plans) cudaFree(kv.second);
     c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
-    c->coef.release(); c->rows.release(); c->misc.release();
+    c->coef.release(); c->rows.release(); c->misc.release(); c->post.release();
     if (c->ev_beg) cudaEventDestroy(c->ev_beg);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->own) cudaStreamDestroy(c->own);
@@ -440,6 +441,29 @@ static int dispatch_generic(pioran_ctx* c, int BS, const BatchArgs& a, int nitem
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
 
+// generic kernel in STEP_STORE / STEP_SIM mode (posterior mean and GP draws)
+template <int BS, int MODE>
+static int launch_generic_mode(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW, false, MODE>;
+    const size_t smem = generic_smem_bytes<BS>(args.Jt);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int MODE>
+static int dispatch_generic_mode(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+    switch (BS) {
+        case 4: return launch_generic_mode<4, MODE>(c, a, nitems);
+        case 5: return launch_generic_mode<5, MODE>(c, a, nitems);
+        case 6: return launch_generic_mode<6, MODE>(c, a, nitems);
+        case 7: return launch_generic_mode<7, MODE>(c, a, nitems);
+        case 8: return launch_generic_mode<8, MODE>(c, a, nitems);
+    }
+    return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
+}
+
 // Splits S series × B parameter vectors into CTA work items of at most NW vectors, sized so that the number of
 // items is close to a multiple of the SM count (one CTA per SM is resident), longest series first.
 struct ItemPlan { std::vector<WorkItem> items; };
@@ -672,6 +696,120 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     args.out = c->out.as<double>();
     if ((rc = dispatch_generic(c, BS, args, (int)ip.items.size()))) return rc;
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ posterior mean, draws
+// Common set-up of the two widening entries: coefficient upload, row map, work items for the generic kernel.
+static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* a, const double* b, const double* cc,
+                         const double* d, const double* mu, const double* nu, const double* y_batch, GenericInputs& gi,
+                         BatchArgs& args, int& BS, int& nitems) {
+    std::vector<int> term_row;
+    const int R = make_term_rows(B, Jt, b, d, term_row);
+    BS = bs_for_rank(R);
+    if (BS > 8 || Jt > 64)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds this build's limit of 64", R, Jt);
+    int rc;
+    if ((rc = upload_generic(c, B, Jt, s->N, a, b, cc, d, mu, nu, y_batch, nullptr, gi))) return rc;
+    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->rows.p, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
+    ItemPlan ip;
+    Series* sp = s;
+    plan_items(c, 1, &sp, nullptr, B, nw_for_bs(BS), false, ip);
+    c->work_key.clear();
+    if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // term_row and ip are locals
+    nitems = (int)ip.items.size();
+    args = BatchArgs{};
+    args.work = c->work.as<WorkItem>();
+    args.a = gi.a; args.b = gi.b; args.c = gi.c; args.d = gi.d;
+    args.Jt = Jt;
+    args.term_row = c->rows.as<int>();
+    args.R = R;
+    args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
+    args.y_batch = gi.yb; args.ystride = s->N;
+    args.out = c->out.as<double>();
+    return 0;
+}
+
+extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                       const double* cc, const double* d, const double* mu, const double* nu, int64_t M,
+                                       const double* tau, double* mean_out) {
+    if (!c || !a || !b || !cc || !d || !tau || !mean_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1 || M < 1) return fail(PIORAN_EINVAL, "B, Jt and M must be >= 1");
+    for (int64_t m = 1; m < M; m++)
+        if (!(tau[m] >= tau[m - 1])) return fail(PIORAN_EINVAL, "tau must be ascending (tau[%lld] < tau[%lld])", (long long)m, (long long)m - 1);
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    const int64_t N = s->N;
+    // n₀ = searchsortedfirst(t, τ) − 1 (celerite_solver.jl:395): the series lives on the device, fetch its times once
+    std::vector<double> th(N);
+    CUDA_TRY(cudaMemcpyAsync(th.data(), s->t, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<int> n0(M);
+    for (int64_t m = 0; m < M; m++) n0[m] = (int)(std::lower_bound(th.begin(), th.end(), tau[m]) - th.begin());
+
+    int rc, BS, nitems;
+    GenericInputs gi;
+    BatchArgs args;
+    if ((rc = generic_setup(c, s, B, Jt, a, b, cc, d, mu, nu, nullptr, gi, args, BS, nitems))) return rc;
+    const int RPL = G * BS;
+    // workspace: W [B·N·RPL] | D [B·N] | z [B·N] | mean [B·M] | tau [M] | n0 [M ints]
+    const size_t nW = (size_t)B * N * RPL, nBN = (size_t)B * N, nBM = (size_t)B * M;
+    if ((rc = c->post.ensure(sizeof(double) * (nW + 2 * nBN + nBM + M) + sizeof(int) * (M + 2)))) return rc;
+    double* W = c->post.as<double>();
+    double* D = W + nW;
+    double* z = D + nBN;
+    double* mean = z + nBN;
+    double* tau_dev = mean + nBM;
+    int* n0_dev = reinterpret_cast<int*>(tau_dev + M);
+    CUDA_TRY(cudaMemcpyAsync(tau_dev, tau, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(n0_dev, n0.data(), sizeof(int) * M, cudaMemcpyHostToDevice, c->stream));
+    args.W_out = W; args.D_out = D; args.zf_out = z;
+    cudaEventRecord(c->ev_beg, c->stream);
+    if ((rc = dispatch_generic_mode<STEP_STORE>(c, BS, args, nitems))) return rc;
+    PostArgs pa{};
+    pa.t = s->t; pa.tau = tau_dev; pa.n0 = n0_dev; pa.N = N; pa.M = M; pa.B = B; pa.Jt = Jt; pa.RPL = RPL;
+    pa.a = gi.a; pa.b = gi.b; pa.c = gi.c; pa.d = gi.d; pa.term_row = c->rows.as<int>(); pa.mu = gi.mu;
+    pa.W = W; pa.D = D; pa.z = z; pa.mean = mean;
+    celerite_backsolve_kernel<<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+    celerite_predict_kernel<<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+    c->launches += 2;
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(mean_out, mean, sizeof(double) * nBM, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // n0 is a local
+    return PIORAN_OK;
+}
+
+extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                        const double* cc, const double* d, const double* nu, const double* q,
+                                        double* y_out) {
+    if (!c || !a || !b || !cc || !d || !q || !y_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    int rc, BS, nitems;
+    GenericInputs gi;
+    BatchArgs args;
+    if ((rc = generic_setup(c, s, B, Jt, a, b, cc, d, nullptr, nu, q, gi, args, BS, nitems))) return rc;
+    const size_t nBN = (size_t)B * s->N;
+    if ((rc = c->post.ensure(sizeof(double) * nBN))) return rc;
+    args.ysim_out = c->post.as<double>();
+    cudaEventRecord(c->ev_beg, c->stream);
+    if ((rc = dispatch_generic_mode<STEP_SIM>(c, BS, args, nitems))) return rc;
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    CUDA_TRY(cudaMemcpyAsync(y_out, c->post.p, sizeof(double) * nBN, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
 }

@@ -135,11 +135,22 @@ __device__ __forceinline__ double fast_rcp(double x) {
 //            step, read from the next record Tnext) is applied at the END of a step, where it is independent of the
 //            reductions still in flight, instead of inside the rank-1 update at the start of the next one.  Same FP64
 //            count (DMUL κ·m + DFMA q·w+m instead of DMUL q·w + DFMA κ·m+qw), shorter critical path.
-template <int BS, bool ODD, bool PRE = false>
+//   MODE   : STEP_LOGL — likelihood only;  STEP_STORE — also write D_n, the forward z_n and W_n (the factor the posterior
+//            mean needs, celerite_solver.jl:381-388) to `aux`;  STEP_SIM — yn carries a standard-normal draw q_n and the
+//            step emits y_n = U_nᵀ f_n + √D_n q_n (sim, celerite_solver.jl:536-546) instead of consuming data.
+enum StepMode : int { STEP_LOGL = 0, STEP_STORE = 1, STEP_SIM = 2 };
+struct StepAux {
+    double* W;     // STEP_STORE: [N × 8·BS] (logical rows)
+    double* D;     // STEP_STORE: [N]
+    double* zf;    // STEP_STORE: [N] forward-substitution z (before the backward pass)
+    double* ysim;  // STEP_SIM:   [N]
+};
+template <int BS, bool ODD, bool PRE = false, int MODE = STEP_LOGL>
 __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* __restrict__ T, double* __restrict__ qs,
                                               double* __restrict__ ws, const LaneMap& lm, const double yn,
                                               const double s2n, const double suma, const double mu, const double nu,
-                                              const int64_t n, const int lane, const double* __restrict__ Tnext = nullptr) {
+                                              const int64_t n, const int lane, const double* __restrict__ Tnext = nullptr,
+                                              const StepAux* aux = nullptr) {
     constexpr int RP = rps_of(BS);
     const int o = lm.o;
     // ---- row-side operands of block-row I
@@ -311,7 +322,11 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     const double An = fma(nu, s2n, suma);
     const double D = An - spart;              // celerite_solver.jl:92
     const double rD = fast_rcp(D);
-    const double z = (yn - mu) - upart;       // celerite_solver.jl:141
+    double z = (yn - mu) - upart;             // celerite_solver.jl:141
+    if (MODE == STEP_SIM) {                   // celerite_solver.jl:539-545: the draw enters where the innovation would
+        z = sqrt(D) * yn;
+        if (lane == 0) aux->ysim[n] = upart + z;
+    }
     st.chi2 = fma(z * z, rD, st.chi2);
     // log|D_n| (celerite_solver.jl:140; no abs on the first pivot, :126): lane n%32 keeps D_n, one log per 32 steps
     if (n == 0) st.dfirst = D;
@@ -320,6 +335,12 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
 
     const double q0 = fma(st.amp[0], v0, -p0), q1 = fma(st.amp[1], v1, -p1);
     const double w0 = q0 * rD, w1 = q1 * rD;
+    if (MODE == STEP_STORE) {
+        const int row0 = (lane >> 2) * BS + o;
+        aux->W[n * (G * BS) + row0] = w0;
+        if (lm.valid1) aux->W[n * (G * BS) + row0 + 4] = w1;
+        if (lane == 0) { aux->D[n] = D; aux->zf[n] = z; }
+    }
     st.g[0] = pn0 * fma(w0, z, st.g[0]);
     st.g[1] = pn1 * fma(w1, z, st.g[1]);
     st.sjj[0] = (pn0 * pn0) * fma(q0, w0, st.sjj[0]);   // celerite_solver.jl:85
@@ -354,6 +375,9 @@ struct BatchArgs {
     const double* s2_batch; // [nθ × ystride] or nullptr
     int64_t ystride;
     double* out;            // logL
+    // generic kernel, STEP_STORE: per-θ factor [nθ × N × 8·BS], [nθ × N], [nθ × N];  STEP_SIM: draws come in through y_batch,
+    // the realisation goes to ysim [nθ × N]
+    double* W_out; double* D_out; double* zf_out; double* ysim_out;
 };
 
 template <int BS>
@@ -488,7 +512,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
 constexpr int GCH = 4;
 
 // CHUNKED = true is the K3 pass-3 variant: one work item per warp, a step range and an injected initial state.
-template <int BS, int NW, bool CHUNKED = false>
+template <int BS, int NW, bool CHUNKED = false, int MODE = STEP_LOGL>
 __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const BatchArgs args) {
     constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -531,6 +555,11 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : wk.y;
     const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : wk.s2;
 
+    StepAux aux{nullptr, nullptr, nullptr, nullptr};
+    if (MODE == STEP_STORE) {
+        aux.W = args.W_out + pi * (size_t)N * (G * BS); aux.D = args.D_out + pi * (size_t)N; aux.zf = args.zf_out + pi * (size_t)N;
+    }
+    if (MODE == STEP_SIM) aux.ysim = args.ysim_out + pi * (size_t)N;
     for (int k = lane; k < 2 * RPS; k += 32) qs[k] = 0.0;
     // zero the table once: padded slots and rows ≥ R never change
     for (int k = lane; k < GCH * SD; k += 32) tab[k] = 0.0;
@@ -599,9 +628,10 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
         for (int s = 0; s < nsteps; s += 2) {
             const double* T0 = tab + s * SD;
             const int64_t n = nbeg + s;
-            celerite_step<BS, false>(st, T0, qs, ws, lm, yb[n], sb[n], suma, mu, nu, n, lane);
+            celerite_step<BS, false, false, MODE>(st, T0, qs, ws, lm, yb[n], sb[n], suma, mu, nu, n, lane, nullptr, &aux);
             if (s + 1 < nsteps)
-                celerite_step<BS, true>(st, T0 + SD, qs, ws, lm, yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane);
+                celerite_step<BS, true, false, MODE>(st, T0 + SD, qs, ws, lm, yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane,
+                                                     nullptr, &aux);
         }
         __syncwarp();
     }
