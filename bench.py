@@ -266,6 +266,46 @@ def measure(torch, ctx, pb, t, y, s2, f_min, f_max, J, basis, theta, steps, warm
     return res
 
 
+def widening_rows(ctx, pb, J):
+    """SURVEY 8f #2/#3 next to the hot path: batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
+    points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
+    bounded sample of the same batch."""
+    from oracle import oracle as orc
+    t, y, s2, f_min, f_max = wl.make_series(1000, 1234)
+    out = {}
+    for basis in ("SHO", "DRWCelerite"):
+        th = wl.prior_theta(4096, f_min, f_max, y.mean(), y.std(), 43, alpha2_max=4.0 if basis == "SHO" else 6.0)
+        spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+        a, b, c, d = ctx.approx_coeffs(spec, th[:, :4])
+        ser = ctx.upload_series(t, y, s2)
+        tau = np.linspace(t[0] - 10.0, t[-1] + 10.0, 2000)
+        Bp = 512
+        ctx.celerite_predict(ser, a[:Bp], b[:Bp], c[:Bp], d[:Bp], tau, mu=th[:Bp, 5], nu=th[:Bp, 4])
+        got = ctx.celerite_predict(ser, a[:Bp], b[:Bp], c[:Bp], d[:Bp], tau, mu=th[:Bp, 5], nu=th[:Bp, 4])
+        ms_p = ctx.last_kernel_ms()
+        t0 = time.perf_counter()
+        ncpu = 4
+        ref = [orc.celerite_predict(a[i], b[i], c[i], d[i], tau, t, y - th[i, 5], th[i, 4] * s2) + th[i, 5] for i in range(ncpu)]
+        cpu_p = (time.perf_counter() - t0) / ncpu
+        ok = np.isfinite(np.array(ref))
+        perr = float(np.max(np.abs(got[:ncpu][ok] - np.array(ref)[ok]) / np.maximum(1.0, np.abs(np.array(ref)[ok]))))
+        q = np.random.default_rng(9).standard_normal((4096, 1000))
+        ctx.celerite_simulate(ser, a, b, c, d, q, nu=th[:, 4])
+        ys = ctx.celerite_simulate(ser, a, b, c, d, q, nu=th[:, 4])
+        ms_s = ctx.last_kernel_ms()
+        t0 = time.perf_counter()
+        refs = [orc.celerite_simulate(a[i], b[i], c[i], d[i], t, th[i, 4] * s2, q[i]) for i in range(ncpu)]
+        cpu_s = (time.perf_counter() - t0) / ncpu
+        oks = np.isfinite(np.array(refs)) & np.isfinite(ys[:ncpu])
+        serr = float(np.max(np.abs(ys[:ncpu][oks] - np.array(refs)[oks]) / np.maximum(1.0, np.abs(np.array(refs)[oks]))))
+        ser.free()
+        out[f"predict_512theta_N1000_M2000_{basis}"] = {"posterior_means_per_s": Bp / (ms_p * 1e-3), "device_ms": ms_p,
+                                                        "cpu_port_1thread_means_per_s": 1.0 / cpu_p, "parity_max_rel_4": perr}
+        out[f"simulate_4096theta_N1000_{basis}"] = {"draws_per_s": 4096 / (ms_s * 1e-3), "device_ms": ms_s,
+                                                    "cpu_port_1thread_draws_per_s": 1.0 / cpu_s, "parity_max_rel_4": serr}
+    return out
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     if not torch.cuda.is_available():
@@ -326,6 +366,9 @@ def run_b200(args, rank, world, local_rank):
                            "k2_ms": m2["k2_ms"], "rank": R2, "fp64_tflops": fl / (m2["k2_ms"] * 1e-3) / 1e12,
                            "fp64_frac": fl / (m2["k2_ms"] * 1e-3) / 1e12 / peak,
                            "finite_frac": float(np.isfinite(m2["out"]).mean())}
+
+    if not args.no_extra and world == 1:
+        extra.update(widening_rows(ctx, pb, args.J))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
