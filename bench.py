@@ -266,6 +266,35 @@ def measure(torch, ctx, pb, t, y, s2, f_min, f_max, J, basis, theta, steps, warm
     return res
 
 
+def config_c3(torch, ctx, pb, J, peak):
+    """BASELINE configs[2] on one GPU: 512 light curves (N ~ N(2000, 300²) clipped to [1000, 3000], ragged) x 400 parameter
+    vectors each, SHO basis, ONE fused call over all series (per-series θ, f_min, f_max)."""
+    rng = np.random.default_rng(2000)
+    S, B = 512, 400
+    lengths = np.clip(np.rint(rng.normal(2000, 300, S)), 1000, 3000).astype(int)
+    series, specs, thetas = [], [], []
+    for k in range(S):
+        t, y, s2, f_min, f_max = wl.make_series_fast(int(lengths[k]), seed=2000 + k)
+        series.append(ctx.upload_series(t, y, s2))
+        specs.append(pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J))
+        thetas.append(wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), seed=5000 + k))
+    theta = np.ascontiguousarray(np.stack(thetas))
+    th_dev = torch.from_numpy(theta.reshape(S * B, -1)).cuda()
+    out_dev = torch.empty(S * B, dtype=torch.float64, device="cuda")
+    ms = []
+    for _ in range(4):
+        ctx.approx_logl_dev(series, specs, B, th_dev.data_ptr(), out_dev.data_ptr(), theta_per_series=True)
+        torch.cuda.current_stream().synchronize()
+        ms.append(ctx.last_kernel_ms())
+    k2 = float(np.mean(ms[1:]))
+    fl = float(B) * float(lengths.sum()) * wl.flops_per_step(wl.rank_of("SHO", J))
+    out = out_dev.cpu().numpy()
+    for ser in series:
+        ser.free()
+    return {"evals_per_s": S * B / (k2 * 1e-3), "k2_ms": k2, "total_steps": int(lengths.sum()) * B, "fp64_tflops": fl / (k2 * 1e-3) / 1e12,
+            "fp64_frac": fl / (k2 * 1e-3) / 1e12 / peak, "finite_frac": float(np.isfinite(out).mean())}
+
+
 def widening_rows(ctx, pb, J):
     """SURVEY 8f #2/#3 next to the hot path: batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
@@ -368,6 +397,7 @@ def run_b200(args, rank, world, local_rank):
                            "finite_frac": float(np.isfinite(m2["out"]).mean())}
 
     if not args.no_extra and world == 1:
+        extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
         extra.update(widening_rows(ctx, pb, args.J))
 
     cpu = None
@@ -379,6 +409,17 @@ def run_b200(args, rank, world, local_rank):
         ok = np.isfinite(ref)
         cpu["parity_max_rel_64"] = float(np.max(np.abs(m["out"][:64][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))))
 
+    traffic = k2_traffic_bytes(args.basis, args.B, args.N)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst)"
+    except Exception:
+        hbm_peak, hbm_src = 6550.0, "fallback of B200_PROFILING.md"
+    hbm_view = None
+    if traffic:
+        gbs = traffic / (k2_ms * 1e-3) / 1e9
+        hbm_view = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src,
+                    "note": "measured DRAM bytes of the launch / launch time: the kernel is three orders of magnitude under the HBM roofline"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -389,7 +430,7 @@ def run_b200(args, rank, world, local_rank):
                                 + (" + NCCL all-gather + D2H of the gathered vector" if dist_on else "") + " per step; series resident (uploaded once per sampler run)"},
                 "gpu_launches": int(m["launches"]),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": k2_traffic_bytes(args.basis, args.B, args.N), "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
+                             "traffic": traffic, "hbm": hbm_view, "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
                              "flops_per_launch": flops_launch,
                              "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d)", "peak_source": peak_src,
                              "note": "FP64-pipe bound: the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},
