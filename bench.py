@@ -135,18 +135,22 @@ def cpu_leg(t, y, s2, f_min, f_max, J, basis, theta, target_s, steps=1, warmup=0
     src/psd.jl:214-289 and src/celerite_solver.jl:12-158 do them, U/V/ϕ materialised, forward + backward pass) with
     OpenMP over θ on all host cores.  Each step evaluates a bounded sample of the workload's θ."""
     from oracle import oracle as orc
-    cores = orc.max_threads()
+    # every host core this process may run on — not OMP_NUM_THREADS, which torchrun pins to 1 for its workers
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     per_round = 1e9
     for _ in range(3):                                       # first call pays library load + thread start-up
         t0 = time.perf_counter()
-        orc.approx_logl_batch("SBPL", theta[:cores], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        orc.approx_logl_batch("SBPL", theta[:cores], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
         per_round = min(per_round, max(time.perf_counter() - t0, 1e-4))   # one eval per thread
     n = int(max(1, min(len(theta) // cores, round(target_s / per_round)))) * cores
     for _ in range(warmup):
-        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} of the step's parameter vectors per step x {steps} step(s), {dt:.1f} s, OpenMP over theta on "
