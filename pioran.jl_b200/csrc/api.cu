@@ -381,6 +381,30 @@ static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+static int nw_for_bs_fwd(int BS);
+// Two parameter vectors per warp for block sizes <= 5 (celerite_shared_pair_kernel); PIORAN_PAIR=0 falls back to one.
+#ifndef PIORAN_NW_PAIR
+#define PIORAN_NW_PAIR 8
+#endif
+static bool pair_enabled(int BS) {
+    static const int env = [] { const char* e = getenv("PIORAN_PAIR"); return e ? atoi(e) : 1; }();
+    return env != 0 && BS <= 5;
+}
+static int theta_per_item(int BS) { return pair_enabled(BS) ? 2 * PIORAN_NW_PAIR : nw_for_bs_fwd(BS); }
+template <int BS>
+static int launch_shared_pair(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS), NW = PIORAN_NW_PAIR;
+    auto kern = celerite_shared_pair_kernel<BS, NW>;
+    const size_t smem = sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)NW * 4 * RPS) + 2 * sizeof(uint64_t) + 16;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 template <int BS>
 static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
@@ -395,6 +419,7 @@ static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
     return 0;
 }
 static int nw_for_bs(int BS) { return BS <= 5 ? PIORAN_NW_SMALL : BS == 6 ? 10 : PIORAN_NW_LARGE; }
+static int nw_for_bs_fwd(int BS) { return nw_for_bs(BS); }
 
 // K3 pass 3: the generic kernel in its chunked variant, 2 warps per CTA so that a few hundred chunks cover every SM.
 constexpr int CHUNK_NW = 2;
@@ -421,6 +446,10 @@ static int dispatch_chunked(pioran_ctx* c, int BS, const BatchArgs& a, int nctas
 }
 
 static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+    if (pair_enabled(BS)) {
+        if (BS == 4) return launch_shared_pair<4>(c, a, nitems);
+        if (BS == 5) return launch_shared_pair<5>(c, a, nitems);
+    }
     switch (BS) {
         case 4: return launch_shared<4>(c, a, nitems);
         case 5: return launch_shared<5>(c, a, nitems);
@@ -571,7 +600,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
     if (key != c->work_key) {
         ItemPlan ip;
-        plan_items(c, S, ser.data(), tabs.data(), B, nw_for_bs(BS), theta_per_series != 0, ip);
+        plan_items(c, S, ser.data(), tabs.data(), B, theta_per_item(BS), theta_per_series != 0, ip);
         c->work_key.clear();
         if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,

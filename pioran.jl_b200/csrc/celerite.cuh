@@ -357,6 +357,203 @@ __device__ __forceinline__ void celerite_step(LaneState<BS>& st, const double* _
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------- paired step
+// Two parameter vectors per warp (block sizes ≤ 5, where two lane states fit the register budget): the θ-independent
+// operands of a step — Ũ, φ∘Ũ, κ, φ slices and the owner-phase scalars — are loaded from shared memory ONCE and used for
+// both states, which removes about a quarter of the LSU wavefronts per evaluation (the co-limiter of the small-rank
+// kernel, profiles/r01_k2_sho_*), and the two independent reduction chains interleave.  Same arithmetic per θ as
+// celerite_step<BS, ODD, /*PRE=*/true>; the two (ŨᵀTŨ, Ũᵀg) pairs share one 4-value all-reduce (9 exchanges, not 12).
+template <int BS, bool ODD>
+__device__ __forceinline__ void celerite_step_pair(LaneState<BS> (&st)[2], const double* __restrict__ T,
+                                                   double* __restrict__ sc0, double* __restrict__ sc1, const LaneMap& lm,
+                                                   const double (&yn)[2], const double (&s2n)[2], const double (&suma)[2],
+                                                   const double (&mu)[2], const double (&nu)[2], const int64_t n,
+                                                   const int lane, const double* __restrict__ Tnext) {
+    constexpr int RP = rps_of(BS);
+    const int o = lm.o;
+    double* const qsv[2] = {sc0, sc1};
+    // ---- row-side operands of block-row I (shared by both states except q)
+    double urow[BS], xrow[BS], prow[BS], qrow[2][BS];
+    load_slice<BS>(urow, T + (ODD ? F_UH : F_UT) * RP + lm.rowI);
+    if (ODD) load_slice<BS>(xrow, T + F_PHI * RP + lm.rowI);
+    else     load_slice<BS>(prow, T + F_PHI * RP + lm.rowI);
+    load_slice<BS>(qrow[0], sc0 + lm.rowI);
+    load_slice<BS>(qrow[1], sc1 + lm.rowI);
+    double rowpart[2][BS], acc[2][BS];
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int r = 0; r < BS; r++) rowpart[k][r] = 0.0;
+
+    const double* uAp = T + (ODD ? F_UT : F_UH) * RP + lm.colA;
+    const double* uBp = T + (ODD ? F_UT : F_UH) * RP + lm.colB;
+#pragma unroll
+    for (int c0 = 0; c0 < BS; c0 += 2) {
+        double uA2[2], uB2[2], wA2[2][2], wB2[2][2];
+        if (c0 + 1 < BS) {
+            const double2 a2 = *reinterpret_cast<const double2*>(uAp + c0), a3 = *reinterpret_cast<const double2*>(uBp + c0);
+            uA2[0] = a2.x; uA2[1] = a2.y; uB2[0] = a3.x; uB2[1] = a3.y;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double* ws = qsv[k] + RP;
+                const double2 a0 = *reinterpret_cast<const double2*>(ws + lm.colA + c0), a1 = *reinterpret_cast<const double2*>(ws + lm.colB + c0);
+                wA2[k][0] = a0.x; wA2[k][1] = a0.y; wB2[k][0] = a1.x; wB2[k][1] = a1.y;
+            }
+        } else {
+            uA2[0] = uAp[c0]; uB2[0] = uBp[c0]; uA2[1] = uB2[1] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double* ws = qsv[k] + RP;
+                wA2[k][0] = ws[lm.colA + c0]; wB2[k][0] = ws[lm.colB + c0]; wA2[k][1] = wB2[k][1] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+            const int c = c0 + cc;
+            if (c < BS) {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    double cA = 0.0, cB = 0.0;
+#pragma unroll
+                    for (int r = 0; r < BS; r++) {
+                        const bool useA = r > c;  // compile-time after unrolling
+                        const double w = useA ? wA2[k][cc] : wB2[k][cc];
+                        const double u = useA ? uA2[cc] : uB2[cc];
+                        const double qr = (r == c) ? (lm.dzero ? 0.0 : qrow[k][r]) : qrow[k][r];
+                        const double m = fma(qr, w, st[k].M[r][c]);      // the decay is already in M (pre-decayed state)
+                        st[k].M[r][c] = m;
+                        rowpart[k][r] = fma(m, u, rowpart[k][r]);
+                        if (useA) cA = fma(m, urow[r], cA);
+                        else      cB = fma(m, urow[r], cB);
+                    }
+                    const double yv = __shfl_sync(FULL, cB + (o ? cA : 0.0), lm.src_lane);
+                    acc[k][c] = yv + (o ? 0.0 : cA);
+                }
+            }
+        }
+    }
+
+    // ---- (ŨᵀTŨ, Ũᵀg) of both states: one 4-value all-reduce
+    const double ut0 = T[F_UT * RP + lm.j0], ut1 = T[F_UT * RP + lm.j1];
+    double sp[2], up[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double sblk = 0.0, sblk2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < BS; r += 2) {
+            sblk = fma(urow[r], rowpart[k][r], sblk);
+            if (r + 1 < BS) sblk2 = fma(urow[r + 1], rowpart[k][r + 1], sblk2);
+        }
+        sblk += sblk2;
+        sp[k] = fma(st[k].sjj[1] * ut1, ut1, fma(st[k].sjj[0] * ut0, ut0, sblk + sblk));
+        up[k] = fma(ut1, st[k].g[1], ut0 * st[k].g[0]);
+    }
+    {
+        // halves: lanes < 16 reduce state 0's pair, lanes ≥ 16 state 1's; quarter bit (lane & 8) picks s or u
+        const bool q8 = (lane & 8) != 0;
+        const double r0 = __shfl_xor_sync(FULL, lm.hi ? sp[0] : sp[1], 16);
+        const double r1 = __shfl_xor_sync(FULL, lm.hi ? up[0] : up[1], 16);
+        const double ks = (lm.hi ? sp[1] : sp[0]) + r0, ku = (lm.hi ? up[1] : up[0]) + r1;
+        const double r2 = __shfl_xor_sync(FULL, q8 ? ks : ku, 8);
+        double keep = (q8 ? ku : ks) + r2;
+#pragma unroll
+        for (int sft = 4; sft >= 1; sft >>= 1) keep += __shfl_xor_sync(FULL, keep, sft);
+        const double oth = __shfl_xor_sync(FULL, keep, 8);
+        const double ms = q8 ? oth : keep, mu_ = q8 ? keep : oth;     // (s, u) of my half's state
+        const double os = __shfl_xor_sync(FULL, ms, 16), ou = __shfl_xor_sync(FULL, mu_, 16);
+        sp[0] = lm.hi ? os : ms; up[0] = lm.hi ? ou : mu_;
+        sp[1] = lm.hi ? ms : os; up[1] = lm.hi ? mu_ : ou;
+    }
+
+    // ---- decay of the coming step (pre-decayed state), factors loaded once for both states
+    if (!ODD) {   // next step is odd: column factors κ_c(n+1)
+        double zA[BS], zB[BS];
+        load_slice<BS>(zA, Tnext + F_KAP * RP + lm.colA);
+        load_slice<BS>(zB, Tnext + F_KAP * RP + lm.colB);
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int c = 0; c < BS; c++)
+#pragma unroll
+                for (int r = 0; r < BS; r++) st[k].M[r][c] *= (r > c) ? zA[c] : zB[c];
+    } else {      // next step is even: row factors κ_r(n+1)
+        double xn[BS];
+        load_slice<BS>(xn, Tnext + F_KAP * RP + lm.rowI);
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+#pragma unroll
+            for (int r = 0; r < BS; r++)
+#pragma unroll
+                for (int c = 0; c < BS; c++) st[k].M[r][c] *= xn[r];
+    }
+
+    // ---- matvec reduction (per state) and owner phase; the table scalars of the owned rows are shared
+    const double v0 = T[F_V * RP + lm.j0], v1 = T[F_V * RP + lm.j1];
+    const double pn0 = T[F_PHN * RP + lm.j0], pn1 = T[F_PHN * RP + lm.j1];
+    const bool bit0 = (o & 1) != 0, bit1 = (o & 2) != 0;
+    double q0[2], q1[2], w0[2], w1[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double tot[BS];
+#pragma unroll
+        for (int c = 0; c < BS; c++) {
+            if (ODD) tot[c] = fma(xrow[c], rowpart[k][c], acc[k][c]);
+            else     tot[c] = fma(prow[c], acc[k][c], rowpart[k][c]);
+        }
+        double e[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            if (2 * m < BS) {
+                const double lo = tot[(2 * m < BS) ? 2 * m : 0];
+                const double hi = (2 * m + 1 < BS) ? tot[(2 * m + 1 < BS) ? 2 * m + 1 : 0] : 0.0;
+                const double recv = __shfl_xor_sync(FULL, bit0 ? lo : hi, 1);
+                e[m] = (bit0 ? hi : lo) + recv;
+            } else {
+                e[m] = 0.0;
+            }
+        }
+        double f0, f1 = 0.0;
+        {
+            const double recv = __shfl_xor_sync(FULL, bit1 ? e[0] : e[1], 2);
+            f0 = (bit1 ? e[1] : e[0]) + recv;
+        }
+        if (BS > 4) {
+            const double recv = __shfl_xor_sync(FULL, bit1 ? e[2] : e[3], 2);
+            f1 = (bit1 ? e[3] : e[2]) + recv;
+        }
+        LaneState<BS>& s_ = st[k];
+        const double p0 = fma(s_.sjj[0], ut0, f0), p1 = fma(s_.sjj[1], ut1, f1);
+        const double D = fma(nu[k], s2n[k], suma[k]) - sp[k];     // celerite_solver.jl:92
+        const double rD = fast_rcp(D);
+        const double z = (yn[k] - mu[k]) - up[k];                 // celerite_solver.jl:141
+        s_.chi2 = fma(z * z, rD, s_.chi2);
+        if (n == 0) s_.dfirst = D;
+        else if ((int)(n & 31) == lane) s_.dkeep = D;
+        if ((n & 31) == 31) { s_.logacc += log(fabs(s_.dkeep)); s_.dkeep = 1.0; }
+        q0[k] = fma(s_.amp[0], v0, -p0); q1[k] = fma(s_.amp[1], v1, -p1);
+        w0[k] = q0[k] * rD; w1[k] = q1[k] * rD;
+        s_.g[0] = pn0 * fma(w0[k], z, s_.g[0]);
+        s_.g[1] = pn1 * fma(w1[k], z, s_.g[1]);
+        s_.sjj[0] = (pn0 * pn0) * fma(q0[k], w0[k], s_.sjj[0]);   // celerite_solver.jl:85
+        s_.sjj[1] = (pn1 * pn1) * fma(q1[k], w1[k], s_.sjj[1]);
+    }
+    __syncwarp();
+    // the NEXT step is odd iff this one is even: odd steps consume (q, φ∘w), even steps (φ∘q, w)
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double* qs = qsv[k];
+        double* ws = qsv[k] + RP;
+        if (!ODD) {
+            qs[lm.j0] = q0[k]; ws[lm.j0] = pn0 * w0[k];
+            if (lm.valid1) { qs[lm.j1] = q1[k]; ws[lm.j1] = pn1 * w1[k]; }
+        } else {
+            qs[lm.j0] = pn0 * q0[k]; ws[lm.j0] = w0[k];
+            if (lm.valid1) { qs[lm.j1] = pn1 * q1[k]; ws[lm.j1] = w1[k]; }
+        }
+    }
+    __syncwarp();
+}
+
 // Per-θ inputs of the batched kernel.
 struct BatchArgs {
     const WorkItem* work;
@@ -504,6 +701,108 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_shared_kernel(const Batch
     }
     const double res = lane_finish(st, N, lane);
     if (active && lane == 0) args.out[wk.out_begin + warp] = res;
+}
+
+// Paired variant of the shared-table kernel: each warp sweeps TWO parameter vectors of the item's series (block sizes ≤ 5).
+// grid = number of work items (≤ 2·NW parameter vectors each); same TMA staging and stage hand-back as above.
+template <int BS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) celerite_shared_pair_kernel(const BatchArgs args) {
+    constexpr int RP = G * BS, RPS = rps_of(BS), SD = table_step_doubles(RPS), STAGE = CHUNK_STEPS * SD;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    double* scratch = stages + 2 * STAGE;                      // per warp: (q, w) of both states, 4·RPS doubles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 4 * RPS);
+    int* done = reinterpret_cast<int*>(bars + 2);
+
+    const WorkItem wk = args.work[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t N = wk.N;
+    const int64_t nchunks = (N + CHUNK_STEPS - 1) / CHUNK_STEPS;
+    constexpr uint32_t STAGE_BYTES = STAGE * sizeof(double);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        done[0] = done[1] = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2 && k < nchunks; k++) {
+            mbar_arrive_expect_tx(&bars[k], STAGE_BYTES);
+            tma_load_1d(stages + k * STAGE, wk.table + (size_t)k * STAGE, STAGE_BYTES, &bars[k]);
+        }
+    }
+
+    const LaneMap lm = make_lane_map<BS>(lane);
+    const int i = lane >> 2, o = lane & 3;
+    LaneState<BS> st[2];
+    bool active[2];
+    double suma[2], mu[2], nu[2];
+    const double* yb[2];
+    const double* sb[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int want = 2 * warp + k;
+        active[k] = want < wk.count;
+        const int slot = active[k] ? want : wk.count - 1;     // surplus slots redo the item's last θ and skip the store
+        const int th = wk.theta_begin + slot;
+        lane_init(st[k]);
+        st[k].amp[0] = args.amp[(size_t)th * RP + i * BS + o];
+        st[k].amp[1] = lm.valid1 ? args.amp[(size_t)th * RP + i * BS + o + 4] : 0.0;
+        suma[k] = args.suma[th];
+        const size_t pi = (size_t)wk.par_begin + slot;
+        mu[k] = args.mu ? args.mu[pi * args.pstride] : 0.0;
+        nu[k] = args.nu ? args.nu[pi * args.pstride] : 1.0;
+        yb[k] = args.y_batch ? args.y_batch + pi * args.ystride : nullptr;
+        sb[k] = args.s2_batch ? args.s2_batch + pi * args.ystride : nullptr;
+    }
+    double* sc0 = scratch + warp * 4 * RPS;
+    double* sc1 = sc0 + 2 * RPS;
+    for (int k = lane; k < 4 * RPS; k += 32) sc0[k] = 0.0;
+    __syncwarp();
+
+    mbar_wait(&bars[0], 0);
+    for (int64_t k = 0; k < nchunks; k++) {
+        const int sidx = (int)(k & 1);
+        const double* stage = stages + sidx * STAGE;
+        const double* nstage = stages + (sidx ^ 1) * STAGE;
+        const bool has_next = k + 1 < nchunks;
+        const int64_t nbeg = k * CHUNK_STEPS;
+        const int nsteps = (int)((N - nbeg) < CHUNK_STEPS ? (N - nbeg) : CHUNK_STEPS);
+        for (int s = 0; s < nsteps; s += 2) {
+            const double* T0 = stage + s * SD;
+            const double* T1 = T0 + SD;
+            const int64_t n = nbeg + s;
+            if (has_next && s + 2 >= nsteps) mbar_wait(&bars[sidx ^ 1], (uint32_t)(((k + 1) >> 1) & 1));
+            double yn[2], s2n[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) { yn[q] = yb[q] ? yb[q][n] : T0[6 * RPS + 0]; s2n[q] = sb[q] ? sb[q][n] : T0[6 * RPS + 1]; }
+            const double* Ta = (s + 1 < nsteps) ? T1 : (has_next ? nstage : T0);
+            celerite_step_pair<BS, false>(st, T0, sc0, sc1, lm, yn, s2n, suma, mu, nu, n, lane, Ta);
+            if (s + 1 < nsteps) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) { yn[q] = yb[q] ? yb[q][n + 1] : T1[6 * RPS + 0]; s2n[q] = sb[q] ? sb[q][n + 1] : T1[6 * RPS + 1]; }
+                const double* Tb = (s + 2 < nsteps) ? T1 + SD : (has_next ? nstage : T1);
+                celerite_step_pair<BS, true>(st, T1, sc0, sc1, lm, yn, s2n, suma, mu, nu, n + 1, lane, Tb);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && k + 2 < nchunks) {
+            __threadfence_block();
+            if (atomicAdd(&done[sidx], 1) == NW - 1) {
+                done[sidx] = 0;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
+                tma_load_1d(stages + sidx * STAGE, wk.table + (size_t)(k + 2) * STAGE, STAGE_BYTES, &bars[sidx]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double res = lane_finish(st[k], N, lane);
+        if (active[k] && lane == 0) args.out[wk.out_begin + 2 * warp + k] = res;
+    }
 }
 
 // ------------------------------------------------------------------------------------------- generic kernel

@@ -1,0 +1,10 @@
+#!/bin/bash
+# development aid: parity tests + short bench of both bases (+ SHO with θ-pairing off)
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+run() { python bench.py --steps 5 --warmup 3 --no-extra --no-cpu --basis $1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms'], d['roofline']['frac'], d['value'], d['e2e']['value'])"; }
+{
+echo -n "DRWCelerite : "; run DRWCelerite
+echo -n "SHO : "; run SHO
+echo -n "SHO PIORAN_PAIR=0 : "; PIORAN_PAIR=0 run SHO
+} 2>&1 | tee gpurun_out/quick.txt
