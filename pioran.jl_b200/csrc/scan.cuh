@@ -223,7 +223,7 @@ __device__ __forceinline__ void sm_store(double* __restrict__ dst, const double*
 // D = op(X)·op(Y) [+ addend (global, row-major)] → dst_s (shared) and/or dst_g (global).  256 threads, 4×4 tiles.
 // dst_s must not alias X or Y.
 template <bool TX, bool TY>
-__device__ __noinline__ void sm_matmul(double* dst_s, double* dst_g, const double* X, const double* Y,
+__device__ __forceinline__ void sm_matmul(double* dst_s, double* dst_g, const double* X, const double* Y,
                                        const double* addend, bool symmetrise) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double acc[4][4];
@@ -275,7 +275,7 @@ __device__ __forceinline__ double sm_matvec_row(const double* X, const double* x
     return acc;
 }
 // In-place LU with partial pivoting of a shared SR×SR matrix; perm[k] = row swapped with k at step k.
-__device__ __noinline__ void sm_lu(double* M, int* perm) {
+__device__ __forceinline__ void sm_lu(double* M, int* perm) {
     __shared__ int piv_s;
     for (int k = 0; k < SR; k++) {
         if (threadIdx.x < 32) {
@@ -304,47 +304,75 @@ __device__ __noinline__ void sm_lu(double* M, int* perm) {
         __syncthreads();
         for (int r = k + 1 + (int)threadIdx.x; r < SR; r += blockDim.x) M[r * SLD + k] *= inv;
         __syncthreads();
-        const int rem = SR - k - 1;
-        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-            const int r = k + 1 + e / rem, c = k + 1 + e % rem;
-            M[r * SLD + c] = fma(-M[r * SLD + k], M[k * SLD + c], M[r * SLD + c]);
+        {   // trailing update, 16×16 thread grid striding over the remaining (SR−k−1)² block
+            const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+            for (int r = k + 1 + ty; r < SR; r += 16) {
+                const double l = M[r * SLD + k];
+                for (int c = k + 1 + tx; c < SR; c += 16) M[r * SLD + c] = fma(-l, M[k * SLD + c], M[r * SLD + c]);
+            }
         }
         __syncthreads();
     }
 }
 // Solves (LU) X = RHS in place for the SR columns of a shared matrix plus nvec shared vectors (vecs + v·SR).
-// One thread per right-hand side, the column held in registers.
-__device__ __noinline__ void sm_lu_solve(const double* LU, const int* perm, double* RHS, double* vecs, int nvec) {
-    const int col = threadIdx.x;
-    const bool is_mat = RHS != nullptr && col < SR;
-    const bool is_vec = !is_mat && col >= SR && col - SR < nvec;
-    if (is_mat || is_vec) {
-        double x[SR];
-        double* base = is_mat ? RHS + col : vecs + (size_t)(col - SR) * SR;
-        const int stride = is_mat ? SLD : 1;
-        // row interchanges (dynamic indices) on the shared copy, then the column moves to registers
+// Three lanes per right-hand side split the inner product of every substitution row (ten columns per warp, 80 ≥ SR + nvec
+// column slots in the CTA); the column stays in shared memory.  Rolled loops: the first version kept each column in the
+// registers of one thread with both triangular sweeps fully unrolled — 8 000 FMAs of straight-line code per call, far
+// beyond the instruction cache, and 0.28 ms per combine.
+__device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, double* RHS, double* vecs, int nvec) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / 3, part = lane - 3 * grp;          // lanes 30, 31 idle (grp = 10)
+    const int slot = warp * 10 + grp;                         // column slot 0 … 79
+    const int ncol_m = RHS ? SR : 0;
+    const bool on = grp < 10 && slot < ncol_m + nvec;
+    double* base = nullptr;
+    int stride = 1;
+    if (on) {
+        if (slot < ncol_m) { base = RHS + slot; stride = SLD; }
+        else               { base = vecs + (size_t)(slot - ncol_m) * SR; stride = 1; }
+    }
+    // row interchanges, one lane per column
+    if (on && part == 0) {
         for (int k = 0; k < SR; k++) {
             const int p = perm[k];
             if (p != k) { const double tmp = base[k * stride]; base[k * stride] = base[p * stride]; base[p * stride] = tmp; }
         }
-#pragma unroll
-        for (int r = 0; r < SR; r++) x[r] = base[r * stride];
-#pragma unroll
-        for (int r = 0; r < SR; r++) {
-            double v = x[r];
-#pragma unroll
-            for (int k = 0; k < r; k++) v = fma(-LU[r * SLD + k], x[k], v);
-            x[r] = v;
+    }
+    __syncwarp();
+    const unsigned gl = on ? (unsigned)(3 * grp) : 0u;        // leader lane of my group
+    // L y = b (unit lower triangle)
+    for (int r = 1; r < SR; r++) {
+        double acc = 0.0, acc2 = 0.0;
+        if (on) {
+            int k = part;
+#pragma unroll 2
+            for (; k + 3 < r; k += 6) {       // two independent chains, loads of the next pair in flight
+                acc = fma(LU[r * SLD + k], base[k * stride], acc);
+                acc2 = fma(LU[r * SLD + k + 3], base[(k + 3) * stride], acc2);
+            }
+            if (k < r) acc = fma(LU[r * SLD + k], base[k * stride], acc);
+            acc += acc2;
         }
-#pragma unroll
-        for (int r = SR - 1; r >= 0; r--) {
-            double v = x[r];
-#pragma unroll
-            for (int k = r + 1; k < SR; k++) v = fma(-LU[r * SLD + k], x[k], v);
-            x[r] = v / LU[r * SLD + r];
+        const double a1 = __shfl_sync(0xffffffffu, acc, (gl + 1) & 31), a2 = __shfl_sync(0xffffffffu, acc, (gl + 2) & 31);
+        if (on && part == 0) base[r * stride] -= acc + a1 + a2;
+        __syncwarp();
+    }
+    // U x = y
+    for (int r = SR - 1; r >= 0; r--) {
+        double acc = 0.0, acc2 = 0.0;
+        if (on) {
+            int k = r + 1 + part;
+#pragma unroll 2
+            for (; k + 3 < SR; k += 6) {
+                acc = fma(LU[r * SLD + k], base[k * stride], acc);
+                acc2 = fma(LU[r * SLD + k + 3], base[(k + 3) * stride], acc2);
+            }
+            if (k < SR) acc = fma(LU[r * SLD + k], base[k * stride], acc);
+            acc += acc2;
         }
-#pragma unroll
-        for (int r = 0; r < SR; r++) base[r * stride] = x[r];
+        const double a1 = __shfl_sync(0xffffffffu, acc, (gl + 1) & 31), a2 = __shfl_sync(0xffffffffu, acc, (gl + 2) & 31);
+        if (on && part == 0) base[r * stride] = (base[r * stride] - (acc + a1 + a2)) / LU[r * SLD + r];
+        __syncwarp();
     }
     __syncthreads();
 }
@@ -368,7 +396,7 @@ constexpr size_t SCAN_SMEM_BYTES = sizeof(double) * (5 * (size_t)SMAT + 8 * SR) 
 // out = ei ⊗ ej (ei earlier).  Composite layout: 𝒜 | C | J | b | η.  out may alias neither input.
 //   M = (I + C_i J_j)⁻¹;  𝒜 = 𝒜_j M 𝒜_i;  b = 𝒜_j M (b_i + C_i η_j) + b_j;  C = 𝒜_j M C_i 𝒜_jᵀ + C_j;
 //   η = 𝒜_iᵀ (r − J_j M C_i r) + η_i,  r = η_j − J_j b_i;   J = 𝒜_iᵀ J_j M 𝒜_i + J_i
-__device__ __noinline__ void scan_combine(const ScanSmem& w, const double* ei, const double* ej, double* out) {
+__device__ __forceinline__ void scan_combine(const ScanSmem& w, const double* ei, const double* ej, double* out) {
     const int tid = threadIdx.x;
     const double *Ai = ei, *Ci = ei + SR * SR, *Ji = ei + 2 * SR * SR, *bi = ei + 3 * SR * SR, *eti = bi + SR;
     const double *Aj = ej, *Cj = ej + SR * SR, *Jj = ej + 2 * SR * SR, *bj = ej + 3 * SR * SR, *etj = bj + SR;
@@ -408,7 +436,7 @@ __device__ __noinline__ void scan_combine(const ScanSmem& w, const double* ei, c
 
 // (S', g') = el applied to (S, g):  S' = 𝒜 (I + S J)⁻¹ S 𝒜ᵀ + C,  g' = 𝒜 (I + S J)⁻¹ (g + S η) + b.
 // in == nullptr means the zero state.  out may alias in.
-__device__ __noinline__ void scan_apply(const ScanSmem& w, const double* el, const double* in, double* out) {
+__device__ __forceinline__ void scan_apply(const ScanSmem& w, const double* el, const double* in, double* out) {
     const int tid = threadIdx.x;
     const double *Ae = el, *Ce = el + SR * SR, *Je = el + 2 * SR * SR, *be = el + 3 * SR * SR, *ete = be + SR;
     if (!in) {
