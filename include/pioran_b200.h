@@ -118,6 +118,19 @@ int pioran_celerite_logl_scan(pioran_ctx *ctx, int series_id, int B, int Jt,
                               const double *a, const double *b, const double *c, const double *d,
                               const double *mu, const double *nu, double *logl_out);
 
+/* The same path with the TIME AXIS split across GPUs: every rank holds the series, folds its own step range
+ * [n_lo, n_hi) and returns the range's composite scan element (pioran_scan_composite_doubles() doubles, ~97 KB);
+ * the ranks all-gather those (NCCL / MPI — outside this library); each rank then passes the composites of the ranges that
+ * precede its own, in time order, and gets (sum log|D_n|, sum z_n^2/D_n) over its range; the caller all-reduces the two
+ * sums and forms  logL = -sums[0]/2 - sums[1]/2 - N log(2 pi)/2  (src/celerite_solver.jl:333).  One coefficient set per
+ * call.  max_prev = upper bound of nprev (workspace sizing).  begin/end must be called in pairs on the same context. */
+int pioran_scan_composite_doubles(void);
+int pioran_celerite_scan_range_begin(pioran_ctx *ctx, int series_id, int Jt,
+                                     const double *a, const double *b, const double *c, const double *d,
+                                     const double *mu, const double *nu, int64_t n_lo, int64_t n_hi, int max_prev,
+                                     double *composite_out);
+int pioran_celerite_scan_range_end(pioran_ctx *ctx, int nprev, const double *composites_prev, double *sums_out);
+
 /* ---- K4: dense cross-check ------------------------------------------------------------------------------- */
 /* Drop-in for  log_likelihood_direct(cov, t, y, σ²)  (src/direct_solver.jl:6-21) with the kernel of
  * src/Celerite.jl:42-44 summed over terms.  Returns +NLL like the reference (tests negate it,

@@ -36,6 +36,9 @@ SYMBOLS = {
     "pioran_approx_logl_dev": (C.c_int, [C.c_void_p, C.c_int, _ip, C.POINTER(ApproxSpec), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "pioran_ctx_set_scan_chunks": (C.c_int, [C.c_void_p, C.c_int]),
     "pioran_celerite_logl_scan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "pioran_scan_composite_doubles": (C.c_int, []),
+    "pioran_celerite_scan_range_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp]),
+    "pioran_celerite_scan_range_end": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     "pioran_direct_logl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
     "pioran_celerite_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp, _dp]),
     "pioran_celerite_simulate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

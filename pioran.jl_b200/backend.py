@@ -170,6 +170,25 @@ class Context:
                                                  _p(out)))
         return out
 
+    # -- K3 with the time axis split across ranks (see parallel.scan_logl_sharded)
+    def scan_range_begin(self, series, a, b, c, d, n_lo, n_hi, mu=None, nu=None, max_prev=8):
+        """Folds steps [n_lo, n_hi) of the series; returns the range's composite scan element (1-D array)."""
+        a, b, c, d = (_f64(x).ravel() for x in (a, b, c, d))
+        mu = _f64([mu]) if mu is not None else None
+        nu = _f64([nu]) if nu is not None else None
+        out = np.empty(self.lib.pioran_scan_composite_doubles())
+        check(self.lib.pioran_celerite_scan_range_begin(self.h, series.id, a.shape[0], _p(a), _p(b), _p(c), _p(d), _p(mu), _p(nu),
+                                                        int(n_lo), int(n_hi), int(max_prev), _p(out)))
+        return out
+
+    def scan_range_end(self, composites_prev):
+        """composites_prev: [nprev × composite] of the ranges before this one, in time order → (Σ log|D|, Σ z²/D)."""
+        prev = _f64(composites_prev) if composites_prev is not None and len(composites_prev) else None
+        nprev = 0 if prev is None else int(np.atleast_2d(prev).shape[0])
+        out = np.empty(2)
+        check(self.lib.pioran_celerite_scan_range_end(self.h, nprev, _p(prev), _p(out)))
+        return out
+
     # -- K4
     def direct_logl(self, series, a, b, c, d, mu=None, nu=None):
         """Batched log_likelihood_direct (src/direct_solver.jl:6-21): returns (+NLL [B], info [B])."""

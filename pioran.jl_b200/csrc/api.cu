@@ -104,6 +104,7 @@ static int bs_for_rank(int R) {
     return bs;
 }
 
+static void scan_forget(pioran_ctx* c);   // drops the range-in-progress record of a context (K3 multi-GPU entries)
 extern "C" int pioran_ctx_destroy(pioran_ctx* c);
 extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
     if (!out) return fail(PIORAN_EINVAL, "out is NULL");
@@ -145,6 +146,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
     if (!c) return PIORAN_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    scan_forget(c);
     for (Series* s : c->series) free_series(s);
     for (auto& kv : c->plans) cudaFree(kv.second);
     c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
@@ -865,6 +867,135 @@ extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) {
     return PIORAN_OK;
 }
 
+// One run of the parallel-in-time path over the step range [n_lo, n_hi) of a series: device buffers (inside ctx workspaces)
+// and shapes, shared by the whole-series entry and by the two-phase range entries (time axis split across GPUs).
+struct ScanRun {
+    bool valid = false;
+    int series_id = -1, B = 0, Jt = 0, R = 0, BS = 0, P = 0, G1 = 0, G2 = 0;
+    int64_t N = 0, n_lo = 0, n_hi = 0;
+    std::vector<int64_t> bounds;
+    GenericInputs gi{};
+    double *elems = nullptr, *pref = nullptr, *gstate = nullptr, *cstate = nullptr, *parts = nullptr, *out = nullptr;
+    double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
+    int64_t* bounds_dev = nullptr;
+    int* term_row_dev = nullptr;
+};
+static std::map<pioran_ctx*, ScanRun> g_scan;
+static std::mutex g_scan_mu;
+static void scan_forget(pioran_ctx* c) { std::lock_guard<std::mutex> g(g_scan_mu); g_scan.erase(c); }
+static ScanRun* scan_slot(pioran_ctx* c) { std::lock_guard<std::mutex> g(g_scan_mu); return &g_scan[c]; }   // std::map nodes are stable
+
+// Phase 1: coefficients, chunking, fold of every chunk into its composite, prefix composites inside the groups and — when
+// want_total — the composite of the whole range.  max_prev = number of earlier-range composites phase 2 may receive.
+static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
+                       const double* cc, const double* d, const double* mu, const double* nu, int64_t n_lo, int64_t n_hi,
+                       bool want_total, int max_prev, ScanRun& run) {
+    std::vector<int> term_row;
+    const int R = make_term_rows(B, Jt, b, d, term_row);
+    const int BS = bs_for_rank(R);
+    if (BS > 8 || R > SR)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
+    const int64_t N = s->N, len = n_hi - n_lo;
+    // chunking: enough chunks to give every SM two re-filter warps, at least 64 steps per chunk
+    int P = c->scan_chunks > 0 ? c->scan_chunks : 2 * c->num_sms;
+    P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
+    const int G2 = (int)std::ceil(std::sqrt((double)P));
+    const int G1 = (P + G2 - 1) / G2;
+    run = ScanRun{};
+    run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2;
+    run.N = N; run.n_lo = n_lo; run.n_hi = n_hi;
+    run.bounds.resize(P + 1);
+    for (int k = 0; k <= P; k++) run.bounds[k] = n_lo + (int64_t)((__int128)len * k / P);
+
+    int rc;
+    if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, run.gi))) return rc;
+    const size_t nch = (size_t)B * P;
+    // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out | total | scratch | init | prev | sums
+    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch + 1);
+    const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
+    const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
+    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B))))
+        return rc;
+    run.elems = c->misc.as<double>();
+    run.pref = run.elems + n_el;
+    run.gstate = run.pref + n_el;
+    run.cstate = run.gstate + n_gs;
+    run.parts = run.cstate + n_cs;
+    run.out = run.parts + n_pt;
+    run.total = run.out + B;
+    run.scratch = run.total + n_tot;
+    run.init = run.scratch + n_scr;
+    run.prev = run.init + n_init;
+    run.sums = run.prev + n_prev;
+    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
+    run.bounds_dev = c->rows.as<int64_t>();
+    run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
+    CUDA_TRY(cudaMemcpyAsync(run.bounds_dev, run.bounds.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(run.term_row_dev, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // term_row is a local
+
+    ScanArgs sa{};
+    sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = run.bounds_dev;
+    sa.a = run.gi.a; sa.b = run.gi.b; sa.c = run.gi.c; sa.d = run.gi.d; sa.Jt = Jt; sa.term_row = run.term_row_dev;
+    sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems;
+    scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
+    c->launches++;
+    CUDA_TRY(cudaFuncSetAttribute(scan_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_total_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    if (P > 1 || want_total) {
+        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.pref, P, G2);
+        c->launches++;
+    }
+    if (want_total) {
+        scan_total_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.scratch, run.total, P, G2, G1);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    run.valid = true;
+    return 0;
+}
+
+// Phase 2: states entering every chunk (from `init_dev`, or from the start of the series when it is null), re-filter of
+// every chunk, partial sums in run.parts.
+static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* init_dev) {
+    const int B = run.B, P = run.P, NW = CHUNK_NW;
+    const size_t nch = (size_t)B * P;
+    const size_t nitems = (nch + NW - 1) / NW * NW;
+    std::vector<WorkItem> items(nitems);
+    for (size_t k = 0; k < nitems; k++) {
+        const size_t q = std::min(k, nch - 1);
+        const int th = (int)(q / P), ch = (int)(q % P);
+        WorkItem& w = items[k];
+        w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = run.N;
+        w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
+        w.n_begin = run.bounds[ch]; w.n_end = run.bounds[ch + 1];
+        w.init = (ch == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
+        w.part = k < nch ? run.parts + 2 * q : run.parts + 2 * nch;   // padding warps write to the dummy pair
+    }
+    int rc;
+    c->work_key.clear();
+    if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // items is a local
+    if (P > 1 || init_dev) {
+        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, P, run.G2, run.G1, init_dev);
+        scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
+                                                                             init_dev ? 1 : 0);
+        c->launches += 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    BatchArgs args{};
+    args.work = c->work.as<WorkItem>();
+    args.a = run.gi.a; args.b = run.gi.b; args.c = run.gi.c; args.d = run.gi.d;
+    args.Jt = run.Jt; args.term_row = run.term_row_dev; args.R = run.R;
+    args.mu = run.gi.mu; args.nu = run.gi.nu; args.pstride = 1;
+    args.out = run.out;
+    return dispatch_chunked(c, run.BS, args, (int)(nitems / NW));
+}
+
 extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                          const double* cc, const double* d, const double* mu, const double* nu,
                                          double* logl_out) {
@@ -874,87 +1005,73 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    std::vector<int> term_row;
-    const int R = make_term_rows(B, Jt, b, d, term_row);
-    const int BS = bs_for_rank(R);
-    if (BS > 8 || R > SR)
-        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
-    const int64_t N = s->N;
-    // chunking: enough chunks to give every SM two re-filter warps, at least 64 steps per chunk
-    int P = c->scan_chunks > 0 ? c->scan_chunks : 2 * c->num_sms;
-    P = (int)std::max<int64_t>(1, std::min<int64_t>(P, N / 64));
-    int G2 = (int)std::ceil(std::sqrt((double)P));
-    int G1 = (P + G2 - 1) / G2;
-    std::vector<int64_t> bounds(P + 1);
-    for (int k = 0; k <= P; k++) bounds[k] = (int64_t)((__int128)N * k / P);
-
+    ScanRun run;
     int rc;
-    GenericInputs gi;
-    if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, gi))) return rc;
-    const int NW = CHUNK_NW;
-    const size_t nch = (size_t)B * P;
-    const size_t nitems = (nch + NW - 1) / NW * NW;
-    // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out
-    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch + 1);
-    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B)))) return rc;
-    double* elems = c->misc.as<double>();
-    double* pref = elems + n_el;
-    double* gstate = pref + n_el;
-    double* cstate = gstate + n_gs;
-    double* parts = cstate + n_cs;
-    double* out = parts + n_pt;
-    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
-    int64_t* bounds_dev = c->rows.as<int64_t>();
-    int* term_row_dev = reinterpret_cast<int*>(bounds_dev + P + 2);
-    CUDA_TRY(cudaMemcpyAsync(bounds_dev, bounds.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(term_row_dev, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
-    std::vector<WorkItem> items(nitems);
-    for (size_t k = 0; k < nitems; k++) {
-        const size_t q = std::min(k, nch - 1);
-        const int th = (int)(q / P), ch = (int)(q % P);
-        WorkItem& w = items[k];
-        w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = N;
-        w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
-        w.n_begin = bounds[ch]; w.n_end = bounds[ch + 1];
-        w.init = ch == 0 ? nullptr : cstate + q * SSTATE;
-        w.part = k < nch ? parts + 2 * q : parts + 2 * nch;   // padding warps write to the dummy pair
-    }
-    c->work_key.clear();
-    if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));   // bounds, term_row, items are locals
-
     cudaEventRecord(c->ev_beg, c->stream);
-    ScanArgs sa{};
-    sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = bounds_dev;
-    sa.a = gi.a; sa.b = gi.b; sa.c = gi.c; sa.d = gi.d; sa.Jt = Jt; sa.term_row = term_row_dev;
-    sa.mu = gi.mu; sa.nu = gi.nu; sa.elems = elems;
-    scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
-    c->launches++;
-    if (P > 1) {
-        CUDA_TRY(cudaFuncSetAttribute(scan_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(scan_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(elems, pref, P, G2);
-        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(pref, gstate, P, G2, G1);
-        scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(pref, gstate, cstate, P, G2, G1);
-        c->launches += 3;
-    }
-    CUDA_TRY(cudaGetLastError());
-    BatchArgs args{};
-    args.work = c->work.as<WorkItem>();
-    args.a = gi.a; args.b = gi.b; args.c = gi.c; args.d = gi.d;
-    args.Jt = Jt; args.term_row = term_row_dev; args.R = R;
-    args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
-    args.out = out;
-    if ((rc = dispatch_chunked(c, BS, args, (int)(nitems / NW)))) return rc;
-    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(parts, P, B, N, out);
+    if ((rc = scan_phase1(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, 0, s->N, false, 0, run))) return rc;
+    if ((rc = scan_phase2(c, s, run, nullptr))) return rc;
+    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.P, B, s->N, run.out);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(logl_out, out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(logl_out, run.out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ---- time axis split across GPUs: each rank folds its own step range, the ranks exchange one composite each,
+// and every rank re-filters its range from the state the earlier ranges leave behind.
+extern "C" int pioran_scan_composite_doubles(void) { return SEL; }
+
+extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, int Jt, const double* a, const double* b,
+                                                const double* cc, const double* d, const double* mu, const double* nu,
+                                                int64_t n_lo, int64_t n_hi, int max_prev, double* composite_out) {
+    if (!c || !a || !b || !cc || !d || !composite_out) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    if (Jt < 1 || n_lo < 0 || n_hi > s->N || n_hi - n_lo < 1 || max_prev < 0)
+        return fail(PIORAN_EINVAL, "bad range [%lld, %lld) of a series of %lld steps", (long long)n_lo, (long long)n_hi, (long long)s->N);
+    ScanRun& run = *scan_slot(c);
+    int rc;
+    cudaEventRecord(c->ev_beg, c->stream);
+    if ((rc = scan_phase1(c, s, series_id, 1, Jt, a, b, cc, d, mu, nu, n_lo, n_hi, true, max_prev, run))) { run.valid = false; return rc; }
+    CUDA_TRY(cudaMemcpyAsync(composite_out, run.total, sizeof(double) * SEL, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const double* composites_prev, double* sums_out) {
+    if (!c || !sums_out || (nprev > 0 && !composites_prev)) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    ScanRun& run = *scan_slot(c);
+    if (!run.valid) return fail(PIORAN_EINVAL, "no range in progress: call pioran_celerite_scan_range_begin first");
+    Series* s = get_series(c, run.series_id);
+    if (!s) return fail(PIORAN_EINVAL, "the series of the range in progress was freed");
+    if (nprev < 0 || (size_t)nprev * SEL > (size_t)(run.sums - run.prev))
+        return fail(PIORAN_EINVAL, "nprev = %d exceeds the max_prev announced to scan_range_begin", nprev);
+    if ((nprev == 0) != (run.n_lo == 0))
+        return fail(PIORAN_EINVAL, "a range starting at step %lld needs %s earlier composites", (long long)run.n_lo, run.n_lo == 0 ? "no" : "the");
+    int rc;
+    const double* init = nullptr;
+    if (nprev > 0) {
+        CUDA_TRY(cudaMemcpyAsync(run.prev, composites_prev, sizeof(double) * (size_t)nprev * SEL, cudaMemcpyHostToDevice, c->stream));
+        scan_chain_kernel<<<dim3(1, 1), 256, SCAN_SMEM_BYTES, c->stream>>>(run.prev, nprev, 1, run.init);
+        c->launches++;
+        init = run.init;
+    }
+    if ((rc = scan_phase2(c, s, run, init))) return rc;
+    scan_partial_kernel<<<1, 32, 0, c->stream>>>(run.parts, run.P, 1, run.sums);
+    c->launches++;
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(sums_out, run.sums, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    run.valid = false;
     return PIORAN_OK;
 }
 

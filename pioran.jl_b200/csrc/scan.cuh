@@ -487,25 +487,27 @@ __global__ void __launch_bounds__(256, 1) scan_prefix_kernel(const double* elems
     }
 }
 // (b) grid = (1, B): state entering each group: st[0] = 0; st[g+1] = pref[g][last] applied to st[g].
+//     init (nullable, [B × SSTATE]): the state entering the first chunk when the chunks cover only the tail of a series
+//     (time axis split across GPUs); nullptr = start of the series (zero state).
 __global__ void __launch_bounds__(256, 1) scan_groups_kernel(const double* pref, double* gstate,
-                                                             int P, int G2, int G1) {
+                                                             int P, int G2, int G1, const double* init) {
     extern __shared__ __align__(16) unsigned char raw[];
     const ScanSmem w = scan_smem(raw);
     const int th = blockIdx.y;
     const double* Q = pref + (size_t)th * P * SEL;
     double* S = gstate + (size_t)th * G1 * SSTATE;
-    for (int k = threadIdx.x; k < SSTATE; k += blockDim.x) S[k] = 0.0;
+    for (int k = threadIdx.x; k < SSTATE; k += blockDim.x) S[k] = init ? init[(size_t)th * SSTATE + k] : 0.0;
     __syncthreads();
     for (int g = 0; g + 1 < G1; g++) {
         const int last = min(P, (g + 1) * G2) - 1;
         __threadfence_block();
-        scan_apply(w, Q + (size_t)last * SEL, g == 0 ? nullptr : S + (size_t)g * SSTATE, S + (size_t)(g + 1) * SSTATE);
+        scan_apply(w, Q + (size_t)last * SEL, (g == 0 && !init) ? nullptr : S + (size_t)g * SSTATE, S + (size_t)(g + 1) * SSTATE);
         __syncthreads();
     }
 }
 // (c) grid = (P, B): state entering chunk ch = pref[g][ch−1−g·G2] applied to the group state (or the group state itself).
 __global__ void __launch_bounds__(256, 1) scan_states_kernel(const double* pref, const double* gstate, double* cstate,
-                                                             int P, int G2, int G1) {
+                                                             int P, int G2, int G1, int has_init) {
     extern __shared__ __align__(16) unsigned char raw[];
     const ScanSmem w = scan_smem(raw);
     const int th = blockIdx.y, ch = blockIdx.x;
@@ -517,7 +519,49 @@ __global__ void __launch_bounds__(256, 1) scan_states_kernel(const double* pref,
         for (int k = threadIdx.x; k < SSTATE; k += blockDim.x) out[k] = Sg[k];
         return;
     }
-    scan_apply(w, Q + (size_t)(ch - 1) * SEL, g == 0 ? nullptr : Sg, out);
+    scan_apply(w, Q + (size_t)(ch - 1) * SEL, (g == 0 && !has_init) ? nullptr : Sg, out);
+}
+
+// (d) time axis split across GPUs: composite of ALL chunks of this range = ordered product of the group totals
+//     pref[g][last].  grid = (1, B); scratch holds two composites per parameter vector (ping-pong: combine may not alias).
+__global__ void __launch_bounds__(256, 1) scan_total_kernel(const double* pref, double* scratch, double* total,
+                                                            int P, int G2, int G1) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const ScanSmem w = scan_smem(raw);
+    const int th = blockIdx.y;
+    const double* Q = pref + (size_t)th * P * SEL;
+    double* buf[2] = {scratch + (size_t)th * 2 * SEL, scratch + (size_t)th * 2 * SEL + SEL};
+    const double* cur = Q + (size_t)(min(P, G2) - 1) * SEL;
+    for (int g = 1; g < G1; g++) {
+        const int last = min(P, (g + 1) * G2) - 1;
+        __threadfence_block();
+        scan_combine(w, cur, Q + (size_t)last * SEL, buf[g & 1]);
+        __syncthreads();
+        cur = buf[g & 1];
+    }
+    __threadfence_block();
+    for (int k = threadIdx.x; k < SEL; k += blockDim.x) total[(size_t)th * SEL + k] = cur[k];
+}
+// (e) state entering this range = the composites of the nprev earlier ranges applied, in order, to the zero state.
+//     elems_prev is [nprev × B × SEL] (rank-major, as gathered); grid = (1, B).
+__global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_prev, int nprev, int B, double* state) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const ScanSmem w = scan_smem(raw);
+    const int th = blockIdx.y;
+    double* S = state + (size_t)th * SSTATE;
+    for (int r = 0; r < nprev; r++) {
+        __threadfence_block();
+        scan_apply(w, elems_prev + ((size_t)r * B + th) * SEL, r == 0 ? nullptr : S, S);
+        __syncthreads();
+    }
+}
+// Σ over chunks of the pass-3 partial sums of a range → (Σ log|D_n|, Σ z_n²/D_n), one thread per parameter vector.
+__global__ void scan_partial_kernel(const double* __restrict__ parts, int P, int B, double* __restrict__ sums) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double ld = 0.0, chi = 0.0;
+    for (int k = 0; k < P; k++) { ld += parts[2 * ((size_t)i * P + k)]; chi += parts[2 * ((size_t)i * P + k) + 1]; }
+    sums[2 * i] = ld; sums[2 * i + 1] = chi;
 }
 
 // Σ over chunks of the pass-3 partial sums → logL (celerite_solver.jl:333).  One thread per parameter vector.

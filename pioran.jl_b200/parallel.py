@@ -63,3 +63,42 @@ class ShardedEvaluator:
         self.dist.all_gather_into_tensor(gathered, buf, group=self.group)
         parts = [gathered[r * m: r * m + int(off[r + 1] - off[r])] for r in range(self.world)]
         return torch.cat(parts)
+
+
+def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=None, all_reduce_sum=None):
+    """Log-likelihood of ONE long series with the time axis split across `world` ranks.
+
+    Rank r owns steps [N·r/world, N·(r+1)/world).  `range_begin(n_lo, n_hi)` folds them and returns the range's composite
+    scan element (Context.scan_range_begin); `all_gather(x) -> [world × len(x)]` exchanges the composites — the only
+    collective on the data path besides the final 2-value sum; `range_end(prev)` re-filters the range from the state the
+    `prev` earlier composites leave behind and returns (Σ log|D_n|, Σ z_n²/D_n); `all_reduce_sum` adds those over the ranks.
+    With world == 1 (or no collectives given) it reduces to the single-GPU scan."""
+    off = shard_bounds(N, world)
+    comp = np.asarray(range_begin(int(off[rank]), int(off[rank + 1])), dtype=np.float64)
+    if world > 1:
+        gathered = np.asarray(all_gather(comp), dtype=np.float64).reshape(world, -1)
+        sums = np.asarray(range_end(gathered[:rank]), dtype=np.float64)
+        sums = np.asarray(all_reduce_sum(sums), dtype=np.float64)
+    else:
+        sums = np.asarray(range_end(None), dtype=np.float64)
+    return float(-0.5 * sums[0] - 0.5 * sums[1] - 0.5 * N * np.log(2.0 * np.pi))   # celerite_solver.jl:333
+
+
+def torch_collectives(device=None, group=None):
+    """all_gather / all_reduce_sum for scan_logl_sharded on top of torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def all_gather(x):
+        t = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=device)
+        out = torch.empty((world * t.numel(),), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.cpu().numpy().reshape(world, -1)
+
+    def all_reduce_sum(x):
+        t = torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
+    return all_gather, all_reduce_sum

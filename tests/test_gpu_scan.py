@@ -92,3 +92,36 @@ def test_config_c4_long_series_n1e6_j30(pb, ctx):
     assert rel_err(got, seq) <= TOL
     assert rel_err(got, want) <= TOL
     ser.free()
+
+
+@pytest.mark.parametrize("world,chunks", [(2, 0), (3, 5), (8, 0), (4, 1)])
+def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks):
+    """the time axis split over `world` ranks — emulated on one GPU with one context per rank, the
+    collectives replaced by plain lists — must reproduce the single-GPU scan and the oracle."""
+    from pioran_b200.parallel import scan_logl_sharded
+    t, y, s2, f_min, f_max = synthetic_series(6000, seed=21)
+    a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, 30, 1.0, basis="SHO")
+    mu, nu = 0.13, 1.7
+    want = orc.celerite_logl_batch(a[None], b[None], c[None], d[None], t, y, s2, mu=np.array([mu]), nu=np.array([nu]))[0]
+    ctxs = [pb.Context(0) for _ in range(world)]
+    sers = [cx.upload_series(t, y, s2) for cx in ctxs]
+    for cx in ctxs:
+        cx.set_scan_chunks(chunks)
+    from pioran_b200.parallel import shard_bounds
+    off = shard_bounds(len(t), world)
+    comps = [ctxs[r].scan_range_begin(sers[r], a, b, c, d, off[r], off[r + 1], mu=mu, nu=nu, max_prev=world) for r in range(world)]
+    sums = [ctxs[r].scan_range_end(np.stack(comps[:r]) if r else None) for r in range(world)]
+    tot = np.sum(sums, axis=0)
+    got = -0.5 * tot[0] - 0.5 * tot[1] - 0.5 * len(t) * np.log(2 * np.pi)
+    assert rel_err(got, want) <= TOL, (got, want)
+    # the orchestration function with list-backed collectives gives the same number on every rank
+    for r in range(world):
+        val = scan_logl_sharded(lambda lo, hi: ctxs[r].scan_range_begin(sers[r], a, b, c, d, lo, hi, mu=mu, nu=nu, max_prev=world),
+                                ctxs[r].scan_range_end, len(t), rank=r, world=world,
+                                all_gather=lambda x: np.stack(comps), all_reduce_sum=lambda s_: s_ - sums[r] + tot)
+        assert rel_err(val, want) <= TOL
+    with pytest.raises(pb.PioranError):
+        ctxs[0].scan_range_end(None)            # no range in progress
+    for s_, cx in zip(sers, ctxs):
+        s_.free()
+        cx.close()

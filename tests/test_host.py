@@ -144,3 +144,50 @@ def test_sharded_allgather_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "OK" in o, o
+
+
+_SCAN_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from pioran_b200.parallel import scan_logl_sharded, torch_collectives, shard_bounds
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), 2
+# stand-in for the device scan with the same data flow: the "composite" of a range is the sum of its x, the state entering a
+# range is the sum of the earlier composites, and the two returned sums depend on that incoming state
+rng = np.random.default_rng(5)
+N = 1001
+x, wgt = rng.normal(size=N), rng.uniform(0.5, 1.5, N)
+seen = dict()
+def range_begin(lo, hi):
+    seen["range"] = (lo, hi)
+    return np.array([x[lo:hi].sum(), float(hi - lo)])
+def range_end(prev):
+    lo, hi = seen["range"]
+    carry = 0.0 if prev is None or len(prev) == 0 else float(np.asarray(prev)[:, 0].sum())
+    run = carry + np.cumsum(x[lo:hi])
+    return np.array([np.sum(run * wgt[lo:hi]), np.sum(run ** 2)])
+ag, ar = torch_collectives()
+got = scan_logl_sharded(range_begin, range_end, N, rank=rank, world=world, all_gather=ag, all_reduce_sum=ar)
+run = np.cumsum(x)
+want = -0.5 * np.sum(run * wgt) - 0.5 * np.sum(run ** 2) - 0.5 * N * np.log(2 * np.pi)
+off = shard_bounds(N, world)
+assert seen["range"] == (int(off[rank]), int(off[rank + 1]))
+assert abs(got - want) <= 1e-9 * abs(want), (got, want)
+dist.destroy_process_group()
+print("OK", flush=True)
+"""
+
+
+def test_scan_time_axis_sharding_gloo_world2(tmp_path):
+    """Host logic of the K3 time-axis split: ranges, all-gather of the composites, earlier composites handed to
+    each rank in time order, 2-value all-reduce — two gloo ranks around a stand-in for the device calls."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "scan_worker.py"
+    script.write_text(_SCAN_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "OK" in o, o
