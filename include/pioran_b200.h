@@ -108,6 +108,19 @@ int pioran_approx_logl(pioran_ctx *ctx, int S, const int *series_ids, const pior
 int pioran_approx_logl_dev(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,
                            int B, const double *theta_dev, int theta_per_series, double *logl_dev);
 
+/* ---- K5: gradient of the fused path (widening row) -------------------------------------------
+ * Replaces  ForwardDiff.gradient(θ -> logpdf(ScalableGP(μ, approx(𝓟(θ…), f_min, f_max, J, norm))(t, ν·σ²), y), θ)
+ * (reference test/test_likelihood.jl:24-43,55; the NUTS runs of examples/turing_distributed/single_pl.jl): forward-mode
+ * derivatives pushed through the same two kernels, one warp per (parameter vector, θ-direction).
+ * theta: [B × (n_psd_par+3)] = psd parameters…, norm, ν, μ.  logl_out: [B] or NULL.  grad_out: [B × (n_psd_par+3)],
+ * ∂logℒ/∂θ in the column order of theta. */
+int pioran_approx_logl_grad(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,
+                            const double *theta, double *logl_out, double *grad_out);
+/* Same with θ and the results resident in device memory (asynchronous on the context's stream once the work-item list is
+ * uploaded). */
+int pioran_approx_logl_grad_dev(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,
+                                const double *theta_dev, double *logl_dev, double *grad_dev);
+
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
 /* Number of time-axis chunks per parameter vector used by pioran_celerite_logl_scan (0 = automatic: two per SM, at

@@ -24,8 +24,8 @@ def build():
 
 
 def _load():
-    src = os.path.join(_HERE, "pioran_oracle.c")
-    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("pioran_oracle.c", "pioran_oracle_grad.c")]
+    if not os.path.exists(_LIB) or any(os.path.getmtime(_LIB) < os.path.getmtime(src) for src in srcs):
         build()
     lib = C.CDLL(_LIB)
     lib.orc_psd_eval.restype = C.c_double
@@ -48,6 +48,10 @@ def _load():
     lib.orc_approx_logl_batch.restype = None
     lib.orc_approx_logl_batch.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                           C.c_double, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_int]
+    lib.orc_approx_logl_grad_batch.restype = None
+    lib.orc_approx_logl_grad_batch.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
+                                               C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp,
+                                               _dp, C.c_int]
     lib.orc_celerite_logl_batch.restype = None
     lib.orc_celerite_logl_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp,
                                             _dp, C.c_int]
@@ -146,6 +150,22 @@ def approx_logl_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO", S_lo
     lib().orc_approx_logl_batch(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high,
                                 int(is_integrated_power), BASES[basis], len(t), _p(t), _p(y), _p(s2), _p(out), nthreads)
     return out
+
+
+def approx_logl_grad_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO", S_low=20.0, S_high=20.0,
+                           is_integrated_power=True, nthreads=1):
+    """Forward-mode gradient (pioran_oracle_grad.c): returns (logL[B], ∂logL/∂θ [B × (npar+3)])."""
+    m = PSD_MODELS[model]
+    theta = np.atleast_2d(_arr(theta))
+    npar = N_PSD_PAR[m]
+    assert theta.shape[1] == npar + 3
+    t, y, s2 = map(_arr, (t, y, s2))
+    out = np.empty(theta.shape[0])
+    grad = np.empty(theta.shape)
+    lib().orc_approx_logl_grad_batch(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high,
+                                     int(is_integrated_power), BASES[basis], len(t), _p(t), _p(y), _p(s2), _p(out),
+                                     _p(grad), nthreads)
+    return out, grad
 
 
 def celerite_logl_batch(a, b, c, d, t, y, s2, mu=None, nu=None, nthreads=1):

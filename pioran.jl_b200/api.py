@@ -288,5 +288,14 @@ class BatchedLikelihood:
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
         return self.ctx.approx_logl(self.series, self.spec, theta)[0]
 
+    def value_and_gradient(self, theta):
+        """(logL [B], ∂logL/∂Θ [B × n_par]) — what ForwardDiff.gradient gives the reference's HMC/NUTS runs
+        (test/test_likelihood.jl:55, examples/turing_distributed/single_pl.jl), for a whole batch of chains at once."""
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        return self.ctx.approx_logl_grad(self.series, self.spec, theta)
+
+    def gradient(self, theta):
+        return self.value_and_gradient(theta)[1]
+
     def close(self):
         self.series.free()

@@ -155,6 +155,23 @@ class Context:
         check(self.lib.pioran_approx_logl_dev(self.h, S, ids, sp, int(B), C.c_void_p(theta_ptr), int(theta_per_series),
                                               C.c_void_p(out_ptr)))
 
+    # -- K5: gradient of the fused path
+    def approx_logl_grad(self, series, spec, theta):
+        """theta rows = [psd parameters…, norm, ν, μ].  Returns (logL [B], ∂logL/∂θ [B × (npar+3)])."""
+        npar = N_PSD_PAR[spec.psd_model]
+        theta = np.atleast_2d(_f64(theta))
+        if theta.shape[1] != npar + 3:
+            raise ValueError(f"theta must have {npar + 3} columns (psd parameters, norm, ν, μ)")
+        B = theta.shape[0]
+        out, grad = np.empty(B), np.empty((B, npar + 3))
+        check(self.lib.pioran_approx_logl_grad(self.h, series.id, C.byref(spec), B, _p(theta), _p(out), _p(grad)))
+        return out, grad
+
+    def approx_logl_grad_dev(self, series, spec, B, theta_ptr, logl_ptr, grad_ptr):
+        """Device-resident variant: raw device pointers (ints); logl_ptr may be 0."""
+        check(self.lib.pioran_approx_logl_grad_dev(self.h, series.id, C.byref(spec), int(B), C.c_void_p(theta_ptr),
+                                                   C.c_void_p(logl_ptr or 0), C.c_void_p(grad_ptr)))
+
     # -- K3
     def set_scan_chunks(self, chunks):
         """Chunks of the time axis per parameter vector in celerite_logl_scan (0 = automatic)."""

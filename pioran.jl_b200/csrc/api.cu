@@ -19,6 +19,7 @@
 #include "scan.cuh"
 #include "posterior.cuh"
 #include "table.cuh"
+#include "grad.cuh"
 
 using namespace pioran;
 
@@ -84,7 +85,7 @@ struct pioran_ctx {
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
-    DevBuf theta, amp, suma, out, work, coef, rows, misc, post;
+    DevBuf theta, amp, suma, out, work, coef, rows, misc, post, gradws, gwork;
     // device time of the most recent main-kernel launch (K2/K3/K4), for bench.py's roofline line
     cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
     bool ev_valid = false;
@@ -150,7 +151,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
     for (Series* s : c->series) free_series(s);
     for (auto& kv : c->plans) cudaFree(kv.second);
     c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
-    c->coef.release(); c->rows.release(); c->misc.release(); c->post.release();
+    c->coef.release(); c->rows.release(); c->misc.release(); c->post.release(); c->gradws.release(); c->gwork.release();
     if (c->ev_beg) cudaEventDestroy(c->ev_beg);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->own) cudaStreamDestroy(c->own);
@@ -649,6 +650,104 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
                                      c->out.as<double>())))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)S * B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ gradient entry (K5)
+constexpr int GRAD_NW = 8;
+template <int BS>
+static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems) {
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    auto kern = celerite_grad_kernel<BS, GRAD_NW>;
+    const size_t smem = sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)GRAD_NW * 4 * RPS) + 2 * sizeof(uint64_t) + 16;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, GRAD_NW * 32, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
+                                       const double* theta_dev, double* logl_dev, double* grad_dev) {
+    int rc;
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    if ((rc = check_spec(*spec))) return rc;
+    Series* ser = get_series(c, series_id);
+    if (!ser) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 3, ND = npar + 1, P = npar + 3;
+    if ((long long)B * P > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "B too large");
+    const int R = rank_of(spec->basis, spec->n_components);
+    const int BS = bs_for_rank(R);
+    if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
+    const int RP = G * BS;
+    Table tab;
+    if ((rc = get_table(c, ser, *spec, &tab))) return rc;
+    ApproxPlan* plan;
+    if ((rc = get_plan(c, *spec, &plan))) return rc;
+    // workspace: amp [B×RP] | damp [B×ND×RP] | Σa [B] | dΣa [B×ND]
+    const size_t n_amp = (size_t)B * RP, n_damp = (size_t)B * ND * RP;
+    if ((rc = c->gradws.ensure(sizeof(double) * (n_amp + n_damp + (size_t)B + (size_t)B * ND)))) return rc;
+    double* amp = c->gradws.as<double>();
+    double* damp = amp + n_amp;
+    double* suma = damp + n_damp;
+    double* dsuma = suma + B;
+    const int nthr = B * ND;
+    approx_grad_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(plan, B, theta_dev, ts, amp, damp, RP, suma, dsuma);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    // one warp per (θ, direction): the work items run over the virtual batch of B·P entries
+    ItemPlan ip;
+    Series* sp[1] = {ser};
+    plan_items(c, 1, sp, &tab, B * P, GRAD_NW, false, ip);
+    if ((rc = c->gwork.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->gwork.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // ip.items is a local
+    GradArgs ga{};
+    ga.work = c->gwork.as<WorkItem>();
+    ga.amp = amp; ga.damp = damp; ga.suma = suma; ga.dsuma = dsuma;
+    ga.theta = theta_dev; ga.pstride = ts; ga.ND = ND;
+    ga.logl = logl_dev; ga.grad = grad_dev;
+    const int nitems = (int)ip.items.size();
+    switch (BS) {
+        case 4: return launch_grad<4>(c, ga, nitems);
+        case 5: return launch_grad<5>(c, ga, nitems);
+        case 6: return launch_grad<6>(c, ga, nitems);
+        case 7: return launch_grad<7>(c, ga, nitems);
+        case 8: return launch_grad<8>(c, ga, nitems);
+    }
+    return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
+}
+
+extern "C" int pioran_approx_logl_grad_dev(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
+                                           const double* theta_dev, double* logl_dev, double* grad_dev) {
+    if (!c || !spec || !theta_dev || !grad_dev) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return approx_logl_grad_dev_locked(c, series_id, spec, B, theta_dev, logl_dev, grad_dev);
+}
+
+extern "C" int pioran_approx_logl_grad(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
+                                       const double* theta, double* logl_out, double* grad_out) {
+    if (!c || !spec || !theta || !grad_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int npar = n_psd_par_of(spec->psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+    const int P = npar + 3;
+    int rc;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * P))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B * (P + 1)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * (size_t)B * P, cudaMemcpyHostToDevice, c->stream));
+    double* gl = c->out.as<double>();
+    double* gg = gl + B;
+    if ((rc = approx_logl_grad_dev_locked(c, series_id, spec, B, c->theta.as<double>(), gl, gg))) return rc;
+    if (logl_out) CUDA_TRY(cudaMemcpyAsync(logl_out, gl, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(grad_out, gg, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
 }

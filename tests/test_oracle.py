@@ -172,3 +172,26 @@ def test_negative_pivot_semantics():
     # Σa > 0 but indefinite: later pivots may be negative, result stays finite
     v = orc.celerite_logl([2.0, -1.5], [0.0, 0.0], [0.1, 5.0], [0.0, 0.0], t, y, s2)
     assert np.isfinite(v)
+
+
+# ---------------------------------------------------------------------------------------------- gradient oracle
+@pytest.mark.parametrize("basis", ["SHO", "DRWCelerite"])
+def test_gradient_oracle_value_and_finite_differences(golden_single, basis):
+    """pioran_oracle_grad.c (forward mode, what ForwardDiff does in test/test_likelihood.jl:55): the value part is the
+    pinned oracle bit for bit, the derivative part agrees with central differences of it, and is finite (:60)."""
+    g = golden_single
+    theta = g.theta[np.linspace(0, len(g.theta) - 1, 6).astype(int)].copy()
+    if basis == "DRWCelerite":
+        theta[:, 2] += 1.0
+    val, grad = orc.approx_logl_grad_batch("SBPL", theta, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)
+    plain = orc.approx_logl_batch("SBPL", theta, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)
+    assert np.array_equal(val, plain)
+    assert np.all(np.isfinite(grad))
+    for k in range(theta.shape[1]):
+        h = 1e-6 * np.maximum(1.0, np.abs(theta[:, k]))
+        tp, tm = theta.copy(), theta.copy()
+        tp[:, k] += h
+        tm[:, k] -= h
+        fd = (orc.approx_logl_batch("SBPL", tp, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)
+              - orc.approx_logl_batch("SBPL", tm, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)) / (2 * h)
+        assert np.allclose(grad[:, k], fd, rtol=2e-5, atol=1e-6 * np.abs(grad[:, k]).max()), (k, grad[:, k], fd)
