@@ -300,7 +300,7 @@ def config_c3(torch, ctx, pb, J, peak):
 
 
 def widening_rows(ctx, pb, J):
-    """SURVEY 8f #2/#3 next to the hot path: batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
+    """SURVEY 8f #1/#2/#3 next to the hot path: gradients (4 096 θ × 6 directions), batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
     bounded sample of the same batch."""
     from oracle import oracle as orc
@@ -332,6 +332,22 @@ def widening_rows(ctx, pb, J):
         oks = np.isfinite(np.array(refs)) & np.isfinite(ys[:ncpu])
         serr = float(np.max(np.abs(ys[:ncpu][oks] - np.array(refs)[oks]) / np.maximum(1.0, np.abs(np.array(refs)[oks]))))
         ser.free()
+        # gradients for HMC/NUTS (K5) — 4 096 parameter vectors, all 6 partial derivatives each
+        like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+        like.value_and_gradient(th)
+        gval, ggrad = like.value_and_gradient(th)
+        ms_g = ctx.last_kernel_ms()
+        like.close()
+        t0 = time.perf_counter()
+        ng = 32
+        oval, ograd = orc.approx_logl_grad_batch("SBPL", th[:ng], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        cpu_g = (time.perf_counter() - t0) / ng
+        okg = np.isfinite(ograd).all(axis=1) & np.isfinite(oval)
+        gscale = np.maximum(np.abs(ograd), np.abs(ograd).max(axis=0, keepdims=True))
+        gerr = float((np.abs(ggrad[:ng] - ograd) / gscale)[okg].max())
+        out[f"gradient_4096theta_N1000_{basis}"] = {"gradients_per_s": 4096 / (ms_g * 1e-3), "device_ms": ms_g,
+                                                    "cpu_port_forward_mode_gradients_per_s": 1.0 / cpu_g,
+                                                    "cpu_threads": orc.max_threads(), "parity_max_rel_32": gerr}
         out[f"predict_512theta_N1000_M2000_{basis}"] = {"posterior_means_per_s": Bp / (ms_p * 1e-3), "device_ms": ms_p,
                                                         "cpu_port_1thread_means_per_s": 1.0 / cpu_p, "parity_max_rel_4": perr}
         out[f"simulate_4096theta_N1000_{basis}"] = {"draws_per_s": 4096 / (ms_s * 1e-3), "device_ms": ms_s,
