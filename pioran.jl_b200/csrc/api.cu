@@ -658,9 +658,8 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
 constexpr int GRAD_NW = 8;
 template <int BS>
 static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems) {
-    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
     auto kern = celerite_grad_kernel<BS, GRAD_NW>;
-    const size_t smem = sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)GRAD_NW * 4 * RPS) + 2 * sizeof(uint64_t) + 16;
+    const size_t smem = grad_smem_bytes<BS, GRAD_NW>();
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
     kern<<<nitems, GRAD_NW * 32, smem, c->stream>>>(args);
