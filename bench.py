@@ -111,6 +111,14 @@ def fp64_peak_tflops():
         return 37.0, "fallback: nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz"
 
 
+def hbm_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6550.0
+
+
 def k2_traffic_bytes(basis, B, N):
     """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch of this shape, from the committed `ncu --set full`
     capture (profiles/r01_k2_traffic.json, written by tools/ncu_summary.py); None when no capture matches the shape."""
@@ -299,6 +307,54 @@ def config_c3(torch, ctx, pb, J, peak):
             "fp64_frac": fl / (k2 * 1e-3) / 1e12 / peak, "finite_frac": float(np.isfinite(out).mean())}
 
 
+def config_c4_c5(ctx, pb, hbm_peak):
+    """BASELINE configs[3] and [4] on one GPU.  C4: one series of N = 1e6, SHO J = 30 (rank 60), parallel-in-time scan (K3):
+    device ms, achieved HBM GB/s on the algorithmic bytes (48 N + composites written and read), parity against ONE evaluation
+    of the CPU restatement.  C5: 64 parameter vectors x N = 2 000, batched dense Cholesky (K4) against the celerite kernel
+    (K2): tolerance report |Δ|/max(1, |logL|)."""
+    from oracle import oracle as orc
+    out = {}
+    N = 1_000_000
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=4)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 30)
+    a, b, c, d = ctx.approx_coeffs(spec, np.array([[0.82, 0.01, 3.3, float(np.var(y))]]))
+    ser = ctx.upload_series(t, y, s2)
+    ms = []
+    for _ in range(4):
+        v = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
+        ms.append(ctx.last_kernel_ms())
+    k3 = float(np.mean(ms[1:]))
+    ser.free()
+    t0 = time.perf_counter()
+    ref = orc.celerite_logl(a[0], b[0], c[0], d[0], t, y, s2)
+    cpu_s = time.perf_counter() - t0
+    P = 296
+    abytes = 48.0 * N + 2.0 * P * (3 * 64 * 64 + 2 * 64) * 8
+    R = 60
+    out["C4_long_series_N1e6_SHO_J30"] = {
+        "device_ms": k3, "cpu_port_1thread_ms": cpu_s * 1e3, "parity_rel": float(abs(v - ref) / max(1.0, abs(ref))),
+        "algorithmic_bytes": abytes, "hbm_gbs": abytes / (k3 * 1e-3) / 1e9, "hbm_frac": abytes / (k3 * 1e-3) / 1e9 / hbm_peak,
+        "fp64_tflops_sequential_model": N * wl.flops_per_step(R) / (k3 * 1e-3) / 1e12,
+        "note": "latency/FP64-bound, not HBM-bound (DESIGN.md K3): three passes over 296 chunks of the time axis"}
+    t, y, s2, f_min, f_max = wl.make_series(2000, 5)
+    th = wl.prior_theta(64, f_min, f_max, y.mean(), y.std(), 7)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20)
+    ser = ctx.upload_series(t, y, s2)
+    a, b, c, d = ctx.approx_coeffs(spec, th[:, :4])
+    for _ in range(2):
+        nll, info = ctx.direct_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4])
+        k4 = ctx.last_kernel_ms()
+    cel = ctx.celerite_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4])
+    ser.free()
+    ok = (info == 0) & np.isfinite(cel)
+    dlt = np.abs(-nll[ok] - cel[ok]) / np.maximum(1.0, np.abs(cel[ok]))
+    out["C5_dense_crosscheck_64theta_N2000"] = {
+        "device_ms": k4, "dense_logl_per_s": 64 / (k4 * 1e-3), "positive_definite": int(ok.sum()),
+        "tolerance_max": float(dlt.max()), "tolerance_median": float(np.median(dlt)),
+        "dense_fp64_tflops": 64 * (2000.0 ** 3 / 3.0) / (k4 * 1e-3) / 1e12}
+    return out
+
+
 def widening_rows(ctx, pb, J):
     """SURVEY 8f #1/#2/#3 next to the hot path: gradients (4 096 θ × 6 directions), batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
@@ -418,6 +474,7 @@ def run_b200(args, rank, world, local_rank):
 
     if not args.no_extra and world == 1:
         extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
+        extra.update(config_c4_c5(ctx, pb, hbm_peak_gbs()))
         extra.update(widening_rows(ctx, pb, args.J))
 
     cpu = None
