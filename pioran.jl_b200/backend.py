@@ -173,6 +173,10 @@ class Context:
                                                    C.c_void_p(logl_ptr or 0), C.c_void_p(grad_ptr)))
 
     # -- K3
+    def set_auto_scan(self, enabled=True):
+        """Whether celerite_logl / approx_logl route ≤ 4 evaluations of a series of ≥ 4 096 steps to the scan path."""
+        check(self.lib.pioran_ctx_set_auto_scan(self.h, int(bool(enabled))))
+
     def set_scan_chunks(self, chunks):
         """Chunks of the time axis per parameter vector in celerite_logl_scan (0 = automatic)."""
         check(self.lib.pioran_ctx_set_scan_chunks(self.h, int(chunks)))

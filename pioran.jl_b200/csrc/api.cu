@@ -20,6 +20,7 @@
 #include "posterior.cuh"
 #include "table.cuh"
 #include "grad.cuh"
+#include "wide.cuh"
 
 using namespace pioran;
 
@@ -94,6 +95,7 @@ struct pioran_ctx {
     std::vector<int64_t> work_key;
     int work_items = 0;
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
+    bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
     std::mutex mu;
 };
 
@@ -104,6 +106,17 @@ static int bs_for_rank(int R) {
     if (bs < 4) bs = 4;
     return bs;
 }
+
+// A handful of evaluations of one long series is latency-bound in the sequential sweep (≈ 0.9 µs per step whatever the rank);
+// from a few thousand steps on the parallel-in-time path K3 is faster (tools/scan_vs_seq.py: 2.0–2.2 vs 3.9–8.2 ms at N = 4 096, 2.5–2.9 vs 7.8–16 ms at N = 8 192,
+// 5–6 vs 62–130 ms at N = 65 536), so the plain entries route such calls to it.  Same value to ≤ 1e-13 relative.
+constexpr int64_t AUTO_SCAN_MIN_STEPS = 4096;
+constexpr int AUTO_SCAN_MAX_BATCH = 4;
+static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R) {
+    return c->auto_scan && N >= AUTO_SCAN_MIN_STEPS && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
+}
+static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
+                            const double* cc, const double* d, const double* mu, const double* nu, double* logl_out);
 
 static void scan_forget(pioran_ctx* c);   // drops the range-in-progress record of a context (K3 multi-GPU entries)
 extern "C" int pioran_ctx_destroy(pioran_ctx* c);
@@ -530,6 +543,22 @@ static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* ta
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wide ranks (K2w)
+// Ranks above 64 (block size > 8): state in shared memory, one CTA per parameter vector (wide.cuh).
+static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    if (args.R > WIDE_MAX_RANK)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", args.R, WIDE_MAX_RANK);
+    const size_t smem = sizeof(double) * wide_smem_doubles(wide_geom(args.R));
+    CUDA_TRY(cudaFuncSetAttribute(celerite_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    celerite_wide_kernel<<<nitems, WIDE_THREADS, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ K1 entry
 extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spec, int B, const double* theta,
                                     double* a, double* b, double* cc, double* d) {
@@ -579,7 +608,47 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     const int npar = n_psd_par_of(specs[0].psd_model), ts = npar + 3;
     const int R = rank_of(specs[0].basis, specs[0].n_components);
     const int BS = bs_for_rank(R);
-    if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
+    if (BS > 8) {
+        // ranks above 64: K1 writes explicit coefficients, the shared-memory-state kernel sweeps one CTA per (series, θ)
+        if (R > WIDE_MAX_RANK) return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", R, WIDE_MAX_RANK);
+        const int J = specs[0].n_components;
+        const int Jt = specs[0].basis == PIORAN_BASIS_SHO ? J : 2 * J;
+        std::vector<int> term_row(Jt);
+        for (int m = 0; m < Jt; m++) term_row[m] = (m < J) ? 2 * m : -(2 * J + (m - J) + 1);   // src/psd.jl:264-275: DRW parts are real terms
+        const size_t n = (size_t)B * Jt;
+        if ((rc = c->coef.ensure(sizeof(double) * (size_t)S * n * 4))) return rc;
+        if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1)))) return rc;
+        if ((rc = c->work.ensure(sizeof(WorkItem) * (size_t)S * B))) return rc;
+        c->work_key.clear();
+        std::vector<WorkItem> items;
+        items.reserve((size_t)S * B);
+        for (int s = 0; s < S; s++) {
+            ItemPlan ip;
+            plan_items(c, 1, &ser[s], nullptr, B, 1, false, ip);
+            items.insert(items.end(), ip.items.begin(), ip.items.end());
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->rows.p, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // term_row and items are locals
+        for (int s = 0; s < S; s++) {
+            ApproxPlan* plan;
+            if ((rc = get_plan(c, specs[s], &plan))) return rc;
+            const double* th = theta_dev + (theta_per_series ? (size_t)s * B * ts : 0);
+            double* da = c->coef.as<double>() + (size_t)s * n * 4;
+            approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, th, ts, da, da + n, da + 2 * n, da + 3 * n, nullptr, 0,
+                                                                 nullptr);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+            BatchArgs args{};
+            args.work = c->work.as<WorkItem>() + (size_t)s * B;
+            args.a = da; args.b = da + n; args.c = da + 2 * n; args.d = da + 3 * n;
+            args.Jt = Jt; args.term_row = c->rows.as<int>(); args.R = R;
+            args.mu = th + npar + 2; args.nu = th + npar + 1; args.pstride = ts;
+            args.out = logl_dev + (size_t)s * B;
+            if ((rc = launch_wide(c, args, B))) return rc;
+        }
+        return 0;
+    }
     const int RP = G * BS;
     for (int s = 0; s < S; s++)
         if ((rc = get_table(c, ser[s], specs[s], &tabs[s]))) return rc;
@@ -643,6 +712,31 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
     const int ts = npar + 3;
     const size_t nth = (size_t)(theta_per_series ? S : 1) * B * ts;
     int rc;
+    if (S == 1 && (rc = check_spec(specs[0])) == 0) {
+        Series* s0 = get_series(c, series_ids[0]);
+        const int R0 = rank_of(specs[0].basis, specs[0].n_components);
+        if (s0 && auto_scan(c, s0->N, B, R0)) {
+            // few parameter vectors, long series: K1 on the device, coefficients back to the host, parallel-in-time sweep
+            ApproxPlan* plan;
+            if ((rc = get_plan(c, specs[0], &plan))) return rc;
+            const int J = specs[0].n_components, Jt = specs[0].basis == PIORAN_BASIS_SHO ? J : 2 * J;
+            const size_t n = (size_t)B * Jt;
+            if ((rc = c->theta.ensure(sizeof(double) * nth))) return rc;
+            if ((rc = c->coef.ensure(sizeof(double) * n * 4))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
+            double* da = c->coef.as<double>();
+            approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, c->theta.as<double>(), ts, da, da + n, da + 2 * n,
+                                                                 da + 3 * n, nullptr, 0, nullptr);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+            std::vector<double> co(4 * n), mu(B), nu(B);
+            CUDA_TRY(cudaMemcpyAsync(co.data(), da, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < B; i++) { nu[i] = theta[(size_t)i * ts + npar + 1]; mu[i] = theta[(size_t)i * ts + npar + 2]; }
+            return scan_logl_locked(c, s0, series_ids[0], B, Jt, co.data(), co.data() + n, co.data() + 2 * n, co.data() + 3 * n,
+                                    mu.data(), nu.data(), logl_out);
+        }
+    }
     if ((rc = c->theta.ensure(sizeof(double) * nth))) return rc;
     if ((rc = c->out.ensure(sizeof(double) * (size_t)S * B))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * nth, cudaMemcpyHostToDevice, c->stream));
@@ -797,9 +891,12 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
     std::vector<int> term_row;
     const int R = make_term_rows(B, Jt, b, d, term_row);
+    if (!y_batch && !s2_batch && auto_scan(c, s->N, B, R))
+        return scan_logl_locked(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, logl_out);
     const int BS = bs_for_rank(R);
-    if (BS > 8)
-        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) needs block size %d > 8; this build supports rank <= 64", R, Jt, BS);
+    const bool wide = BS > 8;
+    if (wide && R > WIDE_MAX_RANK)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds this build's limit of %d", R, Jt, WIDE_MAX_RANK);
     int rc;
     GenericInputs gi;
     if ((rc = upload_generic(c, B, Jt, s->N, a, b, cc, d, mu, nu, y_batch, s2_batch, gi))) return rc;
@@ -808,7 +905,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
     ItemPlan ip;
     Series* sp = s;
-    plan_items(c, 1, &sp, nullptr, B, nw_for_bs(BS), false, ip);
+    plan_items(c, 1, &sp, nullptr, B, wide ? 1 : nw_for_bs(BS), false, ip);
     c->work_key.clear();  // the work buffer is shared with the fused path's cached plan
     if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -823,7 +920,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
     args.y_batch = gi.yb; args.s2_batch = gi.sb; args.ystride = s->N;
     args.out = c->out.as<double>();
-    if ((rc = dispatch_generic(c, BS, args, (int)ip.items.size()))) return rc;
+    if ((rc = wide ? launch_wide(c, args, (int)ip.items.size()) : dispatch_generic(c, BS, args, (int)ip.items.size()))) return rc;
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
@@ -958,6 +1055,12 @@ static int make_term_rows(int B, int Jt, const double* b, const double* d, std::
     return R;
 }
 
+extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    c->auto_scan = enabled != 0;
+    return PIORAN_OK;
+}
+
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
@@ -994,8 +1097,14 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     if (BS > 8 || R > SR)
         return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
     const int64_t N = s->N, len = n_hi - n_lo;
-    // chunking: enough chunks to give every SM two re-filter warps, at least 64 steps per chunk
-    int P = c->scan_chunks > 0 ? c->scan_chunks : 2 * c->num_sms;
+    // chunking.  The path costs ≈ 2·(len/P)·τ_step (fold + re-filter of one chunk, τ_step ≈ 2.2 µs) + 2·√P·τ_comb (the two
+    // sequential levels of the scan, τ_comb ≈ 0.24 ms): the optimum is P ≈ (0.018·len)^(2/3) (37 at 16 k steps, 111 at 65 k),
+    // capped at two chunks per SM (one fold CTA per SM is resident) shared among the B parameter vectors, ≥ 64 steps per chunk.
+    int P = c->scan_chunks;
+    if (P <= 0) {
+        P = (int)std::lround(std::pow(0.018 * (double)len, 2.0 / 3.0));
+        P = std::max(8, std::min(P, std::max(8, 2 * c->num_sms / std::max(1, B))));
+    }
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
     const int G2 = (int)std::ceil(std::sqrt((double)P));
     const int G1 = (P + G2 - 1) / G2;
@@ -1094,15 +1203,8 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     return dispatch_chunked(c, run.BS, args, (int)(nitems / NW));
 }
 
-extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
-                                         const double* cc, const double* d, const double* mu, const double* nu,
-                                         double* logl_out) {
-    if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
-    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
-    CUDA_TRY(cudaSetDevice(c->device));
-    Series* s = get_series(c, series_id);
-    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
+                            const double* cc, const double* d, const double* mu, const double* nu, double* logl_out) {
     ScanRun run;
     int rc;
     cudaEventRecord(c->ev_beg, c->stream);
@@ -1116,6 +1218,18 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
     CUDA_TRY(cudaMemcpyAsync(logl_out, run.out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
+}
+
+extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
+                                         const double* cc, const double* d, const double* mu, const double* nu,
+                                         double* logl_out) {
+    if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    return scan_logl_locked(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, logl_out);
 }
 
 // ---- time axis split across GPUs: each rank folds its own step range, the ranks exchange one composite each,

@@ -79,9 +79,11 @@ def test_config_c4_long_series_n1e6_j30(pb, ctx):
     t0 = time.perf_counter()
     got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
     wall_scan, dev_scan = time.perf_counter() - t0, ctx.last_kernel_ms()
+    ctx.set_auto_scan(False)                                   # the plain entry would route this call to the scan path
     t0 = time.perf_counter()
     seq = ctx.celerite_logl(ser, a, b, c, d)[0]
     wall_seq = time.perf_counter() - t0
+    ctx.set_auto_scan(True)
     t0 = time.perf_counter()
     want = orc.celerite_logl(a, b, c, d, t, y, s2)
     wall_cpu = time.perf_counter() - t0
@@ -125,3 +127,28 @@ def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks):
     for s_, cx in zip(sers, ctxs):
         s_.free()
         cx.close()
+
+
+def test_auto_dispatch_to_scan(pb, ctx):
+    """A single evaluation of a long series through the PLAIN entries (generic and fused) takes the parallel-in-time path
+    (include/pioran_b200.h: pioran_ctx_set_auto_scan) and returns the sequential kernel's value."""
+    t, y, s2, f_min, f_max = synthetic_series(12000, seed=21)
+    theta = np.array([[0.82, 0.01, 3.3, 1.0, 1.3, 0.2]])
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20)
+    a, b, c, d = ctx.approx_coeffs(spec, theta[:, :4])
+    ser = ctx.upload_series(t, y, s2)
+    n0 = ctx.launch_count
+    auto_gen = ctx.celerite_logl(ser, a, b, c, d, mu=theta[:, 5], nu=theta[:, 4])[0]
+    launches_auto = ctx.launch_count - n0
+    auto_fused = ctx.approx_logl(ser, spec, theta)[0, 0]
+    ctx.set_auto_scan(False)
+    n0 = ctx.launch_count
+    seq_gen = ctx.celerite_logl(ser, a, b, c, d, mu=theta[:, 5], nu=theta[:, 4])[0]
+    launches_seq = ctx.launch_count - n0
+    seq_fused = ctx.approx_logl(ser, spec, theta)[0, 0]
+    ctx.set_auto_scan(True)
+    ser.free()
+    assert launches_auto > launches_seq == 1          # the scan path is several kernels, the sequential sweep one
+    want = orc.celerite_logl(a[0], b[0], c[0], d[0], t, y - theta[0, 5], theta[0, 4] * s2)
+    for v in (auto_gen, auto_fused, seq_gen, seq_fused):
+        assert rel_err(v, want) <= TOL, (v, want)
