@@ -93,7 +93,7 @@ struct pioran_ctx {
     // the work-item list of the last fused call, kept on the device while the call shape repeats (a sampler
     // evaluates the same series × batch-size shape ~1e5 times)
     std::vector<int64_t> work_key;
-    int work_items = 0;
+    int work_items = 0, work_tpi = 0;
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
     std::mutex mu;
@@ -384,13 +384,18 @@ static size_t generic_smem_bytes(int Jt) {
     return sizeof(double) * (size_t)KCfg<BS>::NW * ((size_t)GCH * SD + 2 * RPS + (size_t)(((GCH + 2) * Jt + 1) & ~1));
 }
 
-template <int BS>
+// Small batches (at most SMALL_NW parameter vectors per CTA, i.e. S·B ≤ 4 × SMs — a nested sampler's few hundred live
+// points): a CTA of 4 warps, one per SM sub-partition.  The full-size CTA would fill its surplus warps with redundant
+// sweeps that share the FP64 pipe of the useful ones and roughly double the latency of the call.
+constexpr int SMALL_NW = 4;
+template <int BS, int NW = KCfg<BS>::NW>
 static int launch_shared(pioran_ctx* c, const BatchArgs& args, int nitems) {
-    auto kern = celerite_shared_kernel<BS, KCfg<BS>::NW>;
-    const size_t smem = shared_smem_bytes<BS>();
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    auto kern = celerite_shared_kernel<BS, NW>;
+    const size_t smem = sizeof(double) * (2 * (size_t)CHUNK_STEPS * SD + (size_t)NW * 2 * RPS) + 2 * sizeof(uint64_t) + 16;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
-    kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     c->launches++;
@@ -421,13 +426,14 @@ static int launch_shared_pair(pioran_ctx* c, const BatchArgs& args, int nitems) 
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-template <int BS>
+template <int BS, int NW = KCfg<BS>::NW>
 static int launch_generic(pioran_ctx* c, const BatchArgs& args, int nitems) {
-    auto kern = celerite_generic_kernel<BS, KCfg<BS>::NW>;
-    const size_t smem = generic_smem_bytes<BS>(args.Jt);
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS);
+    auto kern = celerite_generic_kernel<BS, NW>;
+    const size_t smem = sizeof(double) * (size_t)NW * ((size_t)GCH * SD + 2 * RPS + (size_t)(((GCH + 2) * args.Jt + 1) & ~1));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
-    kern<<<nitems, KCfg<BS>::NW * 32, smem, c->stream>>>(args);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     c->launches++;
@@ -461,7 +467,23 @@ static int dispatch_chunked(pioran_ctx* c, int BS, const BatchArgs& a, int nctas
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
 
-static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems, int tpi) {
+    if (tpi <= SMALL_NW) {
+        switch (BS) {
+            case 4: return launch_shared<4, SMALL_NW>(c, a, nitems);
+            case 5: return launch_shared<5, SMALL_NW>(c, a, nitems);
+            case 6: return launch_shared<6, SMALL_NW>(c, a, nitems);
+            case 7: return launch_shared<7, SMALL_NW>(c, a, nitems);
+            case 8: return launch_shared<8, SMALL_NW>(c, a, nitems);
+        }
+    }
+    if (tpi <= 8 && BS <= 6) {   // two warps per sub-partition, one parameter vector each
+        switch (BS) {
+            case 4: return launch_shared<4, 8>(c, a, nitems);
+            case 5: return launch_shared<5, 8>(c, a, nitems);
+            case 6: return launch_shared<6, 8>(c, a, nitems);
+        }
+    }
     if (pair_enabled(BS)) {
         if (BS == 4) return launch_shared_pair<4>(c, a, nitems);
         if (BS == 5) return launch_shared_pair<5>(c, a, nitems);
@@ -475,7 +497,16 @@ static int dispatch_shared(pioran_ctx* c, int BS, const BatchArgs& a, int nitems
     }
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
-static int dispatch_generic(pioran_ctx* c, int BS, const BatchArgs& a, int nitems) {
+static int dispatch_generic(pioran_ctx* c, int BS, const BatchArgs& a, int nitems, int tpi) {
+    if (tpi <= SMALL_NW) {
+        switch (BS) {
+            case 4: return launch_generic<4, SMALL_NW>(c, a, nitems);
+            case 5: return launch_generic<5, SMALL_NW>(c, a, nitems);
+            case 6: return launch_generic<6, SMALL_NW>(c, a, nitems);
+            case 7: return launch_generic<7, SMALL_NW>(c, a, nitems);
+            case 8: return launch_generic<8, SMALL_NW>(c, a, nitems);
+        }
+    }
     switch (BS) {
         case 4: return launch_generic<4>(c, a, nitems);
         case 5: return launch_generic<5>(c, a, nitems);
@@ -511,7 +542,7 @@ static int dispatch_generic_mode(pioran_ctx* c, int BS, const BatchArgs& a, int 
 
 // Splits S series × B parameter vectors into CTA work items of at most NW vectors, sized so that the number of
 // items is close to a multiple of the SM count (one CTA per SM is resident), longest series first.
-struct ItemPlan { std::vector<WorkItem> items; };
+struct ItemPlan { std::vector<WorkItem> items; int tpi = 0; };
 static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* tabs, int B, int NW, bool theta_per_series,
                        ItemPlan& ip) {
     const long long E = (long long)S * B;
@@ -521,6 +552,7 @@ static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* ta
     const long long waves = (items + c->num_sms - 1) / c->num_sms;
     const long long target = waves * c->num_sms;
     tpi = (int)std::min<long long>(NW, std::max<long long>(1, (E + target - 1) / target));
+    ip.tpi = tpi;
     std::vector<int> order(S);
     for (int s = 0; s < S; s++) order[s] = s;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return ser[x]->N > ser[y]->N; });
@@ -680,6 +712,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
         CUDA_TRY(cudaStreamSynchronize(c->stream));  // ip.items is a local; only when the call shape changes
         c->work_key = key;
         c->work_items = (int)ip.items.size();
+        c->work_tpi = ip.tpi;
     }
     const int nitems = c->work_items;
     BatchArgs args{};
@@ -690,7 +723,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     args.nu = theta_dev + npar + 1;
     args.pstride = ts;
     args.out = logl_dev;
-    return dispatch_shared(c, BS, args, nitems);
+    return dispatch_shared(c, BS, args, nitems, c->work_tpi);
 }
 
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
@@ -750,18 +783,23 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
 
 // ------------------------------------------------------------------------------------------------ gradient entry (K5)
 constexpr int GRAD_NW = 8;
-template <int BS>
-static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems) {
-    auto kern = celerite_grad_kernel<BS, GRAD_NW>;
-    const size_t smem = grad_smem_bytes<BS, GRAD_NW>();
+template <int BS, int NW>
+static int launch_grad_nw(pioran_ctx* c, const GradArgs& args, int nitems) {
+    auto kern = celerite_grad_kernel<BS, NW>;
+    const size_t smem = grad_smem_bytes<BS, NW>();
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
-    kern<<<nitems, GRAD_NW * 32, smem, c->stream>>>(args);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+// a few chains (≤ 4 (θ, direction) pairs per CTA): one warp per SM sub-partition, as for the likelihood (SMALL_NW)
+template <int BS>
+static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems, int tpi) {
+    return tpi <= SMALL_NW ? launch_grad_nw<BS, SMALL_NW>(c, args, nitems) : launch_grad_nw<BS, GRAD_NW>(c, args, nitems);
 }
 static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                        const double* theta_dev, double* logl_dev, double* grad_dev) {
@@ -806,11 +844,11 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     ga.logl = logl_dev; ga.grad = grad_dev;
     const int nitems = (int)ip.items.size();
     switch (BS) {
-        case 4: return launch_grad<4>(c, ga, nitems);
-        case 5: return launch_grad<5>(c, ga, nitems);
-        case 6: return launch_grad<6>(c, ga, nitems);
-        case 7: return launch_grad<7>(c, ga, nitems);
-        case 8: return launch_grad<8>(c, ga, nitems);
+        case 4: return launch_grad<4>(c, ga, nitems, ip.tpi);
+        case 5: return launch_grad<5>(c, ga, nitems, ip.tpi);
+        case 6: return launch_grad<6>(c, ga, nitems, ip.tpi);
+        case 7: return launch_grad<7>(c, ga, nitems, ip.tpi);
+        case 8: return launch_grad<8>(c, ga, nitems, ip.tpi);
     }
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
@@ -920,7 +958,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
     args.y_batch = gi.yb; args.s2_batch = gi.sb; args.ystride = s->N;
     args.out = c->out.as<double>();
-    if ((rc = wide ? launch_wide(c, args, (int)ip.items.size()) : dispatch_generic(c, BS, args, (int)ip.items.size()))) return rc;
+    if ((rc = wide ? launch_wide(c, args, (int)ip.items.size()) : dispatch_generic(c, BS, args, (int)ip.items.size(), ip.tpi))) return rc;
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
