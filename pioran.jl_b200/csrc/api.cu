@@ -113,7 +113,7 @@ static int bs_for_rank(int R) {
 constexpr int64_t AUTO_SCAN_MIN_STEPS = 4096;
 constexpr int AUTO_SCAN_MAX_BATCH = 4;
 static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R) {
-    return c->auto_scan && N >= AUTO_SCAN_MIN_STEPS && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
+    return c->auto_scan && N >= (R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS) && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
 }
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
                             const double* cc, const double* d, const double* mu, const double* nu, double* logl_out);
@@ -1119,6 +1119,7 @@ struct ScanRun {
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
 };
+static int scan_live_rank(int R) { return std::min(SR, (R + 3) & ~3); }
 static std::map<pioran_ctx*, ScanRun> g_scan;
 static std::mutex g_scan_mu;
 static void scan_forget(pioran_ctx* c) { std::lock_guard<std::mutex> g(g_scan_mu); g_scan.erase(c); }
@@ -1136,11 +1137,13 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
         return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
     const int64_t N = s->N, len = n_hi - n_lo;
     // chunking.  The path costs ≈ 2·(len/P)·τ_step (fold + re-filter of one chunk, τ_step ≈ 2.2 µs) + 2·√P·τ_comb (the two
-    // sequential levels of the scan, τ_comb ≈ 0.24 ms): the optimum is P ≈ (0.018·len)^(2/3) (37 at 16 k steps, 111 at 65 k),
+    // sequential levels of the scan, τ_comb ≈ 0.24 ms at rank 64): the optimum is P ≈ (τ_step·len/τ_comb)^(2/3) (37 at 16 k steps, 111 at 65 k),
     // capped at two chunks per SM (one fold CTA per SM is resident) shared among the B parameter vectors, ≥ 64 steps per chunk.
     int P = c->scan_chunks;
     if (P <= 0) {
-        P = (int)std::lround(std::pow(0.018 * (double)len, 2.0 / 3.0));
+        // τ_comb shrinks with the live rank (the sequential parts of a combine stop at it): ≈ 0.03 + 0.21·R/64 ms
+        const double tau_comb_ms = 0.03 + 0.21 * (double)std::min(SR, (R + 3) & ~3) / SR;
+        P = (int)std::lround(std::pow(4.3e-3 / tau_comb_ms * (double)len, 2.0 / 3.0));
         P = std::max(8, std::min(P, std::max(8, 2 * c->num_sms / std::max(1, B))));
     }
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
@@ -1191,11 +1194,11 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     CUDA_TRY(cudaFuncSetAttribute(scan_total_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     if (P > 1 || want_total) {
-        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.pref, P, G2);
+        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.pref, P, G2, scan_live_rank(run.R));
         c->launches++;
     }
     if (want_total) {
-        scan_total_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.scratch, run.total, P, G2, G1);
+        scan_total_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.scratch, run.total, P, G2, G1, scan_live_rank(run.R));
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1226,9 +1229,9 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // items is a local
     if (P > 1 || init_dev) {
-        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, P, run.G2, run.G1, init_dev);
+        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, P, run.G2, run.G1, init_dev, scan_live_rank(run.R));
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
-                                                                             init_dev ? 1 : 0);
+                                                                             init_dev ? 1 : 0, scan_live_rank(run.R));
         c->launches += 2;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1309,7 +1312,7 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
     const double* init = nullptr;
     if (nprev > 0) {
         CUDA_TRY(cudaMemcpyAsync(run.prev, composites_prev, sizeof(double) * (size_t)nprev * SEL, cudaMemcpyHostToDevice, c->stream));
-        scan_chain_kernel<<<dim3(1, 1), 256, SCAN_SMEM_BYTES, c->stream>>>(run.prev, nprev, 1, run.init);
+        scan_chain_kernel<<<dim3(1, 1), 256, SCAN_SMEM_BYTES, c->stream>>>(run.prev, nprev, 1, run.init, scan_live_rank(run.R));
         c->launches++;
         init = run.init;
     }

@@ -224,14 +224,14 @@ __device__ __forceinline__ void sm_store(double* __restrict__ dst, const double*
 // dst_s must not alias X or Y.
 template <bool TX, bool TY>
 __device__ __forceinline__ void sm_matmul(double* dst_s, double* dst_g, const double* X, const double* Y,
-                                       const double* addend, bool symmetrise) {
+                                       const double* addend, bool symmetrise, int Rr) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double acc[4][4];
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
-    for (int k = 0; k < SR; k++) {
+    for (int k = 0; k < Rr; k++) {
         double xv[4], yv[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) xv[r] = TX ? X[k * SLD + 4 * ty + r] : X[(4 * ty + r) * SLD + k];
@@ -269,18 +269,20 @@ __device__ __forceinline__ void sm_matmul(double* dst_s, double* dst_g, const do
 }
 // y = op(X)·x (+ y0) for a shared matrix and shared vectors; threads 0..63 each one row.  No trailing barrier.
 template <bool TX>
-__device__ __forceinline__ double sm_matvec_row(const double* X, const double* x, int row) {
+__device__ __forceinline__ double sm_matvec_row(const double* X, const double* x, int row, int Rr) {
     double acc = 0.0;
-    for (int k = 0; k < SR; k++) acc = fma(TX ? X[k * SLD + row] : X[row * SLD + k], x[k], acc);
+    for (int k = 0; k < Rr; k++) acc = fma(TX ? X[k * SLD + row] : X[row * SLD + k], x[k], acc);
     return acc;
 }
 // In-place LU with partial pivoting of a shared SR×SR matrix; perm[k] = row swapped with k at step k.
-__device__ __forceinline__ void sm_lu(double* M, int* perm) {
+__device__ __forceinline__ void sm_lu(double* M, int* perm, int Rr) {
     __shared__ int piv_s;
-    for (int k = 0; k < SR; k++) {
+    for (int k = threadIdx.x; k < SR; k += blockDim.x) perm[k] = k;     // rows ≥ Rr: identity, no interchange
+    __syncthreads();
+    for (int k = 0; k < Rr; k++) {
         if (threadIdx.x < 32) {
             double best = -1.0; int bi = k;
-            for (int r = k + (int)threadIdx.x; r < SR; r += 32) {
+            for (int r = k + (int)threadIdx.x; r < Rr; r += 32) {
                 const double v = fabs(M[r * SLD + k]);
                 if (v > best) { best = v; bi = r; }
             }
@@ -302,13 +304,13 @@ __device__ __forceinline__ void sm_lu(double* M, int* perm) {
         __syncthreads();
         const double inv = 1.0 / M[k * SLD + k];
         __syncthreads();
-        for (int r = k + 1 + (int)threadIdx.x; r < SR; r += blockDim.x) M[r * SLD + k] *= inv;
+        for (int r = k + 1 + (int)threadIdx.x; r < Rr; r += blockDim.x) M[r * SLD + k] *= inv;
         __syncthreads();
         {   // trailing update, 16×16 thread grid striding over the remaining (SR−k−1)² block
             const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-            for (int r = k + 1 + ty; r < SR; r += 16) {
+            for (int r = k + 1 + ty; r < Rr; r += 16) {
                 const double l = M[r * SLD + k];
-                for (int c = k + 1 + tx; c < SR; c += 16) M[r * SLD + c] = fma(-l, M[k * SLD + c], M[r * SLD + c]);
+                for (int c = k + 1 + tx; c < Rr; c += 16) M[r * SLD + c] = fma(-l, M[k * SLD + c], M[r * SLD + c]);
             }
         }
         __syncthreads();
@@ -319,7 +321,7 @@ __device__ __forceinline__ void sm_lu(double* M, int* perm) {
 // column slots in the CTA); the column stays in shared memory.  Rolled loops: the first version kept each column in the
 // registers of one thread with both triangular sweeps fully unrolled — 8 000 FMAs of straight-line code per call, far
 // beyond the instruction cache, and 0.28 ms per combine.
-__device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, double* RHS, double* vecs, int nvec) {
+__device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, double* RHS, double* vecs, int nvec, int Rr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / 3, part = lane - 3 * grp;          // lanes 30, 31 idle (grp = 10)
     const int slot = warp * 10 + grp;                         // column slot 0 … 79
@@ -333,7 +335,7 @@ __device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, d
     }
     // row interchanges, one lane per column
     if (on && part == 0) {
-        for (int k = 0; k < SR; k++) {
+        for (int k = 0; k < Rr; k++) {
             const int p = perm[k];
             if (p != k) { const double tmp = base[k * stride]; base[k * stride] = base[p * stride]; base[p * stride] = tmp; }
         }
@@ -341,7 +343,7 @@ __device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, d
     __syncwarp();
     const unsigned gl = on ? (unsigned)(3 * grp) : 0u;        // leader lane of my group
     // L y = b (unit lower triangle)
-    for (int r = 1; r < SR; r++) {
+    for (int r = 1; r < Rr; r++) {
         double acc = 0.0, acc2 = 0.0;
         if (on) {
             int k = part;
@@ -358,16 +360,16 @@ __device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, d
         __syncwarp();
     }
     // U x = y
-    for (int r = SR - 1; r >= 0; r--) {
+    for (int r = Rr - 1; r >= 0; r--) {
         double acc = 0.0, acc2 = 0.0;
         if (on) {
             int k = r + 1 + part;
 #pragma unroll 2
-            for (; k + 3 < SR; k += 6) {
+            for (; k + 3 < Rr; k += 6) {
                 acc = fma(LU[r * SLD + k], base[k * stride], acc);
                 acc2 = fma(LU[r * SLD + k + 3], base[(k + 3) * stride], acc2);
             }
-            if (k < SR) acc = fma(LU[r * SLD + k], base[k * stride], acc);
+            if (k < Rr) acc = fma(LU[r * SLD + k], base[k * stride], acc);
             acc += acc2;
         }
         const double a1 = __shfl_sync(0xffffffffu, acc, (gl + 1) & 31), a2 = __shfl_sync(0xffffffffu, acc, (gl + 2) & 31);
@@ -378,13 +380,18 @@ __device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, d
 }
 
 // Shared-memory workspace of the pass-2 kernels: 5 matrices + 8 vectors + permutation.
+// Rr: live rank rounded up to a multiple of 4 (≤ SR).  Rows and columns ≥ Rr of every composite and state are exactly zero
+// (the fold never touches them), so (I + C J) is the identity there: the sequential parts of combine / apply — pivot steps,
+// substitution rows, the inner index of the products — stop at Rr, which makes a rank-8 combine ~8× shorter than a rank-64 one.
 struct ScanSmem {
     double* m[5];
     double* v[8];
     int* perm;
+    int Rr;
 };
-__device__ __forceinline__ ScanSmem scan_smem(unsigned char* raw) {
+__device__ __forceinline__ ScanSmem scan_smem(unsigned char* raw, int Rr) {
     ScanSmem w;
+    w.Rr = Rr;
     double* p = reinterpret_cast<double*>(raw);
     for (int k = 0; k < 5; k++) { w.m[k] = p; p += SMAT; }
     for (int k = 0; k < 8; k++) { w.v[k] = p; p += SR; }
@@ -405,33 +412,33 @@ __device__ __forceinline__ void scan_combine(const ScanSmem& w, const double* ei
     sm_load(w.m[1], Jj);
     if (tid < SR) { w.v[0][tid] = bi[tid]; w.v[1][tid] = etj[tid]; }
     __syncthreads();
-    sm_matmul<false, false>(w.m[2], nullptr, w.m[0], w.m[1], nullptr, false);        // C_i J_j
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[0], w.m[1], nullptr, false, w.Rr);        // C_i J_j
     if (tid < SR) {
         w.m[2][tid * SLD + tid] += 1.0;
-        w.v[2][tid] = w.v[1][tid] - sm_matvec_row<false>(w.m[1], w.v[0], tid);       // r = η_j − J_j b_i
-        w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid);       // b_i + C_i η_j
+        w.v[2][tid] = w.v[1][tid] - sm_matvec_row<false>(w.m[1], w.v[0], tid, w.Rr);       // r = η_j − J_j b_i
+        w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid, w.Rr);       // b_i + C_i η_j
     }
     __syncthreads();
-    if (tid < SR) w.v[4][tid] = sm_matvec_row<false>(w.m[0], w.v[2], tid);           // C_i r
+    if (tid < SR) w.v[4][tid] = sm_matvec_row<false>(w.m[0], w.v[2], tid, w.Rr);           // C_i r
     __syncthreads();
-    sm_lu(w.m[2], w.perm);
+    sm_lu(w.m[2], w.perm, w.Rr);
     sm_load(w.m[3], Ai);
     __syncthreads();
-    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 2);   // m0 = M C_i;  v3 = M (b_i + C_i η_j);  v4 = M C_i r
-    sm_lu_solve(w.m[2], w.perm, w.m[3], nullptr, 0);  // m3 = M 𝒜_i
+    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 2, w.Rr);   // m0 = M C_i;  v3 = M (b_i + C_i η_j);  v4 = M C_i r
+    sm_lu_solve(w.m[2], w.perm, w.m[3], nullptr, 0, w.Rr);  // m3 = M 𝒜_i
     sm_load(w.m[4], Aj);
     __syncthreads();
-    sm_matmul<false, false>(nullptr, Ao, w.m[4], w.m[3], nullptr, false);            // 𝒜 = 𝒜_j (M 𝒜_i)
-    sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false);        // 𝒜_j (M C_i)
-    if (tid < SR) bo[tid] = sm_matvec_row<false>(w.m[4], w.v[3], tid) + bj[tid];     // b
-    if (tid < SR) w.v[5][tid] = w.v[2][tid] - sm_matvec_row<false>(w.m[1], w.v[4], tid);   // r − J_j M C_i r
+    sm_matmul<false, false>(nullptr, Ao, w.m[4], w.m[3], nullptr, false, w.Rr);            // 𝒜 = 𝒜_j (M 𝒜_i)
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false, w.Rr);        // 𝒜_j (M C_i)
+    if (tid < SR) bo[tid] = sm_matvec_row<false>(w.m[4], w.v[3], tid, w.Rr) + bj[tid];     // b
+    if (tid < SR) w.v[5][tid] = w.v[2][tid] - sm_matvec_row<false>(w.m[1], w.v[4], tid, w.Rr);   // r − J_j M C_i r
     __syncthreads();
-    sm_matmul<false, true>(w.m[0], Co, w.m[2], w.m[4], Cj, true);                    // C = (…) 𝒜_jᵀ + C_j
-    sm_matmul<false, false>(w.m[2], nullptr, w.m[1], w.m[3], nullptr, false);        // J_j (M 𝒜_i)
+    sm_matmul<false, true>(w.m[0], Co, w.m[2], w.m[4], Cj, true, w.Rr);                    // C = (…) 𝒜_jᵀ + C_j
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[1], w.m[3], nullptr, false, w.Rr);        // J_j (M 𝒜_i)
     sm_load(w.m[4], Ai);
     __syncthreads();
-    if (tid < SR) eto[tid] = sm_matvec_row<true>(w.m[4], w.v[5], tid) + eti[tid];    // η
-    sm_matmul<true, false>(w.m[0], Jo, w.m[4], w.m[2], Ji, true);                    // J = 𝒜_iᵀ (…) + J_i
+    if (tid < SR) eto[tid] = sm_matvec_row<true>(w.m[4], w.v[5], tid, w.Rr) + eti[tid];    // η
+    sm_matmul<true, false>(w.m[0], Jo, w.m[4], w.m[2], Ji, true, w.Rr);                    // J = 𝒜_iᵀ (…) + J_i
 }
 
 // (S', g') = el applied to (S, g):  S' = 𝒜 (I + S J)⁻¹ S 𝒜ᵀ + C,  g' = 𝒜 (I + S J)⁻¹ (g + S η) + b.
@@ -449,20 +456,20 @@ __device__ __forceinline__ void scan_apply(const ScanSmem& w, const double* el, 
     sm_load(w.m[1], Je);
     if (tid < SR) { w.v[0][tid] = in[SR * SR + tid]; w.v[1][tid] = ete[tid]; }
     __syncthreads();
-    sm_matmul<false, false>(w.m[2], nullptr, w.m[0], w.m[1], nullptr, false);        // S J
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[0], w.m[1], nullptr, false, w.Rr);        // S J
     if (tid < SR) {
         w.m[2][tid * SLD + tid] += 1.0;
-        w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid);       // g + S η
+        w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid, w.Rr);       // g + S η
     }
     __syncthreads();
-    sm_lu(w.m[2], w.perm);
-    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 1);   // m0 = (I + S J)⁻¹ S;  v3 = (I + S J)⁻¹ (g + S η)
+    sm_lu(w.m[2], w.perm, w.Rr);
+    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 1, w.Rr);   // m0 = (I + S J)⁻¹ S;  v3 = (I + S J)⁻¹ (g + S η)
     sm_load(w.m[4], Ae);
     __syncthreads();
-    sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false);        // 𝒜 W
-    if (tid < SR) w.v[5][tid] = sm_matvec_row<false>(w.m[4], w.v[3], tid) + be[tid];
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false, w.Rr);        // 𝒜 W
+    if (tid < SR) w.v[5][tid] = sm_matvec_row<false>(w.m[4], w.v[3], tid, w.Rr) + be[tid];
     __syncthreads();
-    sm_matmul<false, true>(w.m[0], out, w.m[2], w.m[4], Ce, true);                   // S' = (𝒜 W) 𝒜ᵀ + C
+    sm_matmul<false, true>(w.m[0], out, w.m[2], w.m[4], Ce, true, w.Rr);                   // S' = (𝒜 W) 𝒜ᵀ + C
     if (tid < SR) out[SR * SR + tid] = w.v[5][tid];
     __syncthreads();
 }
@@ -471,9 +478,9 @@ __device__ __forceinline__ void scan_apply(const ScanSmem& w, const double* el, 
 // P chunks are split into G1 groups of G2 consecutive chunks (the last group may be shorter).
 // (a) grid = (G1, B): prefix composites inside each group: pref[g][0] = el[g·G2], pref[g][i] = pref[g][i−1] ⊗ el[g·G2+i].
 __global__ void __launch_bounds__(256, 1) scan_prefix_kernel(const double* elems, double* pref,
-                                                             int P, int G2) {
+                                                             int P, int G2, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw);
+    const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y, g = blockIdx.x;
     const int c0 = g * G2, c1 = min(P, c0 + G2);
     const double* E = elems + (size_t)th * P * SEL;
@@ -490,9 +497,9 @@ __global__ void __launch_bounds__(256, 1) scan_prefix_kernel(const double* elems
 //     init (nullable, [B × SSTATE]): the state entering the first chunk when the chunks cover only the tail of a series
 //     (time axis split across GPUs); nullptr = start of the series (zero state).
 __global__ void __launch_bounds__(256, 1) scan_groups_kernel(const double* pref, double* gstate,
-                                                             int P, int G2, int G1, const double* init) {
+                                                             int P, int G2, int G1, const double* init, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw);
+    const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y;
     const double* Q = pref + (size_t)th * P * SEL;
     double* S = gstate + (size_t)th * G1 * SSTATE;
@@ -507,9 +514,9 @@ __global__ void __launch_bounds__(256, 1) scan_groups_kernel(const double* pref,
 }
 // (c) grid = (P, B): state entering chunk ch = pref[g][ch−1−g·G2] applied to the group state (or the group state itself).
 __global__ void __launch_bounds__(256, 1) scan_states_kernel(const double* pref, const double* gstate, double* cstate,
-                                                             int P, int G2, int G1, int has_init) {
+                                                             int P, int G2, int G1, int has_init, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw);
+    const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y, ch = blockIdx.x;
     const int g = ch / G2;
     const double* Q = pref + (size_t)th * P * SEL;
@@ -525,9 +532,9 @@ __global__ void __launch_bounds__(256, 1) scan_states_kernel(const double* pref,
 // (d) time axis split across GPUs: composite of ALL chunks of this range = ordered product of the group totals
 //     pref[g][last].  grid = (1, B); scratch holds two composites per parameter vector (ping-pong: combine may not alias).
 __global__ void __launch_bounds__(256, 1) scan_total_kernel(const double* pref, double* scratch, double* total,
-                                                            int P, int G2, int G1) {
+                                                            int P, int G2, int G1, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw);
+    const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y;
     const double* Q = pref + (size_t)th * P * SEL;
     double* buf[2] = {scratch + (size_t)th * 2 * SEL, scratch + (size_t)th * 2 * SEL + SEL};
@@ -544,9 +551,10 @@ __global__ void __launch_bounds__(256, 1) scan_total_kernel(const double* pref, 
 }
 // (e) state entering this range = the composites of the nprev earlier ranges applied, in order, to the zero state.
 //     elems_prev is [nprev × B × SEL] (rank-major, as gathered); grid = (1, B).
-__global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_prev, int nprev, int B, double* state) {
+__global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_prev, int nprev, int B, double* state,
+                                                            int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw);
+    const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y;
     double* S = state + (size_t)th * SSTATE;
     for (int r = 0; r < nprev; r++) {
