@@ -94,6 +94,8 @@ struct pioran_ctx {
     // evaluates the same series × batch-size shape ~1e5 times)
     std::vector<int64_t> work_key;
     int work_items = 0, work_tpi = 0;
+    std::vector<int64_t> gwork_key;   // same for the gradient path's work items
+    int gwork_items = 0, gwork_tpi = 0;
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
     std::mutex mu;
@@ -240,6 +242,8 @@ extern "C" int pioran_series_free(pioran_ctx* c, int id) {
     cudaStreamSynchronize(c->stream);
     free_series(s);
     c->series[id] = nullptr;
+    c->work_key.clear();    // cached work items hold the freed series' device pointers
+    c->gwork_key.clear();
     return PIORAN_OK;
 }
 
@@ -830,25 +834,32 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     // one warp per (θ, direction): the work items run over the virtual batch of B·P entries
-    ItemPlan ip;
-    Series* sp[1] = {ser};
-    plan_items(c, 1, sp, &tab, B * P, GRAD_NW, false, ip);
-    if ((rc = c->gwork.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->gwork.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
-                             c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));   // ip.items is a local
+    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * P, BS};
+    if (key != c->gwork_key) {
+        ItemPlan ip;
+        Series* sp[1] = {ser};
+        plan_items(c, 1, sp, &tab, B * P, GRAD_NW, false, ip);
+        c->gwork_key.clear();
+        if ((rc = c->gwork.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->gwork.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
+                                 c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // ip.items is a local; only when the call shape changes
+        c->gwork_key = key;
+        c->gwork_items = (int)ip.items.size();
+        c->gwork_tpi = ip.tpi;
+    }
     GradArgs ga{};
     ga.work = c->gwork.as<WorkItem>();
     ga.amp = amp; ga.damp = damp; ga.suma = suma; ga.dsuma = dsuma;
     ga.theta = theta_dev; ga.pstride = ts; ga.ND = ND;
     ga.logl = logl_dev; ga.grad = grad_dev;
-    const int nitems = (int)ip.items.size();
+    const int nitems = c->gwork_items;
     switch (BS) {
-        case 4: return launch_grad<4>(c, ga, nitems, ip.tpi);
-        case 5: return launch_grad<5>(c, ga, nitems, ip.tpi);
-        case 6: return launch_grad<6>(c, ga, nitems, ip.tpi);
-        case 7: return launch_grad<7>(c, ga, nitems, ip.tpi);
-        case 8: return launch_grad<8>(c, ga, nitems, ip.tpi);
+        case 4: return launch_grad<4>(c, ga, nitems, c->gwork_tpi);
+        case 5: return launch_grad<5>(c, ga, nitems, c->gwork_tpi);
+        case 6: return launch_grad<6>(c, ga, nitems, c->gwork_tpi);
+        case 7: return launch_grad<7>(c, ga, nitems, c->gwork_tpi);
+        case 8: return launch_grad<8>(c, ga, nitems, c->gwork_tpi);
     }
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
