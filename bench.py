@@ -179,7 +179,7 @@ def run_reference(args, rank, world):
             "config": workload_config(args, R), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, R):
@@ -355,6 +355,71 @@ def config_c4_c5(ctx, pb, hbm_peak):
     return out
 
 
+def sharded_configs(torch, dist, ctx, pb, J, rank, world):
+    """BASELINE configs[2] and [3] on `world` GPUs (north_star: "sharded over 2/4/8 B200").
+    C3: the 512 ragged series are assigned to the ranks whole, longest first (parallel.shard_series); every rank runs ONE fused
+    call over its series x 400 parameter vectors, no data-path collective, one all-gather of the logL vectors (padded).
+    C4: ONE series of N = 1e6 with the time axis split over the ranks (parallel.scan_logl_sharded): all-gather of the range
+    composites + a 2-value all-reduce.  Times: CUDA-event device time of the library kernels, max over ranks (C3); wall time
+    around the whole sharded evaluation including the collectives, max over ranks (C4)."""
+    from pioran_b200 import parallel
+    out = {}
+    rng = np.random.default_rng(2000)
+    S, B = 512, 400
+    lengths = np.clip(np.rint(rng.normal(2000, 300, S)), 1000, 3000).astype(int)
+    mine = parallel.shard_series(lengths, world)[rank]
+    series, specs, thetas = [], [], []
+    for k in mine:
+        t, y, s2, f_min, f_max = wl.make_series_fast(int(lengths[k]), seed=2000 + int(k))
+        series.append(ctx.upload_series(t, y, s2))
+        specs.append(pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J))
+        thetas.append(wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), seed=5000 + int(k)))
+    th_dev = torch.from_numpy(np.ascontiguousarray(np.stack(thetas)).reshape(len(mine) * B, -1)).cuda()
+    out_dev = torch.empty(len(mine) * B, dtype=torch.float64, device="cuda")
+    smax = max(len(x) for x in parallel.shard_series(lengths, world))
+    pad = torch.full((smax * B,), float("nan"), dtype=torch.float64, device="cuda")
+    gathered = torch.empty(world * smax * B, dtype=torch.float64, device="cuda")
+    ms = []
+    for _ in range(4):
+        dist.barrier()
+        ctx.approx_logl_dev(series, specs, B, th_dev.data_ptr(), out_dev.data_ptr(), theta_per_series=True)
+        pad[: len(mine) * B] = out_dev
+        dist.all_gather_into_tensor(gathered, pad)
+        torch.cuda.current_stream().synchronize()
+        ms.append(ctx.last_kernel_ms())
+    tt = torch.tensor([float(np.mean(ms[1:]))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    k2 = float(tt.item())
+    for ser in series:
+        ser.free()
+    fin = torch.isfinite(gathered).sum().item()
+    out[f"C3_512series_x_400theta_SHO_{world}gpu"] = {
+        "evals_per_s": S * B / (k2 * 1e-3), "k2_ms_max_over_ranks": k2, "series_per_rank": [int(len(x)) for x in parallel.shard_series(lengths, world)],
+        "finite_evals_gathered": int(fin), "collective": "one all-gather of logL (padded to the largest shard)"}
+    # C4
+    N = 1_000_000
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=4)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 30)
+    a, b, c, d = ctx.approx_coeffs(spec, np.array([[0.82, 0.01, 3.3, float(np.var(y))]]))
+    ser = ctx.upload_series(t, y, s2)
+    ag, ar = parallel.torch_collectives(device="cuda")
+    walls = []
+    for _ in range(3):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        v = parallel.scan_logl_sharded(lambda lo, hi: ctx.scan_range_begin(ser, a, b, c, d, lo, hi, max_prev=world),
+                                       lambda prev: ctx.scan_range_end(prev), N, rank, world, ag, ar)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    ser.free()
+    tt = torch.tensor([min(walls[1:])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out[f"C4_long_series_N1e6_time_axis_over_{world}gpu"] = {"wall_ms_max_over_ranks": float(tt.item()) * 1e3, "logL": v,
+                                                             "collectives": "all-gather of range composites (97 KB each) + 2-value all-reduce"}
+    return out
+
+
 def widening_rows(ctx, pb, J):
     """SURVEY 8f #1/#2/#3 next to the hot path: gradients (4 096 θ × 6 directions), batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
@@ -472,6 +537,9 @@ def run_b200(args, rank, world, local_rank):
                            "fp64_frac": fl / (m2["k2_ms"] * 1e-3) / 1e12 / peak,
                            "finite_frac": float(np.isfinite(m2["out"]).mean())}
 
+    if not args.no_extra and world > 1:
+        extra.update(sharded_configs(torch, dist, ctx, pb, args.J, rank, world))
+
     if not args.no_extra and world == 1:
         extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
         extra.update(config_c4_c5(ctx, pb, hbm_peak_gbs()))
@@ -512,13 +580,31 @@ def run_b200(args, rank, world, local_rank):
                              "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d)", "peak_source": peak_src,
                              "note": "FP64-pipe bound: the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},
                 "cpu_baseline": cpu, "clocks": clocks, "finite_frac": finite, "extra": extra}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist_on:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the process's original stdout; everything else a library prints on fd 1
+    (NCCL's version banner, for one) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -528,7 +614,7 @@ def main():
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port)] + sys.argv
-        raise SystemExit(subprocess.call(cmd))
+        raise SystemExit(subprocess.call(cmd, stdout=_JSON_FD))
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
