@@ -1121,12 +1121,13 @@ extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) {
 // and shapes, shared by the whole-series entry and by the two-phase range entries (time axis split across GPUs).
 struct ScanRun {
     bool valid = false;
-    int series_id = -1, B = 0, Jt = 0, R = 0, BS = 0, P = 0, G1 = 0, G2 = 0;
+    int series_id = -1, B = 0, Jt = 0, R = 0, BS = 0, P = 0, G1 = 0, G2 = 0, SUB = 1;
     int64_t N = 0, n_lo = 0, n_hi = 0;
     std::vector<int64_t> bounds;
     GenericInputs gi{};
     double *elems = nullptr, *pref = nullptr, *gstate = nullptr, *cstate = nullptr, *parts = nullptr, *out = nullptr;
     double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
+    double *subel = nullptr, *substate = nullptr;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
 };
@@ -1160,8 +1161,11 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
     const int G2 = (int)std::ceil(std::sqrt((double)P));
     const int G1 = (P + G2 - 1) / G2;
+    // pass 3 on SUB sub-chunks per chunk (states at the inner boundaries from the fold's running composite): worth one extra
+    // apply per boundary once a chunk is a thousand steps long
+    const int SUB = (len / P >= 1024) ? 4 : 1;
     run = ScanRun{};
-    run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2;
+    run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2; run.SUB = SUB;
     run.N = N; run.n_lo = n_lo; run.n_hi = n_hi;
     run.bounds.resize(P + 1);
     for (int k = 0; k <= P; k++) run.bounds[k] = n_lo + (int64_t)((__int128)len * k / P);
@@ -1170,10 +1174,11 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, run.gi))) return rc;
     const size_t nch = (size_t)B * P;
     // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out | total | scratch | init | prev | sums
-    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch + 1);
+    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch * SUB + 1);
+    const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE;
     const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
     const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
-    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B))))
+    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B + n_sel + n_sst))))
         return rc;
     run.elems = c->misc.as<double>();
     run.pref = run.elems + n_el;
@@ -1186,6 +1191,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.init = run.scratch + n_scr;
     run.prev = run.init + n_init;
     run.sums = run.prev + n_prev;
+    run.subel = run.sums + 2 * (size_t)B;
+    run.substate = run.subel + n_sel;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
@@ -1196,7 +1203,7 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     ScanArgs sa{};
     sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = run.bounds_dev;
     sa.a = run.gi.a; sa.b = run.gi.b; sa.c = run.gi.c; sa.d = run.gi.d; sa.Jt = Jt; sa.term_row = run.term_row_dev;
-    sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems;
+    sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems; sa.SUB = SUB; sa.subel = run.subel;
     scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
     c->launches++;
     CUDA_TRY(cudaFuncSetAttribute(scan_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
@@ -1204,6 +1211,7 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_total_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_substates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     if (P > 1 || want_total) {
         scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.pref, P, G2, scan_live_rank(run.R));
         c->launches++;
@@ -1220,19 +1228,23 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
 // Phase 2: states entering every chunk (from `init_dev`, or from the start of the series when it is null), re-filter of
 // every chunk, partial sums in run.parts.
 static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* init_dev) {
-    const int B = run.B, P = run.P, NW = CHUNK_NW;
-    const size_t nch = (size_t)B * P;
-    const size_t nitems = (nch + NW - 1) / NW * NW;
+    const int B = run.B, P = run.P, NW = CHUNK_NW, SUB = run.SUB;
+    const size_t nch = (size_t)B * P, nsub = nch * SUB;
+    const size_t nitems = (nsub + NW - 1) / NW * NW;
     std::vector<WorkItem> items(nitems);
     for (size_t k = 0; k < nitems; k++) {
-        const size_t q = std::min(k, nch - 1);
+        const size_t e = std::min(k, nsub - 1);
+        const size_t q = e / SUB;
+        const int j = (int)(e % SUB);
         const int th = (int)(q / P), ch = (int)(q % P);
         WorkItem& w = items[k];
         w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = run.N;
         w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
-        w.n_begin = run.bounds[ch]; w.n_end = run.bounds[ch + 1];
-        w.init = (ch == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
-        w.part = k < nch ? run.parts + 2 * q : run.parts + 2 * nch;   // padding warps write to the dummy pair
+        w.n_begin = scan_sub_bound(run.bounds[ch], run.bounds[ch + 1], j, SUB);
+        w.n_end = scan_sub_bound(run.bounds[ch], run.bounds[ch + 1], j + 1, SUB);
+        if (j == 0) w.init = (ch == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
+        else        w.init = run.substate + (q * (SUB - 1) + (j - 1)) * SSTATE;
+        w.part = k < nsub ? run.parts + 2 * e : run.parts + 2 * nsub;   // padding warps write to the dummy pair
     }
     int rc;
     c->work_key.clear();
@@ -1244,6 +1256,11 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
                                                                              init_dev ? 1 : 0, scan_live_rank(run.R));
         c->launches += 2;
+    }
+    if (SUB > 1) {
+        scan_substates_kernel<<<dim3(P * (SUB - 1), B), 256, SCAN_SMEM_BYTES, c->stream>>>(
+            run.subel, run.cstate, run.substate, P, SUB, init_dev ? 1 : 0, scan_live_rank(run.R));
+        c->launches++;
     }
     CUDA_TRY(cudaGetLastError());
     BatchArgs args{};
@@ -1262,7 +1279,7 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
     cudaEventRecord(c->ev_beg, c->stream);
     if ((rc = scan_phase1(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, 0, s->N, false, 0, run))) return rc;
     if ((rc = scan_phase2(c, s, run, nullptr))) return rc;
-    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.P, B, s->N, run.out);
+    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.P * run.SUB, B, s->N, run.out);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -1328,7 +1345,7 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
         init = run.init;
     }
     if ((rc = scan_phase2(c, s, run, init))) return rc;
-    scan_partial_kernel<<<1, 32, 0, c->stream>>>(run.parts, run.P, 1, run.sums);
+    scan_partial_kernel<<<1, 32, 0, c->stream>>>(run.parts, run.P * run.SUB, 1, run.sums);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
