@@ -1127,7 +1127,7 @@ struct ScanRun {
     GenericInputs gi{};
     double *elems = nullptr, *pref = nullptr, *gstate = nullptr, *cstate = nullptr, *parts = nullptr, *out = nullptr;
     double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
-    double *subel = nullptr, *substate = nullptr;
+    double *subel = nullptr, *substate = nullptr, *tot0 = nullptr, *tot1 = nullptr, *tp = nullptr;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
 };
@@ -1148,16 +1148,12 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     if (BS > 8 || R > SR)
         return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
     const int64_t N = s->N, len = n_hi - n_lo;
-    // chunking.  The path costs ≈ 2·(len/P)·τ_step (fold + re-filter of one chunk, τ_step ≈ 2.2 µs) + 2·√P·τ_comb (the two
-    // sequential levels of the scan, τ_comb ≈ 0.24 ms at rank 64): the optimum is P ≈ (τ_step·len/τ_comb)^(2/3) (37 at 16 k steps, 111 at 65 k),
-    // capped at two chunks per SM (one fold CTA per SM is resident) shared among the B parameter vectors, ≥ 64 steps per chunk.
+    // chunking.  With log-depth scan levels the second pass costs little per extra chunk, so the optimum sits where the fold
+    // runs as ONE round of CTAs: one chunk per SM for a single parameter vector (tools/scan_chunks_sweep.py: P = 148
+    // is the best or within 3 % of it from 16 k to 1 M steps at ranks 4 … 60; two chunks per SM are 5 % slower), up to two
+    // per SM in total when several parameter vectors share the device, and at least 64 steps per chunk.
     int P = c->scan_chunks;
-    if (P <= 0) {
-        // τ_comb shrinks with the live rank (the sequential parts of a combine stop at it): ≈ 0.03 + 0.21·R/64 ms
-        const double tau_comb_ms = 0.03 + 0.21 * (double)std::min(SR, (R + 3) & ~3) / SR;
-        P = (int)std::lround(std::pow(4.3e-3 / tau_comb_ms * (double)len, 2.0 / 3.0));
-        P = std::max(8, std::min(P, std::max(8, 2 * c->num_sms / std::max(1, B))));
-    }
+    if (P <= 0) P = std::min(c->num_sms, std::max(16, 2 * c->num_sms / std::max(1, B)));   // two fold CTAs fit an SM: B·P ≤ 2·SMs
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
     const int G2 = (int)std::ceil(std::sqrt((double)P));
     const int G1 = (P + G2 - 1) / G2;
@@ -1175,10 +1171,10 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     const size_t nch = (size_t)B * P;
     // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out | total | scratch | init | prev | sums
     const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch * SUB + 1);
-    const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE;
+    const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE, n_gt = (size_t)B * G1 * SEL;
     const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
     const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
-    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B + n_sel + n_sst))))
+    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B + n_sel + n_sst + 2 * n_gt))))
         return rc;
     run.elems = c->misc.as<double>();
     run.pref = run.elems + n_el;
@@ -1193,6 +1189,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.sums = run.prev + n_prev;
     run.subel = run.sums + 2 * (size_t)B;
     run.substate = run.subel + n_sel;
+    run.tot0 = run.substate + n_sst;
+    run.tot1 = run.tot0 + n_gt;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
@@ -1206,19 +1204,40 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems; sa.SUB = SUB; sa.subel = run.subel;
     scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
     c->launches++;
-    CUDA_TRY(cudaFuncSetAttribute(scan_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(scan_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_group_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(scan_total_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_substates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-    if (P > 1 || want_total) {
-        scan_prefix_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.pref, P, G2, scan_live_rank(run.R));
+    const int Rr = scan_live_rank(run.R);
+    // (a) prefix composites inside the groups: Kogge–Stone over segments of G2 chunks, ping-pong between the two buffers
+    {
+        double* src = run.elems;
+        double* dst = run.pref;
+        for (int dd = 1; dd < G2 && P > 1; dd *= 2) {
+            scan_ks_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(src, dst, P, G2, dd, Rr);
+            c->launches++;
+            std::swap(src, dst);
+        }
+        run.pref = src;      // the buffer the last level wrote (the fold's own output when there is a single chunk per group)
+    }
+    // (b) running products of the group totals; the last one is the composite of the whole range
+    {
+        scan_gather_kernel<<<dim3(G1, B), 256, 0, c->stream>>>(run.pref, run.tot0, P, G2, G1);
         c->launches++;
+        double* src = run.tot0;
+        double* dst = run.tot1;
+        for (int dd = 1; dd < G1; dd *= 2) {
+            scan_ks_kernel<<<dim3(G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(src, dst, G1, G1, dd, Rr);
+            c->launches++;
+            std::swap(src, dst);
+        }
+        run.tp = src;
     }
     if (want_total) {
-        scan_total_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.scratch, run.total, P, G2, G1, scan_live_rank(run.R));
-        c->launches++;
+        for (int i = 0; i < B; i++)
+            CUDA_TRY(cudaMemcpyAsync(run.total + (size_t)i * SEL, run.tp + ((size_t)i * G1 + G1 - 1) * SEL, sizeof(double) * SEL,
+                                     cudaMemcpyDeviceToDevice, c->stream));
     }
     CUDA_TRY(cudaGetLastError());
     run.valid = true;
@@ -1252,7 +1271,7 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // items is a local
     if (P > 1 || init_dev) {
-        scan_groups_kernel<<<dim3(1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, P, run.G2, run.G1, init_dev, scan_live_rank(run.R));
+        scan_group_states_kernel<<<dim3(run.G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tp, run.gstate, run.G1, init_dev, scan_live_rank(run.R));
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
                                                                              init_dev ? 1 : 0, scan_live_rank(run.R));
         c->launches += 2;

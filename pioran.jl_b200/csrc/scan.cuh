@@ -12,9 +12,10 @@
 //      𝒜 ← Φ(𝒜 − w (𝒜ᵀu)ᵀ),  J ← J − (𝒜ᵀu)(𝒜ᵀu)ᵀ/D̂,  η ← η − (𝒜ᵀu) ẑ/D̂   (rank-1 updates).
 //      The three 64×64 matrices live in REGISTERS (4×4 tile of each per thread, 256 threads); shared memory only
 //      carries the per-step vectors.
-//   2. scan_prefix_kernel / scan_groups_kernel / scan_states_kernel — two-level scan over the P composites with the
-//      generic O(R³) combine / apply (64×64 LU with partial pivoting + matrix products in shared memory), giving the
-//      exact state entering every chunk.
+//   2. scan_ks_kernel / scan_gather_kernel / scan_group_states_kernel / scan_states_kernel / scan_substates_kernel — two-level
+//      scan over the P composites, each level a Kogge–Stone sweep of independent generic O(R³) combines (64×64 LU with partial
+//      pivoting + matrix products in shared memory), then one apply per chunk and per inner boundary: the exact state entering
+//      every quarter chunk.
 //   3. the generic K2 kernel (celerite.cuh) re-sweeps every chunk from its incoming state, one warp per chunk, and
 //      returns (Σ log|D_n|, Σ z_n²/D_n); the host adds them up.
 // Algorithmic HBM traffic: 2 passes over (t, y, σ²) = 48 N bytes plus P·(3·64² + 2·64)·8 B of composites written and
@@ -498,42 +499,50 @@ __device__ __forceinline__ void scan_apply(const ScanSmem& w, const double* el, 
 }
 
 // ------------------------------------------------------------------------------------------------ pass 2
-// P chunks are split into G1 groups of G2 consecutive chunks (the last group may be shorter).
-// (a) grid = (G1, B): prefix composites inside each group: pref[g][0] = el[g·G2], pref[g][i] = pref[g][i−1] ⊗ el[g·G2+i].
-__global__ void __launch_bounds__(256, 1) scan_prefix_kernel(const double* elems, double* pref,
-                                                             int P, int G2, int Rr) {
+// P chunks are split into G1 groups of G2 consecutive chunks (the last group may be shorter).  Both levels of the scan are
+// Kogge–Stone sweeps — ⌈log2⌉ kernel launches of independent combines instead of a chain of G2 (then G1) dependent ones:
+// (a) scan_ks_kernel over segments of G2 chunks: after ⌈log2 G2⌉ levels element i holds the product of its group's elements
+//     up to i (the prefix composites inside the groups);
+// (b) scan_gather_kernel copies the group totals, scan_ks_kernel (one segment of G1) turns them into their running products;
+//     the last one is the composite of the whole range (what the multi-GPU path exchanges);
+// (c) scan_group_states_kernel: state entering group g = running product g−1 applied to the incoming state (one apply each).
+// One level: out[i] = in[i−d] ⊗ in[i] if i is at least d into its segment, else in[i].  grid = (n, B).
+__global__ void __launch_bounds__(256, 1) scan_ks_kernel(const double* in, double* out, int n, int seg, int d, int Rr) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const ScanSmem w = scan_smem(raw, Rr);
+    const int th = blockIdx.y, i = blockIdx.x;
+    const size_t base = (size_t)th * n;
+    const double* src = in + (base + i) * SEL;
+    double* dst = out + (base + i) * SEL;
+    if (i % seg >= d) {
+        scan_combine(w, in + (base + i - d) * SEL, src, dst);
+    } else {
+        for (int k = threadIdx.x; k < SEL; k += blockDim.x) dst[k] = src[k];
+    }
+}
+// tot[g] = pref[last chunk of group g].  grid = (G1, B).
+__global__ void scan_gather_kernel(const double* __restrict__ pref, double* __restrict__ tot, int P, int G2, int G1) {
+    const int th = blockIdx.y, g = blockIdx.x;
+    const int last = min(P, (g + 1) * G2) - 1;
+    const double* src = pref + ((size_t)th * P + last) * SEL;
+    double* dst = tot + ((size_t)th * G1 + g) * SEL;
+    for (int k = threadIdx.x; k < SEL; k += blockDim.x) dst[k] = src[k];
+}
+// gstate[0] = incoming state (init, or zero at the start of the series); gstate[g] = tp[g−1] applied to it.  grid = (G1, B).
+//     init (nullable, [B × SSTATE]): the state entering the first chunk when the chunks cover only the tail of a series
+//     (time axis split across GPUs).
+__global__ void __launch_bounds__(256, 1) scan_group_states_kernel(const double* tp, double* gstate, int G1, const double* init,
+                                                                   int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
     const ScanSmem w = scan_smem(raw, Rr);
     const int th = blockIdx.y, g = blockIdx.x;
-    const int c0 = g * G2, c1 = min(P, c0 + G2);
-    const double* E = elems + (size_t)th * P * SEL;
-    double* Q = pref + (size_t)th * P * SEL;
-    for (int k = threadIdx.x; k < SEL; k += blockDim.x) Q[(size_t)c0 * SEL + k] = E[(size_t)c0 * SEL + k];
-    __syncthreads();
-    for (int ch = c0 + 1; ch < c1; ch++) {
-        __threadfence_block();
-        scan_combine(w, Q + (size_t)(ch - 1) * SEL, E + (size_t)ch * SEL, Q + (size_t)ch * SEL);
-        __syncthreads();
+    double* S = gstate + ((size_t)th * G1 + g) * SSTATE;
+    const double* in = init ? init + (size_t)th * SSTATE : nullptr;
+    if (g == 0) {
+        for (int k = threadIdx.x; k < SSTATE; k += blockDim.x) S[k] = in ? in[k] : 0.0;
+        return;
     }
-}
-// (b) grid = (1, B): state entering each group: st[0] = 0; st[g+1] = pref[g][last] applied to st[g].
-//     init (nullable, [B × SSTATE]): the state entering the first chunk when the chunks cover only the tail of a series
-//     (time axis split across GPUs); nullptr = start of the series (zero state).
-__global__ void __launch_bounds__(256, 1) scan_groups_kernel(const double* pref, double* gstate,
-                                                             int P, int G2, int G1, const double* init, int Rr) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw, Rr);
-    const int th = blockIdx.y;
-    const double* Q = pref + (size_t)th * P * SEL;
-    double* S = gstate + (size_t)th * G1 * SSTATE;
-    for (int k = threadIdx.x; k < SSTATE; k += blockDim.x) S[k] = init ? init[(size_t)th * SSTATE + k] : 0.0;
-    __syncthreads();
-    for (int g = 0; g + 1 < G1; g++) {
-        const int last = min(P, (g + 1) * G2) - 1;
-        __threadfence_block();
-        scan_apply(w, Q + (size_t)last * SEL, (g == 0 && !init) ? nullptr : S + (size_t)g * SSTATE, S + (size_t)(g + 1) * SSTATE);
-        __syncthreads();
-    }
+    scan_apply(w, tp + ((size_t)th * G1 + g - 1) * SEL, in, S);
 }
 // (c) grid = (P, B): state entering chunk ch = pref[g][ch−1−g·G2] applied to the group state (or the group state itself).
 __global__ void __launch_bounds__(256, 1) scan_states_kernel(const double* pref, const double* gstate, double* cstate,
@@ -565,26 +574,6 @@ __global__ void __launch_bounds__(256, 1) scan_substates_kernel(const double* su
     scan_apply(w, el, (ch == 0 && !has_init) ? nullptr : cstate + q * SSTATE, out);
 }
 
-// (d) time axis split across GPUs: composite of ALL chunks of this range = ordered product of the group totals
-//     pref[g][last].  grid = (1, B); scratch holds two composites per parameter vector (ping-pong: combine may not alias).
-__global__ void __launch_bounds__(256, 1) scan_total_kernel(const double* pref, double* scratch, double* total,
-                                                            int P, int G2, int G1, int Rr) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    const ScanSmem w = scan_smem(raw, Rr);
-    const int th = blockIdx.y;
-    const double* Q = pref + (size_t)th * P * SEL;
-    double* buf[2] = {scratch + (size_t)th * 2 * SEL, scratch + (size_t)th * 2 * SEL + SEL};
-    const double* cur = Q + (size_t)(min(P, G2) - 1) * SEL;
-    for (int g = 1; g < G1; g++) {
-        const int last = min(P, (g + 1) * G2) - 1;
-        __threadfence_block();
-        scan_combine(w, cur, Q + (size_t)last * SEL, buf[g & 1]);
-        __syncthreads();
-        cur = buf[g & 1];
-    }
-    __threadfence_block();
-    for (int k = threadIdx.x; k < SEL; k += blockDim.x) total[(size_t)th * SEL + k] = cur[k];
-}
 // (e) state entering this range = the composites of the nprev earlier ranges applied, in order, to the zero state.
 //     elems_prev is [nprev × B × SEL] (rank-major, as gathered); grid = (1, B).
 __global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_prev, int nprev, int B, double* state,
