@@ -1405,8 +1405,9 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     double* nll = acc + 2 * (size_t)chunk;
     int* info = reinterpret_cast<int*>(nll + chunk);
     const int ntri = nblk * (nblk + 1) / 2;
-    const size_t fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB);
-    if (fill_smem > 48 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
+    const size_t fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB + 4 * (size_t)Jt * DNB);
+    if (fill_smem > 200 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
+    CUDA_TRY(cudaFuncSetAttribute(dense_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     cudaEventRecord(c->ev_beg, c->stream);
     for (int th0 = 0; th0 < B; th0 += chunk) {
         const int nb = std::min(chunk, B - th0);

@@ -12,7 +12,7 @@
 // Blocked right-looking Cholesky, NB = 64, three kernels per panel, all batched over θ (blockIdx.y):
 //   dense_potrf_kernel : 64×64 diagonal block in shared memory; log-pivots, first non-positive pivot → info
 //   dense_trsm_kernel  : row blocks below the diagonal block, one thread per row, L_kk broadcast from shared memory
-//   dense_syrk_kernel  : trailing update C_ij −= A_ik A_jkᵀ (i ≥ j > k), 64×64 tiles, 4×4 register blocking
+//   dense_syrk_kernel  : trailing update C_ij −= A_ik A_jkᵀ (i ≥ j > k), 64×64 tiles on the FP64 tensor cores (DMMA m8n8k4)
 // Matrices stay in HBM/L2 (32 MB each at N = 2 000; the 126 MB L2 holds the working set of a few of them).
 #pragma once
 #include "common.cuh"
@@ -56,6 +56,62 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
     __syncthreads();
     const double m_ = mu ? mu[theta0 + th] : 0.0, v_ = nu ? nu[theta0 + th] : 1.0;
     double* At = A + (size_t)th * ld * ld;
+    // Off-diagonal tiles of covariance entries only: every row time ≥ every column time, and the kernel separates.  With
+    // α = t_i − t_r0 (r0 = first row of the tile), β = t_r0 − t_c1 (c1 = last column), γ = t_c1 − t_j, all ≥ 0 and τ = α+β+γ:
+    //     e^{−cτ}(a cos dτ + b sin dτ) = P_i X_j + Q_i Y_j,
+    //     P = e^{−cα}(a cos dα + b sin dα),  Q = e^{−cα}(b cos dα − a sin dα),  X = e^{−c(β+γ)} cos d(β+γ),  Y = e^{−c(β+γ)} sin d(β+γ)
+    // — 2·64 transcendental triples per term and tile instead of 64², then two FMAs per entry and term.  No exponent is positive,
+    // so nothing overflows (the celerite instability of separating e^{−c t_i} e^{+c t_j} globally does not arise per tile).
+    if (bi != bj && (int64_t)(bi + 1) * DNB <= N) {
+        double* Ps = tj_s + DNB;            // [Jt][DNB] each
+        double* Qs = Ps + (size_t)Jt * DNB;
+        double* Xs = Qs + (size_t)Jt * DNB;
+        double* Ys = Xs + (size_t)Jt * DNB;
+        const double tr0 = ti_s[0], tc1 = tj_s[DNB - 1];
+        const double beta = tr0 - tc1;
+        for (int e = threadIdx.x; e < 2 * Jt * DNB; e += blockDim.x) {
+            const int side = e / (Jt * DNB), f = e - side * Jt * DNB, m = f / DNB, k = f - m * DNB;
+            double si, co;
+            if (side == 0) {
+                const double al = ti_s[k] - tr0;
+                sincos(cd[m] * al, &si, &co);
+                const double ex = exp(-cc[m] * al);
+                Ps[f] = ex * (ca[m] * co + cb[m] * si);
+                Qs[f] = ex * (cb[m] * co - ca[m] * si);
+            } else {
+                const double bg = beta + (tc1 - tj_s[k]);
+                sincos(cd[m] * bg, &si, &co);
+                const double ex = exp(-cc[m] * bg);
+                Xs[f] = ex * co;
+                Ys[f] = ex * si;
+            }
+        }
+        __syncthreads();
+        const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;      // 4×4 entries per thread
+        double v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int w = 0; w < 4; w++) v[u][w] = 0.0;
+        for (int m = 0; m < Jt; m++) {
+            double pr[4], qr[4], xc[4], yc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { pr[u] = Ps[m * DNB + 4 * ty + u]; qr[u] = Qs[m * DNB + 4 * ty + u]; }
+#pragma unroll
+            for (int w = 0; w < 4; w++) { xc[w] = Xs[m * DNB + 4 * tx + w]; yc[w] = Ys[m * DNB + 4 * tx + w]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int w = 0; w < 4; w++) v[u][w] = fma(pr[u], xc[w], fma(qr[u], yc[w], v[u][w]));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            double* dst = At + ((int64_t)bi * DNB + 4 * ty + u) * ld + (int64_t)bj * DNB + 4 * tx;
+            *reinterpret_cast<double2*>(dst) = make_double2(v[u][0], v[u][1]);
+            *reinterpret_cast<double2*>(dst + 2) = make_double2(v[u][2], v[u][3]);
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < DNB * DNB; e += blockDim.x) {
         const int r = e / DNB, q = e - r * DNB;
         const int64_t gi = (int64_t)bi * DNB + r, gj = (int64_t)bj * DNB + q;
@@ -162,11 +218,23 @@ __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A,
     for (int j = 0; j < DNB; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
 }
 
-// Trailing update: C_ij −= A_ik A_jkᵀ for kb < j ≤ i.  grid = (m(m+1)/2, B) with m = nblk − kb − 1, block = 256.
+// FP64 tensor-core tile product: D(8×8) += A(8×4, row-major) · B(4×8, column-major).  Fragments (PTX ISA, m8n8k4.f64):
+// lane l holds A[l>>2][l&3], B[l&3][l>>2] and D[l>>2][2·(l&3) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Trailing update: C_ij −= A_ik A_jkᵀ for kb < j ≤ i — the one dense contraction of the path, on the FP64 tensor cores
+// (DMMA m8n8k4).  grid = (m(m+1)/2, B) with m = nblk − kb − 1, block = 256 = 8 warps; warp (wy, wx) owns the 32×16 sub-tile
+// rows 32·wy…, columns 16·wx… as 4×2 DMMA tiles.  The two 64×32 panel halves sit in shared memory row-major with a row
+// stride of 36 doubles: the 8 rows × 4 k of a fragment load then fall on 32 distinct banks per half-warp.  Per k-step of 4
+// a warp issues 6 shared loads for 8 DMMAs (2 048 FMAs) — the scalar version needed 4 128-bit loads per 512 FMAs and was
+// bound by the shared-memory pipe (profiles/r01_launches_k3_k4.csv: 20.5 of K4's 36 ms).
 __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb) {
-    constexpr int KH = DNB / 2;
-    __shared__ __align__(16) double As[KH][DNB + 2];   // [k][row], one half of the panel width at a time
-    __shared__ __align__(16) double Bs[KH][DNB + 2];
+    constexpr int KH = DNB / 2, LDSM = KH + 4;
+    __shared__ __align__(16) double As[DNB][LDSM];   // [row][k], one half of the panel width at a time
+    __shared__ __align__(16) double Bs[DNB][LDSM];
     const int th = blockIdx.y;
     int pi, pj;
     tri_index(blockIdx.x, pi, pj);
@@ -174,40 +242,48 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A,
     double* At = A + (size_t)th * ld * ld;
     const double* Ai = At + ((size_t)ib * DNB) * ld + (size_t)kb * DNB;
     const double* Aj = At + ((size_t)jb * DNB) * ld + (size_t)kb * DNB;
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    double acc[4][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = warp >> 2, wx = warp & 3, gr = lane >> 2, gc = lane & 3;
+    double acc[4][2][2];
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
-        for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+        for (int v = 0; v < 2; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
     for (int half = 0; half < 2; half++) {
         if (half) __syncthreads();
         for (int e = threadIdx.x; e < DNB * KH; e += 256) {
             const int r = e / KH, k = e - r * KH;        // coalesced along k
-            As[k][r] = Ai[(size_t)r * ld + half * KH + k];
-            Bs[k][r] = Aj[(size_t)r * ld + half * KH + k];
+            As[r][k] = Ai[(size_t)r * ld + half * KH + k];
+            Bs[r][k] = Aj[(size_t)r * ld + half * KH + k];
         }
         __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < KH; k++) {
-            const double2 a01 = *reinterpret_cast<const double2*>(&As[k][ty * 4]);
-            const double2 a23 = *reinterpret_cast<const double2*>(&As[k][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][tx * 4 + 2]);
-            const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int k4 = 0; k4 < KH / 4; k4++) {
+            double a[4], b[2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) a[u] = As[32 * wy + 8 * u + gr][4 * k4 + gc];
+#pragma unroll
+            for (int v = 0; v < 2; v++) b[v] = Bs[16 * wx + 8 * v + gr][4 * k4 + gc];
 #pragma unroll
             for (int u = 0; u < 4; u++)
 #pragma unroll
-                for (int v = 0; v < 4; v++) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+                for (int v = 0; v < 2; v++) dmma_8x8x4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
     }
     double* C = At + ((size_t)ib * DNB) * ld + (size_t)jb * DNB;
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const int r = ty * 4 + u, q = tx * 4 + v;
-            if (ib != jb || q <= r) C[(size_t)r * ld + q] -= acc[u][v];
+        for (int v = 0; v < 2; v++) {
+            const int r = 32 * wy + 8 * u + gr, q = 16 * wx + 8 * v + 2 * gc;
+            double* dst = C + (size_t)r * ld + q;
+            if (ib != jb || q + 1 <= r) {
+                double2 cv = *reinterpret_cast<double2*>(dst);
+                cv.x -= acc[u][v][0]; cv.y -= acc[u][v][1];
+                *reinterpret_cast<double2*>(dst) = cv;
+            } else if (q <= r) {
+                dst[0] -= acc[u][v][0];
+            }
         }
 }
 
