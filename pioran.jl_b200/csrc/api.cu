@@ -1153,7 +1153,10 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     // is the best or within 3 % of it from 16 k to 1 M steps at ranks 4 … 60; two chunks per SM are 5 % slower), up to two
     // per SM in total when several parameter vectors share the device, and at least 64 steps per chunk.
     int P = c->scan_chunks;
-    if (P <= 0) P = std::min(c->num_sms, std::max(16, 2 * c->num_sms / std::max(1, B)));   // two fold CTAs fit an SM: B·P ≤ 2·SMs
+    if (P <= 0) {
+        P = std::min(c->num_sms, std::max(16, 2 * c->num_sms / std::max(1, B)));   // two fold CTAs fit an SM: B·P ≤ 2·SMs
+        if (B == 1 && len / (2 * c->num_sms) >= 2048) P = 2 * c->num_sms;          // very long series: two chunks per SM (−7 % at 1e6 steps)
+    }
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
     const int G2 = (int)std::ceil(std::sqrt((double)P));
     const int G1 = (P + G2 - 1) / G2;

@@ -52,7 +52,7 @@ __host__ __device__ inline int64_t scan_sub_bound(int64_t n0, int64_t n1, int j,
 
 // ------------------------------------------------------------------------------------------------ pass 1
 // grid = (P, B), block = 256.  Thread (ty, tx) = (tid >> 4, tid & 15) owns rows 4ty..4ty+3 × columns 4tx..4tx+3.
-__global__ void __launch_bounds__(256, 1) scan_fold_kernel(const ScanArgs args) {
+__global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) {
     __shared__ __align__(16) double Us[SB][SR], Vs[SB][SR], Ps[SB][SR];   // U_n, V_n, φ_{n+1}
     __shared__ double An_s[SB], yn_s[SB];
     __shared__ __align__(16) double part[16][SR];     // partial column sums of 𝒜ᵀu per thread row
