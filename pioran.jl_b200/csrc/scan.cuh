@@ -50,8 +50,13 @@ __host__ __device__ inline int64_t scan_sub_bound(int64_t n0, int64_t n1, int j,
     return n0 + ((n1 - n0) * j / SUB) / 8 * 8;
 }
 
+// Rows / columns of the 4×4 register tile of fold thread (ty, tx): two adjacent pairs 32 apart — {2t, 2t+1, 32+2t, 33+2t}.
+// The 128-bit shared-memory accesses of a half-warp are then contiguous (16 lanes × 16 B); with four adjacent entries per
+// thread they were 32 B apart and 4-way bank-conflicted, which made the fold bound by the shared-memory pipe.
+__device__ __forceinline__ int fold_idx(int t, int e) { return (e < 2) ? 2 * t + e : 32 + 2 * t + (e - 2); }
+
 // ------------------------------------------------------------------------------------------------ pass 1
-// grid = (P, B), block = 256.  Thread (ty, tx) = (tid >> 4, tid & 15) owns rows 4ty..4ty+3 × columns 4tx..4tx+3.
+// grid = (P, B), block = 256.  Thread (ty, tx) = (tid >> 4, tid & 15) owns rows fold_idx(ty, ·) × columns fold_idx(tx, ·).
 __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) {
     __shared__ __align__(16) double Us[SB][SR], Vs[SB][SR], Ps[SB][SR];   // U_n, V_n, φ_{n+1}
     __shared__ double An_s[SB], yn_s[SB];
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) 
             for (int r = 0; r < 4; r++)
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    const size_t k = (size_t)(4 * ty + r) * SR + 4 * tx + c;
+                    const size_t k = (size_t)fold_idx(ty, r) * SR + fold_idx(tx, c);
                     E[k] = A[r][c]; E[SR * SR + k] = C[r][c]; E[2 * SR * SR + k] = Jm[r][c];
                 }
             if (tid < SR) { E[3 * SR * SR + tid] = b_s[tid]; E[3 * SR * SR + SR + tid] = eta_s[tid]; }
@@ -124,8 +129,8 @@ __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) 
             // ---- phase A: partial products  C u (rows),  𝒜ᵀ u (columns),  uᵀ b
             double ucol[4], urow[4];
             {
-                const double2 c01 = *reinterpret_cast<const double2*>(&Us[s][4 * tx]), c23 = *reinterpret_cast<const double2*>(&Us[s][4 * tx + 2]);
-                const double2 r01 = *reinterpret_cast<const double2*>(&Us[s][4 * ty]), r23 = *reinterpret_cast<const double2*>(&Us[s][4 * ty + 2]);
+                const double2 c01 = *reinterpret_cast<const double2*>(&Us[s][2 * tx]), c23 = *reinterpret_cast<const double2*>(&Us[s][32 + 2 * tx]);
+                const double2 r01 = *reinterpret_cast<const double2*>(&Us[s][2 * ty]), r23 = *reinterpret_cast<const double2*>(&Us[s][32 + 2 * ty]);
                 ucol[0] = c01.x; ucol[1] = c01.y; ucol[2] = c23.x; ucol[3] = c23.y;
                 urow[0] = r01.x; urow[1] = r01.y; urow[2] = r23.x; urow[3] = r23.y;
             }
@@ -155,10 +160,10 @@ __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) 
                 double f = (h4 ? e1 : e0) + r2;                    // row 2·h8 + h4
                 f += __shfl_xor_sync(0xffffffffu, f, 2);
                 f += __shfl_xor_sync(0xffffffffu, f, 1);
-                if ((tx & 3) == 0) cu_s[4 * ty + 2 * (h8 ? 1 : 0) + (h4 ? 1 : 0)] = f;
+                if ((tx & 3) == 0) cu_s[fold_idx(ty, 2 * (h8 ? 1 : 0) + (h4 ? 1 : 0))] = f;
             }
-            *reinterpret_cast<double2*>(&part[ty][4 * tx]) = make_double2(atp[0], atp[1]);
-            *reinterpret_cast<double2*>(&part[ty][4 * tx + 2]) = make_double2(atp[2], atp[3]);
+            *reinterpret_cast<double2*>(&part[ty][2 * tx]) = make_double2(atp[0], atp[1]);
+            *reinterpret_cast<double2*>(&part[ty][32 + 2 * tx]) = make_double2(atp[2], atp[3]);
             __syncthreads();
 
             // ---- phase B (warps 0-1): D̂, ẑ, w, 𝒜ᵀu;  b, η updates
@@ -193,13 +198,13 @@ __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) 
             // ---- phase C: rank-1 updates and decay of the three tiles
             double phr[4], phc[4], wr[4], wc[4], dwr[4], atc[4], atsr[4];
             {
-                const double2 p0 = *reinterpret_cast<const double2*>(&Ps[s][4 * ty]), p1 = *reinterpret_cast<const double2*>(&Ps[s][4 * ty + 2]);
-                const double2 p2 = *reinterpret_cast<const double2*>(&Ps[s][4 * tx]), p3 = *reinterpret_cast<const double2*>(&Ps[s][4 * tx + 2]);
-                const double2 w0 = *reinterpret_cast<const double2*>(&w_s[4 * ty]), w1 = *reinterpret_cast<const double2*>(&w_s[4 * ty + 2]);
-                const double2 w2 = *reinterpret_cast<const double2*>(&w_s[4 * tx]), w3 = *reinterpret_cast<const double2*>(&w_s[4 * tx + 2]);
-                const double2 d0 = *reinterpret_cast<const double2*>(&dw_s[4 * ty]), d1 = *reinterpret_cast<const double2*>(&dw_s[4 * ty + 2]);
-                const double2 a0 = *reinterpret_cast<const double2*>(&atu_s[4 * tx]), a1 = *reinterpret_cast<const double2*>(&atu_s[4 * tx + 2]);
-                const double2 s0 = *reinterpret_cast<const double2*>(&atus_s[4 * ty]), s1 = *reinterpret_cast<const double2*>(&atus_s[4 * ty + 2]);
+                const double2 p0 = *reinterpret_cast<const double2*>(&Ps[s][2 * ty]), p1 = *reinterpret_cast<const double2*>(&Ps[s][32 + 2 * ty]);
+                const double2 p2 = *reinterpret_cast<const double2*>(&Ps[s][2 * tx]), p3 = *reinterpret_cast<const double2*>(&Ps[s][32 + 2 * tx]);
+                const double2 w0 = *reinterpret_cast<const double2*>(&w_s[2 * ty]), w1 = *reinterpret_cast<const double2*>(&w_s[32 + 2 * ty]);
+                const double2 w2 = *reinterpret_cast<const double2*>(&w_s[2 * tx]), w3 = *reinterpret_cast<const double2*>(&w_s[32 + 2 * tx]);
+                const double2 d0 = *reinterpret_cast<const double2*>(&dw_s[2 * ty]), d1 = *reinterpret_cast<const double2*>(&dw_s[32 + 2 * ty]);
+                const double2 a0 = *reinterpret_cast<const double2*>(&atu_s[2 * tx]), a1 = *reinterpret_cast<const double2*>(&atu_s[32 + 2 * tx]);
+                const double2 s0 = *reinterpret_cast<const double2*>(&atus_s[2 * ty]), s1 = *reinterpret_cast<const double2*>(&atus_s[32 + 2 * ty]);
                 phr[0] = p0.x; phr[1] = p0.y; phr[2] = p1.x; phr[3] = p1.y;
                 phc[0] = p2.x; phc[1] = p2.y; phc[2] = p3.x; phc[3] = p3.y;
                 wr[0] = w0.x; wr[1] = w0.y; wr[2] = w1.x; wr[3] = w1.y;
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(256, 2) scan_fold_kernel(const ScanArgs args) 
     for (int r = 0; r < 4; r++)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const size_t k = (size_t)(4 * ty + r) * SR + 4 * tx + c;
+            const size_t k = (size_t)fold_idx(ty, r) * SR + fold_idx(tx, c);
             E[k] = A[r][c]; E[SR * SR + k] = C[r][c]; E[2 * SR * SR + k] = Jm[r][c];
         }
     if (tid < SR) { E[3 * SR * SR + tid] = b_s[tid]; E[3 * SR * SR + SR + tid] = eta_s[tid]; }
