@@ -307,6 +307,37 @@ def config_c3(torch, ctx, pb, J, peak):
             "fp64_frac": fl / (k2 * 1e-3) / 1e12 / peak, "finite_frac": float(np.isfinite(out).mean())}
 
 
+def config_c1_and_sampler_call(ctx, pb, J):
+    """BASELINE configs[0] — ONE logpdf of ScalableGP from approx(SingleBendingPowerLaw, J = 20, DRWCelerite) on an irregular
+    series of N = 1 000 — and a nested sampler's call (400 live points) on the same series: wall time of the host entry
+    (host θ in, host logL out), best of 20, beside one evaluation of the CPU restatement on one thread."""
+    from oracle import oracle as orc
+    out = {}
+    t, y, s2, f_min, f_max = wl.make_series(1000, 1234)
+    for basis in ("DRWCelerite", "SHO"):
+        like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+        th = wl.prior_theta(400, f_min, f_max, y.mean(), y.std(), 11, 6.0 if basis == "DRWCelerite" else 4.0)
+        th[0, :3] = (0.82, 0.01, 3.3)      # benchmark/benchmarks.jl:36-37
+        row = {}
+        for name, B in (("single_eval", 1), ("call_400_live_points", 400)):
+            like(th[:B])
+            best = 1e30
+            for _ in range(20):
+                t0 = time.perf_counter()
+                got = like(th[:B])
+                best = min(best, time.perf_counter() - t0)
+            row[name + "_wall_ms"] = best * 1e3
+        t0 = time.perf_counter()
+        ref = orc.approx_logl_batch("SBPL", th[:4], f_min, f_max, J, t, y, s2, basis=basis, nthreads=1)
+        row["cpu_port_1thread_ms_per_eval"] = (time.perf_counter() - t0) * 1e3 / 4
+        row["evals_per_s_at_400"] = 400 / (row["call_400_live_points_wall_ms"] * 1e-3)
+        ok = np.isfinite(ref)
+        row["parity_max_rel_4"] = float(np.max(np.abs(got[:4][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))))
+        like.close()
+        out[f"C1_single_logpdf_N1000_J{J}_{basis}"] = row
+    return out
+
+
 def config_c4_c5(ctx, pb, hbm_peak):
     """BASELINE configs[3] and [4] on one GPU.  C4: one series of N = 1e6, SHO J = 30 (rank 60), parallel-in-time scan (K3):
     device ms, achieved HBM GB/s on the algorithmic bytes (48 N + composites written and read), parity against ONE evaluation
@@ -542,6 +573,7 @@ def run_b200(args, rank, world, local_rank):
 
     if not args.no_extra and world == 1:
         extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
+        extra.update(config_c1_and_sampler_call(ctx, pb, args.J))
         extra.update(config_c4_c5(ctx, pb, hbm_peak_gbs()))
         extra.update(widening_rows(ctx, pb, args.J))
 
