@@ -1,0 +1,113 @@
+"""Vectorised sampler bridge: the two callbacks a nested sampler needs, over whole batches of points.
+
+The reference runs ultranest with `vectorized = false` (examples/ultranest/single_pl.jl:118): one `prior_transform(cube)` and
+one `logl(pars)` per point.  With the GPU backend the natural mode is `vectorized = True`: ultranest hands over all proposed
+points of an iteration at once — `transform(cubes [B × P]) → Θ [B × P]`, `loglike(Θ [B × P]) → logL [B]` — and ONE fused call
+evaluates them (0.6–0.8 ms for 400 live points at N = 1 000, J = 20).
+
+The prior transform stays on the HOST on purpose: it is P scalar quantiles per point (≈ 40 µs for 400 × 6 with numpy/scipy),
+an order of magnitude under the call's own launch + copy overhead; moving it to the device would trade a 19 KB θ upload for a
+19 KB cube upload.  Quantiles follow Distributions.jl's definitions (`quantile(d, u)`), which the reference calls.
+"""
+import numpy as np
+
+
+class Uniform:
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def quantile(self, u, prev):
+        return self.a + u * (self.b - self.a)
+
+
+class UniformFrom:
+    """Uniform(θ[col], b): the lower edge is an earlier column of the same point (α₂ ~ U(α₁, 4), single_pl.jl:99)."""
+
+    def __init__(self, col, b):
+        self.col, self.b = col, b
+
+    def quantile(self, u, prev):
+        lo = prev[:, self.col]
+        return lo + u * (self.b - lo)
+
+
+class LogUniform:
+    def __init__(self, a, b):
+        self.la, self.lb = np.log(a), np.log(b)
+
+    def quantile(self, u, prev):
+        return np.exp(self.la + u * (self.lb - self.la))
+
+
+class Normal:
+    def __init__(self, mu, sigma):
+        self.mu, self.sigma = mu, sigma
+
+    def quantile(self, u, prev):
+        from scipy.special import ndtri
+        return self.mu + self.sigma * ndtri(u)
+
+
+class LogNormal(Normal):
+    def quantile(self, u, prev):
+        return np.exp(super().quantile(u, prev))
+
+
+class Gamma:
+    """Gamma(shape k, scale θ) — Distributions.jl's parametrisation (single_pl.jl:101: Gamma(2, 0.5))."""
+
+    def __init__(self, k, theta):
+        self.k, self.theta = k, theta
+
+    def quantile(self, u, prev):
+        from scipy.special import gammaincinv
+        return self.theta * gammaincinv(self.k, u)
+
+
+class PriorTransform:
+    """Column-wise prior transform of unit-cube points; columns are evaluated left to right, so a prior may depend on earlier
+    columns of the same point (UniformFrom)."""
+
+    def __init__(self, priors):
+        self.priors = list(priors)
+
+    def __call__(self, cubes):
+        cubes = np.asarray(cubes, dtype=np.float64)
+        single = cubes.ndim == 1
+        u = np.atleast_2d(cubes)
+        out = np.empty_like(u)
+        for k, p in enumerate(self.priors):
+            out[:, k] = p.quantile(u[:, k], out)
+        return out[0] if single else out
+
+
+def single_bending_power_law_prior(f_min, f_max, xbar, va, mu_v=-1.5, sigma_v=1.0, alpha2_max=4.0, log_data=False):
+    """The prior of examples/ultranest/single_pl.jl:49-56,96-104 for Θ = (α₁, f₁, α₂, variance, ν, μ)."""
+    f0, fM = f_min / 20.0, f_max * 20.0
+    mu_n, sigma_n = 2 * mu_v, np.sqrt(2 * sigma_v ** 2)
+    return PriorTransform([Uniform(0.0, 1.5), LogUniform(f0 * 4.0, fM / 4.0), UniformFrom(0, alpha2_max),
+                           LogNormal(mu_n, sigma_n), Gamma(2, 0.5), Normal(xbar, 5 * np.sqrt(va))])
+
+
+def vectorized_callbacks(t, y, yerr, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
+                         log_transform=True, prior=None, ctx=None, **approx_kw):
+    """(loglike, transform, close) for `ultranest.ReactiveNestedSampler(paramnames, loglike, transform=transform,
+    vectorized=True)`.  log_transform follows single_pl.jl:70-73 (σ² = ν σ²/y², yn = log y); the series is uploaded once."""
+    from .api import BatchedLikelihood
+    t, y, yerr = (np.asarray(x, dtype=np.float64) for x in (t, y, yerr))
+    if log_transform:
+        yn, s2 = np.log(y), yerr ** 2 / y ** 2
+    else:
+        yn, s2 = y, yerr ** 2
+    like = BatchedLikelihood(t, yn, s2, psd_model, n_components, basis_function, ctx=ctx, **approx_kw)
+    if prior is None:
+        f_min, f_max = 1.0 / (t[-1] - t[0]), 1.0 / np.min(np.diff(t)) / 2.0
+        prior = single_bending_power_law_prior(f_min, f_max, float(np.mean(yn)), float(np.var(yn, ddof=1)),
+                                               alpha2_max=4.0 if basis_function == "SHO" else 6.0)
+
+    def loglike(theta):
+        out = like(np.atleast_2d(theta))
+        out[~np.isfinite(out)] = -1e300        # ultranest needs finite values; the reference's scripts never hit non-PD priors
+        return out
+
+    return loglike, prior, like.close
