@@ -242,6 +242,22 @@ def test_permutation_and_split_invariance(pb, ctx, golden_single):
     assert np.array_equal(parts, full)
 
 
+@pytest.mark.parametrize("basis", ["SHO", "DRWCelerite"])
+def test_dispatch_tiers_agree(pb, ctx, golden_single, basis):
+    """The same rows through every CTA shape of the shared-table kernel (csrc/api.cu dispatch_shared): 4-warp CTAs (≤ 592
+    evaluations), 8 un-paired warps (≤ 1 184), the full-size kernel (θ-paired for block sizes ≤ 5)."""
+    g = golden_single
+    like = pb.BatchedLikelihood(g.t, g.y, g.s2, g.model, 20, basis, ctx=ctx)
+    th = g.theta[:3000].copy()
+    if basis == "DRWCelerite":
+        th[:, 2] += 1.0
+    full = like(th)                    # full-size CTAs
+    for B in (1, 7, 592, 593, 1184, 1185):
+        part = like(th[:B])
+        assert rel_err(part, full[:B]).max() <= 1e-12, (basis, B)
+    like.close()
+
+
 # ------------------------------------------------------------------------------------------------- BASELINE sizes
 def test_config_c1_single_n1000_drw(pb, ctx):
     """BASELINE configs[0]: single logpdf, approx(SBPL, J=20, DRWCelerite) on a simulated N=1000 irregular series."""
