@@ -1418,15 +1418,27 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
                                                                          gi.d, gi.mu, gi.nu, th0);
         c->launches++;
-        for (int kb = 0; kb < nblk; kb++) {
+        for (int kb = 0; kb < nblk;) {
             dense_potrf_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, N, kb, acc, info);
             c->launches++;
-            const int m = nblk - kb - 1;
-            if (m > 0) {
-                dense_trsm_kernel<<<dim3(m, nb), DNB, 0, c->stream>>>(A, ld, kb);
-                dense_syrk_kernel<<<dim3(m * (m + 1) / 2, nb), 256, 0, c->stream>>>(A, ld, kb);
-                c->launches += 2;
+            const int m = nblk - kb - 1;            // block rows below panel kb
+            if (m == 0) break;
+            dense_trsm_kernel<<<dim3(m, nb), DNB, 0, c->stream>>>(A, ld, kb);
+            c->launches++;
+            if (m == 1) {                           // one block left: plain single-panel update
+                dense_syrk_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, kb, 1, kb + 1, 0);
+                c->launches++;
+                kb += 1;
+                continue;
             }
+            // two panels per trailing update: panel kb onto block column kb+1 only, factorise it, then both panels onto the rest
+            dense_syrk_kernel<<<dim3(m, nb), 256, 0, c->stream>>>(A, ld, kb, 1, kb + 1, 1);
+            dense_potrf_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, N, kb + 1, acc, info);
+            dense_trsm_kernel<<<dim3(m - 1, nb), DNB, 0, c->stream>>>(A, ld, kb + 1);
+            const int m2 = m - 1;                   // block rows/columns from kb+2 on
+            dense_syrk_kernel<<<dim3(m2 * (m2 + 1) / 2, nb), 256, 0, c->stream>>>(A, ld, kb, 2, kb + 2, 0);
+            c->launches += 4;
+            kb += 2;
         }
         dense_finish_kernel<<<(nb + 127) / 128, 128, 0, c->stream>>>(acc, info, N, nb, nll);
         c->launches++;

@@ -226,19 +226,23 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, const double 
 }
 
 // Trailing update: C_ij −= A_ik A_jkᵀ for kb < j ≤ i — the one dense contraction of the path, on the FP64 tensor cores
-// (DMMA m8n8k4).  grid = (m(m+1)/2, B) with m = nblk − kb − 1, block = 256 = 8 warps; warp (wy, wx) owns the 32×16 sub-tile
+// (DMMA m8n8k4).  grid = (m(m+1)/2, B) with m = nblk − j0 (or (m, B) when narrow), block = 256 = 8 warps; warp (wy, wx) owns the 32×16 sub-tile
 // rows 32·wy…, columns 16·wx… as 4×2 DMMA tiles.  The two 64×32 panel halves sit in shared memory row-major with a row
 // stride of 36 doubles: the 8 rows × 4 k of a fragment load then fall on 32 distinct banks per half-warp.  Per k-step of 4
 // a warp issues 6 shared loads for 8 DMMAs (2 048 FMAs) — the scalar version needed 4 128-bit loads per 512 FMAs and was
 // bound by the shared-memory pipe (profiles/r01_launches_k3_k4.csv: 20.5 of K4's 36 ms).
-__global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb) {
+// Two panels per trailing update: the panels kb … kb+kw−1 (kw = 1 or 2; 64·kw contiguous columns) are applied at once to the
+// tiles (i ≥ j ≥ j0), so a trailing tile is read and written once per TWO panels; in between, the block column kb+1 alone
+// gets panel kb (narrow = 1: tiles (i, j0), i ≥ j0) so that it can be factorised.  Halves the traffic that bounds the kernel.
+__global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb, int kw, int j0, int narrow) {
     constexpr int KH = DNB / 2, LDSM = KH + 4;
-    __shared__ __align__(16) double As[DNB][LDSM];   // [row][k], one half of the panel width at a time
+    __shared__ __align__(16) double As[DNB][LDSM];   // [row][k], one half of a panel's width at a time
     __shared__ __align__(16) double Bs[DNB][LDSM];
     const int th = blockIdx.y;
     int pi, pj;
-    tri_index(blockIdx.x, pi, pj);
-    const int ib = kb + 1 + pi, jb = kb + 1 + pj;
+    if (narrow) { pi = blockIdx.x; pj = 0; }
+    else tri_index(blockIdx.x, pi, pj);
+    const int ib = j0 + pi, jb = j0 + pj;
     double* At = A + (size_t)th * ld * ld;
     const double* Ai = At + ((size_t)ib * DNB) * ld + (size_t)kb * DNB;
     const double* Aj = At + ((size_t)jb * DNB) * ld + (size_t)kb * DNB;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A,
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 2; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
-    for (int half = 0; half < 2; half++) {
+    for (int half = 0; half < 2 * kw; half++) {
         if (half) __syncthreads();
         for (int e = threadIdx.x; e < DNB * KH; e += 256) {
             const int r = e / KH, k = e - r * KH;        // coalesced along k
