@@ -234,7 +234,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, const double 
 // Two panels per trailing update: the panels kb … kb+kw−1 (kw = 1 or 2; 64·kw contiguous columns) are applied at once to the
 // tiles (i ≥ j ≥ j0), so a trailing tile is read and written once per TWO panels; in between, the block column kb+1 alone
 // gets panel kb (narrow = 1: tiles (i, j0), i ≥ j0) so that it can be factorised.  Halves the traffic that bounds the kernel.
-__global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb, int kw, int j0, int narrow) {
+__global__ void __launch_bounds__(256, 2) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb, int kw, int j0, int narrow) {
     constexpr int KH = DNB / 2, LDSM = KH + 4;
     __shared__ __align__(16) double As[DNB][LDSM];   // [row][k], one half of a panel's width at a time
     __shared__ __align__(16) double Bs[DNB][LDSM];
@@ -253,14 +253,41 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A,
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 2; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
-    for (int half = 0; half < 2 * kw; half++) {
+    // software pipeline: the next half-panel travels global → registers while the tensor cores work on the current one, and
+    // the output tile is fetched up front (the update is a read-modify-write)
+    double* C = At + ((size_t)ib * DNB) * ld + (size_t)jb * DNB;
+    double2 cv[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 2; v++)
+            cv[u][v] = *reinterpret_cast<const double2*>(C + (size_t)(32 * wy + 8 * u + gr) * ld + 16 * wx + 8 * v + 2 * gc);
+    constexpr int PER = DNB * KH / 256;      // 8 elements of each panel block per thread and half
+    double pa[PER], pb[PER];
+    const int nhalf = 2 * kw;
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int e = threadIdx.x + q * 256, r = e / KH, k = e - r * KH;        // coalesced along k
+        pa[q] = Ai[(size_t)r * ld + k];
+        pb[q] = Aj[(size_t)r * ld + k];
+    }
+    for (int half = 0; half < nhalf; half++) {
         if (half) __syncthreads();
-        for (int e = threadIdx.x; e < DNB * KH; e += 256) {
-            const int r = e / KH, k = e - r * KH;        // coalesced along k
-            As[r][k] = Ai[(size_t)r * ld + half * KH + k];
-            Bs[r][k] = Aj[(size_t)r * ld + half * KH + k];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int e = threadIdx.x + q * 256, r = e / KH, k = e - r * KH;
+            As[r][k] = pa[q];
+            Bs[r][k] = pb[q];
         }
         __syncthreads();
+        if (half + 1 < nhalf) {
+#pragma unroll
+            for (int q = 0; q < PER; q++) {
+                const int e = threadIdx.x + q * 256, r = e / KH, k = e - r * KH;
+                pa[q] = Ai[(size_t)r * ld + (half + 1) * KH + k];
+                pb[q] = Aj[(size_t)r * ld + (half + 1) * KH + k];
+            }
+        }
 #pragma unroll
         for (int k4 = 0; k4 < KH / 4; k4++) {
             double a[4], b[2];
@@ -274,7 +301,6 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A,
                 for (int v = 0; v < 2; v++) dmma_8x8x4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
     }
-    double* C = At + ((size_t)ib * DNB) * ld + (size_t)jb * DNB;
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
@@ -282,11 +308,9 @@ __global__ void __launch_bounds__(256) dense_syrk_kernel(double* __restrict__ A,
             const int r = 32 * wy + 8 * u + gr, q = 16 * wx + 8 * v + 2 * gc;
             double* dst = C + (size_t)r * ld + q;
             if (ib != jb || q + 1 <= r) {
-                double2 cv = *reinterpret_cast<double2*>(dst);
-                cv.x -= acc[u][v][0]; cv.y -= acc[u][v][1];
-                *reinterpret_cast<double2*>(dst) = cv;
+                *reinterpret_cast<double2*>(dst) = make_double2(cv[u][v].x - acc[u][v][0], cv[u][v].y - acc[u][v][1]);
             } else if (q <= r) {
-                dst[0] -= acc[u][v][0];
+                dst[0] = cv[u][v].x - acc[u][v][0];
             }
         }
 }
