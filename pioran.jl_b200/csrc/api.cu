@@ -7,6 +7,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <new>
+#include <exception>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -34,6 +36,14 @@ static int fail(int code, const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
     return code;
+}
+
+// The C ABI never lets an exception escape (include/pioran_b200.h): every extern "C" entry is a function-try-block ending here.
+static int guard_fail() {
+    try { throw; }
+    catch (const std::bad_alloc&) { return fail(PIORAN_ENOMEM, "out of host memory"); }
+    catch (const std::exception& e) { return fail(PIORAN_EINVAL, "unexpected exception: %s", e.what()); }
+    catch (...) { return fail(PIORAN_EINVAL, "unexpected exception"); }
 }
 #define CUDA_TRY(expr)                                                                                     \
     do {                                                                                                   \
@@ -122,7 +132,7 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
 
 static void scan_forget(pioran_ctx* c);   // drops the range-in-progress record of a context (K3 multi-GPU entries)
 extern "C" int pioran_ctx_destroy(pioran_ctx* c);
-extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
+extern "C" int pioran_ctx_create(int device, pioran_ctx** out) try {
     if (!out) return fail(PIORAN_EINVAL, "out is NULL");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -149,7 +159,7 @@ extern "C" int pioran_ctx_create(int device, pioran_ctx** out) {
     }
     *out = c;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 static void free_series(Series* s) {
     if (!s) return;
@@ -158,7 +168,7 @@ static void free_series(Series* s) {
     delete s;
 }
 
-extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
+extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     if (!c) return PIORAN_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -172,21 +182,21 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) {
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
-extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) {
+extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
     return PIORAN_OK;
-}
-extern "C" int pioran_ctx_synchronize(pioran_ctx* c) {
+} catch (...) { return guard_fail(); }
+extern "C" int pioran_ctx_synchronize(pioran_ctx* c) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) { return c ? c->launches : 0; }
-extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) {
+extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) try {
     if (!c || !ms) return fail(PIORAN_EINVAL, "NULL argument");
     if (!c->ev_valid) return fail(PIORAN_EINVAL, "no main kernel has been launched on this context yet");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -195,10 +205,10 @@ extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) {
     CUDA_TRY(cudaEventElapsedTime(&f, c->ev_beg, c->ev_end));
     *ms = (double)f;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_series_upload(pioran_ctx* c, int64_t N, const double* t, const double* y, const double* s2,
-                                    int* series_id) {
+                                    int* series_id) try {
     if (!c || !t || !y || !s2 || !series_id) return fail(PIORAN_EINVAL, "NULL argument");
     if (N < 1) return fail(PIORAN_EINVAL, "N must be >= 1 (got %lld)", (long long)N);
     for (int64_t n = 1; n < N; n++)
@@ -226,14 +236,14 @@ extern "C" int pioran_series_upload(pioran_ctx* c, int64_t N, const double* t, c
     c->series[id] = s;
     *series_id = id;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 static Series* get_series(pioran_ctx* c, int id) {
     if (id < 0 || id >= (int)c->series.size()) return nullptr;
     return c->series[id];
 }
 
-extern "C" int pioran_series_free(pioran_ctx* c, int id) {
+extern "C" int pioran_series_free(pioran_ctx* c, int id) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     Series* s = get_series(c, id);
@@ -245,15 +255,15 @@ extern "C" int pioran_series_free(pioran_ctx* c, int id) {
     c->work_key.clear();    // cached work items hold the freed series' device pointers
     c->gwork_key.clear();
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
-extern "C" int pioran_series_length(pioran_ctx* c, int id, int64_t* N) {
+extern "C" int pioran_series_length(pioran_ctx* c, int id, int64_t* N) try {
     if (!c || !N) return fail(PIORAN_EINVAL, "NULL argument");
     Series* s = get_series(c, id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
     *N = s->N;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ approx plan
 static int n_psd_par_of(int model) { return model == PIORAN_PSD_SBPL ? 3 : model == PIORAN_PSD_DBPL ? 5 : -1; }
@@ -597,7 +607,7 @@ static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
 
 // ------------------------------------------------------------------------------------------------ K1 entry
 extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spec, int B, const double* theta,
-                                    double* a, double* b, double* cc, double* d) {
+                                    double* a, double* b, double* cc, double* d) try {
     if (!c || !spec || !theta || !a || !b || !cc || !d) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
     int rc = check_spec(*spec);
@@ -623,7 +633,7 @@ extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spe
     CUDA_TRY(cudaMemcpyAsync(d, da + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ fused entry
 static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs, int B,
@@ -731,15 +741,15 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
 }
 
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
-                                      int B, const double* theta_dev, int theta_per_series, double* logl_dev) {
+                                      int B, const double* theta_dev, int theta_per_series, double* logl_dev) try {
     if (!c || !series_ids || !specs || !theta_dev || !logl_dev) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
     return approx_logl_dev_locked(c, S, series_ids, specs, B, theta_dev, theta_per_series, logl_dev);
-}
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs, int B,
-                                  const double* theta, int theta_per_series, double* logl_out) {
+                                  const double* theta, int theta_per_series, double* logl_out) try {
     if (!c || !series_ids || !specs || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -783,7 +793,7 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)S * B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ gradient entry (K5)
 constexpr int GRAD_NW = 8;
@@ -865,15 +875,15 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
 }
 
 extern "C" int pioran_approx_logl_grad_dev(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
-                                           const double* theta_dev, double* logl_dev, double* grad_dev) {
+                                           const double* theta_dev, double* logl_dev, double* grad_dev) try {
     if (!c || !spec || !theta_dev || !grad_dev) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
     return approx_logl_grad_dev_locked(c, series_id, spec, B, theta_dev, logl_dev, grad_dev);
-}
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_approx_logl_grad(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
-                                       const double* theta, double* logl_out, double* grad_out) {
+                                       const double* theta, double* logl_out, double* grad_out) try {
     if (!c || !spec || !theta || !grad_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -892,7 +902,7 @@ extern "C" int pioran_approx_logl_grad(pioran_ctx* c, int series_id, const piora
     CUDA_TRY(cudaMemcpyAsync(grad_out, gg, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ generic entry
 // Uploads [B×Jt] coefficient arrays and per-θ scalars; returns device pointers inside ctx workspaces.
@@ -931,7 +941,7 @@ static int upload_generic(pioran_ctx* c, int B, int Jt, int64_t N, const double*
 
 extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                     const double* cc, const double* d, const double* mu, const double* nu,
-                                    const double* y_batch, const double* s2_batch, double* logl_out) {
+                                    const double* y_batch, const double* s2_batch, double* logl_out) try {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -973,7 +983,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ posterior mean, draws
 // Common set-up of the two widening entries: coefficient upload, row map, work items for the generic kernel.
@@ -1013,7 +1023,7 @@ static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* 
 
 extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                        const double* cc, const double* d, const double* mu, const double* nu, int64_t M,
-                                       const double* tau, double* mean_out) {
+                                       const double* tau, double* mean_out) try {
     if (!c || !a || !b || !cc || !d || !tau || !mean_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1 || M < 1) return fail(PIORAN_EINVAL, "B, Jt and M must be >= 1");
     for (int64_t m = 1; m < M; m++)
@@ -1062,11 +1072,11 @@ extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int 
     CUDA_TRY(cudaMemcpyAsync(mean_out, mean, sizeof(double) * nBM, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // n0 is a local
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                         const double* cc, const double* d, const double* nu, const double* q,
-                                        double* y_out) {
+                                        double* y_out) try {
     if (!c || !a || !b || !cc || !d || !q || !y_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1087,7 +1097,7 @@ extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int
     CUDA_TRY(cudaMemcpyAsync(y_out, c->post.p, sizeof(double) * nBN, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ K3 / K4 entries
 // Rank reduction shared by the generic and the scan entry: a term that is real (b = d = 0) for every coefficient set of
@@ -1104,18 +1114,18 @@ static int make_term_rows(int B, int Jt, const double* b, const double* d, std::
     return R;
 }
 
-extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) {
+extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     c->auto_scan = enabled != 0;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
-extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) {
+extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
     c->scan_chunks = chunks;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 // One run of the parallel-in-time path over the step range [n_lo, n_hi) of a series: device buffers (inside ctx workspaces)
 // and shapes, shared by the whole-series entry and by the two-phase range entries (time axis split across GPUs).
@@ -1313,7 +1323,7 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
 
 extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                          const double* cc, const double* d, const double* mu, const double* nu,
-                                         double* logl_out) {
+                                         double* logl_out) try {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1321,7 +1331,7 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
     return scan_logl_locked(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, logl_out);
-}
+} catch (...) { return guard_fail(); }
 
 // ---- time axis split across GPUs: each rank folds its own step range, the ranks exchange one composite each,
 // and every rank re-filters its range from the state the earlier ranges leave behind.
@@ -1329,7 +1339,7 @@ extern "C" int pioran_scan_composite_doubles(void) { return SEL; }
 
 extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, int Jt, const double* a, const double* b,
                                                 const double* cc, const double* d, const double* mu, const double* nu,
-                                                int64_t n_lo, int64_t n_hi, int max_prev, double* composite_out) {
+                                                int64_t n_lo, int64_t n_hi, int max_prev, double* composite_out) try {
     if (!c || !a || !b || !cc || !d || !composite_out) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1344,9 +1354,9 @@ extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, in
     CUDA_TRY(cudaMemcpyAsync(composite_out, run.total, sizeof(double) * SEL, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
-extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const double* composites_prev, double* sums_out) {
+extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const double* composites_prev, double* sums_out) try {
     if (!c || !sums_out || (nprev > 0 && !composites_prev)) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1376,11 +1386,11 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     run.valid = false;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                   const double* cc, const double* d, const double* mu, const double* nu,
-                                  double* nll_out, int* info_out) {
+                                  double* nll_out, int* info_out) try {
     if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1450,4 +1460,4 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     return PIORAN_OK;
-}
+} catch (...) { return guard_fail(); }
