@@ -594,6 +594,21 @@ static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* ta
 static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
     if (args.R > WIDE_MAX_RANK)
         return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", args.R, WIDE_MAX_RANK);
+    if (args.R <= 128) {   // the state fits the register file of one CTA
+        const int TS = (args.R + 15) / 16;
+        cudaEventRecord(c->ev_beg, c->stream);
+        switch (TS) {
+            case 8: celerite_wide_reg_kernel<8><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            case 7: celerite_wide_reg_kernel<7><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            case 6: celerite_wide_reg_kernel<6><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            default: celerite_wide_reg_kernel<5><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+        }
+        cudaEventRecord(c->ev_end, c->stream);
+        c->ev_valid = true;
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = sizeof(double) * wide_smem_doubles(wide_geom(args.R));
     CUDA_TRY(cudaFuncSetAttribute(celerite_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
