@@ -303,15 +303,20 @@ __device__ __forceinline__ double sm_matvec_row(const double* X, const double* x
     for (int k = 0; k < Rr; k++) acc = fma(TX ? X[k * SLD + row] : X[row * SLD + k], x[k], acc);
     return acc;
 }
-// In-place LU with partial pivoting of a shared SR×SR matrix; perm[k] = row swapped with k at step k.
-__device__ __forceinline__ void sm_lu(double* M, int* perm, int Rr) {
+// X ← M⁻¹ X for up to two shared SR×SR right-hand sides (R1, R2; R2 may be null) and nvec shared vectors (vecs + v·SR), by
+// Gauss–Jordan elimination with partial pivoting on the augmented system [M | R1 | R2 | vecs]; M is destroyed.  One pass of
+// Rr pivot steps, three CTA barriers each (pivot search by warp 0, row interchange, rank-1 elimination of column k from every
+// other row with a 16×16 thread grid over each 64-wide matrix) — one routine instead of an LU factorisation plus two substitution
+// sweeps per right-hand side, at the same speed (the combine is bound by its barriers, not by this arithmetic).  Rows/columns
+// ≥ Rr are the identity.
+__device__ __forceinline__ void sm_gj_solve(double* M, double* R1, double* R2, double* vecs, int nvec, int Rr) {
     __shared__ int piv_s;
-    for (int k = threadIdx.x; k < SR; k += blockDim.x) perm[k] = k;     // rows ≥ Rr: identity, no interchange
-    __syncthreads();
+    __shared__ double fcol_s[SR];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     for (int k = 0; k < Rr; k++) {
-        if (threadIdx.x < 32) {
+        if (tid < 32) {
             double best = -1.0; int bi = k;
-            for (int r = k + (int)threadIdx.x; r < Rr; r += 32) {
+            for (int r = k + tid; r < Rr; r += 32) {
                 const double v = fabs(M[r * SLD + k]);
                 if (v > best) { best = v; bi = r; }
             }
@@ -321,89 +326,55 @@ __device__ __forceinline__ void sm_lu(double* M, int* perm, int Rr) {
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
                 if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
-            if (threadIdx.x == 0) { piv_s = bi; perm[k] = bi; }
+            if (tid == 0) piv_s = bi;
         }
         __syncthreads();
         const int p = piv_s;
-        if (p != k && threadIdx.x < SR) {
-            const double tmp = M[k * SLD + threadIdx.x];
-            M[k * SLD + threadIdx.x] = M[p * SLD + threadIdx.x];
-            M[p * SLD + threadIdx.x] = tmp;
+        if (p != k) {      // interchange rows k and p of the whole augmented system (uniform branch)
+            if (tid < 3 * SR) {
+                double* X = tid < SR ? M : (tid < 2 * SR ? R1 : R2);
+                const int c = tid & (SR - 1);
+                if (X) { const double tmp = X[k * SLD + c]; X[k * SLD + c] = X[p * SLD + c]; X[p * SLD + c] = tmp; }
+            } else if (tid < 3 * SR + nvec) {
+                double* v = vecs + (size_t)(tid - 3 * SR) * SR;
+                const double tmp = v[k]; v[k] = v[p]; v[p] = tmp;
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        // elimination factors of column k (the column itself is not updated: it is e_k from here on)
         const double inv = 1.0 / M[k * SLD + k];
+        if (tid < SR) fcol_s[tid] = (tid == k || tid >= Rr) ? 0.0 : M[tid * SLD + k] * inv;
         __syncthreads();
-        for (int r = k + 1 + (int)threadIdx.x; r < Rr; r += blockDim.x) M[r * SLD + k] *= inv;
-        __syncthreads();
-        {   // trailing update, 16×16 thread grid striding over the remaining (SR−k−1)² block
-            const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-            for (int r = k + 1 + ty; r < Rr; r += 16) {
-                const double l = M[r * SLD + k];
-                for (int c = k + 1 + tx; c < Rr; c += 16) M[r * SLD + c] = fma(-l, M[k * SLD + c], M[r * SLD + c]);
+        // rows r ≠ k: row_r −= f_r · row_k on M (columns > k), R1, R2; then row k is scaled by 1/pivot
+#pragma unroll
+        for (int which = 0; which < 3; which++) {
+            double* X = which == 0 ? M : (which == 1 ? R1 : R2);
+            if (!X) continue;
+            const int c_lo = which == 0 ? k + 1 : 0;
+            for (int c = tx; c < SR; c += 16) {
+                if (c < c_lo) continue;
+                const double rk = X[k * SLD + c];
+                if (rk != 0.0)
+                    for (int r = ty; r < Rr; r += 16)
+                        if (r != k) X[r * SLD + c] = fma(-fcol_s[r], rk, X[r * SLD + c]);
             }
         }
+        if (tid < nvec * 32) {      // one warp per vector
+            double* v = vecs + (size_t)(tid >> 5) * SR;
+            const double vk = v[k];
+            for (int r = (tid & 31); r < Rr; r += 32)
+                if (r != k) v[r] = fma(-fcol_s[r], vk, v[r]);
+        }
         __syncthreads();
-    }
-}
-// Solves (LU) X = RHS in place for the SR columns of a shared matrix plus nvec shared vectors (vecs + v·SR).
-// Three lanes per right-hand side split the inner product of every substitution row (ten columns per warp, 80 ≥ SR + nvec
-// column slots in the CTA); the column stays in shared memory.  Rolled loops: the first version kept each column in the
-// registers of one thread with both triangular sweeps fully unrolled — 8 000 FMAs of straight-line code per call, far
-// beyond the instruction cache, and 0.28 ms per combine.
-__device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, double* RHS, double* vecs, int nvec, int Rr) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / 3, part = lane - 3 * grp;          // lanes 30, 31 idle (grp = 10)
-    const int slot = warp * 10 + grp;                         // column slot 0 … 79
-    const int ncol_m = RHS ? SR : 0;
-    const bool on = grp < 10 && slot < ncol_m + nvec;
-    double* base = nullptr;
-    int stride = 1;
-    if (on) {
-        if (slot < ncol_m) { base = RHS + slot; stride = SLD; }
-        else               { base = vecs + (size_t)(slot - ncol_m) * SR; stride = 1; }
-    }
-    // row interchanges, one lane per column
-    if (on && part == 0) {
-        for (int k = 0; k < Rr; k++) {
-            const int p = perm[k];
-            if (p != k) { const double tmp = base[k * stride]; base[k * stride] = base[p * stride]; base[p * stride] = tmp; }
+        if (tid < 3 * SR) {
+            double* X = tid < SR ? M : (tid < 2 * SR ? R1 : R2);
+            const int c = tid & (SR - 1);
+            if (X && (X != M || c > k)) X[k * SLD + c] *= inv;
+        } else if (tid < 3 * SR + nvec) {
+            vecs[(size_t)(tid - 3 * SR) * SR + k] *= inv;
         }
-    }
-    __syncwarp();
-    const unsigned gl = on ? (unsigned)(3 * grp) : 0u;        // leader lane of my group
-    // L y = b (unit lower triangle)
-    for (int r = 1; r < Rr; r++) {
-        double acc = 0.0, acc2 = 0.0;
-        if (on) {
-            int k = part;
-#pragma unroll 2
-            for (; k + 3 < r; k += 6) {       // two independent chains, loads of the next pair in flight
-                acc = fma(LU[r * SLD + k], base[k * stride], acc);
-                acc2 = fma(LU[r * SLD + k + 3], base[(k + 3) * stride], acc2);
-            }
-            if (k < r) acc = fma(LU[r * SLD + k], base[k * stride], acc);
-            acc += acc2;
-        }
-        const double a1 = __shfl_sync(0xffffffffu, acc, (gl + 1) & 31), a2 = __shfl_sync(0xffffffffu, acc, (gl + 2) & 31);
-        if (on && part == 0) base[r * stride] -= acc + a1 + a2;
-        __syncwarp();
-    }
-    // U x = y
-    for (int r = Rr - 1; r >= 0; r--) {
-        double acc = 0.0, acc2 = 0.0;
-        if (on) {
-            int k = r + 1 + part;
-#pragma unroll 2
-            for (; k + 3 < Rr; k += 6) {
-                acc = fma(LU[r * SLD + k], base[k * stride], acc);
-                acc2 = fma(LU[r * SLD + k + 3], base[(k + 3) * stride], acc2);
-            }
-            if (k < Rr) acc = fma(LU[r * SLD + k], base[k * stride], acc);
-            acc += acc2;
-        }
-        const double a1 = __shfl_sync(0xffffffffu, acc, (gl + 1) & 31), a2 = __shfl_sync(0xffffffffu, acc, (gl + 2) & 31);
-        if (on && part == 0) base[r * stride] = (base[r * stride] - (acc + a1 + a2)) / LU[r * SLD + r];
-        __syncwarp();
+        // the next step's pivot search reads column k+1 of rows ≥ k+1 (written above, before the last barrier) and the
+        // scaled row k is read only after the next barrier
     }
     __syncthreads();
 }
@@ -415,7 +386,7 @@ __device__ __forceinline__ void sm_lu_solve(const double* LU, const int* perm, d
 struct ScanSmem {
     double* m[5];
     double* v[8];
-    int* perm;
+    int* perm;      // (unused since the Gauss–Jordan solve; kept for the workspace layout)
     int Rr;
 };
 __device__ __forceinline__ ScanSmem scan_smem(unsigned char* raw, int Rr) {
@@ -450,11 +421,9 @@ __device__ __forceinline__ void scan_combine(const ScanSmem& w, const double* ei
     __syncthreads();
     if (tid < SR) w.v[4][tid] = sm_matvec_row<false>(w.m[0], w.v[2], tid, w.Rr);           // C_i r
     __syncthreads();
-    sm_lu(w.m[2], w.perm, w.Rr);
     sm_load(w.m[3], Ai);
     __syncthreads();
-    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 2, w.Rr);   // m0 = M C_i;  v3 = M (b_i + C_i η_j);  v4 = M C_i r
-    sm_lu_solve(w.m[2], w.perm, w.m[3], nullptr, 0, w.Rr);  // m3 = M 𝒜_i
+    sm_gj_solve(w.m[2], w.m[0], w.m[3], w.v[3], 2, w.Rr);   // m0 = M C_i;  m3 = M 𝒜_i;  v3 = M (b_i + C_i η_j);  v4 = M C_i r
     sm_load(w.m[4], Aj);
     __syncthreads();
     sm_matmul<false, false>(nullptr, Ao, w.m[4], w.m[3], nullptr, false, w.Rr);            // 𝒜 = 𝒜_j (M 𝒜_i)
@@ -491,8 +460,7 @@ __device__ __forceinline__ void scan_apply(const ScanSmem& w, const double* el, 
         w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid, w.Rr);       // g + S η
     }
     __syncthreads();
-    sm_lu(w.m[2], w.perm, w.Rr);
-    sm_lu_solve(w.m[2], w.perm, w.m[0], w.v[3], 1, w.Rr);   // m0 = (I + S J)⁻¹ S;  v3 = (I + S J)⁻¹ (g + S η)
+    sm_gj_solve(w.m[2], w.m[0], nullptr, w.v[3], 1, w.Rr);   // m0 = (I + S J)⁻¹ S;  v3 = (I + S J)⁻¹ (g + S η)
     sm_load(w.m[4], Ae);
     __syncthreads();
     sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false, w.Rr);        // 𝒜 W
