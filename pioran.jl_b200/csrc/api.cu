@@ -858,12 +858,13 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     approx_grad_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(plan, B, theta_dev, ts, amp, damp, RP, suma, dsuma);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    // one warp per (θ, direction): the work items run over the virtual batch of B·P entries
-    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * P, BS};
+    // one warp per (θ, direction): the work items run over the virtual batch of B·(P−1) entries
+    const int PW = P - 1;     // warps per parameter vector (the μ derivative rides along)
+    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS};
     if (key != c->gwork_key) {
         ItemPlan ip;
         Series* sp[1] = {ser};
-        plan_items(c, 1, sp, &tab, B * P, GRAD_NW, false, ip);
+        plan_items(c, 1, sp, &tab, B * PW, GRAD_NW, false, ip);
         c->gwork_key.clear();
         if ((rc = c->gwork.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->gwork.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,

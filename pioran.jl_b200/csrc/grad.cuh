@@ -10,7 +10,8 @@
 //                          celerite.cuh (non-pre-decayed form) with every θ-dependent quantity a (value, tangent) pair.
 //                          Per stored entry 4 FP64 issues for the value + 5 for the tangent.  Same lane → block mapping,
 //                          same TMA-staged shared series table, same reductions (on pairs).
-// Directions k = 0 … n_psd_par−1: PSD parameters; k = n_psd_par: norm (variance); then ν, μ.
+// Directions k = 0 … n_psd_par−1: PSD parameters; k = n_psd_par: norm (variance); k = n_psd_par+1: ν.  ∂/∂μ needs no block
+// tangent (μ moves only the right-hand side): every warp carries it as two extra vector entries, the k = 0 warp reports it.
 #pragma once
 #include "approx.cuh"
 #include "celerite.cuh"
@@ -132,6 +133,8 @@ struct LaneStateD {
     D2 sjj[2], g[2], amp[2];
     D2 chi2;
     double logacc, dkeep, dfirst, dlog;     // Σ log|D_n| (ring as in LaneState) and its tangent Σ D'_n / D_n
+    double gmu[2], chimu;                   // ∂/∂μ of g and of Σ z²/D: μ moves only the right-hand side (no block tangent), so
+                                            // every warp carries it as two vector entries and the k = 0 warp reports it
 };
 
 template <int BS>
@@ -201,10 +204,12 @@ __device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const
     for (int r = 0; r < BS; r++) sblk = fmac(urow[r], rowpart[r], sblk);
     D2 spart = fmac(ut1 * ut1, st.sjj[1], fmac(ut0 * ut0, st.sjj[0], sblk + sblk));
     D2 upart = fmac(ut1, st.g[1], ut0 * st.g[0]);
+    double umu = fma(ut1, st.gmu[1], ut0 * st.gmu[0]);
 #pragma unroll
     for (int sft = 16; sft >= 1; sft >>= 1) {
         spart = spart + shflx2(spart, sft);
         upart = upart + shflx2(upart, sft);
+        umu += __shfl_xor_sync(FULL, umu, sft);
     }
 
     // matvec reduction: reduce-scatter of the BS row sums over the 4 lanes of the block-row
@@ -249,6 +254,8 @@ __device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const
     rD.d = -D.d * rD.v * rD.v;
     const D2 z = mk2((yn - mu.v) - upart.v, -mu.d - upart.d);   // celerite_solver.jl:141
     st.chi2 = fma2(z * z, rD, st.chi2);
+    const double dzmu = -1.0 - umu;                             // ∂z_n/∂μ
+    st.chimu = fma(2.0 * z.v * dzmu, rD.v, st.chimu);
     if (n == 0) st.dfirst = D.v;
     else if ((int)(n & 31) == lane) st.dkeep = D.v;
     if ((n & 31) == 31) { st.logacc += log(fabs(st.dkeep)); st.dkeep = 1.0; }
@@ -258,6 +265,8 @@ __device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const
     const D2 w0 = q0 * rD, w1 = q1 * rD;
     st.g[0] = pn0 * fma2(w0, z, st.g[0]);
     st.g[1] = pn1 * fma2(w1, z, st.g[1]);
+    st.gmu[0] = pn0 * fma(w0.v, dzmu, st.gmu[0]);
+    st.gmu[1] = pn1 * fma(w1.v, dzmu, st.gmu[1]);
     st.sjj[0] = (pn0 * pn0) * fma2(q0, w0, st.sjj[0]);   // celerite_solver.jl:85
     st.sjj[1] = (pn1 * pn1) * fma2(q1, w1, st.sjj[1]);
     __syncwarp();
@@ -270,14 +279,14 @@ __device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const
 }
 
 struct GradArgs {
-    const WorkItem* work;       // items over the virtual batch e = θ·P + k (theta_begin, count, out_begin in that index space)
+    const WorkItem* work;       // items over the virtual batch e = θ·(ND+1) + k (theta_begin, count, out_begin in that index space)
     const double* amp;          // [nθ × RP] (logical rows)
     const double* damp;         // [nθ × ND × RP]
     const double* suma;         // [nθ]
     const double* dsuma;        // [nθ × ND]
     const double* theta;        // [nθ × pstride]; ν at column ND, μ at column ND + 1
     int pstride;
-    int ND;                     // n_psd_par + 1; P = ND + 2 directions
+    int ND;                     // n_psd_par + 1; ND + 1 warps (directions psd…, norm, ν) and ND + 2 outputs per θ
     double* logl;               // [nθ] or nullptr
     double* grad;               // [nθ × P]
 };
@@ -327,8 +336,9 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
 
     const bool active = warp < wk.count;
     const int e = wk.theta_begin + (active ? warp : wk.count - 1);
-    const int P = args.ND + 2;
-    const int th = e / P, k = e - th * P;
+    const int P = args.ND + 2;          // outputs per parameter vector: psd parameters…, norm, ν, μ
+    const int PW = args.ND + 1;         // warps per parameter vector: the μ derivative rides along (LaneStateD::gmu)
+    const int th = e / PW, k = e - th * PW;
     const LaneMap lm = make_lane_map<BS>(lane);
     const int i = lane >> 2, o = lane & 3;
 
@@ -345,6 +355,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
         }
     st.sjj[0] = st.sjj[1] = st.g[0] = st.g[1] = zero;
     st.chi2 = zero; st.logacc = 0.0; st.dkeep = 1.0; st.dfirst = 1.0; st.dlog = 0.0;
+    st.gmu[0] = st.gmu[1] = 0.0; st.chimu = 0.0;
     const bool amp_dir = k < args.ND;
     const double* av = args.amp + (size_t)th * RP;
     const double* ad = args.damp + ((size_t)th * args.ND + (amp_dir ? k : 0)) * RP;
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
     const D2 suma = mk2(args.suma[th], amp_dir ? args.dsuma[(size_t)th * args.ND + k] : 0.0);
     const double* trow = args.theta + (size_t)th * args.pstride;
     const D2 nu = mk2(trow[args.ND], k == args.ND ? 1.0 : 0.0);
-    const D2 mu = mk2(trow[args.ND + 1], k == args.ND + 1 ? 1.0 : 0.0);
+    const D2 mu = mk2(trow[args.ND + 1], 0.0);
 
     double* sv = scratch + warp * 4 * RPS;
     double* sd = sv + 2 * RPS;
@@ -393,6 +404,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
     if (active && lane == 0) {
         if (k == 0 && args.logl) args.logl[th] = -logdet / 2 - (double)N * 1.8378770664093453 / 2 - st.chi2.v / 2;
         args.grad[(size_t)th * P + k] = -st.dlog / 2 - st.chi2.d / 2;
+        if (k == 0) args.grad[(size_t)th * P + args.ND + 1] = -st.chimu / 2;
     }
 }
 
