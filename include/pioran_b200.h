@@ -111,7 +111,8 @@ int pioran_approx_logl_dev(pioran_ctx *ctx, int S, const int *series_ids, const 
 /* ---- K5: gradient of the fused path (widening row) -------------------------------------------
  * Replaces  ForwardDiff.gradient(θ -> logpdf(ScalableGP(μ, approx(𝓟(θ…), f_min, f_max, J, norm))(t, ν·σ²), y), θ)
  * (reference test/test_likelihood.jl:24-43,55; the NUTS runs of examples/turing_distributed/single_pl.jl): forward-mode
- * derivatives pushed through the same two kernels, one warp per (parameter vector, θ-direction).
+ * derivatives pushed through the same two kernels, one warp per (parameter vector, PSD parameter or ν); the μ and norm
+ * partials come from the same sweeps (right-hand-side tangent; homogeneity of K in (norm, ν)).
  * theta: [B × (n_psd_par+3)] = psd parameters…, norm, ν, μ.  logl_out: [B] or NULL.  grad_out: [B × (n_psd_par+3)],
  * ∂logℒ/∂θ in the column order of theta. */
 int pioran_approx_logl_grad(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,

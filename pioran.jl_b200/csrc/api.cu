@@ -837,7 +837,7 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     if ((rc = check_spec(*spec))) return rc;
     Series* ser = get_series(c, series_id);
     if (!ser) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 3, ND = npar + 1, P = npar + 3;
+    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 3, ND = npar, P = npar + 3;
     if ((long long)B * P > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "B too large");
     const int R = rank_of(spec->basis, spec->n_components);
     const int BS = bs_for_rank(R);
@@ -858,8 +858,8 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     approx_grad_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(plan, B, theta_dev, ts, amp, damp, RP, suma, dsuma);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    // one warp per (θ, direction): the work items run over the virtual batch of B·(P−1) entries
-    const int PW = P - 1;     // warps per parameter vector (the μ derivative rides along)
+    // one warp per (θ, direction): the work items run over the virtual batch of B·(n_psd_par + 1) entries
+    const int PW = ND + 1;    // warps per parameter vector: psd parameters…, ν (∂/∂μ rides along, ∂/∂norm follows from ∂/∂ν)
     const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS};
     if (key != c->gwork_key) {
         ItemPlan ip;

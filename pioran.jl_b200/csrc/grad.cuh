@@ -10,8 +10,9 @@
 //                          celerite.cuh (non-pre-decayed form) with every θ-dependent quantity a (value, tangent) pair.
 //                          Per stored entry 4 FP64 issues for the value + 5 for the tangent.  Same lane → block mapping,
 //                          same TMA-staged shared series table, same reductions (on pairs).
-// Directions k = 0 … n_psd_par−1: PSD parameters; k = n_psd_par: norm (variance); k = n_psd_par+1: ν.  ∂/∂μ needs no block
-// tangent (μ moves only the right-hand side): every warp carries it as two extra vector entries, the k = 0 warp reports it.
+// Directions k = 0 … n_psd_par−1: PSD parameters; k = n_psd_par: ν.  ∂/∂μ needs no block tangent (μ moves only the right-hand
+// side): every warp carries it as two extra vector entries, the k = 0 warp reports it.  ∂/∂norm needs no sweep at all: K is
+// homogeneous of degree 1 in (norm, ν), so norm ∂logL/∂norm + ν ∂logL/∂ν = ½ yᵀK⁻¹y − N/2, and the ν warp reports both.
 #pragma once
 #include "approx.cuh"
 #include "celerite.cuh"
@@ -47,14 +48,14 @@ __device__ __forceinline__ D2 psd_eval2(int model, const D2* p, double f) {
     return v;
 }
 
-// One thread per (parameter vector i, direction k ≤ n_psd_par).  theta: [B × tstride].
+// One thread per (parameter vector i, PSD-parameter direction k < n_psd_par).  theta: [B × tstride].
 //   amp_rows [B × RP], suma [B]                     (written by the k = 0 thread; same values as approx_kernel)
-//   damp_rows [B × ND × RP], dsuma [B × ND]         ND = n_psd_par + 1
+//   damp_rows [B × ND × RP], dsuma [B × ND]         ND = n_psd_par
 __global__ void approx_grad_kernel(const ApproxPlan* __restrict__ plan, int B, const double* __restrict__ theta,
                                    int tstride, double* __restrict__ amp_rows, double* __restrict__ damp_rows, int RP,
                                    double* __restrict__ suma, double* __restrict__ dsuma) {
     const ApproxPlan& P = *plan;
-    const int ND = P.n_psd_par + 1;
+    const int ND = P.n_psd_par;         // the norm direction needs no sweep (celerite_grad_kernel uses the scaling identity)
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= B * ND) return;
     const int i = gid / ND, k = gid - i * ND;
@@ -62,7 +63,7 @@ __global__ void approx_grad_kernel(const ApproxPlan* __restrict__ plan, int B, c
     const double* th = theta + (size_t)i * tstride;
     D2 par[8];
     for (int q = 0; q < P.n_psd_par; q++) par[q] = mk2(th[q], q == k ? 1.0 : 0.0);
-    const D2 norm = mk2(th[P.n_psd_par], k == P.n_psd_par ? 1.0 : 0.0);
+    const D2 norm = mk2(th[P.n_psd_par], 0.0);
     double x[MAXJ], dx[MAXJ];
     {   // get_normalised_psd (src/psd.jl:52-56)
         const D2 p0 = psd_eval2(P.model, par, P.fj[0]);
@@ -284,9 +285,9 @@ struct GradArgs {
     const double* damp;         // [nθ × ND × RP]
     const double* suma;         // [nθ]
     const double* dsuma;        // [nθ × ND]
-    const double* theta;        // [nθ × pstride]; ν at column ND, μ at column ND + 1
+    const double* theta;        // [nθ × pstride]; norm at column ND, ν at ND + 1, μ at ND + 2
     int pstride;
-    int ND;                     // n_psd_par + 1; ND + 1 warps (directions psd…, norm, ν) and ND + 2 outputs per θ
+    int ND;                     // n_psd_par; ND + 1 warps (directions psd…, ν) and ND + 3 outputs per θ
     double* logl;               // [nθ] or nullptr
     double* grad;               // [nθ × P]
 };
@@ -336,8 +337,10 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
 
     const bool active = warp < wk.count;
     const int e = wk.theta_begin + (active ? warp : wk.count - 1);
-    const int P = args.ND + 2;          // outputs per parameter vector: psd parameters…, norm, ν, μ
-    const int PW = args.ND + 1;         // warps per parameter vector: the μ derivative rides along (LaneStateD::gmu)
+    const int P = args.ND + 3;          // outputs per parameter vector: psd parameters…, norm, ν, μ
+    const int PW = args.ND + 1;         // warps per parameter vector: psd parameters…, ν.  ∂/∂μ rides along (LaneStateD::gmu) and
+                                        // ∂/∂norm follows from ∂/∂ν: K = norm·K̂ + ν·Σ is homogeneous of degree 1 in (norm, ν), so
+                                        // norm ∂logL/∂norm + ν ∂logL/∂ν = ½ yᵀK⁻¹y − N/2 (Euler)
     const int th = e / PW, k = e - th * PW;
     const LaneMap lm = make_lane_map<BS>(lane);
     const int i = lane >> 2, o = lane & 3;
@@ -363,8 +366,8 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
     st.amp[1] = lm.valid1 ? mk2(av[i * BS + o + 4], amp_dir ? ad[i * BS + o + 4] : 0.0) : zero;
     const D2 suma = mk2(args.suma[th], amp_dir ? args.dsuma[(size_t)th * args.ND + k] : 0.0);
     const double* trow = args.theta + (size_t)th * args.pstride;
-    const D2 nu = mk2(trow[args.ND], k == args.ND ? 1.0 : 0.0);
-    const D2 mu = mk2(trow[args.ND + 1], 0.0);
+    const D2 nu = mk2(trow[args.ND + 1], k == args.ND ? 1.0 : 0.0);
+    const D2 mu = mk2(trow[args.ND + 2], 0.0);
 
     double* sv = scratch + warp * 4 * RPS;
     double* sd = sv + 2 * RPS;
@@ -403,8 +406,14 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
     const double logdet = log(st.dfirst) + la;
     if (active && lane == 0) {
         if (k == 0 && args.logl) args.logl[th] = -logdet / 2 - (double)N * 1.8378770664093453 / 2 - st.chi2.v / 2;
-        args.grad[(size_t)th * P + k] = -st.dlog / 2 - st.chi2.d / 2;
-        if (k == 0) args.grad[(size_t)th * P + args.ND + 1] = -st.chimu / 2;
+        const double gk = -st.dlog / 2 - st.chi2.d / 2;
+        if (k < args.ND) {
+            args.grad[(size_t)th * P + k] = gk;
+        } else {      // the ν warp also reports ∂/∂norm
+            args.grad[(size_t)th * P + args.ND + 1] = gk;
+            args.grad[(size_t)th * P + args.ND] = (0.5 * st.chi2.v - 0.5 * (double)N - nu.v * gk) / trow[args.ND];
+        }
+        if (k == 0) args.grad[(size_t)th * P + args.ND + 2] = -st.chimu / 2;
     }
 }
 
