@@ -22,6 +22,7 @@
 #include "posterior.cuh"
 #include "table.cuh"
 #include "grad.cuh"
+#include "grad_pipe.cuh"
 #include "wide.cuh"
 
 using namespace pioran;
@@ -825,6 +826,21 @@ static int launch_grad_nw(pioran_ctx* c, const GradArgs& args, int nitems) {
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+template <int BS, int NWARPS>
+static int launch_grad_pipe(pioran_ctx* c, const GradArgs& args, int nitems) {
+    constexpr int RPS = rps_of(BS), SD = table_step_doubles(RPS), nthreads = NWARPS * 32;
+    auto kern = celerite_grad_pipe_kernel<BS, NWARPS>;
+    const size_t smem = sizeof(double) * (2 * (size_t)PIPE_CS * SD + 3 * (size_t)pipe_slot_doubles<BS>() +
+                                          (size_t)(args.ND + 1) * 2 * RPS + 2) + 2 * sizeof(uint64_t) + 16;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, nthreads, smem, c->stream>>>(args);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 // a few chains (≤ 4 (θ, direction) pairs per CTA): one warp per SM sub-partition, as for the likelihood (SMALL_NW)
 template <int BS>
 static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems, int tpi) {
@@ -859,12 +875,14 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     // one warp per (θ, direction): the work items run over the virtual batch of B·(n_psd_par + 1) entries
-    const int PW = ND + 1;    // warps per parameter vector: psd parameters…, ν (∂/∂μ rides along, ∂/∂norm follows from ∂/∂ν)
-    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS};
+    const bool pipe = BS >= 6;   // one CTA per parameter vector: value warp + tangent-only warps (grad_pipe.cuh)
+    const int PW = pipe ? 1 : ND + 1;    // work-item entries per parameter vector (warps: psd parameters…, ν; ∂/∂μ rides along,
+                                         // ∂/∂norm follows from ∂/∂ν)
+    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS, (int64_t)pipe};
     if (key != c->gwork_key) {
         ItemPlan ip;
         Series* sp[1] = {ser};
-        plan_items(c, 1, sp, &tab, B * PW, GRAD_NW, false, ip);
+        plan_items(c, 1, sp, &tab, B * PW, pipe ? 1 : GRAD_NW, false, ip);
         c->gwork_key.clear();
         if ((rc = c->gwork.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->gwork.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -880,12 +898,26 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     ga.theta = theta_dev; ga.pstride = ts; ga.ND = ND;
     ga.logl = logl_dev; ga.grad = grad_dev;
     const int nitems = c->gwork_items;
+    if (pipe) {
+        const int nwarps = 1 + ND + 1;
+        if (nwarps == 5) {
+            switch (BS) {
+                case 6: return launch_grad_pipe<6, 5>(c, ga, nitems);
+                case 7: return launch_grad_pipe<7, 5>(c, ga, nitems);
+                case 8: return launch_grad_pipe<8, 5>(c, ga, nitems);
+            }
+        } else if (nwarps == 7) {
+            switch (BS) {
+                case 6: return launch_grad_pipe<6, 7>(c, ga, nitems);
+                case 7: return launch_grad_pipe<7, 7>(c, ga, nitems);
+                case 8: return launch_grad_pipe<8, 7>(c, ga, nitems);
+            }
+        }
+        return fail(PIORAN_EUNSUPPORTED, "no gradient kernel for %d PSD parameters", ND);
+    }
     switch (BS) {
         case 4: return launch_grad<4>(c, ga, nitems, c->gwork_tpi);
         case 5: return launch_grad<5>(c, ga, nitems, c->gwork_tpi);
-        case 6: return launch_grad<6>(c, ga, nitems, c->gwork_tpi);
-        case 7: return launch_grad<7>(c, ga, nitems, c->gwork_tpi);
-        case 8: return launch_grad<8>(c, ga, nitems, c->gwork_tpi);
     }
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }

@@ -6,8 +6,8 @@
 //   approx_grad_kernel     (K1 on duals)  θ → row amplitudes and Σa with their derivative along one θ-direction.  On the
 //                          approx path c_j, d_j depend on the spectral grid only (src/psd.jl:250,266-267), so the series
 //                          table (cos/sin/exp) carries no tangent: only amp, Σa, ν and μ do.
-//   celerite_grad_kernel   (K2 on duals)  one WARP per (parameter vector, θ-direction): the celerite_step recursion of
-//                          celerite.cuh (non-pre-decayed form) with every θ-dependent quantity a (value, tangent) pair.
+//   celerite_grad_kernel   (K2 on duals, block sizes ≤ 5)  one WARP per (parameter vector, θ-direction): the celerite_step
+//                          recursion of celerite.cuh (non-pre-decayed form) with every θ-dependent quantity a (value, tangent) pair.
 //                          Per stored entry 4 FP64 issues for the value + 5 for the tangent.  Same lane → block mapping,
 //                          same TMA-staged shared series table, same reductions (on pairs).
 // Directions k = 0 … n_psd_par−1: PSD parameters; k = n_psd_par: ν.  ∂/∂μ needs no block tangent (μ moves only the right-hand
@@ -125,12 +125,12 @@ __global__ void approx_grad_kernel(const ApproxPlan* __restrict__ plan, int B, c
 }
 
 // ------------------------------------------------------------------------------------------------ K2 on pairs
-// SM = true (block sizes ≥ 6): the tangent half of the block lives in shared memory, one 8-byte column per lane
-// ([entry][lane], conflict-free), because 2·BS² doubles per lane do not fit the register file next to the step's operands.
-template <int BS, bool SM>
+// Block sizes ≤ 5 only: 2·BS² doubles per lane fit the register file next to the step's operands.  Larger blocks go through
+// grad_pipe.cuh (the value recursion once per parameter vector, tangent-only warps).
+template <int BS>
 struct LaneStateD {
     double Mv[BS][BS];
-    double Md[SM ? 1 : BS][SM ? 1 : BS];
+    double Md[BS][BS];
     D2 sjj[2], g[2], amp[2];
     D2 chi2;
     double logacc, dkeep, dfirst, dlog;     // Σ log|D_n| (ring as in LaneState) and its tangent Σ D'_n / D_n
@@ -149,12 +149,11 @@ __device__ __forceinline__ void load_slice2(D2 (&dst)[BS], const double* __restr
 
 // One step on pairs — the structure of celerite_step<BS, ODD, /*PRE=*/false> (celerite.cuh), line by line.
 //   sv, sd : per-warp scratch, values and tangents: q at [0, RPS), w at [RPS, 2·RPS)
-//   md     : SM only — this lane's column of the tangent block in shared memory, entry (r, c) at md[(r·BS + c)·32]
-template <int BS, bool ODD, bool SM>
-__device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const double* __restrict__ T, double* __restrict__ sv,
-                                                   double* __restrict__ sd, double* __restrict__ md, const LaneMap& lm,
-                                                   const double yn, const double s2n, const D2 suma, const D2 mu,
-                                                   const D2 nu, const int64_t n, const int lane) {
+template <int BS, bool ODD>
+__device__ __forceinline__ void celerite_step_dual(LaneStateD<BS>& st, const double* __restrict__ T, double* __restrict__ sv,
+                                                   double* __restrict__ sd, const LaneMap& lm, const double yn,
+                                                   const double s2n, const D2 suma, const D2 mu, const D2 nu,
+                                                   const int64_t n, const int lane) {
     constexpr int RP = rps_of(BS);
     const int o = lm.o;
     const D2 zero = mk2(0.0, 0.0);
@@ -186,11 +185,9 @@ __device__ __forceinline__ void celerite_step_dual(LaneStateD<BS, SM>& st, const
             const D2 w = useA ? wA : wB;
             const double u = useA ? uA : uB;
             const D2 qr = (r == c) ? sel2(lm.dzero, zero, qrow[r]) : qrow[r];
-            const D2 old = mk2(st.Mv[r][c], SM ? md[(r * BS + c) * 32] : st.Md[SM ? 0 : r][SM ? 0 : c]);
-            const D2 m = fmac(ODD ? (useA ? zA : zB) : xrow[r], old, qr * w);
+            const D2 m = fmac(ODD ? (useA ? zA : zB) : xrow[r], mk2(st.Mv[r][c], st.Md[r][c]), qr * w);
             st.Mv[r][c] = m.v;
-            if (SM) md[(r * BS + c) * 32] = m.d;
-            else    st.Md[SM ? 0 : r][SM ? 0 : c] = m.d;
+            st.Md[r][c] = m.d;
             rowpart[r] = fmac(u, m, rowpart[r]);
             if (useA) cA = fmac(urow[r], m, cA);
             else      cB = fmac(urow[r], m, cB);
@@ -292,27 +289,22 @@ struct GradArgs {
     double* grad;               // [nθ × P]
 };
 
-// grid = work items; block = NW warps; each warp one (θ, direction).  Shared memory: 2 TMA stages of CS table records |
-// NW × 4·RPS scratch | SM: NW × BS²·32 tangent blocks | 2 mbarriers | 2 stage counters (as celerite_shared_kernel).
-template <int BS> struct GradCfg {
-    static constexpr bool SM = BS >= 6;
-    static constexpr int CS = BS >= 7 ? CHUNK_STEPS / 2 : CHUNK_STEPS;   // steps per TMA stage (the tangent blocks need the room)
-};
+// grid = work items; block = NW warps; each warp one (θ, direction).  Shared memory: 2 TMA stages of the series table |
+// NW × 4·RPS scratch | 2 mbarriers | 2 stage counters (as celerite_shared_kernel).
 template <int BS, int NW>
 constexpr size_t grad_smem_bytes() {
-    return sizeof(double) * (2 * (size_t)GradCfg<BS>::CS * table_step_doubles(rps_of(BS)) + (size_t)NW * 4 * rps_of(BS) +
-                             (GradCfg<BS>::SM ? (size_t)NW * BS * BS * 32 : 0)) + 2 * sizeof(uint64_t) + 16;
+    return sizeof(double) * (2 * (size_t)CHUNK_STEPS * table_step_doubles(rps_of(BS)) + (size_t)NW * 4 * rps_of(BS)) +
+           2 * sizeof(uint64_t) + 16;
 }
 template <int BS, int NW>
 __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArgs args) {
-    constexpr bool SM = GradCfg<BS>::SM;
-    constexpr int CS = GradCfg<BS>::CS;
+    static_assert(BS <= 5, "block sizes >= 6: grad_pipe.cuh");
+    constexpr int CS = CHUNK_STEPS;
     constexpr int RP = G * BS, RPS = rps_of(BS), SD = table_step_doubles(RPS), STAGE = CS * SD;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     double* scratch = stages + 2 * STAGE;
-    double* tang = scratch + NW * 4 * RPS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tang + (SM ? NW * BS * BS * 32 : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + NW * 4 * RPS);
     int* done = reinterpret_cast<int*>(bars + 2);
 
     const WorkItem wk = args.work[blockIdx.x];
@@ -345,17 +337,12 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
     const LaneMap lm = make_lane_map<BS>(lane);
     const int i = lane >> 2, o = lane & 3;
 
-    LaneStateD<BS, SM> st;
+    LaneStateD<BS> st;
     const D2 zero = mk2(0.0, 0.0);
-    double* md = tang + (size_t)warp * BS * BS * 32 + lane;
 #pragma unroll
     for (int r = 0; r < BS; r++)
 #pragma unroll
-        for (int c = 0; c < BS; c++) {
-            st.Mv[r][c] = 0.0;
-            if (SM) md[(r * BS + c) * 32] = 0.0;
-            else    st.Md[SM ? 0 : r][SM ? 0 : c] = 0.0;
-        }
+        for (int c = 0; c < BS; c++) { st.Mv[r][c] = 0.0; st.Md[r][c] = 0.0; }
     st.sjj[0] = st.sjj[1] = st.g[0] = st.g[1] = zero;
     st.chi2 = zero; st.logacc = 0.0; st.dkeep = 1.0; st.dfirst = 1.0; st.dlog = 0.0;
     st.gmu[0] = st.gmu[1] = 0.0; st.chimu = 0.0;
@@ -384,9 +371,9 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_grad_kernel(const GradArg
             const double* T0 = stage + s * SD;
             const double* T1 = T0 + SD;
             const int64_t n = nbeg + s;
-            celerite_step_dual<BS, false, SM>(st, T0, sv, sd, md, lm, T0[6 * RPS + 0], T0[6 * RPS + 1], suma, mu, nu, n, lane);
+            celerite_step_dual<BS, false>(st, T0, sv, sd, lm, T0[6 * RPS + 0], T0[6 * RPS + 1], suma, mu, nu, n, lane);
             if (s + 1 < nsteps)
-                celerite_step_dual<BS, true, SM>(st, T1, sv, sd, md, lm, T1[6 * RPS + 0], T1[6 * RPS + 1], suma, mu, nu, n + 1, lane);
+                celerite_step_dual<BS, true>(st, T1, sv, sd, lm, T1[6 * RPS + 0], T1[6 * RPS + 1], suma, mu, nu, n + 1, lane);
         }
         __syncwarp();
         if (lane == 0 && kc + 2 < nchunks) {
