@@ -90,3 +90,20 @@ def test_grad_batch_sizes(pb, ctx, golden_single):
         v, gr = like.value_and_gradient(g.theta[-B:])
         assert np.array_equal(v, ref_val[-B:]) and np.array_equal(gr, ref_grad[-B:])
     like.close()
+
+
+@pytest.mark.parametrize("basis", ["SHO", "DRWCelerite"])
+@pytest.mark.parametrize("N", [1, 2, 7, 8, 9, 17, 33])
+def test_grad_short_series(pb, ctx, golden_single, basis, N):
+    """Edge lengths around the TMA stage sizes (8 and 16 steps) and the two-stage pipeline's start-up (N = 1, 2)."""
+    g = golden_single
+    t, y, s2 = g.t[:N].copy(), g.y[:N].copy(), g.s2[:N].copy()
+    theta = g.theta[[10, 2000, 6000]].copy()
+    if basis == "DRWCelerite":
+        theta[:, 2] += 1.0
+    like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", 20, basis, f_min=g.f_min, f_max=g.f_max, ctx=ctx)
+    val, grad = like.value_and_gradient(theta)
+    like.close()
+    oval, ograd = orc.approx_logl_grad_batch("SBPL", theta, g.f_min, g.f_max, 20, t, y, s2, basis=basis, nthreads=0)
+    assert np.abs(val - oval).max() <= 1e-9 * np.maximum(1.0, np.abs(oval)).max()
+    _check(grad, ograd)
