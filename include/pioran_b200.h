@@ -124,9 +124,10 @@ int pioran_approx_logl_grad_dev(pioran_ctx *ctx, int series_id, const pioran_app
 
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
-/* pioran_celerite_logl and pioran_approx_logl hand calls with at most 4 parameter vectors on a series of at least 4 096 (2 048 at rank <= 32)
- * steps (rank <= 64, no per-vector data) to the parallel-in-time path: a lone sequential sweep costs ~0.9 us per step
- * whatever the rank.  enabled = 0 keeps them on the sequential kernels (default: enabled). */
+/* pioran_celerite_logl and pioran_approx_logl hand calls with at most 4 parameter vectors on a long series (fused path: at
+ * least 4 096 steps, 2 048 at rank <= 32; explicit coefficients: half of that; rank <= 64, no per-vector data) to the
+ * parallel-in-time path: a lone sequential sweep costs 0.5-1.5 us per step whatever the batch.  enabled = 0 keeps them on the
+ * sequential kernels (default: enabled). */
 int pioran_ctx_set_auto_scan(pioran_ctx *ctx, int enabled);
 
 /* Number of time-axis chunks per parameter vector used by pioran_celerite_logl_scan (0 = automatic: two per SM, at

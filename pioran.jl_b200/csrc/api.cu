@@ -125,8 +125,13 @@ static int bs_for_rank(int R) {
 // 5–6 vs 62–130 ms at N = 65 536), so the plain entries route such calls to it.  Same value to ≤ 1e-13 relative.
 constexpr int64_t AUTO_SCAN_MIN_STEPS = 4096;
 constexpr int AUTO_SCAN_MAX_BATCH = 4;
-static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R) {
-    return c->auto_scan && N >= (R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS) && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
+// Thresholds from tools/scan_threshold.py (one evaluation): the fused path's sequential sweep (shared table, pre-decayed state)
+// costs 0.5–0.66 µs per step and is overtaken at 2 048 (rank ≤ 32) / 4 096 steps; the explicit-coefficient sweep builds its
+// own table (0.65–1.5 µs per step) and is overtaken at 1 024 / 2 048 steps.
+static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R, bool explicit_coefficients = false) {
+    int64_t min_steps = R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS;
+    if (explicit_coefficients) min_steps /= 2;
+    return c->auto_scan && N >= min_steps && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
 }
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
                             const double* cc, const double* d, const double* mu, const double* nu, double* logl_out);
@@ -998,7 +1003,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
     std::vector<int> term_row;
     const int R = make_term_rows(B, Jt, b, d, term_row);
-    if (!y_batch && !s2_batch && auto_scan(c, s->N, B, R))
+    if (!y_batch && !s2_batch && auto_scan(c, s->N, B, R, true))
         return scan_logl_locked(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, logl_out);
     const int BS = bs_for_rank(R);
     const bool wide = BS > 8;

@@ -17,8 +17,10 @@ for Jt in (2, 8, 16, 30):
     a, b, c, d = (np.ascontiguousarray(coef[:Jt, k][None, :]) for k in range(4))
     for N in (2 ** 12, 2 ** 13, 2 ** 14, 2 ** 16, 2 ** 18):
         ser = ctx.upload_series(t_all[:N], y_all[:N], s2_all[:N])
+        ctx.set_auto_scan(False)          # the plain entry would hand these calls to the scan path itself
         seq = wall(lambda: ctx.celerite_logl(ser, a, b, c, d)); v1 = ctx.celerite_logl(ser, a, b, c, d)[0]
-        row = {"Jt": Jt, "N": N, "seq_ms": seq}
+        ctx.set_auto_scan(True)
+        row = {"Jt": Jt, "N": N, "seq_ms": seq, "auto_ms": wall(lambda: ctx.celerite_logl(ser, a, b, c, d))}
         for P in (0, 37, 74, 148):
             ctx.set_scan_chunks(P)
             row[f"scan_P{P}_ms"] = wall(lambda: ctx.celerite_logl_scan(ser, a, b, c, d))
