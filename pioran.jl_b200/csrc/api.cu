@@ -1187,6 +1187,8 @@ struct ScanRun {
     int series_id = -1, B = 0, Jt = 0, R = 0, BS = 0, P = 0, G1 = 0, G2 = 0, SUB = 1;
     int64_t N = 0, n_lo = 0, n_hi = 0;
     std::vector<int64_t> bounds;
+    std::vector<int> term_row_host;        // host sources of the asynchronous uploads: kept alive with the run
+    std::vector<WorkItem> items_host;
     GenericInputs gi{};
     double *elems = nullptr, *pref = nullptr, *gstate = nullptr, *cstate = nullptr, *parts = nullptr, *out = nullptr;
     double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
@@ -1261,8 +1263,9 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
     CUDA_TRY(cudaMemcpyAsync(run.bounds_dev, run.bounds.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(run.term_row_dev, term_row.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));   // term_row is a local
+    run.term_row_host = term_row;            // (run = ScanRun{} above dropped the previous one)
+    CUDA_TRY(cudaMemcpyAsync(run.term_row_dev, run.term_row_host.data(), sizeof(int) * Jt, cudaMemcpyHostToDevice, c->stream));
+    // no host synchronisation here: the sources live in `run`, and a copy from pageable memory is staged before the call returns
 
     ScanArgs sa{};
     sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = run.bounds_dev;
@@ -1316,7 +1319,8 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     const int B = run.B, P = run.P, NW = CHUNK_NW, SUB = run.SUB;
     const size_t nch = (size_t)B * P, nsub = nch * SUB;
     const size_t nitems = (nsub + NW - 1) / NW * NW;
-    std::vector<WorkItem> items(nitems);
+    std::vector<WorkItem>& items = run.items_host;
+    items.assign(nitems, WorkItem{});
     for (size_t k = 0; k < nitems; k++) {
         const size_t e = std::min(k, nsub - 1);
         const size_t q = e / SUB;
@@ -1335,7 +1339,6 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     c->work_key.clear();
     if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));   // items is a local
     if (P > 1 || init_dev) {
         scan_group_states_kernel<<<dim3(run.G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tp, run.gstate, run.G1, init_dev, scan_live_rank(run.R));
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
