@@ -181,6 +181,17 @@ class Context:
         """Chunks of the time axis per parameter vector in celerite_logl_scan (0 = automatic)."""
         check(self.lib.pioran_ctx_set_scan_chunks(self.h, int(chunks)))
 
+    def set_scan_tolerance(self, tol):
+        """Self-check of the scan path: parameter vectors whose deviation estimate exceeds tol·max(1, |log L|) are evaluated
+        again by the sequential sweep (default 1e-10; ≤ 0: never)."""
+        check(self.lib.pioran_ctx_set_scan_tolerance(self.h, float(tol)))
+
+    def last_scan_check(self):
+        """(largest relative deviation estimate, parameter vectors sent to the sequential sweep) of the last scan call."""
+        est, nfb = C.c_double(0.0), C.c_int(0)
+        check(self.lib.pioran_ctx_last_scan_check(self.h, C.byref(est), C.byref(nfb)))
+        return est.value, nfb.value
+
     def celerite_logl_scan(self, series, a, b, c, d, mu=None, nu=None):
         a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))
         B, Jt = a.shape

@@ -109,6 +109,9 @@ struct pioran_ctx {
     int gwork_items = 0, gwork_tpi = 0;
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
+    double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
+    double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
+    int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
     std::mutex mu;
 };
 
@@ -135,6 +138,9 @@ static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R, bool explici
 }
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
                             const double* cc, const double* d, const double* mu, const double* nu, double* logl_out);
+static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const double* a, const double* b, const double* cc,
+                               const double* d, const double* mu, const double* nu, const double* y_batch,
+                               const double* s2_batch, double* logl_out);
 
 static void scan_forget(pioran_ctx* c);   // drops the range-in-progress record of a context (K3 multi-GPU entries)
 extern "C" int pioran_ctx_destroy(pioran_ctx* c);
@@ -1005,6 +1011,15 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     const int R = make_term_rows(B, Jt, b, d, term_row);
     if (!y_batch && !s2_batch && auto_scan(c, s->N, B, R, true))
         return scan_logl_locked(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, logl_out);
+    return generic_logl_locked(c, s, B, Jt, a, b, cc, d, mu, nu, y_batch, s2_batch, logl_out);
+} catch (...) { return guard_fail(); }
+
+// The sequential sweep on explicit coefficients (generic K2, K2w above rank 64); the context is locked by the caller.
+static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const double* a, const double* b, const double* cc,
+                               const double* d, const double* mu, const double* nu, const double* y_batch,
+                               const double* s2_batch, double* logl_out) {
+    std::vector<int> term_row;
+    const int R = make_term_rows(B, Jt, b, d, term_row);
     const int BS = bs_for_rank(R);
     const bool wide = BS > 8;
     if (wide && R > WIDE_MAX_RANK)
@@ -1036,7 +1051,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
-} catch (...) { return guard_fail(); }
+}
 
 // ------------------------------------------------------------------------------------------------ posterior mean, draws
 // Common set-up of the two widening entries: coefficient upload, row map, work items for the generic kernel.
@@ -1173,6 +1188,18 @@ extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 
+extern "C" int pioran_ctx_set_scan_tolerance(pioran_ctx* c, double tol) try {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (tol != tol) return fail(PIORAN_EINVAL, "tol is NaN");
+    c->scan_tol = tol;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* n_fallback) try {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (estimate) *estimate = c->scan_last_est;
+    if (n_fallback) *n_fallback = c->scan_last_fallback;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
@@ -1193,10 +1220,15 @@ struct ScanRun {
     double *elems = nullptr, *pref = nullptr, *gstate = nullptr, *cstate = nullptr, *parts = nullptr, *out = nullptr;
     double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
     double *subel = nullptr, *substate = nullptr, *tot0 = nullptr, *tot1 = nullptr, *tp = nullptr;
+    double *chk = nullptr, *err = nullptr;   // self-check sums (4 per sub-chunk) and the per-θ deviation estimate
+    double check_scale = 1.0;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
 };
 static int scan_live_rank(int R) { return std::min(SR, (R + 3) & ~3); }
+// Steps of the self-check at a sub-chunk boundary: SCAN_CHECK_STEPS, or the (even part of the) sub-chunk when it is shorter.
+constexpr int SCAN_CHECK_STEPS = 8;
+static int scan_check_steps(int64_t sub_len) { return (int)std::min<int64_t>(SCAN_CHECK_STEPS, sub_len & ~(int64_t)1); }
 static std::map<pioran_ctx*, ScanRun> g_scan;
 static std::mutex g_scan_mu;
 static void scan_forget(pioran_ctx* c) { std::lock_guard<std::mutex> g(g_scan_mu); g_scan.erase(c); }
@@ -1232,17 +1264,19 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2; run.SUB = SUB;
     run.N = N; run.n_lo = n_lo; run.n_hi = n_hi;
     run.bounds.resize(P + 1);
-    for (int k = 0; k <= P; k++) run.bounds[k] = n_lo + (int64_t)((__int128)len * k / P);
+    // inner bounds at even offsets: every sub-chunk but the last has an even length (the self-check sweeps on across a bound)
+    for (int k = 0; k <= P; k++) run.bounds[k] = k == P ? n_hi : n_lo + ((int64_t)((__int128)len * k / P) & ~(int64_t)1);
 
     int rc;
     if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, run.gi))) return rc;
     const size_t nch = (size_t)B * P;
     // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out | total | scratch | init | prev | sums
     const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch * SUB + 1);
+    const size_t n_chk = 4 * (nch * SUB + 1);
     const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE, n_gt = (size_t)B * G1 * SEL;
     const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
     const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
-    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 2 * (size_t)B + n_sel + n_sst + 2 * n_gt))))
+    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
         return rc;
     run.elems = c->misc.as<double>();
     run.pref = run.elems + n_el;
@@ -1255,10 +1289,12 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.init = run.scratch + n_scr;
     run.prev = run.init + n_init;
     run.sums = run.prev + n_prev;
-    run.subel = run.sums + 2 * (size_t)B;
+    run.subel = run.sums + 3 * (size_t)B;
     run.substate = run.subel + n_sel;
     run.tot0 = run.substate + n_sst;
     run.tot1 = run.tot0 + n_gt;
+    run.chk = run.tot1 + n_gt;
+    run.err = run.chk + n_chk;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
@@ -1334,7 +1370,19 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
         if (j == 0) w.init = (ch == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
         else        w.init = run.substate + (q * (SUB - 1) + (j - 1)) * SSTATE;
         w.part = k < nsub ? run.parts + 2 * e : run.parts + 2 * nsub;   // padding warps write to the dummy pair
+        w.chk = k < nsub ? run.chk + 4 * e : run.chk + 4 * nsub;
+        // self-check: re-sweep the first steps of the NEXT sub-chunk from this sweep's own state (n_ext), and sum the first
+        // steps of this one separately (n_head) for the previous work item's comparison
+        const bool first = ch == 0 && j == 0, last = ch == P - 1 && j == SUB - 1;
+        w.n_head = first ? 0 : scan_check_steps(w.n_end - w.n_begin);
+        if (last) w.n_ext = 0;
+        else {
+            const int ch2 = j == SUB - 1 ? ch + 1 : ch, j2 = j == SUB - 1 ? 0 : j + 1;
+            w.n_ext = scan_check_steps(scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2 + 1, SUB) -
+                                       scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2, SUB));
+        }
     }
+    run.check_scale = std::max(1.0, (double)(run.n_hi - run.n_lo) / ((double)P * SUB * SCAN_CHECK_STEPS));
     int rc;
     c->work_key.clear();
     if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
@@ -1367,13 +1415,45 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
     cudaEventRecord(c->ev_beg, c->stream);
     if ((rc = scan_phase1(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, 0, s->N, false, 0, run))) return rc;
     if ((rc = scan_phase2(c, s, run, nullptr))) return rc;
-    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.P * run.SUB, B, s->N, run.out);
+    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.chk, run.check_scale, run.P * run.SUB, B, s->N, run.out,
+                                                                 run.err);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
+    std::vector<double> est(B);
     CUDA_TRY(cudaMemcpyAsync(logl_out, run.out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(est.data(), run.err, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // Self-check (scan.cuh, scan_check_estimate).  The composites lose accuracy where the covariance is ill-conditioned (steep
+    // PSD slopes: the scan's value was seen 1e-8 … 1e-6 away from the sequential sweep's, which stays within 1e-9 of an 80-bit
+    // evaluation there): parameter vectors whose estimate exceeds the tolerance are evaluated again by the sequential sweep.
+    c->scan_last_est = 0.0; c->scan_last_fallback = 0;
+    {
+        std::vector<int> redo;
+        for (int i = 0; i < B; i++) {
+            const double rel = est[i] / std::max(1.0, std::fabs(logl_out[i]));
+            if (c->scan_tol > 0.0 && !(rel <= c->scan_tol)) redo.push_back(i);
+            if (!(rel <= c->scan_last_est)) c->scan_last_est = rel;     // NaN sticks
+        }
+        if (!redo.empty()) {
+            const size_t nr = redo.size();
+            std::vector<double> ra(nr * Jt), rb(nr * Jt), rcc(nr * Jt), rd(nr * Jt), rmu(nr), rnu(nr), rout(nr);
+            for (size_t k = 0; k < nr; k++) {
+                const size_t i = (size_t)redo[k];
+                std::copy(a + i * Jt, a + (i + 1) * Jt, ra.begin() + k * Jt);
+                std::copy(b + i * Jt, b + (i + 1) * Jt, rb.begin() + k * Jt);
+                std::copy(cc + i * Jt, cc + (i + 1) * Jt, rcc.begin() + k * Jt);
+                std::copy(d + i * Jt, d + (i + 1) * Jt, rd.begin() + k * Jt);
+                rmu[k] = mu ? mu[i] : 0.0; rnu[k] = nu ? nu[i] : 1.0;
+            }
+            if ((rc = generic_logl_locked(c, s, (int)nr, Jt, ra.data(), rb.data(), rcc.data(), rd.data(), rmu.data(), rnu.data(),
+                                          nullptr, nullptr, rout.data())))
+                return rc;
+            for (size_t k = 0; k < nr; k++) logl_out[redo[k]] = rout[k];
+            c->scan_last_fallback = (int)nr;
+        }
+    }
     return PIORAN_OK;
 }
 
@@ -1433,13 +1513,18 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
         init = run.init;
     }
     if ((rc = scan_phase2(c, s, run, init))) return rc;
-    scan_partial_kernel<<<1, 32, 0, c->stream>>>(run.parts, run.P * run.SUB, 1, run.sums);
+    scan_partial_kernel<<<1, 32, 0, c->stream>>>(run.parts, run.chk, run.check_scale, run.P * run.SUB, 1, run.sums);
     c->launches++;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(sums_out, run.sums, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    double sums3[3];
+    CUDA_TRY(cudaMemcpyAsync(sums3, run.sums, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    sums_out[0] = sums3[0]; sums_out[1] = sums3[1];
+    // this range's part of the self-check estimate, in log L units (the caller sums the ranks' parts and divides by |log L|;
+    // the hand-over between ranges is not covered): pioran_ctx_last_scan_check
+    c->scan_last_est = sums3[2]; c->scan_last_fallback = 0;
     run.valid = false;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }

@@ -66,6 +66,11 @@ struct WorkItem {
     int64_t n_begin, n_end;
     const double* init;
     double* part;
+    // K3 self-check: the sums of the first n_head steps go to chk[0..1] as well, and the sweep continues over the n_ext
+    // steps after n_end into chk[2..3] (not part of `part`).  The next work item sweeps those same steps from the state the
+    // scan handed it: the two pairs agree to rounding exactly when that state is the one this sweep arrives at.
+    int n_head, n_ext;
+    double* chk;
 };
 
 // sin and cos of a large FP64 argument.  The celerite rows take cos/sin(d_j·t_n) at ABSOLUTE times

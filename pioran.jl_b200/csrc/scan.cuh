@@ -562,21 +562,38 @@ __global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_
     }
 }
 // Σ over chunks of the pass-3 partial sums of a range → (Σ log|D_n|, Σ z_n²/D_n), one thread per parameter vector.
-__global__ void scan_partial_kernel(const double* __restrict__ parts, int P, int B, double* __restrict__ sums) {
+// Deviation estimate of one parameter vector from the self-check sums (WorkItem::chk): at every sub-chunk boundary the
+// steps right after it were swept twice — by the previous warp, continuing from its own state, and by the next warp from the
+// state the scan handed it.  The two contributions to log L differ by the effect of the scan's state error on those steps;
+// `scale` (sub-chunk length / check length, ≥ 1) extends it to the whole sub-chunk — an upper bound while the effect of a state
+// perturbation does not grow along the sweep.  NaN when any of the sums is not finite.
+__device__ inline double scan_check_estimate(const double* __restrict__ chk, int P, double scale) {
+    double est = 0.0;
+    for (int k = 0; k + 1 < P; k++) {
+        const double* a = chk + 4 * (size_t)k;
+        est += 0.5 * (fabs(a[2] - a[4]) + fabs(a[3] - a[5]));
+    }
+    return est * scale;
+}
+
+__global__ void scan_partial_kernel(const double* __restrict__ parts, const double* __restrict__ chk, double scale, int P, int B,
+                                    double* __restrict__ sums) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     double ld = 0.0, chi = 0.0;
     for (int k = 0; k < P; k++) { ld += parts[2 * ((size_t)i * P + k)]; chi += parts[2 * ((size_t)i * P + k) + 1]; }
-    sums[2 * i] = ld; sums[2 * i + 1] = chi;
+    sums[3 * i] = ld; sums[3 * i + 1] = chi; sums[3 * i + 2] = scan_check_estimate(chk + 4 * (size_t)i * P, P, scale);
 }
 
 // Σ over chunks of the pass-3 partial sums → logL (celerite_solver.jl:333).  One thread per parameter vector.
-__global__ void scan_finish_kernel(const double* __restrict__ parts, int P, int B, int64_t N, double* __restrict__ out) {
+__global__ void scan_finish_kernel(const double* __restrict__ parts, const double* __restrict__ chk, double scale, int P, int B,
+                                   int64_t N, double* __restrict__ out, double* __restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     double ld = 0.0, chi = 0.0;
     for (int k = 0; k < P; k++) { ld += parts[2 * ((size_t)i * P + k)]; chi += parts[2 * ((size_t)i * P + k) + 1]; }
     out[i] = -ld / 2 - (double)N * 1.8378770664093453 / 2 - chi / 2;
+    err[i] = scan_check_estimate(chk + 4 * (size_t)i * P, P, scale);
 }
 
 }  // namespace pioran

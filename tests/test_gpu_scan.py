@@ -154,3 +154,58 @@ def test_auto_dispatch_to_scan(pb, ctx):
     want = orc.celerite_logl(a[0], b[0], c[0], d[0], t, y - theta[0, 5], theta[0, 4] * s2)
     for v in (auto_gen, auto_fused, seq_gen, seq_fused):
         assert rel_err(v, want) <= TOL, (v, want)
+
+
+def _steep_prior_draws(B, f_min, f_max, seed, alpha2_max):
+    """(α₁, f₁, α₂, variance) rows of the reference's example prior (examples/ultranest/single_pl.jl:96-118) with slopes up to
+    alpha2_max: the steep ones make the celerite covariance ill-conditioned."""
+    rng = np.random.default_rng(seed)
+    a1 = rng.uniform(0.0, 1.5, B)
+    f1 = np.exp(rng.uniform(np.log(f_min / 5), np.log(f_max * 5), B))
+    a2 = a1 + rng.uniform(size=B) * (alpha2_max - a1)
+    return np.stack([a1, f1, a2, np.ones(B)], axis=1)
+
+
+@pytest.mark.parametrize("basis,J", [("DRWCelerite", 5), ("DRWCelerite", 2), ("DRWCelerite", 20)])
+def test_scan_self_check_keeps_sequential_accuracy(pb, ctx, basis, J):
+    """The composites of the scan lose accuracy on ill-conditioned covariances (steep slopes: up to 1e-6, far more on the
+    J = 2 grid).  Every call checks itself at the chunk boundaries and re-evaluates the offending parameter vectors with
+    the sequential sweep (include/pioran_b200.h: pioran_ctx_set_scan_tolerance), so the caller sees the sequential value."""
+    t, y, s2, f_min, f_max = synthetic_series(4200, seed=33)
+    psd = _steep_prior_draws(64, f_min, f_max, seed=J, alpha2_max=6.0)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+    a, b, c, d = ctx.approx_coeffs(spec, psd)
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_auto_scan(False)
+    seq = ctx.celerite_logl(ser, a, b, c, d)
+    ctx.set_auto_scan(True)
+    ctx.set_scan_chunks(0)
+    got, nfb = [], 0
+    for i in range(0, 64, 4):
+        got.append(ctx.celerite_logl(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]))   # auto-routed to the scan path
+        nfb += ctx.last_scan_check()[1]
+    got = np.concatenate(got)
+    ctx.set_scan_tolerance(0.0)
+    raw = np.concatenate([ctx.celerite_logl_scan(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]) for i in range(0, 64, 4)])
+    assert ctx.last_scan_check()[1] == 0
+    ctx.set_scan_tolerance(1e-10)
+    ser.free()
+    ok = np.isfinite(seq)
+    err = np.abs(got[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
+    err_raw = np.abs(raw[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
+    print(f"\n{basis} J={J}: checked max {np.nanmax(err):.1e} ({nfb} of 64 re-evaluated), raw scan max {np.nanmax(err_raw):.1e}")
+    assert np.all(err <= TOL), err.max()
+    if np.nanmax(err_raw) > TOL:
+        assert nfb > 0
+    assert np.array_equal(np.isfinite(got), ok)
+
+
+def test_scan_self_check_leaves_well_conditioned_calls_alone(pb, ctx):
+    t, y, s2, f_min, f_max = synthetic_series(12000, seed=21)
+    theta = np.array([[0.82, 0.01, 3.3, 1.0, 1.3, 0.2], [0.3, 0.05, 2.5, 0.7, 1.0, -0.1]])
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20)
+    ser = ctx.upload_series(t, y, s2)
+    ctx.approx_logl(ser, spec, theta)
+    est, nfb = ctx.last_scan_check()
+    ser.free()
+    assert nfb == 0 and 0.0 <= est <= 1e-12, (est, nfb)

@@ -19,8 +19,9 @@ if which in ("k3", "both"):
         print(f"K3 N={N} R=60: logL {v:.6f}  device {ctx.last_kernel_ms():.2f} ms  wall {dt*1e3:.1f} ms", flush=True)
     B = 8
     aa, bb, cc, dd = (np.repeat(x, B, axis=0) for x in (a, b, c, d))
-    v = ctx.celerite_logl_scan(ser, aa, bb, cc, dd)
-    print(f"K3 B=8: device {ctx.last_kernel_ms():.2f} ms", flush=True)
+    for rep in range(2):
+        v = ctx.celerite_logl_scan(ser, aa, bb, cc, dd)
+        print(f"K3 B=8: device {ctx.last_kernel_ms():.2f} ms, self-check (estimate, re-evaluated) {ctx.last_scan_check()}", flush=True)
 if which in ("k4", "both"):
     t, y, s2, f_min, f_max = wl.make_series(2000, 5)
     th = wl.prior_theta(64, f_min, f_max, y.mean(), y.std(), 7)

@@ -1,0 +1,82 @@
+"""Accuracy of the parallel-in-time path against the sequential sweep over prior draws (ill-conditioned θ included)."""
+import sys
+import numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tools")
+import pioran_b200 as pb
+import workloads as wl
+from oracle import oracle as orc
+ctx = pb.get_context(0)
+for basis, J in (("SHO", 20), ("DRWCelerite", 20), ("DRWCelerite", 10), ("SHO", 10), ("DRWCelerite", 5), ("DRWCelerite", 2)):
+    for N in (4200, 20000):
+        t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=5)
+        th = wl.prior_theta(256, f_min, f_max, y.mean(), y.std(), 9, 4.0 if basis == "SHO" else 6.0)
+        spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+        a, b, c, d = ctx.approx_coeffs(spec, th[:, :4])
+        ser = ctx.upload_series(t, y, s2)
+        ctx.set_auto_scan(False)
+        seq = ctx.celerite_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4])
+        ctx.set_auto_scan(True)
+        ok = np.isfinite(seq)
+        # with the self-check (default tolerance): what the caller gets, and how many parameter vectors were re-evaluated
+        nfb, chk, ests = 0, [], []
+        for i in range(0, 256, 4):
+            chk.append(ctx.celerite_logl_scan(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4], mu=th[i:i + 4, 5], nu=th[i:i + 4, 4]))
+            e, k = ctx.last_scan_check()
+            nfb += k; ests.append(e)
+        chk = np.concatenate(chk)
+        errc = np.abs(chk[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
+        errc = np.where(np.isfinite(errc), errc, 1.0)
+        print(f"{basis} J={J} N={N}: WITH self-check: max {errc.max():.1e}, {nfb} of 256 re-evaluated sequentially, "
+              f"largest estimate per call: median {np.nanmedian(ests):.1e}", flush=True)
+        ctx.set_scan_tolerance(0.0)     # raw scan
+        scan, est1 = [], []
+        for i in range(256):
+            scan.append(ctx.celerite_logl_scan(ser, a[i:i + 1], b[i:i + 1], c[i:i + 1], d[i:i + 1], mu=th[i:i + 1, 5], nu=th[i:i + 1, 4]))
+            est1.append(ctx.last_scan_check()[0])
+        scan = np.concatenate(scan); est1 = np.array(est1)
+        ctx.set_scan_tolerance(1e-10)
+        ser.free()
+        raw = np.abs(scan - seq) / np.maximum(1.0, np.abs(seq))
+        m = ok & np.isfinite(raw) & (raw > 1e-11)
+        if m.any():
+            ratio = est1[m] / raw[m]
+            print(f"    estimate / actual deviation where the latter > 1e-11 (n={m.sum()}): min {np.nanmin(ratio):.2g}, median {np.nanmedian(ratio):.2g}, "
+                  f"max {np.nanmax(ratio):.2g}; rows with deviation > 1e-9 and estimate <= 1e-10: {int(((raw > 1e-9) & ok & (est1 <= 1e-10)).sum())}", flush=True)
+        err = np.abs(scan[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
+        err = np.where(np.isfinite(err), err, 1.0)
+        # the sequential kernel's own distance from the 80-bit evaluation on the worst rows
+        worst = np.argsort(-err)[:3]
+        ld = []
+        idx = np.flatnonzero(ok)[worst]
+        for i in idx:
+            ld.append(orc.celerite_logl(a[i], b[i], c[i], d[i], t, y - th[i, 5], th[i, 4] * s2, long_double=True))
+        eseq = np.abs(seq[idx] - np.array(ld)) / np.maximum(1.0, np.abs(ld))
+        print(f"{basis} J={J} N={N}: scan-vs-seq median {np.median(err):.1e}, 99% {np.quantile(err, 0.99):.1e}, max {err.max():.1e}; "
+              f"worst rows: scan-vs-seq {err[worst]}, seq-vs-80bit {eseq}, nonfinite scan {int((~np.isfinite(scan[ok])).sum())}", flush=True)
+
+print("--- conditioning indicator kappa = sum|a| / |sum a| against the scan's deviation")
+for basis, J in (("DRWCelerite", 20), ("DRWCelerite", 10), ("DRWCelerite", 5), ("SHO", 20), ("SHO", 5), ("DRWCelerite", 2)):
+    N = 8000
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=6)
+    th = wl.prior_theta(512, f_min, f_max, y.mean(), y.std(), 10, 4.0 if basis == "SHO" else 6.0)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+    a, b, c, d = ctx.approx_coeffs(spec, th[:, :4])
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_auto_scan(False)
+    seq = ctx.celerite_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4])
+    ctx.set_auto_scan(True)
+    ctx.set_scan_tolerance(0.0)
+    scan = np.concatenate([ctx.celerite_logl_scan(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4], mu=th[i:i + 4, 5], nu=th[i:i + 4, 4])
+                           for i in range(0, 512, 4)])
+    ctx.set_scan_tolerance(1e-10)
+    ser.free()
+    kappa = np.abs(a).sum(axis=1) / np.abs(a.sum(axis=1))
+    err = np.abs(scan - seq) / np.maximum(1.0, np.abs(seq))
+    err = np.where(np.isfinite(err), err, 1.0)
+    edges = [1, 1.5, 3, 10, 30, 100, 1e3, 1e4, 1e6, 1e12]
+    line = []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        m = (kappa >= lo) & (kappa < hi)
+        if m.any():
+            line.append(f"[{lo:g},{hi:g}): n={m.sum()} max {err[m].max():.1e}")
+    print(basis, J, "; ".join(line), flush=True)
