@@ -434,20 +434,22 @@ def sharded_configs(torch, dist, ctx, pb, J, rank, world):
     a, b, c, d = ctx.approx_coeffs(spec, np.array([[0.82, 0.01, 3.3, float(np.var(y))]]))
     ser = ctx.upload_series(t, y, s2)
     ag, ar = parallel.torch_collectives(device="cuda")
-    walls = []
+    walls, chk = [], {}
     for _ in range(3):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         v = parallel.scan_logl_sharded(lambda lo, hi: ctx.scan_range_begin(ser, a, b, c, d, lo, hi, max_prev=world),
-                                       lambda prev: ctx.scan_range_end(prev), N, rank, world, ag, ar)
+                                       lambda prev: ctx.scan_range_end(prev), N, rank, world, ag, ar,
+                                       range_check=ctx.scan_range_check, info=chk)
         torch.cuda.synchronize()
         walls.append(time.perf_counter() - t0)
     ser.free()
     tt = torch.tensor([min(walls[1:])], dtype=torch.float64, device="cuda")
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     out[f"C4_long_series_N1e6_time_axis_over_{world}gpu"] = {"wall_ms_max_over_ranks": float(tt.item()) * 1e3, "logL": v,
-                                                             "collectives": "all-gather of range composites (97 KB each) + 2-value all-reduce"}
+                                                             "self_check_estimate_rel": chk.get("estimate"),
+                                                             "collectives": "all-gather of range composites (97 KB each) + 2-value all-reduce + all-gather of the self-check rows (64 B each)"}
     return out
 
 

@@ -164,6 +164,17 @@ int pioran_celerite_scan_range_begin(pioran_ctx *ctx, int series_id, int Jt,
                                      double *composite_out);
 int pioran_celerite_scan_range_end(pioran_ctx *ctx, int nprev, const double *composites_prev, double *sums_out);
 
+/* Self-check data of the range pioran_celerite_scan_range_end just finished, out8 =
+ *   [0]    this range's inner estimate (log L units; see pioran_ctx_set_scan_tolerance),
+ *   [1..2] (sum log|D|, sum z^2/D) of the first out8[5] steps of the range, swept from the state the earlier composites gave,
+ *   [3..4] the same sums over the out8[6] steps AFTER the range, swept on from this range's own final state,
+ *   [5], [6] those step counts (0 at the two ends of the series),  [7] the scale (sub-chunk length / check length).
+ * The hand-over from rank r-1 to rank r is consistent when [3..4] of r-1 equal [1..2] of r; the caller gathers the eight
+ * values of every rank, adds scale * (|d sum log|D|| + |d sum z^2/D|) / 2 of each hand-over to the inner estimates and
+ * falls back to a sequential evaluation when the total exceeds its tolerance (pioran.jl_b200/parallel.py:
+ * scan_logl_sharded does exactly that). */
+int pioran_celerite_scan_range_check(pioran_ctx *ctx, double *out8);
+
 /* ---- K4: dense cross-check ------------------------------------------------------------------------------- */
 /* Drop-in for  log_likelihood_direct(cov, t, y, σ²)  (src/direct_solver.jl:6-21) with the kernel of
  * src/Celerite.jl:42-44 summed over terms.  Returns +NLL like the reference (tests negate it,

@@ -221,6 +221,12 @@ class Context:
         check(self.lib.pioran_celerite_scan_range_end(self.h, nprev, _p(prev), _p(out)))
         return out
 
+    def scan_range_check(self):
+        """Self-check data of the range scan_range_end just finished (include/pioran_b200.h: pioran_celerite_scan_range_check)."""
+        out = np.empty(8)
+        check(self.lib.pioran_celerite_scan_range_check(self.h, _p(out)))
+        return out
+
     # -- K4
     def direct_logl(self, series, a, b, c, d, mu=None, nu=None):
         """Batched log_likelihood_direct (src/direct_solver.jl:6-21): returns (+NLL [B], info [B])."""

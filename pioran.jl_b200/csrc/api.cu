@@ -112,6 +112,7 @@ struct pioran_ctx {
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
     double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
     int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
+    double scan_range_chk[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pioran_celerite_scan_range_check
     std::mutex mu;
 };
 
@@ -1373,9 +1374,11 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
         w.chk = k < nsub ? run.chk + 4 * e : run.chk + 4 * nsub;
         // self-check: re-sweep the first steps of the NEXT sub-chunk from this sweep's own state (n_ext), and sum the first
         // steps of this one separately (n_head) for the previous work item's comparison
+        // (a range in the middle of a series also checks its hand-over: its first sub-chunk sums its head for the rank before,
+        // its last one sweeps on into the next rank's range — pioran_celerite_scan_range_check)
         const bool first = ch == 0 && j == 0, last = ch == P - 1 && j == SUB - 1;
-        w.n_head = first ? 0 : scan_check_steps(w.n_end - w.n_begin);
-        if (last) w.n_ext = 0;
+        w.n_head = (first && !init_dev) ? 0 : scan_check_steps(w.n_end - w.n_begin);
+        if (last) w.n_ext = run.n_hi < run.N ? scan_check_steps(run.N - run.n_hi) : 0;
         else {
             const int ch2 = j == SUB - 1 ? ch + 1 : ch, j2 = j == SUB - 1 ? 0 : j + 1;
             w.n_ext = scan_check_steps(scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2 + 1, SUB) -
@@ -1518,14 +1521,31 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     CUDA_TRY(cudaGetLastError());
-    double sums3[3];
+    double sums3[3], chk_first[4], chk_last[4];
+    const size_t nsub = (size_t)run.P * run.SUB;
     CUDA_TRY(cudaMemcpyAsync(sums3, run.sums, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(chk_first, run.chk, sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(chk_last, run.chk + 4 * (nsub - 1), sizeof(double) * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    {
+        const WorkItem& wf = run.items_host[0];
+        const WorkItem& wl = run.items_host[nsub - 1];
+        double* k = c->scan_range_chk;
+        k[0] = sums3[2]; k[1] = chk_first[0]; k[2] = chk_first[1]; k[3] = chk_last[2]; k[4] = chk_last[3];
+        k[5] = wf.n_head; k[6] = wl.n_ext; k[7] = run.check_scale;
+    }
     sums_out[0] = sums3[0]; sums_out[1] = sums3[1];
     // this range's part of the self-check estimate, in log L units (the caller sums the ranks' parts and divides by |log L|;
     // the hand-over between ranges is not covered): pioran_ctx_last_scan_check
     c->scan_last_est = sums3[2]; c->scan_last_fallback = 0;
     run.valid = false;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
+extern "C" int pioran_celerite_scan_range_check(pioran_ctx* c, double* out8) try {
+    if (!c || !out8) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    std::copy(c->scan_range_chk, c->scan_range_chk + 8, out8);
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 

@@ -65,14 +65,35 @@ class ShardedEvaluator:
         return torch.cat(parts)
 
 
-def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=None, all_reduce_sum=None):
+def scan_check_total(checks):
+    """Deviation estimate (log L units) of a time-axis-sharded scan from the ranks' self-check rows [world × 8]
+    (Context.scan_range_check): the inner estimates plus, per hand-over r-1 → r, the difference between the sums rank r-1 got
+    by sweeping on into rank r's first steps and the sums rank r got for them from the chained composites.  NaN propagates."""
+    checks = np.asarray(checks, dtype=np.float64).reshape(-1, 8)
+    est = float(np.sum(checks[:, 0]))
+    for r in range(1, checks.shape[0]):
+        prev, cur = checks[r - 1], checks[r]
+        if prev[6] > 0 and prev[6] == cur[5]:
+            est += 0.5 * cur[7] * (abs(prev[3] - cur[1]) + abs(prev[4] - cur[2]))
+        else:
+            est = float("nan")      # a range too short to be checked
+    return est
+
+
+def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=None, all_reduce_sum=None, range_check=None,
+                      sequential=None, tol=1e-10, info=None):
     """Log-likelihood of ONE long series with the time axis split across `world` ranks.
 
     Rank r owns steps [N·r/world, N·(r+1)/world).  `range_begin(n_lo, n_hi)` folds them and returns the range's composite
     scan element (Context.scan_range_begin); `all_gather(x) -> [world × len(x)]` exchanges the composites — the only
     collective on the data path besides the final 2-value sum; `range_end(prev)` re-filters the range from the state the
     `prev` earlier composites leave behind and returns (Σ log|D_n|, Σ z_n²/D_n); `all_reduce_sum` adds those over the ranks.
-    With world == 1 (or no collectives given) it reduces to the single-GPU scan."""
+    With world == 1 (or no collectives given) it reduces to the single-GPU scan.
+
+    Self-check (the composites lose accuracy on ill-conditioned covariances): with `range_check` (Context.scan_range_check)
+    the ranks also gather their check rows; when the estimated deviation exceeds tol·max(1, |log L|) and `sequential` — a
+    callable returning the sequential sweep's value of the whole series — is given, every rank returns that instead (all
+    ranks see the same gathered rows and take the same decision).  `info`, a dict, receives 'estimate' and 'fallback'."""
     off = shard_bounds(N, world)
     comp = np.asarray(range_begin(int(off[rank]), int(off[rank + 1])), dtype=np.float64)
     if world > 1:
@@ -81,7 +102,17 @@ def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=Non
         sums = np.asarray(all_reduce_sum(sums), dtype=np.float64)
     else:
         sums = np.asarray(range_end(None), dtype=np.float64)
-    return float(-0.5 * sums[0] - 0.5 * sums[1] - 0.5 * N * np.log(2.0 * np.pi))   # celerite_solver.jl:333
+    value = float(-0.5 * sums[0] - 0.5 * sums[1] - 0.5 * N * np.log(2.0 * np.pi))   # celerite_solver.jl:333
+    if range_check is not None:
+        row = np.asarray(range_check(), dtype=np.float64)
+        rows = np.asarray(all_gather(row), dtype=np.float64).reshape(world, 8) if world > 1 else row.reshape(1, 8)
+        rel = scan_check_total(rows) / max(1.0, abs(value))
+        fallback = sequential is not None and not (rel <= tol)
+        if info is not None:
+            info["estimate"], info["fallback"] = rel, fallback
+        if fallback:
+            value = float(sequential())
+    return value
 
 
 def torch_collectives(device=None, group=None):

@@ -118,6 +118,11 @@ def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks):
     tot = np.sum(sums, axis=0)
     got = -0.5 * tot[0] - 0.5 * tot[1] - 0.5 * len(t) * np.log(2 * np.pi)
     assert rel_err(got, want) <= TOL, (got, want)
+    # self-check rows: inner estimates + the hand-overs between the ranks (8 steps swept by both neighbours)
+    from pioran_b200.parallel import scan_check_total
+    rows = np.stack([ctxs[r].scan_range_check() for r in range(world)])
+    assert np.all(rows[1:, 5] == 8) and np.all(rows[:-1, 6] == 8) and rows[0, 5] == 0 and rows[-1, 6] == 0
+    assert 0.0 <= scan_check_total(rows) / abs(want) <= 1e-11
     # the orchestration function with list-backed collectives gives the same number on every rank
     for r in range(world):
         val = scan_logl_sharded(lambda lo, hi: ctxs[r].scan_range_begin(sers[r], a, b, c, d, lo, hi, mu=mu, nu=nu, max_prev=world),
@@ -209,3 +214,49 @@ def test_scan_self_check_leaves_well_conditioned_calls_alone(pb, ctx):
     est, nfb = ctx.last_scan_check()
     ser.free()
     assert nfb == 0 and 0.0 <= est <= 1e-12, (est, nfb)
+
+
+def test_scan_time_axis_split_self_check_and_fallback(pb, ctx):
+    """Ill-conditioned covariance with the time axis split over 3 ranks: the gathered self-check rows (inner estimates and
+    hand-overs) flag the deviation, and scan_logl_sharded then returns the sequential sweep's value on every rank."""
+    from pioran_b200.parallel import scan_logl_sharded, scan_check_total, shard_bounds
+    world = 3
+    t, y, s2, f_min, f_max = synthetic_series(6000, seed=33)
+    psd = _steep_prior_draws(48, f_min, f_max, seed=5, alpha2_max=6.0)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 5, basis_function="DRWCelerite")
+    a, b, c, d = ctx.approx_coeffs(spec, psd)
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_auto_scan(False)
+    seq = ctx.celerite_logl(ser, a, b, c, d)
+    ctx.set_auto_scan(True)
+    ser.free()
+    ctxs = [pb.Context(0) for _ in range(world)]
+    sers = [cx.upload_series(t, y, s2) for cx in ctxs]
+    off = shard_bounds(len(t), world)
+    flagged = 0
+    for i in np.flatnonzero(np.isfinite(seq)):
+        ai, bi, ci, di = a[i], b[i], c[i], d[i]
+        comps = [ctxs[r].scan_range_begin(sers[r], ai, bi, ci, di, off[r], off[r + 1], max_prev=world) for r in range(world)]
+        sums = [ctxs[r].scan_range_end(np.stack(comps[:r]) if r else None) for r in range(world)]
+        rows = np.stack([ctxs[r].scan_range_check() for r in range(world)])
+        tot = np.sum(sums, axis=0)
+        raw = -0.5 * tot[0] - 0.5 * tot[1] - 0.5 * len(t) * np.log(2 * np.pi)
+        rel = scan_check_total(rows) / max(1.0, abs(raw))
+        dev = rel_err(raw, seq[i])
+        assert dev <= 1e-9 or not (rel <= 1e-10), (i, dev, rel)       # no large deviation goes unnoticed
+        if not (rel <= 1e-10):
+            flagged += 1
+            if flagged <= 2:            # the orchestration function, rank by rank, with list-backed collectives
+                for r in range(world):
+                    info = {}
+                    gathers = iter([np.stack(comps), rows])
+                    val = scan_logl_sharded(lambda lo, hi: ctxs[r].scan_range_begin(sers[r], ai, bi, ci, di, lo, hi, max_prev=world),
+                                            ctxs[r].scan_range_end, len(t), rank=r, world=world,
+                                            all_gather=lambda x: next(gathers), all_reduce_sum=lambda s_: s_ - sums[r] + tot,
+                                            range_check=ctxs[r].scan_range_check, sequential=lambda: seq[i], info=info)
+                    assert info["fallback"] and val == seq[i]
+    print(f"\ntime axis over {world} ranks, DRWCelerite J=5 steep draws: {flagged} of {int(np.isfinite(seq).sum())} flagged")
+    assert flagged >= 1
+    for s_, cx in zip(sers, ctxs):
+        s_.free()
+        cx.close()

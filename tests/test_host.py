@@ -174,9 +174,34 @@ want = -0.5 * np.sum(run * wgt) - 0.5 * np.sum(run ** 2) - 0.5 * N * np.log(2 * 
 off = shard_bounds(N, world)
 assert seen["range"] == (int(off[rank]), int(off[rank + 1]))
 assert abs(got - want) <= 1e-9 * abs(want), (got, want)
+# self-check rows (Context.scan_range_check): consistent hand-over -> the scan's value; inconsistent -> every rank falls back
+for delta, expect_fallback in ((0.0, False), (1e-3, True)):
+    def range_check():
+        if rank == 0:
+            return np.array([1e-9, 0.0, 0.0, 3.5, 7.25, 0.0, 8.0, 10.0])
+        return np.array([2e-9, 3.5 + delta, 7.25, 0.0, 0.0, 8.0, 0.0, 10.0])
+    info = dict()
+    got = scan_logl_sharded(range_begin, range_end, N, rank=rank, world=world, all_gather=ag, all_reduce_sum=ar,
+                            range_check=range_check, sequential=lambda: 123.0, info=info)
+    assert info["fallback"] == expect_fallback, info
+    assert got == 123.0 if expect_fallback else abs(got - want) <= 1e-9 * abs(want)
+    assert abs(info["estimate"] * max(1.0, abs(want)) - (3e-9 + 0.5 * 10.0 * delta)) <= 1e-12
 dist.destroy_process_group()
 print("OK", flush=True)
 """
+
+
+def test_scan_check_total_rows():
+    """parallel.scan_check_total: inner estimates + hand-over differences; a hand-over that was not swept twice, or a
+    non-finite sum, gives NaN (which reads as 'not verified')."""
+    from pioran_b200.parallel import scan_check_total
+    rows = np.array([[1e-9, 0, 0, 2.0, 5.0, 0, 8, 4.0], [2e-9, 2.5, 5.0, 1.0, 1.0, 8, 8, 4.0], [0.0, 1.0, 1.5, 0, 0, 8, 0, 4.0]])
+    assert abs(scan_check_total(rows) - (3e-9 + 0.5 * 4.0 * 0.5 + 0.5 * 4.0 * 0.5)) < 1e-15
+    assert scan_check_total(rows[:1]) == 1e-9
+    bad = rows.copy(); bad[1, 5] = 6
+    assert np.isnan(scan_check_total(bad))
+    bad = rows.copy(); bad[2, 1] = np.nan
+    assert np.isnan(scan_check_total(bad))
 
 
 def test_scan_time_axis_sharding_gloo_world2(tmp_path):

@@ -33,7 +33,8 @@ for rep in range(5):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    val = scan_logl_sharded(begin, ctx.scan_range_end, N, rank=rank, world=world, all_gather=ag, all_reduce_sum=ar)
+    val = scan_logl_sharded(begin, ctx.scan_range_end, N, rank=rank, world=world, all_gather=ag, all_reduce_sum=ar,
+                            range_check=ctx.scan_range_check)
     torch.cuda.synchronize()
     wall.append((time.perf_counter() - t0) * 1e3)
     ms.append(ctx.last_kernel_ms())
