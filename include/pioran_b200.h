@@ -168,7 +168,8 @@ int pioran_celerite_scan_range_end(pioran_ctx *ctx, int nprev, const double *com
  *   [0]    this range's inner estimate (log L units; see pioran_ctx_set_scan_tolerance),
  *   [1..2] (sum log|D|, sum z^2/D) of the first out8[5] steps of the range, swept from the state the earlier composites gave,
  *   [3..4] the same sums over the out8[6] steps AFTER the range, swept on from this range's own final state,
- *   [5], [6] those step counts (0 at the two ends of the series),  [7] the scale (sub-chunk length / check length).
+ *   [5], [6] those step counts (0 at the two ends of the series; [6] is also 0 after a range of odd length - split
+ *            the time axis at even steps),  [7] the scale (sub-chunk length / check length).
  * The hand-over from rank r-1 to rank r is consistent when [3..4] of r-1 equal [1..2] of r; the caller gathers the eight
  * values of every rank, adds scale * (|d sum log|D|| + |d sum z^2/D|) / 2 of each hand-over to the inner estimates and
  * falls back to a sequential evaluation when the total exceeds its tolerance (pioran.jl_b200/parallel.py:

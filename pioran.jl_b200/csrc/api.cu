@@ -1378,7 +1378,9 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
         // its last one sweeps on into the next rank's range — pioran_celerite_scan_range_check)
         const bool first = ch == 0 && j == 0, last = ch == P - 1 && j == SUB - 1;
         w.n_head = (first && !init_dev) ? 0 : scan_check_steps(w.n_end - w.n_begin);
-        if (last) w.n_ext = run.n_hi < run.N ? scan_check_steps(run.N - run.n_hi) : 0;
+        // (after a range of odd length the look-ahead would break the even/odd alternation of the steps: no look-ahead then,
+        // and the caller's comparison reads "not verified" — parallel.scan_bounds keeps the inner bounds even)
+        if (last) w.n_ext = (run.n_hi < run.N && ((run.n_hi - run.n_lo) & 1) == 0) ? scan_check_steps(run.N - run.n_hi) : 0;
         else {
             const int ch2 = j == SUB - 1 ? ch + 1 : ch, j2 = j == SUB - 1 ? 0 : j + 1;
             w.n_ext = scan_check_steps(scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2 + 1, SUB) -

@@ -16,6 +16,14 @@ def shard_bounds(n, world):
     return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
+def scan_bounds(n, world):
+    """Step ranges of the time-axis split (scan_logl_sharded): the near-equal split with the inner bounds at even steps —
+    the self-check sweeps on across a hand-over, which the kernel's even/odd step alternation allows after an even count."""
+    off = shard_bounds(n, world)
+    off[1:-1] &= ~np.int64(1)
+    return off
+
+
 def shard_series(lengths, world):
     """Longest-processing-time assignment of whole series to ranks (ragged multi-source batches, config C3):
     returns a list of index arrays, one per rank, balancing Σ N_s."""
@@ -84,7 +92,7 @@ def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=Non
                       sequential=None, tol=1e-10, info=None):
     """Log-likelihood of ONE long series with the time axis split across `world` ranks.
 
-    Rank r owns steps [N·r/world, N·(r+1)/world).  `range_begin(n_lo, n_hi)` folds them and returns the range's composite
+    Rank r owns steps scan_bounds(N, world)[r : r + 2] (near-equal, inner bounds even).  `range_begin(n_lo, n_hi)` folds them and returns the range's composite
     scan element (Context.scan_range_begin); `all_gather(x) -> [world × len(x)]` exchanges the composites — the only
     collective on the data path besides the final 2-value sum; `range_end(prev)` re-filters the range from the state the
     `prev` earlier composites leave behind and returns (Σ log|D_n|, Σ z_n²/D_n); `all_reduce_sum` adds those over the ranks.
@@ -94,7 +102,7 @@ def scan_logl_sharded(range_begin, range_end, N, rank=0, world=1, all_gather=Non
     the ranks also gather their check rows; when the estimated deviation exceeds tol·max(1, |log L|) and `sequential` — a
     callable returning the sequential sweep's value of the whole series — is given, every rank returns that instead (all
     ranks see the same gathered rows and take the same decision).  `info`, a dict, receives 'estimate' and 'fallback'."""
-    off = shard_bounds(N, world)
+    off = scan_bounds(N, world)
     comp = np.asarray(range_begin(int(off[rank]), int(off[rank + 1])), dtype=np.float64)
     if world > 1:
         gathered = np.asarray(all_gather(comp), dtype=np.float64).reshape(world, -1)

@@ -98,12 +98,12 @@ def test_config_c4_long_series_n1e6_j30(pb, ctx):
     ser.free()
 
 
-@pytest.mark.parametrize("world,chunks", [(2, 0), (3, 5), (8, 0), (4, 1)])
-def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks):
+@pytest.mark.parametrize("world,chunks,N", [(2, 0, 6000), (3, 5, 6001), (8, 0, 5995), (4, 1, 6000)])
+def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks, N):
     """the time axis split over `world` ranks — emulated on one GPU with one context per rank, the
     collectives replaced by plain lists — must reproduce the single-GPU scan and the oracle."""
     from pioran_b200.parallel import scan_logl_sharded
-    t, y, s2, f_min, f_max = synthetic_series(6000, seed=21)
+    t, y, s2, f_min, f_max = synthetic_series(N, seed=21)
     a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, 30, 1.0, basis="SHO")
     mu, nu = 0.13, 1.7
     want = orc.celerite_logl_batch(a[None], b[None], c[None], d[None], t, y, s2, mu=np.array([mu]), nu=np.array([nu]))[0]
@@ -111,8 +111,8 @@ def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks):
     sers = [cx.upload_series(t, y, s2) for cx in ctxs]
     for cx in ctxs:
         cx.set_scan_chunks(chunks)
-    from pioran_b200.parallel import shard_bounds
-    off = shard_bounds(len(t), world)
+    from pioran_b200.parallel import scan_bounds
+    off = scan_bounds(len(t), world)
     comps = [ctxs[r].scan_range_begin(sers[r], a, b, c, d, off[r], off[r + 1], mu=mu, nu=nu, max_prev=world) for r in range(world)]
     sums = [ctxs[r].scan_range_end(np.stack(comps[:r]) if r else None) for r in range(world)]
     tot = np.sum(sums, axis=0)
@@ -219,7 +219,7 @@ def test_scan_self_check_leaves_well_conditioned_calls_alone(pb, ctx):
 def test_scan_time_axis_split_self_check_and_fallback(pb, ctx):
     """Ill-conditioned covariance with the time axis split over 3 ranks: the gathered self-check rows (inner estimates and
     hand-overs) flag the deviation, and scan_logl_sharded then returns the sequential sweep's value on every rank."""
-    from pioran_b200.parallel import scan_logl_sharded, scan_check_total, shard_bounds
+    from pioran_b200.parallel import scan_logl_sharded, scan_check_total, scan_bounds
     world = 3
     t, y, s2, f_min, f_max = synthetic_series(6000, seed=33)
     psd = _steep_prior_draws(48, f_min, f_max, seed=5, alpha2_max=6.0)
@@ -232,7 +232,7 @@ def test_scan_time_axis_split_self_check_and_fallback(pb, ctx):
     ser.free()
     ctxs = [pb.Context(0) for _ in range(world)]
     sers = [cx.upload_series(t, y, s2) for cx in ctxs]
-    off = shard_bounds(len(t), world)
+    off = scan_bounds(len(t), world)
     flagged = 0
     for i in np.flatnonzero(np.isfinite(seq)):
         ai, bi, ci, di = a[i], b[i], c[i], d[i]

@@ -150,7 +150,7 @@ _SCAN_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})
 import numpy as np, torch, torch.distributed as dist
-from pioran_b200.parallel import scan_logl_sharded, torch_collectives, shard_bounds
+from pioran_b200.parallel import scan_logl_sharded, torch_collectives, scan_bounds
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank, world = dist.get_rank(), 2
 # stand-in for the device scan with the same data flow: the "composite" of a range is the sum of its x, the state entering a
@@ -171,7 +171,8 @@ ag, ar = torch_collectives()
 got = scan_logl_sharded(range_begin, range_end, N, rank=rank, world=world, all_gather=ag, all_reduce_sum=ar)
 run = np.cumsum(x)
 want = -0.5 * np.sum(run * wgt) - 0.5 * np.sum(run ** 2) - 0.5 * N * np.log(2 * np.pi)
-off = shard_bounds(N, world)
+off = scan_bounds(N, world)
+assert off[1] % 2 == 0
 assert seen["range"] == (int(off[rank]), int(off[rank + 1]))
 assert abs(got - want) <= 1e-9 * abs(want), (got, want)
 # self-check rows (Context.scan_range_check): consistent hand-over -> the scan's value; inconsistent -> every rank falls back

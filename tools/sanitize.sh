@@ -19,7 +19,16 @@ t, y, s2, f_min, f_max = wl.make_series_fast(5000, 3)
 spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20)
 a, b, c, d = ctx.approx_coeffs(spec, np.array([[0.82, 0.01, 3.3, 1.0]]))
 ser = ctx.upload_series(t, y, s2)
-print("scan", ctx.celerite_logl(ser, a, b, c, d))
+print("scan", ctx.celerite_logl(ser, a, b, c, d), ctx.last_scan_check())
+# the self-check's segments at range ends: a range in the middle of the series (head and look-ahead both live), odd bounds
+comp = ctx.scan_range_begin(ser, a, b, c, d, 0, 1702, max_prev=2)
+print("range 0", ctx.scan_range_end(None), ctx.scan_range_check())
+comp1 = ctx.scan_range_begin(ser, a, b, c, d, 1702, 3405, max_prev=2)
+print("range 1", ctx.scan_range_end(comp[None]), ctx.scan_range_check())
+# steep slope on a coarse grid: the call falls back to the sequential sweep
+spec5 = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 2, basis_function="DRWCelerite")
+a5, b5, c5, d5 = ctx.approx_coeffs(spec5, np.array([[0.3, 0.02, 5.7, 1.0], [1.2, 0.3, 5.9, 1.0]]))
+print("scan steep", ctx.celerite_logl(ser, a5, b5, c5, d5), ctx.last_scan_check())
 ser.free()
 t, y, s2, f_min, f_max = wl.make_series(200, 5)
 ser = ctx.upload_series(t, y, s2)
@@ -30,6 +39,7 @@ print("dense", ctx.direct_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4]))
 PY
 compute-sanitizer --tool memcheck --error-exitcode 1 python /tmp/san_case.py > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"
 tail -4 gpurun_out/memcheck.log
+[ "${1:-}" = "memcheck" ] && exit 0
 cat > /tmp/race_case.py <<'PY'
 import sys, numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tools")
