@@ -24,7 +24,7 @@ def build():
 
 
 def _load():
-    srcs = [os.path.join(_HERE, f) for f in ("pioran_oracle.c", "pioran_oracle_grad.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("pioran_oracle.c", "pioran_oracle_grad.c", "pioran_oracle_grad_ld.c")]
     if not os.path.exists(_LIB) or any(os.path.getmtime(_LIB) < os.path.getmtime(src) for src in srcs):
         build()
     lib = C.CDLL(_LIB)
@@ -48,10 +48,11 @@ def _load():
     lib.orc_approx_logl_batch.restype = None
     lib.orc_approx_logl_batch.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                           C.c_double, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_int]
-    lib.orc_approx_logl_grad_batch.restype = None
-    lib.orc_approx_logl_grad_batch.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int,
-                                               C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp,
-                                               _dp, C.c_int]
+    for name in ("orc_approx_logl_grad_batch", "orc_approx_logl_grad_batch_ld"):
+        fn = getattr(lib, name)
+        fn.restype = None
+        fn.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                       C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp, C.c_int]
     lib.orc_celerite_logl_batch.restype = None
     lib.orc_celerite_logl_batch.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp,
                                             _dp, C.c_int]
@@ -153,8 +154,9 @@ def approx_logl_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO", S_lo
 
 
 def approx_logl_grad_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO", S_low=20.0, S_high=20.0,
-                           is_integrated_power=True, nthreads=1):
-    """Forward-mode gradient (pioran_oracle_grad.c): returns (logL[B], ∂logL/∂θ [B × (npar+3)])."""
+                           is_integrated_power=True, nthreads=1, long_double=False):
+    """Forward-mode gradient (pioran_oracle_grad.c): returns (logL[B], ∂logL/∂θ [B × (npar+3)]).  long_double: the same
+    code in 80-bit arithmetic (pioran_oracle_grad_ld.c), results rounded to FP64 — conditioning triage only."""
     m = PSD_MODELS[model]
     theta = np.atleast_2d(_arr(theta))
     npar = N_PSD_PAR[m]
@@ -162,9 +164,9 @@ def approx_logl_grad_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO",
     t, y, s2 = map(_arr, (t, y, s2))
     out = np.empty(theta.shape[0])
     grad = np.empty(theta.shape)
-    lib().orc_approx_logl_grad_batch(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high,
-                                     int(is_integrated_power), BASES[basis], len(t), _p(t), _p(y), _p(s2), _p(out),
-                                     _p(grad), nthreads)
+    fn = lib().orc_approx_logl_grad_batch_ld if long_double else lib().orc_approx_logl_grad_batch
+    fn(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high, int(is_integrated_power), BASES[basis], len(t),
+       _p(t), _p(y), _p(s2), _p(out), _p(grad), nthreads)
     return out, grad
 
 

@@ -27,28 +27,45 @@
 
 void orc_build_approx(int J, double f0, double fM, int basis, double *fj, double *B);
 
-typedef struct { double v, d; } dual;
+/* The arithmetic type.  The FP64 build is the oracle proper (the reference's precision); compiled a second time with
+ * ORC_GRAD_LONG_DOUBLE (pioran_oracle_grad_ld.c) the same code runs in x87 80-bit arithmetic and exports
+ * orc_approx_logl_grad_batch_ld — used only to tell conditioning from error when a gradient comparison at an
+ * ill-conditioned parameter vector exceeds the tolerance (the role orc_celerite_logl_ld plays for the likelihood). */
+#ifdef ORC_GRAD_LONG_DOUBLE
+typedef long double real;
+#define RM(f) f##l
+#define R_PI 3.14159265358979323846264338327950288L
+#define ORC_GRAD_ENTRY orc_approx_logl_grad_batch_ld
+#else
+typedef double real;
+#define RM(f) f
+#define R_PI M_PI
+#define ORC_GRAD_ENTRY orc_approx_logl_grad_batch
+#endif
 
-static inline dual dk(double v) { dual r = {v, 0.0}; return r; }
-static inline dual dmk(double v, double d) { dual r = {v, d}; return r; }
+
+typedef struct { real v, d; } dual;
+
+static inline dual dk(real v) { dual r = {v, 0.0}; return r; }
+static inline dual dmk(real v, real d) { dual r = {v, d}; return r; }
 static inline dual dadd(dual a, dual b) { return dmk(a.v + b.v, a.d + b.d); }
 static inline dual dsub(dual a, dual b) { return dmk(a.v - b.v, a.d - b.d); }
 static inline dual dneg(dual a) { return dmk(-a.v, -a.d); }
 static inline dual dmul(dual a, dual b) { return dmk(a.v * b.v, a.d * b.v + a.v * b.d); }
-static inline dual dmulc(dual a, double c) { return dmk(a.v * c, a.d * c); }
-static inline dual ddivc(dual a, double c) { return dmk(a.v / c, a.d / c); }
-static inline dual ddiv(dual a, dual b) { double q = a.v / b.v; return dmk(q, (a.d - q * b.d) / b.v); }
-static inline dual dlog(dual a) { return dmk(log(a.v), a.d / a.v); }
-static inline dual dlogabs(dual a) { return dmk(log(fabs(a.v)), a.d / a.v); }
+static inline dual dmulc(dual a, real c) { return dmk(a.v * c, a.d * c); }
+static inline dual ddivc(dual a, real c) { return dmk(a.v / c, a.d / c); }
+static inline dual ddiv(dual a, dual b) { real q = a.v / b.v; return dmk(q, (a.d - q * b.d) / b.v); }
+static inline dual dlog(dual a) { return dmk(RM(log)(a.v), a.d / a.v); }
+static inline dual dlogabs(dual a) { return dmk(RM(log)(RM(fabs)(a.v)), a.d / a.v); }
 /* x^e with both dual: d = x^e (e' ln x + e x'/x) */
 static inline dual dpow(dual x, dual e)
 {
-    double p = pow(x.v, e.v);
-    return dmk(p, p * (e.d * log(x.v) + e.v * x.d / x.v));
+    real p = RM(pow)(x.v, e.v);
+    return dmk(p, p * (e.d * RM(log)(x.v) + e.v * x.d / x.v));
 }
 
 /* test/test_psd.jl:6,12 (Tonari closed forms) on duals */
-static dual psd_eval_dual(int model, const dual *p, double f)
+static dual psd_eval_dual(int model, const dual *p, real f)
 {
     dual x = ddiv(dk(f), p[1]);
     dual v = ddiv(dpow(x, dneg(p[0])), dadd(dk(1.0), dpow(x, dsub(p[2], p[0]))));
@@ -58,28 +75,28 @@ static dual psd_eval_dual(int model, const dual *p, double f)
 }
 
 /* LU with partial pivoting on a constant matrix, dual right-hand side (src/psd.jl:109-112) */
-static int lu_solve_dual(int n, double *A, dual *x)
+static int lu_solve_dual(int n, real *A, dual *x)
 {
     for (int k = 0; k < n; k++) {
         int piv = k;
-        double best = fabs(A[k + (size_t)k * n]);
+        real best = RM(fabs)(A[k + (size_t)k * n]);
         for (int i = k + 1; i < n; i++) {
-            double v = fabs(A[i + (size_t)k * n]);
+            real v = RM(fabs)(A[i + (size_t)k * n]);
             if (v > best) { best = v; piv = i; }
         }
         if (best == 0.0) return -1;
         if (piv != k) {
             for (int j = 0; j < n; j++) {
-                double tmp = A[k + (size_t)j * n];
+                real tmp = A[k + (size_t)j * n];
                 A[k + (size_t)j * n] = A[piv + (size_t)j * n];
                 A[piv + (size_t)j * n] = tmp;
             }
             dual tmp = x[k]; x[k] = x[piv]; x[piv] = tmp;
         }
-        double inv = 1.0 / A[k + (size_t)k * n];
+        real inv = 1.0 / A[k + (size_t)k * n];
         for (int i = k + 1; i < n; i++) A[i + (size_t)k * n] *= inv;
         for (int j = k + 1; j < n; j++) {
-            double akj = A[k + (size_t)j * n];
+            real akj = A[k + (size_t)j * n];
             for (int i = k + 1; i < n; i++) A[i + (size_t)j * n] -= A[i + (size_t)k * n] * akj;
         }
     }
@@ -93,22 +110,22 @@ static int lu_solve_dual(int n, double *A, dual *x)
 }
 
 /* src/psd.jl:301-305, 318-324: the antiderivatives are linear in the amplitudes; the bracket is a constant */
-static dual integral_basis_dual(int J, const dual *a, const double *c, double x, int basis)
+static dual integral_basis_dual(int J, const dual *a, const real *c, real x, int basis)
 {
     dual acc = dk(0.0);
     if (basis == ORC_BASIS_SHO) {
-        const double s2 = sqrt(2.0);
+        const real s2 = RM(sqrt)(2.0);
         for (int j = 0; j < J; j++) {
-            double poly = (x * x + s2 * c[j] * x + c[j] * c[j]) / (x * x - s2 * c[j] * x + c[j] * c[j]);
-            double br = log(poly) + 2.0 * atan2(c[j] * s2 * x, c[j] * c[j] - x * x);
+            real poly = (x * x + s2 * c[j] * x + c[j] * c[j]) / (x * x - s2 * c[j] * x + c[j] * c[j]);
+            real br = RM(log)(poly) + 2.0 * RM(atan2)(c[j] * s2 * x, c[j] * c[j] - x * x);
             acc = dadd(acc, dmulc(ddivc(dmulc(a[j], c[j]), 4.0 * s2), br));
         }
     } else {
-        const double s3 = sqrt(3.0);
+        const real s3 = RM(sqrt)(3.0);
         for (int j = 0; j < J; j++) {
-            double drw = atan(x / c[j]);
-            double poly = (x * x + s3 * c[j] * x + c[j] * c[j]) / (x * x - s3 * c[j] * x + c[j] * c[j]);
-            double cel = 0.5 * atan2(x * x - c[j] * c[j], c[j] * x) + s3 / 4.0 * log(poly);
+            real drw = RM(atan)(x / c[j]);
+            real poly = (x * x + s3 * c[j] * x + c[j] * c[j]) / (x * x - s3 * c[j] * x + c[j] * c[j]);
+            real cel = 0.5 * RM(atan2)(x * x - c[j] * c[j], c[j] * x) + s3 / 4.0 * RM(log)(poly);
             acc = dadd(acc, dmulc(ddivc(dmulc(a[j], c[j]), 3.0), drw + cel));
         }
     }
@@ -116,15 +133,20 @@ static dual integral_basis_dual(int J, const dual *a, const double *c, double x,
 }
 
 /* src/psd.jl:214-289 approx on duals; c, d are θ-independent.  Returns Jt. */
-static int approx_dual(int model, const dual *psd_par, double f_min, double f_max, int J, dual norm, double S_low,
-                       double S_high, int is_integrated_power, int basis, dual *a, dual *b, double *c, double *d)
+static int approx_dual(int model, const dual *psd_par, real f_min, real f_max, int J, dual norm, real S_low,
+                       real S_high, int is_integrated_power, int basis, dual *a, dual *b, real *c, real *d)
 {
-    double f0 = f_min / S_low, fM = f_max * S_high;
-    double *B = (double *)malloc(sizeof(double) * (size_t)J * J);
-    double *fj = (double *)malloc(sizeof(double) * J);
+    real f0 = f_min / S_low, fM = f_max * S_high;
+    real *B = (real *)malloc(sizeof(real) * (size_t)J * J);
+    real *fj = (real *)malloc(sizeof(real) * J);
     dual *amp = (dual *)malloc(sizeof(dual) * J);
-    if (!B || !fj || !amp) { free(B); free(fj); free(amp); return -2; }
-    orc_build_approx(J, f0, fM, basis, fj, B);
+    double *Bd = (double *)malloc(sizeof(double) * (size_t)J * J);      /* the grid and its matrix come from pioran_oracle.c */
+    double *fd = (double *)malloc(sizeof(double) * J);
+    if (!B || !fj || !amp || !Bd || !fd) { free(B); free(fj); free(amp); free(Bd); free(fd); return -2; }
+    orc_build_approx(J, (double)f0, (double)fM, basis, fd, Bd);
+    for (int j = 0; j < J; j++) fj[j] = fd[j];
+    for (size_t q = 0; q < (size_t)J * J; q++) B[q] = Bd[q];
+    free(Bd); free(fd);
     dual p0 = psd_eval_dual(model, psd_par, fj[0]);
     for (int j = 0; j < J; j++) amp[j] = ddiv(psd_eval_dual(model, psd_par, fj[j]), p0);
     int rc = lu_solve_dual(J, B, amp);
@@ -135,24 +157,24 @@ static int approx_dual(int model, const dual *psd_par, double f_min, double f_ma
     } else {
         dual s = dk(0.0);
         for (int j = 0; j < J; j++) s = dadd(s, dmulc(amp[j], fj[j]));
-        integ = (basis == ORC_BASIS_SHO) ? ddivc(dmulc(s, M_PI), sqrt(2.0)) : ddivc(dmulc(s, 2.0 * M_PI), 3.0);
+        integ = (basis == ORC_BASIS_SHO) ? ddivc(dmulc(s, R_PI), RM(sqrt)(2.0)) : ddivc(dmulc(s, 2.0 * R_PI), 3.0);
     }
     dual scale = ddiv(norm, integ);
     for (int j = 0; j < J; j++) amp[j] = dmul(amp[j], scale);
     int Jt;
     if (basis == ORC_BASIS_SHO) {
         for (int j = 0; j < J; j++) {
-            a[j] = ddivc(dmulc(dmulc(amp[j], fj[j]), M_PI), sqrt(2.0));
+            a[j] = ddivc(dmulc(dmulc(amp[j], fj[j]), R_PI), RM(sqrt)(2.0));
             b[j] = a[j];
-            c[j] = sqrt(2.0) * M_PI * fj[j];
+            c[j] = RM(sqrt)(2.0) * R_PI * fj[j];
             d[j] = c[j];
         }
         Jt = J;
     } else {
         for (int j = 0; j < J; j++) {
-            dual aj = ddivc(dmulc(dmulc(amp[j], fj[j]), M_PI), 3.0);
-            double cj = M_PI * fj[j];
-            a[j] = aj;     b[j] = dmulc(aj, sqrt(3.0)); c[j] = cj;           d[j] = sqrt(3.0) * cj;
+            dual aj = ddivc(dmulc(dmulc(amp[j], fj[j]), R_PI), 3.0);
+            real cj = R_PI * fj[j];
+            a[j] = aj;     b[j] = dmulc(aj, RM(sqrt)(3.0)); c[j] = cj;           d[j] = RM(sqrt)(3.0) * cj;
             a[J + j] = aj; b[J + j] = dk(0.0);          c[J + j] = 2.0 * cj; d[J + j] = 0.0;
         }
         Jt = 2 * J;
@@ -162,12 +184,12 @@ static int approx_dual(int model, const dual *psd_par, double f_min, double f_ma
 }
 
 /* src/celerite_solver.jl:312-334 on duals: a, b, y, σ² carry tangents; c, d, t do not. */
-static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const double *c, const double *d, int64_t N,
+static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const real *c, const real *d, int64_t N,
                                const double *t, const dual *y, const dual *s2)
 {
     const int R = 2 * Jt;
     dual *S = (dual *)calloc((size_t)R * R, sizeof(dual));
-    double *phi = (double *)malloc(sizeof(double) * (size_t)R * (N > 1 ? N - 1 : 1));
+    real *phi = (real *)malloc(sizeof(real) * (size_t)R * (N > 1 ? N - 1 : 1));
     dual *U = (dual *)malloc(sizeof(dual) * (size_t)R * N);
     dual *V = (dual *)malloc(sizeof(dual) * (size_t)R * N);
     dual *D = (dual *)malloc(sizeof(dual) * N);
@@ -183,7 +205,7 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
     {
         dual buff = ddiv(dk(1.0), D[0]);
         for (int j = 0; j < Jt; j++) {
-            double co = cos(d[j] * t[0]), si = sin(d[j] * t[0]);
+            real co = RM(cos)(d[j] * t[0]), si = RM(sin)(d[j] * t[0]);
             V[2 * j + 1] = dmulc(buff, si);
             V[2 * j] = dmulc(buff, co);
             U[2 * j + 1] = dsub(dmulc(a[j], si), dmulc(b[j], co));
@@ -192,11 +214,11 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
     }
     for (int64_t n = 1; n < N; n++) {
         dual s = dk(0.0);
-        double tn = t[n], dt = tn - t[n - 1];
+        real tn = t[n], dt = tn - (real)t[n - 1];
         dual *Un = U + (size_t)R * n, *Vn = V + (size_t)R * n, *Vp = V + (size_t)R * (n - 1);
-        double *ph = phi + (size_t)R * (n - 1);
+        real *ph = phi + (size_t)R * (n - 1);
         for (int j = 0; j < Jt; j++) {
-            double co = cos(d[j] * tn), si = sin(d[j] * tn), ec = exp(-c[j] * dt);
+            real co = RM(cos)(d[j] * tn), si = RM(sin)(d[j] * tn), ec = RM(exp)(-c[j] * dt);
             ph[2 * j + 1] = ec; ph[2 * j] = ec;
             Un[2 * j + 1] = dsub(dmulc(a[j], si), dmulc(b[j], co));
             Un[2 * j] = dadd(dmulc(a[j], co), dmulc(b[j], si));
@@ -204,7 +226,7 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
         }
         for (int j = 0; j < R; j++) {
             dual uj = Un[j], vn = Vp[j];
-            double phj = ph[j];
+            real phj = ph[j];
             dual dn = dmul(D[n - 1], vn);
             dual vnj = Vn[j];
             for (int k = 0; k < j; k++) {
@@ -231,7 +253,7 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
         for (int64_t n = 1; n < N; n++) {
             dual s = dk(0.0), zp = z[n - 1];
             const dual *Wp = V + (size_t)R * (n - 1), *Un = U + (size_t)R * n;
-            const double *ph = phi + (size_t)R * (n - 1);
+            const real *ph = phi + (size_t)R * (n - 1);
             for (int j = 0; j < R; j++) {
                 f[j] = dmulc(dadd(f[j], dmul(Wp[j], zp)), ph[j]);
                 s = dadd(s, dmul(Un[j], f[j]));
@@ -243,7 +265,7 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
         for (int64_t n = N - 2; n >= 0; n--) {
             dual s = dk(0.0), zn = z[n + 1];
             const dual *Un1 = U + (size_t)R * (n + 1), *Wn = V + (size_t)R * n;
-            const double *ph = phi + (size_t)R * n;
+            const real *ph = phi + (size_t)R * n;
             for (int j = 0; j < R; j++) {
                 g[j] = dmulc(dadd(g[j], dmul(Un1[j], zn)), ph[j]);
                 s = dadd(s, dmul(Wn[j], g[j]));
@@ -252,7 +274,7 @@ static dual celerite_logl_dual(int Jt, const dual *a, const dual *b, const doubl
         }
         dual yz = dk(0.0);
         for (int64_t n = 0; n < N; n++) yz = dadd(yz, dmul(y[n], z[n]));
-        result = dsub(dsub(ddivc(dneg(logdetD), 2.0), dk((double)N * log(2 * M_PI) / 2)), ddivc(yz, 2.0));
+        result = dsub(dsub(ddivc(dneg(logdetD), 2.0), dk((real)N * RM(log)(2 * R_PI) / 2)), ddivc(yz, 2.0));
     }
 done:
     free(S); free(phi); free(U); free(V); free(D); free(z); free(f); free(g);
@@ -261,7 +283,7 @@ done:
 
 /* Batched driver: θ row = [psd params…, norm, ν, μ] (as orc_approx_logl_batch).  logl_out [B] (may be NULL),
  * grad_out [B × (n_psd_par + 3)] = ∂logL/∂θ, one forward sweep per direction. */
-void orc_approx_logl_grad_batch(int model, int n_psd_par, int B, const double *theta, double f_min, double f_max, int J,
+void ORC_GRAD_ENTRY(int model, int n_psd_par, int B, const double *theta, double f_min, double f_max, int J,
                                 double S_low, double S_high, int is_integrated_power, int basis, int64_t N,
                                 const double *t, const double *y, const double *s2_base, double *logl_out,
                                 double *grad_out, int nthreads)
@@ -279,7 +301,7 @@ void orc_approx_logl_grad_batch(int model, int n_psd_par, int B, const double *t
             dual norm = par[n_psd_par], nu = par[n_psd_par + 1], mu = par[n_psd_par + 2];
             int Jt_max = 2 * J;
             dual *ab = (dual *)malloc(sizeof(dual) * 2 * Jt_max);
-            double *cd = (double *)malloc(sizeof(double) * 2 * Jt_max);
+            real *cd = (real *)malloc(sizeof(real) * 2 * Jt_max);
             dual *yy = (dual *)malloc(sizeof(dual) * N);
             dual *ss = (dual *)malloc(sizeof(dual) * N);
             for (int64_t n = 0; n < N; n++) { yy[n] = dsub(dk(y[n]), mu); ss[n] = dmulc(nu, s2_base[n]); }
@@ -287,8 +309,8 @@ void orc_approx_logl_grad_batch(int model, int n_psd_par, int B, const double *t
                                  ab + Jt_max, cd, cd + Jt_max);
             dual r = dmk(NAN, NAN);
             if (Jt > 0) r = celerite_logl_dual(Jt, ab, ab + Jt_max, cd, cd + Jt_max, N, t, yy, ss);
-            if (logl_out && k == 0) logl_out[i] = r.v;
-            grad_out[(size_t)i * P + k] = r.d;
+            if (logl_out && k == 0) logl_out[i] = (double)r.v;
+            grad_out[(size_t)i * P + k] = (double)r.d;
             free(ab); free(cd); free(yy); free(ss);
         }
     }

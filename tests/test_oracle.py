@@ -195,3 +195,9 @@ def test_gradient_oracle_value_and_finite_differences(golden_single, basis):
         fd = (orc.approx_logl_batch("SBPL", tp, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)
               - orc.approx_logl_batch("SBPL", tm, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0)) / (2 * h)
         assert np.allclose(grad[:, k], fd, rtol=2e-5, atol=1e-6 * np.abs(grad[:, k]).max()), (k, grad[:, k], fd)
+    # the 80-bit twin (pioran_oracle_grad_ld.c: the same source compiled with long double — conditioning triage for gradient
+    # comparisons) agrees with the FP64 oracle far below the parity tolerance on these well-conditioned rows
+    val_ld, grad_ld = orc.approx_logl_grad_batch("SBPL", theta, g.f_min, g.f_max, 20, g.t, g.y, g.s2, basis=basis, nthreads=0,
+                                                  long_double=True)
+    assert np.max(np.abs(val_ld - val) / np.abs(val)) <= 1e-10
+    assert np.max(np.abs(grad_ld - grad) / np.maximum(np.abs(grad), np.abs(grad).max(axis=0))) <= 1e-8
