@@ -134,14 +134,17 @@ int pioran_ctx_set_auto_scan(pioran_ctx *ctx, int enabled);
  * PSD slopes), so every call verifies itself: at each chunk boundary the 8 steps after it are swept twice - continuing
  * the sweep of the previous chunk, and from the state the scan computed - and the difference of their contributions to
  * log L, scaled to the chunk length and summed over the boundaries, estimates the deviation from the sequential sweep.
- * Parameter vectors whose estimate exceeds tol * max(1, |log L|) are evaluated again by the sequential kernel, so
- * pioran_celerite_logl_scan and the automatically routed calls return the sequential kernel's accuracy for every input
- * (reference: src/celerite_solver.jl:312-334 has one formulation only).  Default tol = 1e-10; tol <= 0 disables the
- * fallback (the estimate is still computed).  pioran_ctx_last_scan_check reports the largest relative estimate of the
- * last call and how many parameter vectors went to the sequential kernel; after pioran_celerite_scan_range_end it
- * reports that range's part of the estimate in log L units (no fallback across ranks: the caller decides). */
+ * Parameter vectors whose estimate exceeds tol * max(1, |log L|) are swept again with a run-up of 1, then 3 chunks in
+ * front of every chunk (the filter forgets the error of the injected state; only the last pass of the path is repeated)
+ * and verified the same way; what still fails is evaluated by the sequential kernel.  So pioran_celerite_logl_scan and
+ * the automatically routed calls return the sequential kernel's accuracy for every input (reference:
+ * src/celerite_solver.jl:312-334 has one formulation only).  Default tol = 1e-10; tol <= 0 disables refinement and
+ * fallback (the estimate is still computed).  pioran_ctx_last_scan_check reports the largest relative estimate among
+ * the results of the last call, how many parameter vectors went to the sequential kernel and how many were accepted
+ * after a run-up pass (any pointer may be NULL); after pioran_celerite_scan_range_end it reports that range's part of
+ * the estimate in log L units (no refinement across ranks: the caller decides). */
 int pioran_ctx_set_scan_tolerance(pioran_ctx *ctx, double tol);
-int pioran_ctx_last_scan_check(pioran_ctx *ctx, double *estimate, int *n_fallback);
+int pioran_ctx_last_scan_check(pioran_ctx *ctx, double *estimate, int *n_fallback, int *n_refined);
 
 /* Number of time-axis chunks per parameter vector used by pioran_celerite_logl_scan (0 = automatic: two per SM, at
  * least 64 steps each).  The result does not depend on it beyond rounding; tests use it to exercise the scan on short

@@ -1,5 +1,6 @@
 """Thin Python handle on a libpioran_b200 context (one CUDA device).  numpy in, numpy out; every call runs
 the sm_100a kernels through the C ABI of include/pioran_b200.h."""
+import collections
 import ctypes as C
 import os
 
@@ -44,6 +45,9 @@ class Series:
         if self.id is not None:
             check(self.ctx.lib.pioran_series_free(self.ctx.h, self.id))
             self.id = None
+
+
+ScanCheck = collections.namedtuple("ScanCheck", "estimate fallback refined")
 
 
 class Context:
@@ -187,10 +191,11 @@ class Context:
         check(self.lib.pioran_ctx_set_scan_tolerance(self.h, float(tol)))
 
     def last_scan_check(self):
-        """(largest relative deviation estimate, parameter vectors sent to the sequential sweep) of the last scan call."""
-        est, nfb = C.c_double(0.0), C.c_int(0)
-        check(self.lib.pioran_ctx_last_scan_check(self.h, C.byref(est), C.byref(nfb)))
-        return est.value, nfb.value
+        """ScanCheck(estimate, fallback, refined) of the last scan call: largest relative deviation estimate among its results,
+        parameter vectors sent to the sequential sweep, parameter vectors accepted after a run-up pass."""
+        est, nfb, nrf = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        check(self.lib.pioran_ctx_last_scan_check(self.h, C.byref(est), C.byref(nfb), C.byref(nrf)))
+        return ScanCheck(est.value, nfb.value, nrf.value)
 
     def celerite_logl_scan(self, series, a, b, c, d, mu=None, nu=None):
         a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))

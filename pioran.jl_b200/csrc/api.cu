@@ -112,6 +112,7 @@ struct pioran_ctx {
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
     double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
     int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
+    int scan_last_refined = 0;     // … that were accepted after a run-up pass
     double scan_range_chk[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pioran_celerite_scan_range_check
     std::mutex mu;
 };
@@ -1195,10 +1196,11 @@ extern "C" int pioran_ctx_set_scan_tolerance(pioran_ctx* c, double tol) try {
     c->scan_tol = tol;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
-extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* n_fallback) try {
+extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* n_fallback, int* n_refined) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (estimate) *estimate = c->scan_last_est;
     if (n_fallback) *n_fallback = c->scan_last_fallback;
+    if (n_refined) *n_refined = c->scan_last_refined;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
@@ -1229,6 +1231,7 @@ struct ScanRun {
 static int scan_live_rank(int R) { return std::min(SR, (R + 3) & ~3); }
 // Steps of the self-check at a sub-chunk boundary: SCAN_CHECK_STEPS, or the (even part of the) sub-chunk when it is shorter.
 constexpr int SCAN_CHECK_STEPS = 8;
+constexpr int SCAN_MAX_WARM_SUBS = 3;   // refinement ladder: run-ups of 1 and 3 sub-chunks, then the sequential sweep
 static int scan_check_steps(int64_t sub_len) { return (int)std::min<int64_t>(SCAN_CHECK_STEPS, sub_len & ~(int64_t)1); }
 static std::map<pioran_ctx*, ScanRun> g_scan;
 static std::mutex g_scan_mu;
@@ -1352,53 +1355,57 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
 
 // Phase 2: states entering every chunk (from `init_dev`, or from the start of the series when it is null), re-filter of
 // every chunk, partial sums in run.parts.
-static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* init_dev) {
+static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* init_dev, int warm_subs = 0, bool states_ready = false) {
     const int B = run.B, P = run.P, NW = CHUNK_NW, SUB = run.SUB;
     const size_t nch = (size_t)B * P, nsub = nch * SUB;
     const size_t nitems = (nsub + NW - 1) / NW * NW;
     std::vector<WorkItem>& items = run.items_host;
     items.assign(nitems, WorkItem{});
+    const int PS = P * SUB;     // sub-chunks per parameter vector, g = ch·SUB + j
+    auto bound = [&](int g) { return g >= PS ? run.bounds[P] : scan_sub_bound(run.bounds[g / SUB], run.bounds[g / SUB + 1], g % SUB, SUB); };
+    auto state_at = [&](int th, int g) -> const double* {       // the state entering sub-chunk g of parameter vector th
+        const size_t q = (size_t)th * P + g / SUB;
+        const int j = g % SUB;
+        if (j == 0) return (g == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
+        return run.substate + (q * (SUB - 1) + (j - 1)) * SSTATE;
+    };
     for (size_t k = 0; k < nitems; k++) {
         const size_t e = std::min(k, nsub - 1);
-        const size_t q = e / SUB;
-        const int j = (int)(e % SUB);
-        const int th = (int)(q / P), ch = (int)(q % P);
+        const int th = (int)(e / PS), g = (int)(e % PS);
         WorkItem& w = items[k];
         w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = run.N;
         w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
-        w.n_begin = scan_sub_bound(run.bounds[ch], run.bounds[ch + 1], j, SUB);
-        w.n_end = scan_sub_bound(run.bounds[ch], run.bounds[ch + 1], j + 1, SUB);
-        if (j == 0) w.init = (ch == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
-        else        w.init = run.substate + (q * (SUB - 1) + (j - 1)) * SSTATE;
+        // refinement pass: start warm_subs sub-chunks earlier (at most at the start of the range) and discard the run-up
+        const int gs = std::max(0, g - warm_subs);
+        w.n_begin = bound(gs);
+        w.n_warm = bound(g) - bound(gs);
+        w.n_end = bound(g + 1);
+        w.init = state_at(th, gs);
         w.part = k < nsub ? run.parts + 2 * e : run.parts + 2 * nsub;   // padding warps write to the dummy pair
         w.chk = k < nsub ? run.chk + 4 * e : run.chk + 4 * nsub;
         // self-check: re-sweep the first steps of the NEXT sub-chunk from this sweep's own state (n_ext), and sum the first
         // steps of this one separately (n_head) for the previous work item's comparison
         // (a range in the middle of a series also checks its hand-over: its first sub-chunk sums its head for the rank before,
         // its last one sweeps on into the next rank's range — pioran_celerite_scan_range_check)
-        const bool first = ch == 0 && j == 0, last = ch == P - 1 && j == SUB - 1;
-        w.n_head = (first && !init_dev) ? 0 : scan_check_steps(w.n_end - w.n_begin);
+        const bool first = g == 0, last = g == PS - 1;
+        w.n_head = (first && !init_dev) ? 0 : scan_check_steps(bound(g + 1) - bound(g));
         // (after a range of odd length the look-ahead would break the even/odd alternation of the steps: no look-ahead then,
         // and the caller's comparison reads "not verified" — parallel.scan_bounds keeps the inner bounds even)
         if (last) w.n_ext = (run.n_hi < run.N && ((run.n_hi - run.n_lo) & 1) == 0) ? scan_check_steps(run.N - run.n_hi) : 0;
-        else {
-            const int ch2 = j == SUB - 1 ? ch + 1 : ch, j2 = j == SUB - 1 ? 0 : j + 1;
-            w.n_ext = scan_check_steps(scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2 + 1, SUB) -
-                                       scan_sub_bound(run.bounds[ch2], run.bounds[ch2 + 1], j2, SUB));
-        }
+        else w.n_ext = scan_check_steps(bound(g + 2) - bound(g + 1));
     }
     run.check_scale = std::max(1.0, (double)(run.n_hi - run.n_lo) / ((double)P * SUB * SCAN_CHECK_STEPS));
     int rc;
     c->work_key.clear();
     if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
-    if (P > 1 || init_dev) {
+    if (!states_ready && (P > 1 || init_dev)) {
         scan_group_states_kernel<<<dim3(run.G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tp, run.gstate, run.G1, init_dev, scan_live_rank(run.R));
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
                                                                              init_dev ? 1 : 0, scan_live_rank(run.R));
         c->launches += 2;
     }
-    if (SUB > 1) {
+    if (!states_ready && SUB > 1) {
         scan_substates_kernel<<<dim3(P * (SUB - 1), B), 256, SCAN_SMEM_BYTES, c->stream>>>(
             run.subel, run.cstate, run.substate, P, SUB, init_dev ? 1 : 0, scan_live_rank(run.R));
         c->launches++;
@@ -1419,27 +1426,47 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
     int rc;
     cudaEventRecord(c->ev_beg, c->stream);
     if ((rc = scan_phase1(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, 0, s->N, false, 0, run))) return rc;
-    if ((rc = scan_phase2(c, s, run, nullptr))) return rc;
-    scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.chk, run.check_scale, run.P * run.SUB, B, s->N, run.out,
-                                                                 run.err);
-    c->launches++;
-    cudaEventRecord(c->ev_end, c->stream);
-    c->ev_valid = true;
-    CUDA_TRY(cudaGetLastError());
-    std::vector<double> est(B);
-    CUDA_TRY(cudaMemcpyAsync(logl_out, run.out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(est.data(), run.err, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    // Self-check (scan.cuh, scan_check_estimate).  The composites lose accuracy where the covariance is ill-conditioned (steep
-    // PSD slopes: the scan's value was seen 1e-8 … 1e-6 away from the sequential sweep's, which stays within 1e-9 of an 80-bit
-    // evaluation there): parameter vectors whose estimate exceeds the tolerance are evaluated again by the sequential sweep.
-    c->scan_last_est = 0.0; c->scan_last_fallback = 0;
-    {
-        std::vector<int> redo;
+    // Self-check and refinement ladder (scan.cuh, scan_check_estimate).  The composites lose accuracy where the covariance is
+    // ill-conditioned (steep PSD slopes: the scan's value was seen 1e-8 … 1e-6 away from the sequential sweep's, which stays
+    // within 1e-9 of an 80-bit evaluation there).  Parameter vectors whose estimate exceeds the tolerance are swept again with a
+    // run-up of 1, then 3 sub-chunks in front of every sub-chunk (the filter forgets the error of the injected state; pass 3
+    // only, (1 + run-up)× its cost), verified the same way; what still fails goes to the sequential sweep.
+    c->scan_last_est = 0.0; c->scan_last_fallback = 0; c->scan_last_refined = 0;
+    std::vector<double> est(B), val(B);
+    std::vector<char> accepted(B, 0);
+    std::vector<int> redo;
+    const int PS = run.P * run.SUB;
+    for (int level = 0, warm = 0;; level++, warm = 2 * warm + 1) {
+        if ((rc = scan_phase2(c, s, run, nullptr, warm, level > 0))) return rc;
+        scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.chk, run.check_scale, PS, B, s->N, run.out, run.err);
+        c->launches++;
+        cudaEventRecord(c->ev_end, c->stream);
+        c->ev_valid = true;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(val.data(), run.out, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(est.data(), run.err, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        redo.clear();
         for (int i = 0; i < B; i++) {
-            const double rel = est[i] / std::max(1.0, std::fabs(logl_out[i]));
-            if (c->scan_tol > 0.0 && !(rel <= c->scan_tol)) redo.push_back(i);
-            if (!(rel <= c->scan_last_est)) c->scan_last_est = rel;     // NaN sticks
+            if (accepted[i]) continue;
+            const double rel = est[i] / std::max(1.0, std::fabs(val[i]));
+            const bool ok = !(c->scan_tol > 0.0) || rel <= c->scan_tol;
+            if (ok || level == 0) logl_out[i] = val[i];
+            if (ok) {
+                accepted[i] = 1;
+                if (level > 0) c->scan_last_refined++;
+                if (!(rel <= c->scan_last_est)) c->scan_last_est = rel;     // NaN sticks
+            } else {
+                redo.push_back(i);
+            }
+        }
+        // a run-up pass pays while it is much shorter than the sequential sweep
+        if (redo.empty() || warm >= SCAN_MAX_WARM_SUBS || 4 * (2 * warm + 2) > PS) break;
+    }
+    {
+        for (int i : redo) {
+            const double rel = est[i] / std::max(1.0, std::fabs(val[i]));
+            if (!(rel <= c->scan_last_est)) c->scan_last_est = rel;
         }
         if (!redo.empty()) {
             const size_t nr = redo.size();
@@ -1539,7 +1566,7 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
     sums_out[0] = sums3[0]; sums_out[1] = sums3[1];
     // this range's part of the self-check estimate, in log L units (the caller sums the ranks' parts and divides by |log L|;
     // the hand-over between ranges is not covered): pioran_ctx_last_scan_check
-    c->scan_last_est = sums3[2]; c->scan_last_fallback = 0;
+    c->scan_last_est = sums3[2]; c->scan_last_fallback = 0; c->scan_last_refined = 0;
     run.valid = false;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }

@@ -885,11 +885,13 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
         }
     }
 
-    // CHUNKED: three segments — [n0, n0 + n_head) | … n1) | [n1, n1 + n_ext) — with the sums taken and reset in between (every
+    // CHUNKED: three segments — [nb, nb + n_head) | … n1) | [n1, n1 + n_ext) — with the sums taken and reset in between (every
     // segment but the last has an even length, so the even/odd alternation of the steps runs through)
-    for (int seg = 0; seg < (CHUNKED ? 3 : 1); seg++) {
-    const int64_t sbeg = !CHUNKED ? n0 : seg == 0 ? n0 : seg == 1 ? n0 + wk.n_head : n1;
-    const int64_t send = !CHUNKED ? n1 : seg == 0 ? n0 + wk.n_head : seg == 1 ? n1 : n1 + wk.n_ext;
+    // (seg = −1: the run-up of a refinement pass, [n0, n0 + n_warm), sums discarded; the sub-chunk proper starts at nb)
+    const int64_t nb = CHUNKED ? n0 + wk.n_warm : n0;
+    for (int seg = (CHUNKED && wk.n_warm > 0) ? -1 : 0; seg < (CHUNKED ? 3 : 1); seg++) {
+    const int64_t sbeg = !CHUNKED ? n0 : seg < 0 ? n0 : seg == 0 ? nb : seg == 1 ? nb + wk.n_head : n1;
+    const int64_t send = !CHUNKED ? n1 : seg < 0 ? nb : seg == 0 ? nb + wk.n_head : seg == 1 ? n1 : n1 + wk.n_ext;
     for (int64_t nbeg = sbeg; nbeg < send; nbeg += GCH) {
         const int nsteps = (int)((send - nbeg) < GCH ? (send - nbeg) : GCH);
         // pass 1: φ for steps nbeg-1 … nbeg+GCH  (φ_0 = 0, φ_N = 0; chunk start of K3: φ := 1 up to step n0)
@@ -941,7 +943,7 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
     }
     if (CHUNKED) {
         const double logdet = lane_logdet(st);
-        if (lane == 0) {
+        if (lane == 0 && seg >= 0) {
             if (seg == 0) { wk.chk[0] = logdet; wk.chk[1] = st.chi2; }
             else if (seg == 1) { wk.part[0] = wk.chk[0] + logdet; wk.part[1] = wk.chk[1] + st.chi2; }
             else { wk.chk[2] = logdet; wk.chk[3] = st.chi2; }

@@ -71,6 +71,9 @@ struct WorkItem {
     // scan handed it: the two pairs agree to rounding exactly when that state is the one this sweep arrives at.
     int n_head, n_ext;
     double* chk;
+    // K3 refinement: the sweep starts n_warm steps before the sub-chunk (n_begin and `init` refer to that earlier point) and
+    // the sums of those steps are discarded — the filter forgets the error of the injected state while it runs up.
+    int64_t n_warm;
 };
 
 // sin and cos of a large FP64 argument.  The celerite rows take cos/sin(d_j·t_n) at ABSOLUTE times
