@@ -103,6 +103,14 @@ int pioran_celerite_logl(pioran_ctx *ctx, int series_id, int B, int Jt,
 int pioran_approx_logl(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,
                        int B, const double *theta, int theta_per_series, double *logl_out);
 
+/* Fused path for log-normally distributed series (reference: docs/src/timeseries.md:16-21 and the likelihood of
+ * docs/src/ultranest.md:197-217):  yn = log(y - c),  sigma2 = nu * sigma^2 / (y - c)^2,  logpdf(ScalableGP(mu, R)(t, sigma2), yn).
+ * theta: [B x (n_psd_par+4)] row-major = psd parameters..., norm, nu, mu, c.  The transform runs on the device (one pass
+ * over B x N, in theta-chunks of at most 1 GiB) in front of the same K1 + K2 as pioran_approx_logl; y - c <= 0 gives a
+ * NaN log-likelihood (the reference throws DomainError).  One resident series, ranks <= 64.  logl_out: [B]. */
+int pioran_approx_logl_logshift(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,
+                                const double *theta, double *logl_out);
+
 /* Same as pioran_approx_logl with θ and the result resident in device memory; asynchronous on the context's
  * stream (no host synchronisation).  theta_dev: [S or 1][B][n_psd_par+3]; logl_dev: [S × B]. */
 int pioran_approx_logl_dev(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,

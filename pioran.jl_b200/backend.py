@@ -151,6 +151,17 @@ class Context:
         check(self.lib.pioran_approx_logl(self.h, S, ids, sp, B, _p(theta), int(theta_per_series), _p(out)))
         return out
 
+    def approx_logl_logshift(self, series, spec, theta):
+        """Log-normal series (docs/src/timeseries.md:16-21): theta rows = [psd parameters…, norm, ν, μ, c];
+        yn = log(y − c), σ² = ν σ²/(y − c)², transformed on the device.  Returns logL [B]."""
+        npar = N_PSD_PAR[spec.psd_model]
+        theta = np.atleast_2d(_f64(theta))
+        if theta.shape[1] != npar + 4:
+            raise ValueError(f"theta must have {npar + 4} columns (psd parameters, norm, ν, μ, c)")
+        out = np.empty(theta.shape[0])
+        check(self.lib.pioran_approx_logl_logshift(self.h, series.id, C.byref(spec), theta.shape[0], _p(theta), _p(out)))
+        return out
+
     def approx_logl_dev(self, series_list, specs, B, theta_ptr, out_ptr, theta_per_series=False):
         """Device-resident variant: raw device pointers (ints), asynchronous on the context's stream."""
         S = len(series_list)

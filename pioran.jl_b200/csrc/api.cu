@@ -665,8 +665,11 @@ extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spe
 } catch (...) { return guard_fail(); }
 
 // ------------------------------------------------------------------------------------------------ fused entry
+// theta_stride: doubles per θ row (0 = n_psd_par + 3; larger rows carry extra columns the sweep ignores).  y_batch / s2_batch:
+// device [B × N] per-θ data replacing the resident y / σ² (single series, ranks ≤ 64) — the log-shift entry fills them.
 static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs, int B,
-                                  const double* theta_dev, int theta_per_series, double* logl_dev) {
+                                  const double* theta_dev, int theta_per_series, double* logl_dev, int theta_stride = 0,
+                                  const double* y_batch = nullptr, const double* s2_batch = nullptr) {
     int rc;
     if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
     if ((long long)S * B > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "S*B too large");
@@ -680,9 +683,11 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
         ser[s] = get_series(c, series_ids[s]);
         if (!ser[s]) return fail(PIORAN_EINVAL, "unknown series id %d", series_ids[s]);
     }
-    const int npar = n_psd_par_of(specs[0].psd_model), ts = npar + 3;
+    const int npar = n_psd_par_of(specs[0].psd_model), ts = theta_stride > 0 ? theta_stride : npar + 3;
     const int R = rank_of(specs[0].basis, specs[0].n_components);
     const int BS = bs_for_rank(R);
+    if ((y_batch || s2_batch) && (S != 1 || BS > 8))
+        return fail(PIORAN_EUNSUPPORTED, "per-parameter-vector data need a single series and a rank <= 64 (rank %d, %d series)", R, S);
     if (BS > 8) {
         // ranks above 64: K1 writes explicit coefficients, the shared-memory-state kernel sweeps one CTA per (series, θ)
         if (R > WIDE_MAX_RANK) return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", R, WIDE_MAX_RANK);
@@ -765,9 +770,59 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     args.mu = theta_dev + npar + 2;
     args.nu = theta_dev + npar + 1;
     args.pstride = ts;
+    args.y_batch = y_batch; args.s2_batch = s2_batch; args.ystride = ser[0]->N;
     args.out = logl_dev;
     return dispatch_shared(c, BS, args, nitems, c->work_tpi);
 }
+
+// Log-normal time series (docs/src/timeseries.md:16-21, docs/src/ultranest.md:197-217): yn = log(y − c), σ² = σ²/(y − c)² per
+// parameter vector (ν is applied by the sweep).  y − c <= 0 gives NaN, which the likelihood carries through as data.
+__global__ void log_shift_kernel(const double* __restrict__ y, const double* __restrict__ s2, int64_t N, const double* __restrict__ theta,
+                                 int ts, int c_col, int B, double* __restrict__ yb, double* __restrict__ sb) {
+    const int64_t total = (int64_t)B * N;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = k / N, n = k - i * N;
+        const double dlt = y[n] - theta[i * ts + c_col];
+        yb[k] = log(dlt);
+        sb[k] = s2[n] / (dlt * dlt);
+    }
+}
+
+extern "C" int pioran_approx_logl_logshift(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B, const double* theta,
+                                           double* logl_out) try {
+    if (!c || !spec || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = check_spec(*spec))) return rc;
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 4;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * ts))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * (size_t)B * ts, cudaMemcpyHostToDevice, c->stream));
+    // θ-chunks: 16 N bytes of transformed data per parameter vector, at most 1 GiB at a time (written and read once: ≈ 0.3 ms
+    // per 65 536 × 1 000 block against tens of ms of sweep)
+    const int64_t N = s->N;
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 30) / (16 * std::max<int64_t>(N, 1))));
+    if ((rc = c->post.ensure(sizeof(double) * 2 * (size_t)chunk * N))) return rc;
+    double* yb = c->post.as<double>();
+    double* sb = yb + (size_t)chunk * N;
+    for (int off = 0; off < B; off += chunk) {
+        const int nb = std::min(chunk, B - off);
+        const double* th = c->theta.as<double>() + (size_t)off * ts;
+        const int64_t total = (int64_t)nb * N;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->num_sms * 16);
+        log_shift_kernel<<<grid, 256, 0, c->stream>>>(s->y, s->s2, N, th, ts, npar + 3, nb, yb, sb);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = approx_logl_dev_locked(c, 1, &series_id, spec, nb, th, 0, c->out.as<double>() + off, ts, yb, sb))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
 
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
                                       int B, const double* theta_dev, int theta_per_series, double* logl_dev) try {

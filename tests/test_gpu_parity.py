@@ -313,3 +313,50 @@ def test_config_c3_multi_source_full_size(pb, ctx):
         assert np.array_equal(single, got[s], equal_nan=True)
     for ser in series:
         ser.free()
+
+
+@pytest.mark.parametrize("basis,J,B", [("SHO", 20, 37), ("DRWCelerite", 20, 5), ("SHO", 12, 700)])
+def test_log_shift_fused_entry_vs_oracle(pb, ctx, basis, J, B):
+    """Log-normally distributed series (docs/src/timeseries.md:16-21; likelihood of docs/src/ultranest.md:197-217):
+    yn = log(y − c), σ² = ν σ²/(y − c)² per parameter vector.  The fused entry transforms on the device; the oracle gets the
+    transformed arrays row by row.  Also: the same numbers through the generic entry's host-side y_batch / s2_batch, and NaN
+    where y − c ≤ 0 (the reference's log throws DomainError)."""
+    t, y, s2, f_min, f_max = synthetic_series(300, seed=77)
+    flux = np.exp(0.4 * y) + 0.3                      # positive series
+    sig2 = s2 * flux ** 2
+    rng = np.random.default_rng(B)
+    theta = np.empty((B, 7))
+    theta[:, 0] = rng.uniform(0.0, 1.25, B)
+    theta[:, 1] = np.exp(rng.uniform(np.log(f_min), np.log(f_max), B))
+    theta[:, 2] = theta[:, 0] + rng.uniform(size=B) * (4.0 - theta[:, 0])
+    theta[:, 3] = np.exp(rng.normal(-3.0, 1.0, B))
+    theta[:, 4] = rng.gamma(2.0, 0.5, B)
+    theta[:, 5] = rng.normal(np.log(flux).mean(), 0.5, B)
+    theta[:, 6] = np.exp(rng.uniform(np.log(1e-6), np.log(flux.min() * 0.99), B))
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function=basis)
+    ser = ctx.upload_series(t, flux, sig2)
+    got = ctx.approx_logl_logshift(ser, spec, theta)
+    rows = np.unique(np.concatenate([[0, B - 1], rng.choice(B, size=min(B, 6), replace=False)]))
+    for i in rows:
+        yn = np.log(flux - theta[i, 6])
+        s2n = sig2 / (flux - theta[i, 6]) ** 2
+        want = orc.approx_logl_batch("SBPL", theta[i:i + 1, :6], f_min, f_max, J, t, yn, s2n, basis=basis)[0]
+        if rel_err(got[i], want) > TOL:     # ill-conditioned draw: no farther from the 80-bit value than 4× the reference order
+            a_, b_, c_, d_ = orc.approx("SBPL", theta[i, :3], f_min, f_max, J, theta[i, 3], basis=basis)
+            ld = orc.celerite_logl(a_, b_, c_, d_, t, yn - theta[i, 5], theta[i, 4] * s2n, long_double=True)
+            assert rel_err(got[i], ld) <= 4 * rel_err(want, ld), (i, got[i], want, ld)
+    # generic entry with host-transformed per-θ data: same sweep, explicit coefficients
+    sub = rows[:4]
+    a, b, c, d = ctx.approx_coeffs(spec, theta[sub, :4])
+    yb = np.log(flux[None, :] - theta[sub, 6:7])
+    sb = sig2[None, :] / (flux[None, :] - theta[sub, 6:7]) ** 2
+    gen = ctx.celerite_logl(ser, a, b, c, d, mu=theta[sub, 5], nu=theta[sub, 4], y_batch=yb, s2_batch=sb)
+    assert np.max(np.abs(gen - got[sub]) / np.maximum(1.0, np.abs(got[sub]))) <= TOL
+    # c above the smallest flux: log of a negative number
+    bad = theta[:2].copy()
+    bad[1, 6] = flux.min() * 1.5
+    out = ctx.approx_logl_logshift(ser, spec, bad)
+    assert np.isfinite(out[0]) and np.isnan(out[1])
+    with pytest.raises(ValueError):
+        ctx.approx_logl_logshift(ser, spec, theta[:, :6])
+    ser.free()
