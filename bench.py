@@ -338,6 +338,33 @@ def config_c1_and_sampler_call(ctx, pb, J):
     return out
 
 
+def config_log_shift(ctx, pb, J):
+    """the log-normal likelihood (docs/src/ultranest.md:197-217) — 65 536 θ × N = 1 000, SHO: host θ (7 columns) in,
+    device-side transform into per-θ data, K1 + K2, host logL out; wall time of the host entry, best of 5, beside the plain
+    fused entry on the same batch."""
+    t, y, s2, f_min, f_max = wl.make_series(1000, 1234)
+    flux = np.exp(0.4 * y) + 0.3
+    sig2 = s2 * flux ** 2
+    B = 65536
+    th = wl.prior_theta(B, f_min, f_max, np.log(flux).mean(), np.log(flux).std(), 17, 4.0)
+    th7 = np.concatenate([th, np.exp(np.random.default_rng(3).uniform(np.log(1e-6), np.log(flux.min() * 0.99), (B, 1)))], axis=1)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J)
+    ser = ctx.upload_series(t, flux, sig2)
+    row = {}
+    for name, fn in (("log_shift_entry", lambda: ctx.approx_logl_logshift(ser, spec, th7)), ("plain_fused_entry", lambda: ctx.approx_logl(ser, spec, th))):
+        fn()
+        best = 1e30
+        for _ in range(5):
+            t0 = time.perf_counter()
+            out = fn()
+            best = min(best, time.perf_counter() - t0)
+        row[name + "_wall_ms"] = best * 1e3
+        row[name + "_finite"] = int(np.isfinite(out).sum())
+    ser.free()
+    row["evals_per_s"] = B / (row["log_shift_entry_wall_ms"] * 1e-3)
+    return {"log_shift_65536theta_N1000_SHO": row}
+
+
 def config_c4_c5(ctx, pb, hbm_peak):
     """BASELINE configs[3] and [4] on one GPU.  C4: one series of N = 1e6, SHO J = 30 (rank 60), parallel-in-time scan (K3):
     device ms, achieved HBM GB/s on the algorithmic bytes (48 N + composites written and read), parity against ONE evaluation
@@ -577,6 +604,7 @@ def run_b200(args, rank, world, local_rank):
         extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
         extra.update(config_c1_and_sampler_call(ctx, pb, args.J))
         extra.update(config_c4_c5(ctx, pb, hbm_peak_gbs()))
+        extra.update(config_log_shift(ctx, pb, args.J))
         extra.update(widening_rows(ctx, pb, args.J))
 
     cpu = None

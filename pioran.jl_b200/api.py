@@ -271,7 +271,10 @@ class BatchedLikelihood:
     The series (and its trig/exp table) is uploaded once; each call runs K1 + K2 on the whole batch."""
 
     def __init__(self, t, y, σ2, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
-                 f_min=None, f_max=None, S_low=20.0, S_high=20.0, is_integrated_power=True, ctx=None):
+                 f_min=None, f_max=None, S_low=20.0, S_high=20.0, is_integrated_power=True, ctx=None, log_shift=False):
+        # log_shift: Θ rows carry a 7th column c and the data enter as yn = log(y − c), σ² = ν σ²/(y − c)²
+        # (docs/src/ultranest.md:197-217); t, y, σ2 are then the untransformed flux and its measurement variance
+        self.log_shift = bool(log_shift)
         self.ctx = ctx or get_context()
         t = np.asarray(t, dtype=np.float64)
         if f_min is None:
@@ -282,16 +285,20 @@ class BatchedLikelihood:
             psd_model = psd_model.model_name
         self.spec = make_spec(psd_model, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
         self.series = self.ctx.upload_series(t, y, σ2)
-        self.n_par = backend.N_PSD_PAR[self.spec.psd_model] + 3
+        self.n_par = backend.N_PSD_PAR[self.spec.psd_model] + 3 + int(self.log_shift)
 
     def __call__(self, theta):
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if self.log_shift:
+            return self.ctx.approx_logl_logshift(self.series, self.spec, theta)
         return self.ctx.approx_logl(self.series, self.spec, theta)[0]
 
     def value_and_gradient(self, theta):
         """(logL [B], ∂logL/∂Θ [B × n_par]) — what ForwardDiff.gradient gives the reference's HMC/NUTS runs
         (test/test_likelihood.jl:55, examples/turing_distributed/single_pl.jl), for a whole batch of chains at once."""
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if self.log_shift:
+            raise NotImplementedError("gradients of the log-shift likelihood (∂/∂c moves the data) are not built")
         return self.ctx.approx_logl_grad(self.series, self.spec, theta)
 
     def gradient(self, theta):

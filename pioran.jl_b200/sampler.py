@@ -89,6 +89,38 @@ def single_bending_power_law_prior(f_min, f_max, xbar, va, mu_v=-1.5, sigma_v=1.
                            LogNormal(mu_n, sigma_n), Gamma(2, 0.5), Normal(xbar, 5 * np.sqrt(va))])
 
 
+def log_normal_prior(f_min, f_max, y, mu_v=-1.5, sigma_v=1.0, alpha1_max=1.25, alpha2_max=4.0):
+    """The prior of docs/src/ultranest.md:165-190,220-229 for Θ = (α₁, f₁, α₂, variance, ν, μ, c) — the log-normal model with
+    an offset c ~ LogUniform(1e-6, 0.99·min y); x̄ and va are the mean and variance of log(y), f₁ ~ LogUniform(f0·4, fM/4)."""
+    y = np.asarray(y, dtype=np.float64)
+    f0, fM = f_min / 20.0, f_max * 20.0
+    mu_n, sigma_n = 2 * mu_v, np.sqrt(2 * sigma_v ** 2)
+    xbar, va = float(np.mean(np.log(y))), float(np.var(np.log(y), ddof=1))
+    return PriorTransform([Uniform(0.0, alpha1_max), LogUniform(f0 * 4.0, fM / 4.0), UniformFrom(0, alpha2_max),
+                           LogNormal(mu_n, sigma_n), Gamma(2, 0.5), Normal(xbar, 5 * np.sqrt(va)),
+                           LogUniform(1e-6, float(np.min(y)) * 0.99)])
+
+
+def vectorized_callbacks_log_normal(t, y, yerr, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
+                                    prior=None, ctx=None, **approx_kw):
+    """Same as vectorized_callbacks for the seven-parameter log-normal likelihood of docs/src/ultranest.md:197-217: the offset c
+    is sampled, so the transform yn = log(y − c), σ² = ν σ²/(y − c)² is per point and runs on the device
+    (pioran_approx_logl_logshift)."""
+    from .api import BatchedLikelihood
+    t, y, yerr = (np.asarray(x, dtype=np.float64) for x in (t, y, yerr))
+    like = BatchedLikelihood(t, y, yerr ** 2, psd_model, n_components, basis_function, ctx=ctx, log_shift=True, **approx_kw)
+    if prior is None:
+        f_min, f_max = 1.0 / (t[-1] - t[0]), 1.0 / np.min(np.diff(t)) / 2.0
+        prior = log_normal_prior(f_min, f_max, y, alpha2_max=4.0 if basis_function == "SHO" else 6.0)
+
+    def loglike(theta):
+        out = like(np.atleast_2d(theta))
+        out[~np.isfinite(out)] = -1e300
+        return out
+
+    return loglike, prior, like.close
+
+
 def vectorized_callbacks(t, y, yerr, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
                          log_transform=True, prior=None, ctx=None, **approx_kw):
     """(loglike, transform, close) for `ultranest.ReactiveNestedSampler(paramnames, loglike, transform=transform,

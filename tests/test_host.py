@@ -237,3 +237,22 @@ def test_prior_transform_matches_reference_prior():
     assert np.allclose(th[:, 5], stats.norm(xbar, 5 * np.sqrt(va)).ppf(u[:, 5]), rtol=1e-10, atol=1e-12)
     assert np.array_equal(tr(u[7]), th[7])
     assert np.all(th[:, 2] >= th[:, 0]) and np.all(th[:, 3] > 0) and np.all(th[:, 4] > 0)
+
+
+def test_log_normal_prior_transform():
+    """sampler.log_normal_prior restates the seven-parameter prior of docs/src/ultranest.md:220-229: the six columns of the
+    single-bending-power-law prior (α₁ ≤ 1.25 there) plus c ~ LogUniform(1e-6, 0.99·min y)."""
+    from scipy import stats
+    import pioran_b200 as pb
+    rng = np.random.default_rng(8)
+    y = np.exp(rng.normal(0.3, 0.4, 200)) + 0.2
+    f_min, f_max = 1e-3, 2.0
+    tr = pb.sampler.log_normal_prior(f_min, f_max, y)
+    u = rng.uniform(size=(129, 7))
+    th = tr(u)
+    assert np.allclose(th[:, 0], 1.25 * u[:, 0], rtol=1e-15)
+    assert np.allclose(th[:, 2], th[:, 0] + u[:, 2] * (4.0 - th[:, 0]), rtol=1e-15)
+    assert np.allclose(th[:, 5], stats.norm(np.log(y).mean(), 5 * np.log(y).std(ddof=1)).ppf(u[:, 5]), rtol=1e-10)
+    assert np.allclose(th[:, 6], stats.loguniform(1e-6, 0.99 * y.min()).ppf(u[:, 6]), rtol=1e-12)
+    assert np.all(th[:, 6] < y.min())
+    assert np.allclose(tr(u[3]), th[3])
