@@ -92,10 +92,105 @@ class SumOfCelerite(SemiSeparable):
         return SumOfCelerite(*(np.concatenate([x, y]) for x, y in zip(celerite_coefs(self), o)))
 
 
+# ----------------------------------------------------------------------------------------------- CARMA front end
+# covariances whose decay rates and frequencies depend on the sampled parameters reach the GPU through the
+# generic coefficient entry.  CARMA (src/CARMA.jl) is the reference's own example: host arithmetic on p roots, then (a, b, c, d).
+def quad2roots(quad):
+    """Roots of the product of quadratic factors x² + quad[k+1] x + quad[k] (k = 0, 2, …) and, for an odd count, the linear
+    factor x + quad[-1]  (src/CARMA.jl:201-223; test/test_carma.jl:3-17)."""
+    quad = np.asarray(quad, dtype=np.float64)
+    n = quad.shape[0]
+    r = np.zeros(n, dtype=np.complex128)
+    if n % 2 == 1:
+        r[-1] = -quad[-1]
+    for k in range(0, n - n % 2, 2):
+        lin, const = quad[k + 1], quad[k]
+        disc = lin * lin - 4.0 * const
+        if disc < 0:
+            r[k] = (-lin + 1j * np.sqrt(-disc)) / 2.0
+            r[k + 1] = np.conj(r[k])
+        else:
+            r[k], r[k + 1] = (-lin + np.sqrt(disc)) / 2.0, (-lin - np.sqrt(disc)) / 2.0
+    return r
+
+
+def roots2coeffs(r):
+    """Coefficients, constant term first, of the monic polynomial with roots r (src/CARMA.jl:185-188)."""
+    return np.poly(np.asarray(r, dtype=np.complex128))[::-1]
+
+
+def _carma_residue(rk, roots, beta):
+    """β(r_k) β(−r_k) / (−2 Re r_k ∏_{j: r_j ≠ r_k} (r_j − r_k)(conj r_j + r_k)): the weight of exp(r_k |τ|) in the CARMA
+    autocovariance (src/CARMA.jl:230-247)."""
+    powers = np.arange(beta.shape[0])
+    num = np.sum(beta * rk ** powers) * np.sum(beta * (-rk) ** powers)
+    den = -2.0 * rk.real
+    for rj in roots:
+        if rj != rk:
+            den = den * ((rj - rk) * (np.conj(rj) + rk))
+    return num / den
+
+
+class CARMA(SemiSeparable):
+    """CARMA(p, q, rα, β, norm=1, is_integrated_power=True)  (src/CARMA.jl:1-43): rα the p roots of the autoregressive polynomial
+    (conjugate pairs next to each other, a real root last when p is odd), β the q + 1 moving-average coefficients."""
+
+    def __init__(self, p, q, rα, β, norm=1.0, is_integrated_power=True):
+        p, q = int(p), int(q)
+        rα = np.asarray(rα, dtype=np.complex128).ravel()
+        β = np.asarray(β, dtype=np.float64).ravel()
+        if p < 1 or q < 0:
+            raise ValueError("The order of the autoregressive and moving average polynomials must be positive")
+        if q > p:
+            raise ValueError("The order of the moving average polynomial must be less than or equal to the order of the "
+                             "autoregressive polynomial")
+        if rα.shape[0] != p:
+            raise ValueError("The length of the roots of the autoregressive polynomial must be equal to the order of the "
+                             "autoregressive polynomial")
+        if β.shape[0] != q + 1:
+            raise ValueError("The length of the moving average coefficients must be equal to q + 1")
+        self.p, self.q, self.rα, self.β = p, q, rα, β
+        self.norm, self.is_integrated_power = float(norm), bool(is_integrated_power)
+
+    def covariance(self, τ):
+        """CARMA_covariance(τ, cov) (src/CARMA.jl:230-275): Σ_k residue_k exp(r_k |τ|), normalised like celerite_coefs."""
+        τ = np.abs(np.asarray(τ, dtype=np.float64))
+        res = np.array([_carma_residue(rk, self.rα, self.β) for rk in self.rα])
+        acv = np.real(np.sum(res[:, None] * np.exp(self.rα[:, None] * τ.ravel()[None, :]), axis=0)).reshape(τ.shape)
+        scale = self.norm / np.real(np.sum(res)) if self.is_integrated_power else self.norm
+        return acv * scale
+
+
+def carma_celerite_coefs(p, rα, β, norm=1.0, is_integrated_power=True):
+    """CARMA_celerite_coefs (src/CARMA.jl:98-143): one celerite term per conjugate pair (a + i b = 2 × the pair's residue,
+    c = −Re r, d = −Im r) and a real term (b = d = 0) for the unpaired last root of an odd p; with is_integrated_power the
+    amplitudes are rescaled so that Σa = norm.  Pinned by test/test_carma.jl:53-70."""
+    rα = np.asarray(rα, dtype=np.complex128).ravel()
+    β = np.asarray(β, dtype=np.float64).ravel()
+    J = (p + 1) // 2
+    a, b, c, d = (np.empty(J) for _ in range(4))
+    for k in range(J):
+        rk = rα[2 * k]
+        frac = 2.0 * _carma_residue(rk, rα, β)        # −β(r)β(−r)/Re r / ∏ …
+        if k != J - 1 or p % 2 == 0:
+            a[k], b[k], c[k], d[k] = 2.0 * frac.real, 2.0 * frac.imag, -rk.real, -rk.imag
+        else:
+            a[k], b[k], c[k], d[k] = frac.real, 0.0, -rk.real, 0.0
+    scale = norm / np.sum(a) if is_integrated_power else norm
+    return a * scale, b * scale, c, d
+
+
+def celerite_repr(cov):
+    """celerite_repr(cov::CARMA) (src/CARMA.jl:55-70) → SumOfCelerite."""
+    return SumOfCelerite(*celerite_coefs(cov))
+
+
 def celerite_coefs(cov):
-    """(a, b, c, d) vectors of a covariance (src/acvf.jl:119-127, src/Celerite.jl:33-39)."""
+    """(a, b, c, d) vectors of a covariance (src/acvf.jl:119-127, src/Celerite.jl:33-39, src/CARMA.jl:73-75)."""
     if isinstance(cov, SumOfCelerite):
         return cov.a, cov.b, cov.c, cov.d
+    if isinstance(cov, CARMA):
+        return carma_celerite_coefs(cov.p, cov.rα, cov.β, cov.norm, cov.is_integrated_power)
     if isinstance(cov, Celerite):
         return (np.array([cov.a]), np.array([cov.b]), np.array([cov.c]), np.array([cov.d]))
     raise TypeError(f"no celerite coefficients for {type(cov).__name__}")

@@ -360,3 +360,34 @@ def test_log_shift_fused_entry_vs_oracle(pb, ctx, basis, J, B):
     with pytest.raises(ValueError):
         ctx.approx_logl_logshift(ser, spec, theta[:, :6])
     ser.free()
+
+
+def test_carma_covariance_through_generic_entry(pb, ctx):
+    """a covariance with parameter-dependent decay rates and frequencies — the reference's CARMA(3, 2) literal
+    of test/test_carma.jl:53-70 — through log_likelihood(cov::CARMA, …) (src/celerite_solver.jl:272-282): coefficients on the
+    host, then the generic kernel (one complex term with a negative frequency and a real term with a negative amplitude: rank 3).
+    Checked against the oracle's celerite recursion and its dense Cholesky; batched over roots drawn around the literal."""
+    rα = np.array([-0.042163209825323775 + 1.1115603157767922j, -0.042163209825323775 - 1.1115603157767922j, -0.7599101571312047])
+    β = [3.9413022090550216, 11.38193903188344, 1.0]
+    t, y, s2, _, _ = synthetic_series(400, seed=9)
+    cov = pb.CARMA(3, 2, rα, β, 1.3)
+    got = pb.log_likelihood(cov, t, y, s2, ctx=ctx)
+    a, b, c, d = pb.celerite_coefs(cov)
+    want = orc.celerite_logl(a, b, c, d, t, y, s2)
+    assert rel_err(got, want) <= TOL
+    nll, info = orc.direct_nll(a, b, c, d, t, y, s2)
+    assert info == 0 and rel_err(-nll, want) <= 1e-8                             # celerite ≡ dense for this covariance
+    rng = np.random.default_rng(2)
+    B = 64
+    coefs = []
+    for i in range(B):
+        quad = np.array([1.2 * np.exp(rng.normal(0, 0.3)), 0.09 * np.exp(rng.normal(0, 0.3)), 0.76 * np.exp(rng.normal(0, 0.3))])
+        coefs.append(pb.carma_celerite_coefs(3, pb.quad2roots(quad), β, np.exp(rng.normal(0, 0.5))))
+    A, Bc, Cc, D = (np.stack([k[j] for k in coefs]) for j in range(4))
+    ser = ctx.upload_series(t, y, s2)
+    gotb = ctx.celerite_logl(ser, A, Bc, Cc, D)
+    ser.free()
+    wantb = orc.celerite_logl_batch(A, Bc, Cc, D, t, y, s2, nthreads=0)
+    ok = np.isfinite(wantb)
+    assert ok.sum() >= B // 2
+    assert np.max(np.abs(gotb[ok] - wantb[ok]) / np.maximum(1.0, np.abs(wantb[ok]))) <= TOL

@@ -256,3 +256,39 @@ def test_log_normal_prior_transform():
     assert np.allclose(th[:, 6], stats.loguniform(1e-6, 0.99 * y.min()).ppf(u[:, 6]), rtol=1e-12)
     assert np.all(th[:, 6] < y.min())
     assert np.allclose(tr(u[3]), th[3])
+
+
+_CARMA32 = dict(rα=[-0.042163209825323775 + 1.1115603157767922j, -0.042163209825323775 - 1.1115603157767922j,
+                    -0.7599101571312047 + 0.0j], β=[3.9413022090550216, 11.38193903188344, 1.0])
+
+
+def test_carma_front_end_golden_vectors():
+    """Host-side CARMA → celerite conversion against the reference's own literals: test/test_carma.jl:3-17
+    (quad2roots), :19-33 (roots2coeffs), :53-70 (celerite_coefs), :96-113 (celerite ACVF ≡ CARMA ACVF), and the constructor's
+    argument checks (src/CARMA.jl:28-37)."""
+    import pioran_b200 as pb
+    r = pb.quad2roots([0.025443151049354032, 0.04252858046335997, 2.5980088198563633])
+    assert np.allclose(r, [-0.021264290231679986 + 0.1580853598860341j, -0.021264290231679986 - 0.1580853598860341j,
+                           -2.5980088198563633 + 0.0j], rtol=1e-14)
+    α = pb.roots2coeffs([-0.012721575524677016 + 0.20583182936448363j, -0.012721575524677016 - 0.20583182936448363j,
+                         -2.5980088198563633 + 0.0j])
+    assert np.allclose(α, [0.11048962713978024, 0.10863011129451944, 2.6234519709057174, 1], rtol=1e-13)
+    cov = pb.CARMA(3, 2, _CARMA32["rα"], _CARMA32["β"], 1.3)
+    a, b, c, d = pb.celerite_coefs(cov)
+    assert np.allclose(a, [1.332733901854476, -0.03273390185447589], rtol=1e-12)
+    assert np.allclose(b, [-0.026820976815752837, 0.0], rtol=1e-12)
+    assert np.allclose(c, [0.042163209825323775, 0.7599101571312047], rtol=1e-15)
+    assert np.allclose(d, [-1.1115603157767922, 0.0], rtol=1e-15)
+    rep = pb.celerite_repr(cov)
+    assert isinstance(rep, pb.SumOfCelerite) and np.array_equal(rep.a, a)
+    t = np.linspace(0, 150, 1000)
+    assert np.allclose([rep(x, 0.0) for x in t], cov.covariance(t), rtol=1e-10, atol=1e-14)
+    assert abs(np.sum(a) - 1.3) < 1e-14                                   # integrated power: Σa = norm
+    a2, _, _, _ = pb.celerite_coefs(pb.CARMA(3, 2, _CARMA32["rα"], _CARMA32["β"], 1.0, False))
+    assert np.allclose(a2 / a2[0], a / a[0], rtol=1e-13)
+    # even order: every term is a conjugate pair
+    a4, b4, c4, d4 = pb.carma_celerite_coefs(4, pb.quad2roots([0.5, 0.2, 3.0, 0.4]), [1.0, 0.3])
+    assert a4.shape == (2,) and np.all(d4 != 0.0) and abs(a4.sum() - 1.0) < 1e-14
+    for bad in ((0, 0, [], [1.0]), (2, 3, [1j, -1j], [1, 1, 1, 1]), (3, 2, [1j, -1j], [1, 1, 1]), (3, 2, _CARMA32["rα"], [1, 1])):
+        with pytest.raises(ValueError):
+            pb.CARMA(*bad)
