@@ -20,7 +20,10 @@
 //      returns (Σ log|D_n|, Σ z_n²/D_n); the host adds them up.
 // Algorithmic HBM traffic: 2 passes over (t, y, σ²) = 48 N bytes plus P·(3·64² + 2·64)·8 B of composites written and
 // read a few times (≈ 0.1 GB at P = 296) — the path is FP64/latency-bound, not HBM-bound.
-// Accuracy: verified against the sequential recursion to ≤ 1e-13 relative (tests/test_gpu_scan.py).
+// Accuracy: rounding-level agreement with the sequential recursion on well-conditioned covariances (median 2–5e-15 over prior
+// draws); on ill-conditioned ones (steep DRWCelerite slopes) the composites lose digits (1e-8 … 1e-6 seen), so pass 3 carries
+// a self-check — every warp sweeps 8 steps beyond its sub-chunk and the next warp sums its first 8 steps separately; the two
+// must agree (scan_check_estimate) — and the host re-evaluates what fails (api.cu: scan_logl_locked; tests/test_gpu_scan.py).
 #pragma once
 #include "common.cuh"
 
