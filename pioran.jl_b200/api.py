@@ -401,3 +401,62 @@ class BatchedLikelihood:
 
     def close(self):
         self.series.free()
+
+
+class BatchedCARMALikelihood:
+    """Vectorised log-likelihood of the reference's CARMA(p, q) model (docs/src/carma.md:20-58):
+        Θ row = [qa (p quadratic coefficients of the AR polynomial), qb (q, of the MA polynomial), variance, ν, μ(, c)]
+        rα = quad2roots(qa), rβ = quad2roots(qb), β = roots2coeffs(rβ), 𝓒 = CARMA(p, q, rα, β, variance),
+        logpdf(ScalableGP(μ, 𝓒)(t, σ²), yn)   with  yn = log(y − c), σ² = ν σ²/(y − c)²  when log_shift (else yn = y, σ² = ν σ²).
+    Rows whose roots leave (−f_max, −f_min) × (−f_max, f_max) get −Inf, as the model's `@addlogprob! -Inf` does.  The decay
+    rates and frequencies depend on Θ, so this goes through the generic coefficient entry (host arithmetic on p + q numbers per
+    row, then ONE kernel call for the batch); the per-row data of the log-shift ride along as y_batch / s2_batch."""
+
+    def __init__(self, t, y, σ2, p, q, f_min, f_max, log_shift=True, ctx=None):
+        self.ctx = ctx or get_context()
+        self.p, self.q, self.f_min, self.f_max, self.log_shift = int(p), int(q), float(f_min), float(f_max), bool(log_shift)
+        if self.p < 1 or self.q < 0 or self.q > self.p:
+            raise ValueError("need 1 <= p and 0 <= q <= p")
+        self.y, self.σ2 = np.asarray(y, dtype=np.float64), np.asarray(σ2, dtype=np.float64)
+        self.series = self.ctx.upload_series(t, self.y, self.σ2)
+        self.n_par = self.p + self.q + 3 + int(self.log_shift)
+
+    def _roots_ok(self, r):
+        return bool(np.all((-self.f_max < r.real) & (r.real < -self.f_min) & (-self.f_max < r.imag) & (r.imag < self.f_max)))
+
+    def coefficients(self, theta):
+        """(ok [B], a, b, c, d [B × J]) for the rows of Θ; rows outside the root bounds keep placeholder coefficients."""
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if theta.shape[1] != self.n_par:
+            raise ValueError(f"theta must have {self.n_par} columns")
+        B, J = theta.shape[0], (self.p + 1) // 2
+        ok = np.zeros(B, dtype=bool)
+        a, b, c, d = (np.ones((B, J)) for _ in range(4))
+        for i in range(B):
+            rα = quad2roots(theta[i, :self.p])
+            rβ = quad2roots(theta[i, self.p:self.p + self.q])
+            if not (self._roots_ok(rα) and (self.q == 0 or self._roots_ok(rβ))):
+                continue
+            β = np.real(roots2coeffs(rβ)) if self.q > 0 else np.ones(1)
+            a[i], b[i], c[i], d[i] = carma_celerite_coefs(self.p, rα, β, theta[i, self.p + self.q])
+            ok[i] = True
+        return ok, a, b, c, d
+
+    def __call__(self, theta):
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        ok, a, b, c, d = self.coefficients(theta)
+        k = self.p + self.q
+        out = np.full(theta.shape[0], -np.inf)
+        if ok.any():
+            sel = np.flatnonzero(ok)
+            yb = sb = None
+            if self.log_shift:
+                shift = self.y[None, :] - theta[sel, k + 3:k + 4]
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    yb, sb = np.log(shift), self.σ2[None, :] / shift ** 2
+            out[sel] = self.ctx.celerite_logl(self.series, a[sel], b[sel], c[sel], d[sel], mu=theta[sel, k + 2], nu=theta[sel, k + 1],
+                                              y_batch=yb, s2_batch=sb)
+        return out
+
+    def close(self):
+        self.series.free()

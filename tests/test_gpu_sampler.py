@@ -62,3 +62,32 @@ def test_vectorized_callbacks_log_normal_model(pb, golden_single):
         if np.isfinite(want):
             assert abs(logl[i] - want) / max(1.0, abs(want)) <= 1e-7, (i, logl[i], want)
     close()
+
+
+def test_batched_carma_likelihood_log_shift(pb):
+    """The reference's CARMA(3, 2) model with the log-shift of the data (docs/src/carma.md:20-58) for a batch of points:
+    coefficients on the host, one generic-kernel call with per-row data; against the oracle row by row, −Inf outside the
+    root bounds."""
+    from conftest import synthetic_series
+    t, y, s2, _, _ = synthetic_series(300, seed=4)
+    flux = np.exp(0.3 * y) + 0.4
+    sig2 = s2 * flux ** 2
+    f_min, f_max = 1e-3, 50.0
+    like = pb.BatchedCARMALikelihood(t, flux, sig2, 3, 2, f_min, f_max, ctx=pb.get_context(0))
+    rng = np.random.default_rng(6)
+    B = 48
+    th = np.empty((B, 9))
+    th[:, 0] = 1.24 * np.exp(rng.normal(0, 0.3, B)); th[:, 1] = 0.0843 * np.exp(rng.normal(0, 0.3, B)); th[:, 2] = 0.76 * np.exp(rng.normal(0, 0.3, B))
+    th[:, 3] = 3.94 * np.exp(rng.normal(0, 0.2, B)); th[:, 4] = 11.38 * np.exp(rng.normal(0, 0.2, B))
+    th[:, 5] = np.exp(rng.normal(-2.0, 0.5, B)); th[:, 6] = rng.gamma(2.0, 0.5, B)
+    th[:, 7] = rng.normal(np.log(flux).mean(), 0.3, B); th[:, 8] = rng.uniform(0.0, 0.9 * flux.min(), B)
+    th[5, 2] = 100.0                                    # real root at −100 < −f_max
+    got = like(th)
+    assert got.shape == (B,) and got[5] == -np.inf and np.all(np.isfinite(np.delete(got, 5)))
+    ok, a, b, c, d = like.coefficients(th)
+    assert not ok[5] and ok.sum() == B - 1
+    for i in (0, 1, 7, 20, 47):
+        shift = flux - th[i, 8]
+        want = orc.celerite_logl(a[i], b[i], c[i], d[i], t, np.log(shift) - th[i, 7], th[i, 6] * sig2 / shift ** 2)
+        assert abs(got[i] - want) / max(1.0, abs(want)) <= 1e-9, (i, got[i], want)
+    like.close()

@@ -292,3 +292,24 @@ def test_carma_front_end_golden_vectors():
     for bad in ((0, 0, [], [1.0]), (2, 3, [1j, -1j], [1, 1, 1, 1]), (3, 2, [1j, -1j], [1, 1, 1]), (3, 2, _CARMA32["rα"], [1, 1])):
         with pytest.raises(ValueError):
             pb.CARMA(*bad)
+
+
+def test_batched_carma_coefficients_host_logic():
+    """BatchedCARMALikelihood.coefficients (no device needed): quad → roots → bounds check → celerite coefficients, with the
+    MA coefficients β = roots2coeffs(quad2roots(qb)) (docs/src/carma.md:26-42); the literal of test/test_carma.jl:53-70 comes back."""
+    import pioran_b200 as pb
+    like = pb.BatchedCARMALikelihood.__new__(pb.BatchedCARMALikelihood)
+    like.p, like.q, like.f_min, like.f_max, like.log_shift, like.n_par = 3, 2, 1e-3, 50.0, False, 8
+    rα = np.array(_CARMA32["rα"])
+    qa = [abs(rα[0]) ** 2, -2 * rα[0].real, -rα[2].real]            # x² + qa[1] x + qa[0], x + qa[2]
+    rβ = np.roots([1.0, 11.38193903188344, 3.9413022090550216])
+    qb = [np.prod(rβ).real, -np.sum(rβ).real]
+    th = np.array([qa + qb + [1.3, 1.0, 0.0], qa[:2] + [100.0] + qb + [1.3, 1.0, 0.0]])
+    ok, a, b, c, d = like.coefficients(th)
+    assert ok.tolist() == [True, False]
+    assert np.allclose(a[0], [1.332733901854476, -0.03273390185447589], rtol=1e-10)
+    assert np.allclose(b[0], [-0.026820976815752837, 0.0], rtol=1e-9)
+    assert np.allclose(c[0], [0.042163209825323775, 0.7599101571312047], rtol=1e-12)
+    assert np.allclose(d[0], [-1.1115603157767922, 0.0], rtol=1e-12)
+    with pytest.raises(ValueError):
+        like.coefficients(th[:, :5])
