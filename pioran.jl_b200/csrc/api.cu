@@ -1248,11 +1248,13 @@ extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
 extern "C" int pioran_ctx_set_scan_tolerance(pioran_ctx* c, double tol) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (tol != tol) return fail(PIORAN_EINVAL, "tol is NaN");
+    std::lock_guard<std::mutex> lk(c->mu);
     c->scan_tol = tol;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* n_fallback, int* n_refined) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
     if (estimate) *estimate = c->scan_last_est;
     if (n_fallback) *n_fallback = c->scan_last_fallback;
     if (n_refined) *n_refined = c->scan_last_refined;
