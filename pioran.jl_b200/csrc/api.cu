@@ -127,7 +127,8 @@ static int bs_for_rank(int R) {
 
 // A handful of evaluations of one long series is latency-bound in the sequential sweep (≈ 0.9 µs per step whatever the rank);
 // from a few thousand steps on the parallel-in-time path K3 is faster (tools/scan_vs_seq.py: 2.0–2.2 vs 3.9–8.2 ms at N = 4 096, 2.5–2.9 vs 7.8–16 ms at N = 8 192,
-// 5–6 vs 62–130 ms at N = 65 536), so the plain entries route such calls to it.  Same value to ≤ 1e-13 relative.
+// 5–6 vs 62–130 ms at N = 65 536), so the plain entries route such calls to it.  Same value as the sequential sweep: every
+// routed call verifies itself and ill-conditioned parameter vectors are re-evaluated sequentially (scan_logl_locked).
 constexpr int64_t AUTO_SCAN_MIN_STEPS = 4096;
 constexpr int AUTO_SCAN_MAX_BATCH = 4;
 // Thresholds from tools/scan_threshold.py (one evaluation): the fused path's sequential sweep (shared table, pre-decayed state)
