@@ -67,6 +67,11 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+    # measurement helpers under tools/ stay clear of it too (the checker scripts that need it live under tests/tools/)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", f), errors="replace").read()
+            assert not re.search(r"(from|import)\s+oracle", txt), f"tools/{f} imports the oracle"
 
 
 def test_spec_validation_mirrors_reference():

@@ -1,6 +1,6 @@
 """Quick GPU sanity script (development aid): parity of K1/K2 vs the oracle and the golden chains + rough timing."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import pioran_b200 as pb
 from oracle import oracle as orc
