@@ -130,6 +130,14 @@ int pioran_approx_logl_grad(pioran_ctx *ctx, int series_id, const pioran_approx_
 int pioran_approx_logl_grad_dev(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,
                                 const double *theta_dev, double *logl_dev, double *grad_dev);
 
+/* Which kernel sweeps the fused (approx) path at ranks <= 63.  PIORAN_SWEEP_AUTO (default): the tensor-pipe kernel
+ * (csrc/blocked.cuh: the recursion of src/celerite_solver.jl:69-98 blocked over 8 steps, its O(R^2) work on FP64 mma.sync);
+ * PIORAN_SWEEP_SCALAR: the scalar-pipe kernel (csrc/celerite.cuh), kept for ranks 64, explicit coefficients and as the
+ * in-process cross-check of the blocked one.  Both evaluate the same log-likelihood. */
+#define PIORAN_SWEEP_AUTO 0
+#define PIORAN_SWEEP_SCALAR 1
+int pioran_ctx_set_sweep_kernel(pioran_ctx *ctx, int which);
+
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
 /* pioran_celerite_logl and pioran_approx_logl hand calls with at most 4 parameter vectors on a long series (fused path: at

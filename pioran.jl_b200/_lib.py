@@ -38,6 +38,7 @@ SYMBOLS = {
     "pioran_approx_logl_grad": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ApproxSpec), C.c_int, _dp, _dp, _dp]),
     "pioran_approx_logl_grad_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ApproxSpec), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pioran_ctx_set_auto_scan": (C.c_int, [C.c_void_p, C.c_int]),
+    "pioran_ctx_set_sweep_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "pioran_ctx_set_scan_chunks": (C.c_int, [C.c_void_p, C.c_int]),
     "pioran_ctx_set_scan_tolerance": (C.c_int, [C.c_void_p, C.c_double]),
     "pioran_celerite_scan_range_check": (C.c_int, [C.c_void_p, _dp]),

@@ -187,6 +187,10 @@ class Context:
         check(self.lib.pioran_approx_logl_grad_dev(self.h, series.id, C.byref(spec), int(B), C.c_void_p(theta_ptr),
                                                    C.c_void_p(logl_ptr or 0), C.c_void_p(grad_ptr)))
 
+    def set_sweep_kernel(self, which="auto"):
+        """Kernel of the fused path at ranks ≤ 63: "auto" (tensor-pipe, csrc/blocked.cuh) or "scalar" (csrc/celerite.cuh)."""
+        check(self.lib.pioran_ctx_set_sweep_kernel(self.h, {"auto": 0, "scalar": 1}[which]))
+
     # -- K3
     def set_auto_scan(self, enabled=True):
         """Whether celerite_logl / approx_logl route ≤ 4 evaluations of a series of ≥ 4 096 steps to the scan path."""

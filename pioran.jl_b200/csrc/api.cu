@@ -16,6 +16,7 @@
 #include "../../include/pioran_b200.h"
 #include "approx.cuh"
 #include "celerite.cuh"
+#include "blocked.cuh"
 #include "common.cuh"
 #include "dense.cuh"
 #include "scan.cuh"
@@ -84,6 +85,7 @@ struct Series {
     int64_t N = 0;
     double *t = nullptr, *y = nullptr, *s2 = nullptr;
     std::map<TableKey, Table> tables;
+    std::map<TableKey, Table> btables;   // block tables of the tensor-pipe kernel (blocked.cuh)
 };
 
 using PlanKey = std::tuple<int, int, int, int, double, double, double, double>;
@@ -109,6 +111,7 @@ struct pioran_ctx {
     int gwork_items = 0, gwork_tpi = 0;
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
+    int sweep_kernel = PIORAN_SWEEP_AUTO;   // pioran_ctx_set_sweep_kernel
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
     double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
     int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
@@ -180,6 +183,7 @@ static void free_series(Series* s) {
     if (!s) return;
     cudaFree(s->t); cudaFree(s->y); cudaFree(s->s2);
     for (auto& kv : s->tables) cudaFree(kv.second.d);
+    for (auto& kv : s->btables) cudaFree(kv.second.d);
     delete s;
 }
 
@@ -391,6 +395,83 @@ static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Tab
     s->tables[key] = tb;
     *out = tb;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K2t (blocked.cuh)
+// The tensor-pipe kernel serves the shared-table path at ranks <= 63 (64 needs a 9th row tile for the data row).
+// pioran_ctx_set_sweep_kernel(ctx, PIORAN_SWEEP_SCALAR) or PIORAN_K2=scalar in the environment select the scalar-pipe kernel
+// of celerite.cuh instead (A/B timing, tests of both paths).
+static bool blocked_enabled(const pioran_ctx* c, int R) {
+    static const int mode = [] { const char* e = getenv("PIORAN_K2"); return (e && (!strcmp(e, "scalar") || !strcmp(e, "0"))) ? 0 : 1; }();
+    return mode != 0 && c->sweep_kernel != PIORAN_SWEEP_SCALAR && R >= 1 && blk_ntr(R) <= 8;
+}
+static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out) {
+    const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
+    TableKey key{sp.basis, sp.n_components, f0, fM};
+    auto it = s->btables.find(key);
+    if (it != s->btables.end()) { *out = it->second; return 0; }
+    const int R = rank_of(sp.basis, sp.n_components);
+    const int NT = blk_nt(R), NTR = blk_ntr(R), RPT = 8 * NTR;
+    std::vector<RowDesc> rows;
+    make_rows(sp, RPT, rows);
+    rows[R] = RowDesc{0, 0, 0, ROW_AUG, 0};
+    int rc = c->rows.ensure(sizeof(RowDesc) * RPT);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->rows.p, rows.data(), sizeof(RowDesc) * RPT, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // rows is a local
+    Table tb;
+    tb.rpad = RPT;
+    const int64_t nblocks = (s->N + BLK - 1) / BLK;
+    tb.npad = nblocks * BLK;
+    const size_t bytes = sizeof(double) * (size_t)nblocks * blk_doubles(NT, NTR);
+    CUDA_TRY(cudaMalloc(&tb.d, bytes));
+    const int64_t total = nblocks * RPT;
+    const int tpb = 128;
+    blocked_table_kernel<<<(unsigned)((total + tpb - 1) / tpb), tpb, 0, c->stream>>>(tb.d, s->t, s->y, s->s2, s->N, nblocks,
+                                                                                    c->rows.as<RowDesc>(), NT, NTR);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(tb.d); return fail(PIORAN_ECUDA, "blocked_table_kernel launch failed: %s", cudaGetErrorString(e)); }
+    s->btables[key] = tb;
+    *out = tb;
+    return 0;
+}
+// Warps per CTA: the register budget of the state (NT(NT+1) doubles per lane) decides it.
+static int blocked_nw(int NT) { return NT >= 7 ? 8 : NT >= 5 ? 12 : 16; }
+template <int NT, int NTR, int NW>
+static int launch_blocked_nw(pioran_ctx* c, const BatchArgs& args, int nitems, int R, int amp_stride) {
+    auto kern = celerite_blocked_kernel<NT, NTR, NW, 1>;
+    const size_t smem = sizeof(double) * ((size_t)BLK_NSTAGE * blk_doubles(NT, NTR) + (size_t)NW * 8 * NTR) +
+                        BLK_NSTAGE * (sizeof(uint64_t) + sizeof(int)) + 16;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args, R, amp_stride);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int NT, int NTR>
+static int launch_blocked(pioran_ctx* c, const BatchArgs& args, int nitems, int tpi, int R, int amp_stride) {
+    constexpr int NWF = NT >= 7 ? 8 : NT >= 5 ? 12 : 16;
+    if (tpi <= 4) return launch_blocked_nw<NT, NTR, 4>(c, args, nitems, R, amp_stride);
+    if (tpi <= 8) return launch_blocked_nw<NT, NTR, 8>(c, args, nitems, R, amp_stride);
+    return launch_blocked_nw<NT, NTR, NWF>(c, args, nitems, R, amp_stride);
+}
+static int dispatch_blocked(pioran_ctx* c, const BatchArgs& a, int nitems, int tpi, int R, int amp_stride) {
+    const int NT = blk_nt(R);
+    const bool xrow = blk_ntr(R) != NT;
+#define PIORAN_BLK_CASE(nt)                                                                          \
+    case nt: return xrow ? launch_blocked<nt, nt + 1>(c, a, nitems, tpi, R, amp_stride)              \
+                         : launch_blocked<nt, nt>(c, a, nitems, tpi, R, amp_stride);
+    switch (NT) {
+        PIORAN_BLK_CASE(1) PIORAN_BLK_CASE(2) PIORAN_BLK_CASE(3) PIORAN_BLK_CASE(4)
+        PIORAN_BLK_CASE(5) PIORAN_BLK_CASE(6) PIORAN_BLK_CASE(7)
+        case 8: if (!xrow) return launch_blocked<8, 8>(c, a, nitems, tpi, R, amp_stride); break;
+    }
+#undef PIORAN_BLK_CASE
+    return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the blocked kernel", R);
 }
 
 // ------------------------------------------------------------------------------------------------ K2 launchers
@@ -731,8 +812,9 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
         return 0;
     }
     const int RP = G * BS;
+    const bool blocked = blocked_enabled(c, R);
     for (int s = 0; s < S; s++)
-        if ((rc = get_table(c, ser[s], specs[s], &tabs[s]))) return rc;
+        if ((rc = blocked ? get_btable(c, ser[s], specs[s], &tabs[s]) : get_table(c, ser[s], specs[s], &tabs[s]))) return rc;
     // K1: amplitudes for every (series, θ)
     if ((rc = c->amp.ensure(sizeof(double) * (size_t)S * B * RP))) return rc;
     if ((rc = c->suma.ensure(sizeof(double) * (size_t)S * B))) return rc;
@@ -749,11 +831,11 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     // K2
     std::vector<int64_t> key;
     key.reserve(4 + 3 * (size_t)S);
-    key.push_back(S); key.push_back(B); key.push_back(BS); key.push_back(theta_per_series != 0);
+    key.push_back(S); key.push_back(B); key.push_back(blocked ? -R : BS); key.push_back(theta_per_series != 0);
     for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
     if (key != c->work_key) {
         ItemPlan ip;
-        plan_items(c, S, ser.data(), tabs.data(), B, theta_per_item(BS), theta_per_series != 0, ip);
+        plan_items(c, S, ser.data(), tabs.data(), B, blocked ? blocked_nw(blk_nt(R)) : theta_per_item(BS), theta_per_series != 0, ip);
         c->work_key.clear();
         if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -773,6 +855,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     args.pstride = ts;
     args.y_batch = y_batch; args.s2_batch = s2_batch; args.ystride = ser[0]->N;
     args.out = logl_dev;
+    if (blocked) return dispatch_blocked(c, args, nitems, c->work_tpi, R, RP);
     return dispatch_shared(c, BS, args, nitems, c->work_tpi);
 }
 
@@ -1243,6 +1326,14 @@ static int make_term_rows(int B, int Jt, const double* b, const double* d, std::
 extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     c->auto_scan = enabled != 0;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
+extern "C" int pioran_ctx_set_sweep_kernel(pioran_ctx* c, int which) try {
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (which != PIORAN_SWEEP_AUTO && which != PIORAN_SWEEP_SCALAR) return fail(PIORAN_EINVAL, "unknown sweep kernel %d", which);
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->sweep_kernel = which;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 

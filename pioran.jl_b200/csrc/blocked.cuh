@@ -1,0 +1,406 @@
+// blocked.cuh — K2t: batched celerite factorisation + solve + log-determinant on the FP64 tensor pipe (sm_100a).
+//
+// Same job as celerite.cuh (logl = init_semi_separable! + solve_prec!, src/celerite_solver.jl:12-100, 115-158, 312-334)
+// for the shared-table (approx) path, but the recursion is BLOCKED over 8 time steps so that its two O(R²) operations
+// become small matrix products that run on DMMA (mma.sync.m8n8k4.f64; tcgen05 has no FP64 kind):
+//
+// With X = T_n + q_n w_nᵀ (the amplitude-scaled state of celerite.cuh after step n0, before its decay) and for the
+// steps s = 1…8 of a block, Ψ_{a→b} = Π_{a<i≤b} φ_{n0+i} (all factors ≤ 1: nothing can overflow),
+//     Û[:,s]  = Ψ_{0→s}∘Ũ_s          V̂[:,s] = Ψ_{s→8}∘V_s          ψ8 = Ψ_{0→8}            (θ-independent table)
+//     P0      = X·Û                                                   (R×R · R×8  → DMMA)
+//     C       = K_blk − Ûᵀ·P0                                         (8×8 conditional covariance of the block;  DMMA)
+//               K_blk[s][s'] = Σ_j amp_j·H[s][s'][j],  H = Ũ_s Ψ_{s'→s} V_{s'} (table);  diagonal Σa + ν σ²_s
+//     C       = L D Lᵀ                                                (D_s are the pivots D_n of celerite_solver.jl:92)
+//     Q̂       = (amp∘V̂ − ψ8∘P0)·L⁻ᵀ ,  Ŵ = Q̂ D⁻¹                     (R×8 · 8×8 → DMMA;  q̂_s = Ψ_{s→8}∘q_s, celerite_solver.jl:95-98)
+//     X       ← (ψ8ψ8ᵀ)∘X + Q̂·Ŵᵀ                                     (rank-8 update → DMMA;  celerite_solver.jl:69-90)
+// The forward substitution (celerite_solver.jl:132-142) rides along as one more ROW of the state: row RG holds g⁺ᵀ,
+// its "amp∘V̂" entry is (y_s − μ), its decay factor 1; then P0[RG][s] is the prediction Û_sᵀg⁺, Q̂[RG][s] the innovation
+// z_s, and yᵀK⁻¹y = Σ z_s²/D_s = Σ Q̂[RG][s]·Ŵ[RG][s].
+//
+// Mapping.  One warp per (parameter vector, series).  X is symmetric: the lower-triangular 8×8 tiles (I ≥ K) live in
+// registers in the DMMA accumulator layout (lane (g = lane>>2, t = lane&3) holds rows 8I+g, columns 8K+2t, 8K+2t+1), which
+// is directly the A operand of P0 = X·Û when the contraction index of chunk c is read as column 8K+2t+c (the B operand —
+// the table — is stored in that order).  The upper tiles are produced on the fly by a 2-exchange register transpose.
+// Every product of the block chains without leaving registers: P0 (accumulator layout) → Bm → A operand of Q̂ = Bm·L⁻ᵀ →
+// Q̂ is the A operand and Ŵ the B operand of the update.  Only C needs P0ᵀ (one more transpose per row tile).
+// The 8×8 LDLᵀ is distributed over the warp (row g on lanes (g,·)); the inverse factor is carried along by the same
+// eliminations, so the sequential part of a block is 8 pivots of ~100 cycles, overlapped by the other warps' products.
+//
+// FP64 work per block of 8 steps at NT = 8 row tiles: 232 DMMA (= 1 856 DFMA-equivalents) + ≈ 360 scalar issues, against
+// 2 688 issues for 8 steps of the scalar kernel — and no per-entry operand traffic: 1 operand load per 8 DMMAs.
+#pragma once
+#include "celerite.cuh"
+
+namespace pioran {
+
+constexpr int BLK = 8;            // steps per block
+constexpr int BLK_NSTAGE = 3;     // TMA stages (one block each)
+constexpr int ROW_AUG = 4;        // RowKind of the augmented (data) row
+
+// Rows of the blocked state: R celerite rows + the augmented row RG = R.  NT = tiles that carry celerite rows (columns of
+// the state), NTR = row tiles (NT, or NT+1 when R is a multiple of 8 and the augmented row needs a tile of its own).
+__host__ __device__ constexpr int blk_nt(int R) { return (R + 7) / 8; }
+__host__ __device__ constexpr int blk_ntr(int R) { return (R + 8) / 8; }
+// Block record (doubles):  UT [NT][8 steps][8 rows] | VH [8·NTR rows][8 steps] | PSI8 [8·NTR] | H [28 pairs][8·NT] | y[8] σ²[8] mask[8] pad[8]
+__host__ __device__ constexpr int blk_off_vh(int NT, int NTR) { return 64 * NT; }
+__host__ __device__ constexpr int blk_off_psi(int NT, int NTR) { return 64 * NT + 64 * NTR; }
+__host__ __device__ constexpr int blk_off_h(int NT, int NTR) { return 64 * NT + 72 * NTR; }
+__host__ __device__ constexpr int blk_off_sc(int NT, int NTR) { return 64 * NT + 72 * NTR + 224 * NT; }
+__host__ __device__ constexpr int blk_doubles(int NT, int NTR) { return 64 * NT + 72 * NTR + 224 * NT + 32; }
+__host__ __device__ constexpr int pair_slot(int s, int sp) { return s * (s - 1) / 2 + sp; }   // s > sp
+
+// ------------------------------------------------------------------------------------------- K0b: block table
+// One thread per (block, row).  rows[] describes the 8·NTR rows (ROW_PAD beyond R, ROW_AUG at RG = R).
+__global__ void blocked_table_kernel(double* __restrict__ table, const double* __restrict__ t, const double* __restrict__ y,
+                                     const double* __restrict__ s2, int64_t N, int64_t nblocks,
+                                     const RowDesc* __restrict__ rows, int NT, int NTR) {
+    const int RPT = 8 * NTR, RP = 8 * NT;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nblocks * RPT) return;
+    const int64_t b = gid / RPT;
+    const int r = (int)(gid - b * RPT);
+    double* tab = table + b * (int64_t)blk_doubles(NT, NTR);
+    const RowDesc rd = rows[r];
+    const int64_t n0 = b * BLK;
+    double ph[BLK], ut[BLK], vv[BLK];
+#pragma unroll
+    for (int s = 0; s < BLK; s++) {
+        const int64_t n = n0 + s;
+        ph[s] = 1.0; ut[s] = 0.0; vv[s] = 0.0;
+        if (rd.kind == ROW_PAD) { ph[s] = 0.0; continue; }
+        if (n >= N) continue;                         // padded step: no decay, no coupling
+        if (rd.kind == ROW_AUG) { vv[s] = y[n]; continue; }
+        const double tn = t[n];
+        ph[s] = (n >= 1) ? exp(-rd.c * (tn - t[n - 1])) : 0.0;      // celerite_solver.jl:54 (φ_0 := 0: nothing precedes step 0)
+        if (rd.kind == ROW_REAL) { ut[s] = 1.0; vv[s] = 1.0; }
+        else {
+            double si, co;
+            sincos_large(rd.d * tn, &si, &co);                        // celerite_solver.jl:52-53 (absolute time)
+            if (rd.kind == ROW_COS) { ut[s] = fma(rd.ratio, si, co); vv[s] = co; }     // (a·co + b·si)/a
+            else                    { ut[s] = fma(-rd.ratio, co, si); vv[s] = si; }    // (a·si − b·co)/a
+        }
+    }
+    // Ψ_{0→s} and Ψ_{s→8}
+    double p0[BLK], pe[BLK];
+    p0[0] = ph[0];
+#pragma unroll
+    for (int s = 1; s < BLK; s++) p0[s] = p0[s - 1] * ph[s];
+    pe[BLK - 1] = 1.0;
+#pragma unroll
+    for (int s = BLK - 2; s >= 0; s--) pe[s] = pe[s + 1] * ph[s + 1];
+    if (r < RP) {
+        const int K = r >> 3, rr = r & 7;
+#pragma unroll
+        for (int s = 0; s < BLK; s++) tab[K * 64 + s * 8 + rr] = p0[s] * ut[s];
+#pragma unroll
+        for (int s = 1; s < BLK; s++) {
+            double dec = 1.0;
+#pragma unroll
+            for (int sp = s - 1; sp >= 0; sp--) {
+                dec *= ph[sp + 1];
+                tab[blk_off_h(NT, NTR) + pair_slot(s, sp) * RP + r] = ut[s] * dec * vv[sp];
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < BLK; s++) tab[blk_off_vh(NT, NTR) + r * 8 + s] = pe[s] * vv[s];
+    tab[blk_off_psi(NT, NTR) + r] = (rd.kind == ROW_AUG) ? 1.0 : p0[BLK - 1];
+    for (int q = r; q < 32; q += RPT) {
+        const int s = q & 7, f = q >> 3;
+        const int64_t n = n0 + s;
+        double sc = 0.0;
+        if (n < N) sc = (f == 0) ? y[n] : (f == 1) ? s2[n] : (f == 2) ? 1.0 : 0.0;
+        tab[blk_off_sc(NT, NTR) + q] = sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- device helpers
+// D(8×8) += A(8×4)·B(4×8), FP64 tensor pipe.  Fragments: A lane(g,t) = A[g][t];  B lane(g,t) = B[t][g];  C/D lane(g,t) = [g][2t], [g][2t+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct BlkLane {
+    int g, t;
+    bool odd;          // g & 1
+    int src1, src2;    // transpose: source lanes of the two exchanges
+    int csrc0, csrc1;  // lane whose K_blk slot is C[g][2t], C[g][2t+1]
+    bool cdiag0, cdiag1;
+};
+__device__ __forceinline__ BlkLane make_blk_lane(int lane) {
+    BlkLane L;
+    L.g = lane >> 2; L.t = lane & 3;
+    L.odd = (L.g & 1) != 0;
+    L.src1 = 4 * (2 * L.t + (L.g & 1)) + (L.g >> 1);
+    L.src2 = 4 * (2 * L.t + 1 - (L.g & 1)) + (L.g >> 1);
+    const int c0 = 2 * L.t, c1 = 2 * L.t + 1;
+    const int h0 = max(L.g, c0), l0 = min(L.g, c0), h1 = max(L.g, c1), l1 = min(L.g, c1);
+    L.cdiag0 = (L.g == c0); L.cdiag1 = (L.g == c1);
+    L.csrc0 = L.cdiag0 ? 0 : pair_slot(h0, l0);
+    L.csrc1 = L.cdiag1 ? 0 : pair_slot(h1, l1);
+    return L;
+}
+// Transpose of an 8×8 tile held in the accumulator layout: 2 exchanges (each lane's two values come from two lanes).
+__device__ __forceinline__ void tile_transpose(const BlkLane& L, const double e0, const double e1, double& f0, double& f1) {
+    const double r1 = __shfl_sync(FULL, L.odd ? e1 : e0, L.src1);
+    const double r2 = __shfl_sync(FULL, L.odd ? e0 : e1, L.src2);
+    f0 = L.odd ? r2 : r1;
+    f1 = L.odd ? r1 : r2;
+}
+
+// Per-lane persistent state of one evaluation.
+template <int NT, int NTR>
+struct BlkState {
+    double x[NTR][NT][2];   // tiles I ≥ K only (the others are never touched and take no registers)
+    double chi2, logacc, dkeep, dfirst;
+};
+
+// One block of 8 steps.  tab: this block's record in shared memory; amp_s: per-warp amplitudes (8·NTR doubles, amp[RG] = 1).
+template <int NT, int NTR>
+__device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double* __restrict__ tab,
+                                             const double* __restrict__ amp_s, const BlkLane& L, const int lane,
+                                             const double ampk0, const double ampk1, const int hoff, const double suma,
+                                             const double mu, const double nu, const int64_t n0, const int64_t N,
+                                             const double* __restrict__ yb, const double* __restrict__ sb, const int RG) {
+    constexpr int RP = 8 * NT;
+    constexpr int O_VH = blk_off_vh(NT, NTR), O_PSI = blk_off_psi(NT, NTR), O_H = blk_off_h(NT, NTR), O_SC = blk_off_sc(NT, NTR);
+    const int g = L.g, t = L.t;
+
+    // ---- K_blk: partial sums over this lane's two rows, then a reduce-scatter: lane l ends with the total of pair slot l
+    double cm0, cm1;
+    {
+        double v[32];
+        const double* Hp = tab + O_H + hoff;
+#pragma unroll
+        for (int p = 0; p < 28; p++) {
+            const double2 h = *reinterpret_cast<const double2*>(Hp + p * RP);
+            v[p] = fma(ampk1, h.y, ampk0 * h.x);
+        }
+#pragma unroll
+        for (int p = 28; p < 32; p++) v[p] = 0.0;
+#pragma unroll
+        for (int half = 16; half >= 1; half >>= 1) {
+            const bool bit = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; i++) {
+                const double send = bit ? v[i] : v[i + half];
+                const double keep = bit ? v[i + half] : v[i];
+                v[i] = keep + __shfl_xor_sync(FULL, send, half);
+            }
+        }
+        const double o0 = __shfl_sync(FULL, v[0], L.csrc0);
+        const double o1 = __shfl_sync(FULL, v[0], L.csrc1);
+        // diagonal: A_n = Σa + ν σ²_n (celerite_solver.jl:92); padded steps are unit pivots
+        const int64_t n = n0 + g;
+        const double mk = tab[O_SC + 16 + g];
+        const double s2v = sb ? (n < N ? sb[n] : 0.0) : tab[O_SC + 8 + g];
+        const double dg = fma(fma(nu, s2v, suma), mk, 1.0 - mk);
+        cm0 = L.cdiag0 ? dg : o0;
+        cm1 = L.cdiag1 ? dg : o1;
+    }
+
+    // ---- P0 = X·Û (row tiles I, contraction over column tiles K)
+    double P0[NTR][2];
+#pragma unroll
+    for (int I = 0; I < NTR; I++) P0[I][0] = P0[I][1] = 0.0;
+#pragma unroll
+    for (int K = 0; K < NT; K++) {
+        const double2 u = *reinterpret_cast<const double2*>(tab + K * 64 + g * 8 + 2 * t);
+#pragma unroll
+        for (int I = 0; I < NTR; I++) {
+            double a0, a1;
+            if (I >= K) { a0 = st.x[I][K][0]; a1 = st.x[I][K][1]; }
+            else tile_transpose(L, st.x[K][I][0], st.x[K][I][1], a0, a1);
+            dmma(P0[I][0], P0[I][1], a0, u.x);
+            dmma(P0[I][0], P0[I][1], a1, u.y);
+        }
+    }
+
+    // ---- C = K_blk − Ûᵀ·P0 (needs P0ᵀ as the B operand), two accumulation chains
+    {
+        double ca0 = 0.0, ca1 = 0.0, cb0 = 0.0, cb1 = 0.0;
+#pragma unroll
+        for (int J = 0; J < NT; J++) {
+            const double2 u = *reinterpret_cast<const double2*>(tab + J * 64 + g * 8 + 2 * t);
+            double p0, p1;
+            tile_transpose(L, P0[J][0], P0[J][1], p0, p1);
+            if (J & 1) { dmma(cb0, cb1, u.x, p0); dmma(cb0, cb1, u.y, p1); }
+            else       { dmma(ca0, ca1, u.x, p0); dmma(ca0, ca1, u.y, p1); }
+        }
+        cm0 -= ca0 + cb0;
+        cm1 -= ca1 + cb1;
+    }
+
+    // ---- Bm = amp∘V̂ − ψ8∘P0 (in place); the augmented row carries (y − μ) − prediction
+    double psr[NTR];
+#pragma unroll
+    for (int I = 0; I < NTR; I++) {
+        const int row = 8 * I + g;
+        double2 vh = *reinterpret_cast<const double2*>(tab + O_VH + row * 8 + 2 * t);
+        psr[I] = tab[O_PSI + row];
+        const double am = amp_s[row];
+        if (I == NTR - 1) {
+            const bool isrg = (row == RG);
+            const double2 mk = *reinterpret_cast<const double2*>(tab + O_SC + 16 + 2 * t);
+            if (yb && isrg) {
+                const int64_t n = n0 + 2 * t;
+                vh.x = (n < N) ? yb[n] : 0.0;
+                vh.y = (n + 1 < N) ? yb[n + 1] : 0.0;
+            }
+            const double m_ = isrg ? mu : 0.0;
+            vh.x = fma(-m_, mk.x, vh.x);
+            vh.y = fma(-m_, mk.y, vh.y);
+        }
+        P0[I][0] = fma(-psr[I], P0[I][0], am * vh.x);
+        P0[I][1] = fma(-psr[I], P0[I][1], am * vh.y);
+    }
+
+    // ---- 8×8 LDLᵀ of C, distributed: lane (g,t) holds C[g][2t], C[g][2t+1]; E becomes L⁻¹ by the same eliminations
+    double e0 = L.cdiag0 ? 1.0 : 0.0, e1 = L.cdiag1 ? 1.0 : 0.0;
+    double rd[BLK];
+    const int rowbase = lane & ~3;
+    const int ring = (int)(n0 & 31);
+#pragma unroll
+    for (int j = 0; j < BLK; j++) {
+        const int tj = j >> 1;
+        const double cme = (j & 1) ? cm1 : cm0;
+        const double dj = __shfl_sync(FULL, cme, 4 * j + tj);          // pivot D_{n0+j} (celerite_solver.jl:92)
+        const double cgj = __shfl_sync(FULL, cme, rowbase | tj);       // C[g][j]
+        rd[j] = fast_rcp(dj);
+        const double l = cgj * rd[j];
+        const double cj0 = __shfl_sync(FULL, cm0, 4 * j + t), cj1 = __shfl_sync(FULL, cm1, 4 * j + t);
+        const double ej0 = __shfl_sync(FULL, e0, 4 * j + t), ej1 = __shfl_sync(FULL, e1, 4 * j + t);
+        const double lm = (g > j) ? l : 0.0;
+        cm0 = fma(-lm, cj0, cm0); cm1 = fma(-lm, cj1, cm1);
+        e0 = fma(-lm, ej0, e0);   e1 = fma(-lm, ej1, e1);
+        // log|D_n| (celerite_solver.jl:140; no abs on the first pivot, :126): lane n%32 keeps D_n, one log per 32 steps
+        if (j == 0 && n0 == 0) st.dfirst = dj;
+        else if (lane == ring + j) st.dkeep = dj;
+    }
+    if (ring == 24) { st.logacc += log(fabs(st.dkeep)); st.dkeep = 1.0; }
+
+    // ---- Q̂ = Bm·L⁻ᵀ
+    double Q[NTR][2];
+#pragma unroll
+    for (int I = 0; I < NTR; I++) {
+        Q[I][0] = Q[I][1] = 0.0;
+        dmma(Q[I][0], Q[I][1], P0[I][0], e0);
+        dmma(Q[I][0], Q[I][1], P0[I][1], e1);
+    }
+    // 1/D of this lane's two steps
+    double rd0 = rd[0], rd1 = rd[1];
+    if (t == 1) { rd0 = rd[2]; rd1 = rd[3]; }
+    if (t == 2) { rd0 = rd[4]; rd1 = rd[5]; }
+    if (t == 3) { rd0 = rd[6]; rd1 = rd[7]; }
+
+    // ---- yᵀK⁻¹y += Σ_s z_s²/D_s  (celerite_solver.jl:333) on the lanes that hold the augmented row
+    {
+        const bool isrg = (8 * (NTR - 1) + g == RG);
+        const double zz = fma(Q[NTR - 1][0] * rd0, Q[NTR - 1][0], (Q[NTR - 1][1] * rd1) * Q[NTR - 1][1]);
+        st.chi2 += isrg ? zz : 0.0;
+    }
+
+    // ---- X ← (ψ8ψ8ᵀ)∘X + Q̂·Ŵᵀ
+#pragma unroll
+    for (int K = 0; K < NT; K++) {
+        const double w0 = Q[K][0] * rd0, w1 = Q[K][1] * rd1;
+        const double2 pc = *reinterpret_cast<const double2*>(tab + O_PSI + 8 * K + 2 * t);
+#pragma unroll
+        for (int I = K; I < NTR; I++) {
+            double x0 = st.x[I][K][0] * (psr[I] * pc.x), x1 = st.x[I][K][1] * (psr[I] * pc.y);
+            dmma(x0, x1, Q[I][0], w0);
+            dmma(x0, x1, Q[I][1], w1);
+            st.x[I][K][0] = x0; st.x[I][K][1] = x1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- kernel
+// grid = work items; block = NW warps, one parameter vector each; dynamic smem: BLK_NSTAGE block records | NW × 8·NTR amplitudes |
+// BLK_NSTAGE mbarriers | BLK_NSTAGE stage counters.  Same stage hand-back as celerite_shared_kernel (last warp out refills).
+template <int NT, int NTR, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const BatchArgs args, const int R, const int amp_stride) {
+    constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR;
+    constexpr uint32_t STAGE_BYTES = BD * sizeof(double);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stages = reinterpret_cast<double*>(smem_raw);
+    double* amps = stages + BLK_NSTAGE * BD;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(amps + NW * RPT);
+    int* done = reinterpret_cast<int*>(bars + BLK_NSTAGE);
+
+    const WorkItem wk = args.work[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t N = wk.N;
+    const int64_t nblocks = (N + BLK - 1) / BLK;
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < BLK_NSTAGE; k++) { mbar_init(&bars[k], 1); done[k] = 0; }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < BLK_NSTAGE && k < nblocks; k++) {
+            mbar_arrive_expect_tx(&bars[k], STAGE_BYTES);
+            tma_load_1d(stages + k * BD, wk.table + (size_t)k * BD, STAGE_BYTES, &bars[k]);
+        }
+    }
+
+    const bool active = warp < wk.count;
+    const int slot = active ? warp : wk.count - 1;       // surplus warps redo the item's last θ and skip the store
+    const int th = wk.theta_begin + slot;
+    const BlkLane L = make_blk_lane(lane);
+    const int RG = R;
+
+    double* amp_s = amps + warp * RPT;
+    for (int k = lane; k < RPT; k += 32) amp_s[k] = (k < R) ? args.amp[(size_t)th * amp_stride + k] : (k == RG ? 1.0 : 0.0);
+    __syncwarp();
+    const int hoff = (lane < 4 * NT) ? 2 * lane : 0;
+    const double ampk0 = (2 * lane < R) ? amp_s[2 * lane] : 0.0;
+    const double ampk1 = (2 * lane + 1 < R) ? amp_s[2 * lane + 1] : 0.0;
+    const double suma = args.suma[th];
+    const size_t pi = (size_t)wk.par_begin + slot;
+    const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
+    const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
+    const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : nullptr;
+    const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : nullptr;
+
+    BlkState<NT, NTR> st;
+#pragma unroll
+    for (int I = 0; I < NTR; I++)
+#pragma unroll
+        for (int K = 0; K < NT; K++) st.x[I][K][0] = st.x[I][K][1] = 0.0;
+    st.chi2 = 0.0; st.logacc = 0.0; st.dkeep = 1.0; st.dfirst = 1.0;
+
+    int sidx = 0;
+    uint32_t parity = 0;
+    for (int64_t b = 0; b < nblocks; b++) {
+        mbar_wait(&bars[sidx], parity);
+        blocked_step<NT, NTR>(st, stages + sidx * BD, amp_s, L, lane, ampk0, ampk1, hoff, suma, mu, nu, b * BLK, N, yb, sb, RG);
+        __syncwarp();
+        if (lane == 0 && b + BLK_NSTAGE < nblocks) {
+            __threadfence_block();
+            if (atomicAdd(&done[sidx], 1) == NW - 1) {
+                done[sidx] = 0;
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
+                tma_load_1d(stages + sidx * BD, wk.table + (size_t)(b + BLK_NSTAGE) * BD, STAGE_BYTES, &bars[sidx]);
+            }
+        }
+        if (++sidx == BLK_NSTAGE) { sidx = 0; parity ^= 1; }
+    }
+    // Σ log|D_n| (first pivot without abs) and the χ² term
+    double la = st.logacc + log(fabs(st.dkeep));
+    double ch = st.chi2;
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) {
+        la += __shfl_xor_sync(FULL, la, sft);
+        ch += __shfl_xor_sync(FULL, ch, sft);
+    }
+    const double dfirst = __shfl_sync(FULL, st.dfirst, 0);
+    const double logdet = log(dfirst) + la;
+    // celerite_solver.jl:333
+    const double res = -logdet / 2 - (double)N * 1.8378770664093453 / 2 - ch / 2;
+    if (active && lane == 0) args.out[wk.out_begin + warp] = res;
+}
+
+}  // namespace pioran
