@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpioran_b200.so")
+# PIORAN_B200_LIB: another build of the same library (kernel-variant timing, tools/variants_gpu.py); never a fallback
+LIB_PATH = os.environ.get("PIORAN_B200_LIB") or os.path.join(HERE, "libpioran_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

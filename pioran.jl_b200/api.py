@@ -157,7 +157,8 @@ class CARMA(SemiSeparable):
         τ = np.abs(np.asarray(τ, dtype=np.float64))
         res = np.array([_carma_residue(rk, self.rα, self.β) for rk in self.rα])
         acv = np.real(np.sum(res[:, None] * np.exp(self.rα[:, None] * τ.ravel()[None, :]), axis=0)).reshape(τ.shape)
-        scale = self.norm / np.real(np.sum(res)) if self.is_integrated_power else self.norm
+        # src/CARMA.jl:269-273: Cov = Re(R)·norm, divided by 2·Re(variance) when integrated, and 2·Cov is returned
+        scale = self.norm / np.real(np.sum(res)) if self.is_integrated_power else 2.0 * self.norm
         return acv * scale
 
 
@@ -258,10 +259,11 @@ class FiniteScalableGP:
 
 def log_likelihood(cov, τ, y, σ2, *, solver="celerite", ctx=None):
     """log_likelihood(cov, τ, y, σ2; solver)  (src/celerite_solver.jl:262-294).
-    `celerite` and `celerite_gpu` both run the B200 kernel (there is no CPU path in this package)."""
+    `celerite`, `celerite_matrix` (the reference's second solver name, :266-270) and `celerite_gpu` all run the B200 kernel
+    (there is no CPU path in this package)."""
     solver = str(solver).lstrip(":")
-    if solver not in ("celerite", "celerite_gpu"):
-        raise ValueError(f"solver {solver} not recognised, use either :celerite or :celerite_gpu")
+    if solver not in ("celerite", "celerite_matrix", "celerite_gpu"):
+        raise ValueError(f"solver {solver} not recognised, use either :celerite or :celerite_matrix")
     ctx = ctx or get_context()
     a, b, c, d = celerite_coefs(cov)
     ser = ctx.upload_series(τ, y, σ2)

@@ -79,7 +79,8 @@ struct DevBuf {  // grow-only device workspace
 };
 
 using TableKey = std::tuple<int, int, double, double>;  // basis, J, f0, fM
-struct Table { double* d = nullptr; int rpad = 0; int64_t npad = 0; };
+struct Table { double* d = nullptr; int rpad = 0; int64_t npad = 0; uint64_t last_use = 0; };
+constexpr size_t MAX_TABLES_PER_SERIES = 8;   // per kind; least recently used first out (a table of N = 1e6 at rank 60 is 3.9 GB)
 
 struct Series {
     int64_t N = 0;
@@ -112,6 +113,8 @@ struct pioran_ctx {
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
     int sweep_kernel = PIORAN_SWEEP_AUTO;   // pioran_ctx_set_sweep_kernel
+    uint64_t epoch = 0;    // bumped by every entry that uses the shared workspaces (a pending scan range checks it)
+    uint64_t use_clock = 0;   // LRU stamp source of the per-series table caches
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
     double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
     int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
@@ -120,6 +123,9 @@ struct pioran_ctx {
     std::mutex mu;
 };
 
+// Entry points that launch work or touch the context's workspaces: take the lock and invalidate a range left pending by
+// pioran_celerite_scan_range_begin (its record points into those workspaces).
+#define PIORAN_COMPUTE_LOCK(c) std::lock_guard<std::mutex> lk((c)->mu); (c)->epoch++
 static int make_term_rows(int B, int Jt, const double* b, const double* d, std::vector<int>& term_row);
 
 static int bs_for_rank(int R) {
@@ -205,7 +211,14 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
 
 extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
-    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t next = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
+    if (next != c->stream) {
+        // the workspaces and the cached work items are ordered on the old stream only: drain it before switching
+        CUDA_TRY(cudaSetDevice(c->device));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->stream = next;
+    }
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_synchronize(pioran_ctx* c) try {
@@ -214,7 +227,11 @@ extern "C" int pioran_ctx_synchronize(pioran_ctx* c) try {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
-extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) {
+    if (!c) return 0;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return c->launches;
+}
 extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) try {
     if (!c || !ms) return fail(PIORAN_EINVAL, "NULL argument");
     if (!c->ev_valid) return fail(PIORAN_EINVAL, "no main kernel has been launched on this context yet");
@@ -264,7 +281,7 @@ static Series* get_series(pioran_ctx* c, int id) {
 
 extern "C" int pioran_series_free(pioran_ctx* c, int id) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     Series* s = get_series(c, id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
     cudaSetDevice(c->device);
@@ -278,6 +295,7 @@ extern "C" int pioran_series_free(pioran_ctx* c, int id) try {
 
 extern "C" int pioran_series_length(pioran_ctx* c, int id, int64_t* N) try {
     if (!c || !N) return fail(PIORAN_EINVAL, "NULL argument");
+    std::lock_guard<std::mutex> lk(c->mu);
     Series* s = get_series(c, id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
     *N = s->N;
@@ -366,11 +384,34 @@ static void make_rows(const pioran_approx_spec& sp, int RP, std::vector<RowDesc>
     }
 }
 
+// Cache discipline of the per-series tables: a hit refreshes the LRU stamp; an insert beyond MAX_TABLES_PER_SERIES evicts the
+// least recently used table (after draining the stream: a kernel may still read it; cached work items hold its pointer).
+static bool table_lookup(pioran_ctx* c, std::map<TableKey, Table>& cache, const TableKey& key, Table* out) {
+    auto it = cache.find(key);
+    if (it == cache.end()) return false;
+    it->second.last_use = ++c->use_clock;
+    *out = it->second;
+    return true;
+}
+static void table_insert(pioran_ctx* c, std::map<TableKey, Table>& cache, const TableKey& key, Table& tb) {
+    if (cache.size() >= MAX_TABLES_PER_SERIES) {
+        auto victim = cache.begin();
+        for (auto it = cache.begin(); it != cache.end(); ++it)
+            if (it->second.last_use < victim->second.last_use) victim = it;
+        cudaStreamSynchronize(c->stream);
+        cudaFree(victim->second.d);
+        cache.erase(victim);
+        c->work_key.clear();
+        c->gwork_key.clear();
+    }
+    tb.last_use = ++c->use_clock;
+    cache[key] = tb;
+}
+
 static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out) {
     const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
     TableKey key{sp.basis, sp.n_components, f0, fM};
-    auto it = s->tables.find(key);
-    if (it != s->tables.end()) { *out = it->second; return 0; }
+    if (table_lookup(c, s->tables, key, out)) return 0;
     const int R = rank_of(sp.basis, sp.n_components);
     const int BS = bs_for_rank(R);
     if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8 (n_components too large for this build)", R, BS);
@@ -391,8 +432,9 @@ static int get_table(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Tab
     table_build_kernel<<<(unsigned)((total + tpb - 1) / tpb), tpb, 0, c->stream>>>(tb.d, s->t, s->y, s->s2, s->N, tb.npad,
                                                                                  c->rows.as<RowDesc>(), BS);
     c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    s->tables[key] = tb;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(tb.d); return fail(PIORAN_ECUDA, "table_build_kernel launch failed: %s", cudaGetErrorString(e)); }
+    table_insert(c, s->tables, key, tb);
     *out = tb;
     return 0;
 }
@@ -408,13 +450,17 @@ static bool blocked_enabled(const pioran_ctx* c, int R) {
 static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out) {
     const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
     TableKey key{sp.basis, sp.n_components, f0, fM};
-    auto it = s->btables.find(key);
-    if (it != s->btables.end()) { *out = it->second; return 0; }
+    if (table_lookup(c, s->btables, key, out)) return 0;
     const int R = rank_of(sp.basis, sp.n_components);
     const int NT = blk_nt(R), NTR = blk_ntr(R), RPT = 8 * NTR;
-    std::vector<RowDesc> rows;
-    make_rows(sp, RPT, rows);
-    rows[R] = RowDesc{0, 0, 0, ROW_AUG, 0};
+    std::vector<RowDesc> lrows, rows(RPT, RowDesc{0, 0, 0, ROW_PAD, 0});
+    make_rows(sp, RPT, lrows);
+    for (int r = 0; r < R; r++) {            // physical order; term = logical row index (the K_blk table is indexed by it)
+        RowDesc rd = lrows[r];
+        rd.term = r;
+        rows[blk_phys_row(r, R)] = rd;
+    }
+    rows[blk_phys_row(R, R)] = RowDesc{0, 0, 0, ROW_AUG, 0};
     int rc = c->rows.ensure(sizeof(RowDesc) * RPT);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->rows.p, rows.data(), sizeof(RowDesc) * RPT, cudaMemcpyHostToDevice, c->stream));
@@ -425,6 +471,7 @@ static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Ta
     tb.npad = nblocks * BLK;
     const size_t bytes = sizeof(double) * (size_t)nblocks * blk_doubles(NT, NTR);
     CUDA_TRY(cudaMalloc(&tb.d, bytes));
+    if (cudaMemsetAsync(tb.d, 0, bytes, c->stream) != cudaSuccess) { cudaFree(tb.d); return fail(PIORAN_ECUDA, "cudaMemsetAsync failed"); }
     const int64_t total = nblocks * RPT;
     const int tpb = 128;
     blocked_table_kernel<<<(unsigned)((total + tpb - 1) / tpb), tpb, 0, c->stream>>>(tb.d, s->t, s->y, s->s2, s->N, nblocks,
@@ -432,16 +479,26 @@ static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Ta
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(tb.d); return fail(PIORAN_ECUDA, "blocked_table_kernel launch failed: %s", cudaGetErrorString(e)); }
-    s->btables[key] = tb;
+    table_insert(c, s->btables, key, tb);
     *out = tb;
     return 0;
 }
 // Warps per CTA: the register budget of the state (NT(NT+1) doubles per lane) decides it.
-static int blocked_nw(int NT) { return NT >= 7 ? 8 : NT >= 5 ? 12 : 16; }
-template <int NT, int NTR, int NW>
+#ifndef PIORAN_BLK_NW_LARGE
+#define PIORAN_BLK_NW_LARGE 8     // warps per CTA at 7, 8 row tiles (255 registers per thread)
+#endif
+#ifndef PIORAN_BLK_NW_MID
+#define PIORAN_BLK_NW_MID 12      // 5, 6 row tiles (168 registers)
+#endif
+static int blocked_nw(int NT) {
+    static const int force_nw = [] { const char* e = getenv("PIORAN_BLK_NW"); return e ? atoi(e) : 0; }();
+    if (force_nw == 8) return 8;
+    return NT >= 7 ? PIORAN_BLK_NW_LARGE : NT >= 5 ? PIORAN_BLK_NW_MID : 16;
+}
+template <int NT, int NTR, bool HALF, int NW>
 static int launch_blocked_nw(pioran_ctx* c, const BatchArgs& args, int nitems, int R, int amp_stride) {
-    auto kern = celerite_blocked_kernel<NT, NTR, NW, 1>;
-    const size_t smem = sizeof(double) * ((size_t)BLK_NSTAGE * blk_doubles(NT, NTR) + (size_t)NW * 8 * NTR) +
+    auto kern = celerite_blocked_kernel<NT, NTR, HALF, NW, 1>;
+    const size_t smem = sizeof(double) * ((size_t)BLK_NSTAGE * blk_doubles(NT, NTR) + (size_t)NW * (8 * NTR + 8 * NT)) +
                         BLK_NSTAGE * (sizeof(uint64_t) + sizeof(int)) + 16;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
@@ -452,23 +509,29 @@ static int launch_blocked_nw(pioran_ctx* c, const BatchArgs& args, int nitems, i
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-template <int NT, int NTR>
+template <int NT, int NTR, bool HALF>
 static int launch_blocked(pioran_ctx* c, const BatchArgs& args, int nitems, int tpi, int R, int amp_stride) {
-    constexpr int NWF = NT >= 7 ? 8 : NT >= 5 ? 12 : 16;
-    if (tpi <= 4) return launch_blocked_nw<NT, NTR, 4>(c, args, nitems, R, amp_stride);
-    if (tpi <= 8) return launch_blocked_nw<NT, NTR, 8>(c, args, nitems, R, amp_stride);
-    return launch_blocked_nw<NT, NTR, NWF>(c, args, nitems, R, amp_stride);
+    constexpr int NWF = NT >= 7 ? PIORAN_BLK_NW_LARGE : NT >= 5 ? PIORAN_BLK_NW_MID : 16;
+    static const int force_nw = [] { const char* e = getenv("PIORAN_BLK_NW"); return e ? atoi(e) : 0; }();   // experiments only
+    if (force_nw == 8 && tpi > 4) return launch_blocked_nw<NT, NTR, HALF, 8>(c, args, nitems, R, amp_stride);
+    if (tpi <= 4) return launch_blocked_nw<NT, NTR, HALF, 4>(c, args, nitems, R, amp_stride);
+    if (tpi <= 8) return launch_blocked_nw<NT, NTR, HALF, 8>(c, args, nitems, R, amp_stride);
+    return launch_blocked_nw<NT, NTR, HALF, NWF>(c, args, nitems, R, amp_stride);
 }
 static int dispatch_blocked(pioran_ctx* c, const BatchArgs& a, int nitems, int tpi, int R, int amp_stride) {
     const int NT = blk_nt(R);
-    const bool xrow = blk_ntr(R) != NT;
-#define PIORAN_BLK_CASE(nt)                                                                          \
-    case nt: return xrow ? launch_blocked<nt, nt + 1>(c, a, nitems, tpi, R, amp_stride)              \
-                         : launch_blocked<nt, nt>(c, a, nitems, tpi, R, amp_stride);
+    const bool xrow = blk_ntr(R) != NT, half = blk_half(R);
+#define PIORAN_BLK_CASE(nt)                                                                                   \
+    case nt: return xrow ? launch_blocked<nt, nt + 1, false>(c, a, nitems, tpi, R, amp_stride)                \
+                  : half ? launch_blocked<nt, nt, true>(c, a, nitems, tpi, R, amp_stride)                     \
+                         : launch_blocked<nt, nt, false>(c, a, nitems, tpi, R, amp_stride);
     switch (NT) {
         PIORAN_BLK_CASE(1) PIORAN_BLK_CASE(2) PIORAN_BLK_CASE(3) PIORAN_BLK_CASE(4)
         PIORAN_BLK_CASE(5) PIORAN_BLK_CASE(6) PIORAN_BLK_CASE(7)
-        case 8: if (!xrow) return launch_blocked<8, 8>(c, a, nitems, tpi, R, amp_stride); break;
+        case 8:
+            if (xrow) break;
+            return half ? launch_blocked<8, 8, true>(c, a, nitems, tpi, R, amp_stride)
+                        : launch_blocked<8, 8, false>(c, a, nitems, tpi, R, amp_stride);
     }
 #undef PIORAN_BLK_CASE
     return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the blocked kernel", R);
@@ -654,8 +717,33 @@ static int dispatch_generic_mode(pioran_ctx* c, int BS, const BatchArgs& a, int 
 // items is close to a multiple of the SM count (one CTA per SM is resident), longest series first.
 struct ItemPlan { std::vector<WorkItem> items; int tpi = 0; };
 static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* tabs, int B, int NW, bool theta_per_series,
-                       ItemPlan& ip) {
+                       ItemPlan& ip, bool tail_items = false) {
     const long long E = (long long)S * B;
+    if (tail_items && S == 1 && E > (long long)NW * c->num_sms) {
+        // One series, more than one wave of full items: whole waves of NW-vector items, then the remainder spread evenly over
+        // all SMs as ONE last wave of smaller items (their surplus warps exit, blocked.cuh), instead of a last wave that is
+        // partly empty but runs at the full item's duration.
+        const long long per_wave = (long long)NW * c->num_sms;
+        const long long full = (E / per_wave) * per_wave;
+        const long long rem = E - full;
+        ip.tpi = NW;
+        ip.items.clear();
+        auto push = [&](long long beg, long long end) {
+            WorkItem w;
+            w.table = tabs ? tabs[0].d : nullptr;
+            w.t = ser[0]->t; w.y = ser[0]->y; w.s2 = ser[0]->s2;
+            w.N = ser[0]->N;
+            w.theta_begin = (int)beg; w.par_begin = (int)beg; w.count = (int)(end - beg); w.out_begin = (int)beg;
+            w.n_begin = 0; w.n_end = ser[0]->N; w.init = nullptr; w.part = nullptr;
+            ip.items.push_back(w);
+        };
+        for (long long b0 = 0; b0 < full; b0 += NW) push(b0, b0 + NW);
+        if (rem > 0) {
+            const long long nit = std::min<long long>(c->num_sms, rem);
+            for (long long k = 0; k < nit; k++) push(full + rem * k / nit, full + rem * (k + 1) / nit);
+        }
+        return;
+    }
     int tpi = (int)std::min<long long>(NW, std::max<long long>(1, (E + c->num_sms - 1) / c->num_sms));
     long long items = 0;
     for (int s = 0; s < S; s++) items += (B + tpi - 1) / tpi;
@@ -723,7 +811,7 @@ extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spe
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
     int rc = check_spec(*spec);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     ApproxPlan* plan;
     if ((rc = get_plan(c, *spec, &plan))) return rc;
@@ -835,7 +923,8 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
     if (key != c->work_key) {
         ItemPlan ip;
-        plan_items(c, S, ser.data(), tabs.data(), B, blocked ? blocked_nw(blk_nt(R)) : theta_per_item(BS), theta_per_series != 0, ip);
+        plan_items(c, S, ser.data(), tabs.data(), B, blocked ? blocked_nw(blk_nt(R)) : theta_per_item(BS), theta_per_series != 0, ip,
+                   blocked);
         c->work_key.clear();
         if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -876,7 +965,7 @@ extern "C" int pioran_approx_logl_logshift(pioran_ctx* c, int series_id, const p
                                            double* logl_out) try {
     if (!c || !spec || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     int rc;
     if ((rc = check_spec(*spec))) return rc;
@@ -911,7 +1000,7 @@ extern "C" int pioran_approx_logl_logshift(pioran_ctx* c, int series_id, const p
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
                                       int B, const double* theta_dev, int theta_per_series, double* logl_dev) try {
     if (!c || !series_ids || !specs || !theta_dev || !logl_dev) return fail(PIORAN_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     return approx_logl_dev_locked(c, S, series_ids, specs, B, theta_dev, theta_per_series, logl_dev);
 } catch (...) { return guard_fail(); }
@@ -920,7 +1009,7 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
                                   const double* theta, int theta_per_series, double* logl_out) try {
     if (!c || !series_ids || !specs || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     const int npar = n_psd_par_of(specs[0].psd_model);
     if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", specs[0].psd_model);
@@ -1077,7 +1166,7 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
 extern "C" int pioran_approx_logl_grad_dev(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                            const double* theta_dev, double* logl_dev, double* grad_dev) try {
     if (!c || !spec || !theta_dev || !grad_dev) return fail(PIORAN_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     return approx_logl_grad_dev_locked(c, series_id, spec, B, theta_dev, logl_dev, grad_dev);
 } catch (...) { return guard_fail(); }
@@ -1086,7 +1175,7 @@ extern "C" int pioran_approx_logl_grad(pioran_ctx* c, int series_id, const piora
                                        const double* theta, double* logl_out, double* grad_out) try {
     if (!c || !spec || !theta || !grad_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     const int npar = n_psd_par_of(spec->psd_model);
     if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
@@ -1144,7 +1233,7 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
                                     const double* y_batch, const double* s2_batch, double* logl_out) try {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
@@ -1237,7 +1326,7 @@ extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int 
     if (B < 1 || Jt < 1 || M < 1) return fail(PIORAN_EINVAL, "B, Jt and M must be >= 1");
     for (int64_t m = 1; m < M; m++)
         if (!(tau[m] >= tau[m - 1])) return fail(PIORAN_EINVAL, "tau must be ascending (tau[%lld] < tau[%lld])", (long long)m, (long long)m - 1);
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
@@ -1288,7 +1377,7 @@ extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int
                                         double* y_out) try {
     if (!c || !a || !b || !cc || !d || !q || !y_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
@@ -1325,6 +1414,7 @@ static int make_term_rows(int B, int Jt, const double* b, const double* d, std::
 
 extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
     c->auto_scan = enabled != 0;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
@@ -1355,6 +1445,7 @@ extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* 
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
+    std::lock_guard<std::mutex> lk(c->mu);
     c->scan_chunks = chunks;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
@@ -1362,6 +1453,7 @@ extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
 // One run of the parallel-in-time path over the step range [n_lo, n_hi) of a series: device buffers (inside ctx workspaces)
 // and shapes, shared by the whole-series entry and by the two-phase range entries (time axis split across GPUs).
 struct ScanRun {
+    uint64_t epoch = 0;   // context epoch at range_begin; any later compute entry invalidates the record
     bool valid = false;
     int series_id = -1, B = 0, Jt = 0, R = 0, BS = 0, P = 0, G1 = 0, G2 = 0, SUB = 1;
     int64_t N = 0, n_lo = 0, n_hi = 0;
@@ -1643,7 +1735,7 @@ extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, in
                                          double* logl_out) try {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
@@ -1658,7 +1750,7 @@ extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, in
                                                 const double* cc, const double* d, const double* mu, const double* nu,
                                                 int64_t n_lo, int64_t n_hi, int max_prev, double* composite_out) try {
     if (!c || !a || !b || !cc || !d || !composite_out) return fail(PIORAN_EINVAL, "NULL argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
@@ -1668,6 +1760,7 @@ extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, in
     int rc;
     cudaEventRecord(c->ev_beg, c->stream);
     if ((rc = scan_phase1(c, s, series_id, 1, Jt, a, b, cc, d, mu, nu, n_lo, n_hi, true, max_prev, run))) { run.valid = false; return rc; }
+    run.epoch = c->epoch;
     CUDA_TRY(cudaMemcpyAsync(composite_out, run.total, sizeof(double) * SEL, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
@@ -1679,6 +1772,11 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
     CUDA_TRY(cudaSetDevice(c->device));
     ScanRun& run = *scan_slot(c);
     if (!run.valid) return fail(PIORAN_EINVAL, "no range in progress: call pioran_celerite_scan_range_begin first");
+    if (run.epoch != c->epoch) {
+        run.valid = false;
+        return fail(PIORAN_EINVAL, "the range in progress was invalidated by another call on this context between "
+                                   "pioran_celerite_scan_range_begin and _end (they share its workspaces)");
+    }
     Series* s = get_series(c, run.series_id);
     if (!s) return fail(PIORAN_EINVAL, "the series of the range in progress was freed");
     if (nprev < 0 || (size_t)nprev * SEL > (size_t)(run.sums - run.prev))
@@ -1732,7 +1830,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
                                   double* nll_out, int* info_out) try {
     if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
-    std::lock_guard<std::mutex> lk(c->mu);
+    PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);

@@ -41,16 +41,26 @@ constexpr int ROW_AUG = 4;        // RowKind of the augmented (data) row
 // the state), NTR = row tiles (NT, or NT+1 when R is a multiple of 8 and the augmented row needs a tile of its own).
 __host__ __device__ constexpr int blk_nt(int R) { return (R + 7) / 8; }
 __host__ __device__ constexpr int blk_ntr(int R) { return (R + 8) / 8; }
-// Block record (doubles):  UT [NT][8 steps][8 rows] | VH [8·NTR rows][8 steps] | PSI8 [8·NTR] | H [28 pairs][8·NT] | y[8] σ²[8] mask[8] pad[8]
+// Block record (doubles):  UT [NT][8 steps][8 rows] | VH [8·NTR rows][8 steps] | PSI8 [8·NTR] | H2 [4·NT row pairs][32 slots][2] |
+// y[8] σ²[8] mask[8] pad[8].  Rows of UT/VH/PSI8 are PHYSICAL rows (blk_phys_row); H2 is indexed by the LOGICAL celerite row.
 __host__ __device__ constexpr int blk_off_vh(int NT, int NTR) { return 64 * NT; }
 __host__ __device__ constexpr int blk_off_psi(int NT, int NTR) { return 64 * NT + 64 * NTR; }
 __host__ __device__ constexpr int blk_off_h(int NT, int NTR) { return 64 * NT + 72 * NTR; }
-__host__ __device__ constexpr int blk_off_sc(int NT, int NTR) { return 64 * NT + 72 * NTR + 224 * NT; }
-__host__ __device__ constexpr int blk_doubles(int NT, int NTR) { return 64 * NT + 72 * NTR + 224 * NT + 32; }
+__host__ __device__ constexpr int blk_off_sc(int NT, int NTR) { return 64 * NT + 72 * NTR + 256 * NT; }
+__host__ __device__ constexpr int blk_doubles(int NT, int NTR) { return 64 * NT + 72 * NTR + 256 * NT + 32; }
+// HALF mode: the last column tile carries at most 4 celerite rows.  They sit at its even positions and the augmented row at
+// position 1, so the odd contraction chunk of that tile multiplies zeros only and its products are skipped.
+__host__ __device__ constexpr bool blk_half(int R) { return (R % 8) >= 1 && (R % 8) <= 4; }
+__host__ __device__ constexpr int blk_phys_row(int r, int R) {          // logical row (R = the augmented row) → physical row
+    const int base = 8 * ((R + 7) / 8 - 1);
+    if (!blk_half(R) || r < base) return r;
+    return r == R ? base + 1 : base + 2 * (r - base);
+}
 __host__ __device__ constexpr int pair_slot(int s, int sp) { return s * (s - 1) / 2 + sp; }   // s > sp
 
 // ------------------------------------------------------------------------------------------- K0b: block table
-// One thread per (block, row).  rows[] describes the 8·NTR rows (ROW_PAD beyond R, ROW_AUG at RG = R).
+// One thread per (block, physical row).  rows[] describes the 8·NTR physical rows (ROW_PAD where nothing lives, ROW_AUG at the
+// augmented row); RowDesc::term holds the logical row index of a celerite row.  The table is zero-filled before the launch.
 __global__ void blocked_table_kernel(double* __restrict__ table, const double* __restrict__ t, const double* __restrict__ y,
                                      const double* __restrict__ s2, int64_t N, int64_t nblocks,
                                      const RowDesc* __restrict__ rows, int NT, int NTR) {
@@ -92,13 +102,18 @@ __global__ void blocked_table_kernel(double* __restrict__ table, const double* _
         const int K = r >> 3, rr = r & 7;
 #pragma unroll
         for (int s = 0; s < BLK; s++) tab[K * 64 + s * 8 + rr] = p0[s] * ut[s];
+    }
+    // H2[logical row pair][slot][2]: coupling of steps (s, s') through this row; rows without a logical index stay zero (memset)
+    if (rd.kind == ROW_COS || rd.kind == ROW_SIN || rd.kind == ROW_REAL) {
+        const int lr = rd.term;
+        double* H = tab + blk_off_h(NT, NTR) + (lr >> 1) * 64 + (lr & 1);
 #pragma unroll
         for (int s = 1; s < BLK; s++) {
             double dec = 1.0;
 #pragma unroll
             for (int sp = s - 1; sp >= 0; sp--) {
                 dec *= ph[sp + 1];
-                tab[blk_off_h(NT, NTR) + pair_slot(s, sp) * RP + r] = ut[s] * dec * vv[sp];
+                H[pair_slot(s, sp) * 2] = ut[s] * dec * vv[sp];
             }
         }
     }
@@ -155,49 +170,59 @@ struct BlkState {
     double chi2, logacc, dkeep, dfirst;
 };
 
-// One block of 8 steps.  tab: this block's record in shared memory; amp_s: per-warp amplitudes (8·NTR doubles, amp[RG] = 1).
-template <int NT, int NTR>
-__device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double* __restrict__ tab,
-                                             const double* __restrict__ amp_s, const BlkLane& L, const int lane,
-                                             const double ampk0, const double ampk1, const int hoff, const double suma,
-                                             const double mu, const double nu, const int64_t n0, const int64_t N,
-                                             const double* __restrict__ yb, const double* __restrict__ sb, const int RG) {
-    constexpr int RP = 8 * NT;
-    constexpr int O_VH = blk_off_vh(NT, NTR), O_PSI = blk_off_psi(NT, NTR), O_H = blk_off_h(NT, NTR), O_SC = blk_off_sc(NT, NTR);
-    const int g = L.g, t = L.t;
+#ifndef PIORAN_BLK_PREFETCH
+#define PIORAN_BLK_PREFETCH 0      // 1: K_blk of block b+1 is formed during block b (measured slower: 41.0 vs 38.5 ms, profiles/r02_k2t_variants.txt)
+#endif
+#ifndef PIORAN_BLK_EARLY_DECAY
+#define PIORAN_BLK_EARLY_DECAY 1   // (ψ8ψ8ᵀ)∘X is applied right after P0, ahead of the pivot chain, not inside the update
+#endif
 
-    // ---- K_blk: partial sums over this lane's two rows, then a reduce-scatter: lane l ends with the total of pair slot l
-    double cm0, cm1;
-    {
-        double v[32];
-        const double* Hp = tab + O_H + hoff;
+// K_blk of one block in the accumulator layout (lane (g,t): C[g][2t], C[g][2t+1]).  Lane l < 28 sums pair slot l over all
+// celerite rows (4 accumulation chains, no cross-lane reduction); two exchanges then hand every lane its two entries.  The
+// diagonal is A_n = Σa + ν σ²_n.  amp_l: per-warp amplitudes by LOGICAL row (8·NT doubles, zero-padded).
+template <int NT, int NTR>
+__device__ __forceinline__ void blk_kblk(const double* __restrict__ tab, const double* __restrict__ amp_l, const BlkLane& L,
+                                         const int lane, const double suma, const double nu, const int64_t n0,
+                                         const int64_t N, const double* __restrict__ sb, double& cm0, double& cm1) {
+    constexpr int O_H = blk_off_h(NT, NTR), O_SC = blk_off_sc(NT, NTR);
+    const int g = L.g;
+    const double2* Hq = reinterpret_cast<const double2*>(tab + O_H) + lane;
+    const double2* Aq = reinterpret_cast<const double2*>(amp_l);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int p = 0; p < 28; p++) {
-            const double2 h = *reinterpret_cast<const double2*>(Hp + p * RP);
-            v[p] = fma(ampk1, h.y, ampk0 * h.x);
-        }
-#pragma unroll
-        for (int p = 28; p < 32; p++) v[p] = 0.0;
-#pragma unroll
-        for (int half = 16; half >= 1; half >>= 1) {
-            const bool bit = (lane & half) != 0;
-#pragma unroll
-            for (int i = 0; i < half; i++) {
-                const double send = bit ? v[i] : v[i + half];
-                const double keep = bit ? v[i + half] : v[i];
-                v[i] = keep + __shfl_xor_sync(FULL, send, half);
-            }
-        }
-        const double o0 = __shfl_sync(FULL, v[0], L.csrc0);
-        const double o1 = __shfl_sync(FULL, v[0], L.csrc1);
-        // diagonal: A_n = Σa + ν σ²_n (celerite_solver.jl:92); padded steps are unit pivots
-        const int64_t n = n0 + g;
-        const double mk = tab[O_SC + 16 + g];
-        const double s2v = sb ? (n < N ? sb[n] : 0.0) : tab[O_SC + 8 + g];
-        const double dg = fma(fma(nu, s2v, suma), mk, 1.0 - mk);
-        cm0 = L.cdiag0 ? dg : o0;
-        cm1 = L.cdiag1 ? dg : o1;
+    for (int jp = 0; jp < 4 * NT; jp += 2) {
+        const double2 h0 = Hq[jp * 32], h1 = Hq[(jp + 1) * 32];
+        const double2 m0 = Aq[jp], m1 = Aq[jp + 1];
+        a0 = fma(m0.x, h0.x, a0); a1 = fma(m0.y, h0.y, a1);
+        a2 = fma(m1.x, h1.x, a2); a3 = fma(m1.y, h1.y, a3);
     }
+    const double v = (a0 + a1) + (a2 + a3);
+    const double o0 = __shfl_sync(FULL, v, L.csrc0);
+    const double o1 = __shfl_sync(FULL, v, L.csrc1);
+    // diagonal: A_n = Σa + ν σ²_n (celerite_solver.jl:92); padded steps are unit pivots
+    const int64_t n = n0 + g;
+    const double mk = tab[O_SC + 16 + g];
+    const double s2v = sb ? (n < N ? sb[n] : 0.0) : tab[O_SC + 8 + g];
+    const double dg = fma(fma(nu, s2v, suma), mk, 1.0 - mk);
+    cm0 = L.cdiag0 ? dg : o0;
+    cm1 = L.cdiag1 ? dg : o1;
+}
+
+// One block of 8 steps.  tab: this block's record in shared memory; amp_s: per-warp amplitudes (8·NTR doubles, amp[RG] = 1);
+// (cm0, cm1): K_blk of this block on entry, of the NEXT block (record tabn, first step n0 + 8) on exit.
+template <int NT, int NTR, bool HALF>
+__device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double* __restrict__ tab,
+                                             const double* __restrict__ tabn, const double* __restrict__ amp_s,
+                                             const double* __restrict__ amp_l, const BlkLane& L, const int lane,
+                                             const double suma, const double mu, const double nu,
+                                             const int64_t n0, const int64_t N, const double* __restrict__ yb,
+                                             const double* __restrict__ sb, const int RG, double& cm0_io, double& cm1_io) {
+    constexpr int O_VH = blk_off_vh(NT, NTR), O_PSI = blk_off_psi(NT, NTR), O_SC = blk_off_sc(NT, NTR);
+    const int g = L.g, t = L.t;
+    double cm0 = cm0_io, cm1 = cm1_io;
+#if !PIORAN_BLK_PREFETCH
+    blk_kblk<NT, NTR>(tab, amp_l, L, lane, suma, nu, n0, N, sb, cm0, cm1);
+#endif
 
     // ---- P0 = X·Û (row tiles I, contraction over column tiles K)
     double P0[NTR][2];
@@ -212,7 +237,7 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
             if (I >= K) { a0 = st.x[I][K][0]; a1 = st.x[I][K][1]; }
             else tile_transpose(L, st.x[K][I][0], st.x[K][I][1], a0, a1);
             dmma(P0[I][0], P0[I][1], a0, u.x);
-            dmma(P0[I][0], P0[I][1], a1, u.y);
+            if (!(HALF && K == NT - 1)) dmma(P0[I][0], P0[I][1], a1, u.y);   // HALF: the odd chunk of the last tile is all zeros
         }
     }
 
@@ -224,20 +249,40 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
             const double2 u = *reinterpret_cast<const double2*>(tab + J * 64 + g * 8 + 2 * t);
             double p0, p1;
             tile_transpose(L, P0[J][0], P0[J][1], p0, p1);
-            if (J & 1) { dmma(cb0, cb1, u.x, p0); dmma(cb0, cb1, u.y, p1); }
-            else       { dmma(ca0, ca1, u.x, p0); dmma(ca0, ca1, u.y, p1); }
+            const bool both = !(HALF && J == NT - 1);
+            if (J & 1) { dmma(cb0, cb1, u.x, p0); if (both) dmma(cb0, cb1, u.y, p1); }
+            else       { dmma(ca0, ca1, u.x, p0); if (both) dmma(ca0, ca1, u.y, p1); }
         }
         cm0 -= ca0 + cb0;
         cm1 -= ca1 + cb1;
     }
 
-    // ---- Bm = amp∘V̂ − ψ8∘P0 (in place); the augmented row carries (y − μ) − prediction
     double psr[NTR];
+#pragma unroll
+    for (int I = 0; I < NTR; I++) psr[I] = tab[O_PSI + 8 * I + g];
+#if PIORAN_BLK_EARLY_DECAY
+    // ---- X ← (ψ8ψ8ᵀ)∘X now: the un-decayed state is no longer needed, and these products fill the pivot chain's latency
+#pragma unroll
+    for (int K = 0; K < NT; K++) {
+        const double2 pc = *reinterpret_cast<const double2*>(tab + O_PSI + 8 * K + 2 * t);
+#pragma unroll
+        for (int I = K; I < NTR; I++) {
+            st.x[I][K][0] *= psr[I] * pc.x;
+            st.x[I][K][1] *= psr[I] * pc.y;
+        }
+    }
+#endif
+#if PIORAN_BLK_PREFETCH
+    double cn0, cn1;
+    blk_kblk<NT, NTR>(tabn, amp_l, L, lane, suma, nu, n0 + BLK, N, sb, cn0, cn1);
+    cm0_io = cn0; cm1_io = cn1;
+#endif
+
+    // ---- Bm = amp∘V̂ − ψ8∘P0 (in place); the augmented row carries (y − μ) − prediction
 #pragma unroll
     for (int I = 0; I < NTR; I++) {
         const int row = 8 * I + g;
         double2 vh = *reinterpret_cast<const double2*>(tab + O_VH + row * 8 + 2 * t);
-        psr[I] = tab[O_PSI + row];
         const double am = amp_s[row];
         if (I == NTR - 1) {
             const bool isrg = (row == RG);
@@ -257,7 +302,7 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
 
     // ---- 8×8 LDLᵀ of C, distributed: lane (g,t) holds C[g][2t], C[g][2t+1]; E becomes L⁻¹ by the same eliminations
     double e0 = L.cdiag0 ? 1.0 : 0.0, e1 = L.cdiag1 ? 1.0 : 0.0;
-    double rd[BLK];
+    double rd0 = 0.0, rd1 = 0.0;      // 1/D of this lane's two steps (2t, 2t+1)
     const int rowbase = lane & ~3;
     const int ring = (int)(n0 & 31);
 #pragma unroll
@@ -266,8 +311,10 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
         const double cme = (j & 1) ? cm1 : cm0;
         const double dj = __shfl_sync(FULL, cme, 4 * j + tj);          // pivot D_{n0+j} (celerite_solver.jl:92)
         const double cgj = __shfl_sync(FULL, cme, rowbase | tj);       // C[g][j]
-        rd[j] = fast_rcp(dj);
-        const double l = cgj * rd[j];
+        const double rdj = fast_rcp(dj);
+        if (j & 1) rd1 = (t == tj) ? rdj : rd1;
+        else       rd0 = (t == tj) ? rdj : rd0;
+        const double l = cgj * rdj;
         const double cj0 = __shfl_sync(FULL, cm0, 4 * j + t), cj1 = __shfl_sync(FULL, cm1, 4 * j + t);
         const double ej0 = __shfl_sync(FULL, e0, 4 * j + t), ej1 = __shfl_sync(FULL, e1, 4 * j + t);
         const double lm = (g > j) ? l : 0.0;
@@ -287,11 +334,6 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
         dmma(Q[I][0], Q[I][1], P0[I][0], e0);
         dmma(Q[I][0], Q[I][1], P0[I][1], e1);
     }
-    // 1/D of this lane's two steps
-    double rd0 = rd[0], rd1 = rd[1];
-    if (t == 1) { rd0 = rd[2]; rd1 = rd[3]; }
-    if (t == 2) { rd0 = rd[4]; rd1 = rd[5]; }
-    if (t == 3) { rd0 = rd[6]; rd1 = rd[7]; }
 
     // ---- yᵀK⁻¹y += Σ_s z_s²/D_s  (celerite_solver.jl:333) on the lanes that hold the augmented row
     {
@@ -304,10 +346,16 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
 #pragma unroll
     for (int K = 0; K < NT; K++) {
         const double w0 = Q[K][0] * rd0, w1 = Q[K][1] * rd1;
+#if !PIORAN_BLK_EARLY_DECAY
         const double2 pc = *reinterpret_cast<const double2*>(tab + O_PSI + 8 * K + 2 * t);
+#endif
 #pragma unroll
         for (int I = K; I < NTR; I++) {
+#if PIORAN_BLK_EARLY_DECAY
+            double x0 = st.x[I][K][0], x1 = st.x[I][K][1];
+#else
             double x0 = st.x[I][K][0] * (psr[I] * pc.x), x1 = st.x[I][K][1] * (psr[I] * pc.y);
+#endif
             dmma(x0, x1, Q[I][0], w0);
             dmma(x0, x1, Q[I][1], w1);
             st.x[I][K][0] = x0; st.x[I][K][1] = x1;
@@ -318,14 +366,14 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
 // ------------------------------------------------------------------------------------------- kernel
 // grid = work items; block = NW warps, one parameter vector each; dynamic smem: BLK_NSTAGE block records | NW × 8·NTR amplitudes |
 // BLK_NSTAGE mbarriers | BLK_NSTAGE stage counters.  Same stage hand-back as celerite_shared_kernel (last warp out refills).
-template <int NT, int NTR, int NW, int MINB>
+template <int NT, int NTR, bool HALF, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const BatchArgs args, const int R, const int amp_stride) {
-    constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR;
+    constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR, APW = RPT + 8 * NT;   // per warp: amplitudes by physical and by logical row
     constexpr uint32_t STAGE_BYTES = BD * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
     double* amps = stages + BLK_NSTAGE * BD;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(amps + NW * RPT);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(amps + NW * APW);
     int* done = reinterpret_cast<int*>(bars + BLK_NSTAGE);
 
     const WorkItem wk = args.work[blockIdx.x];
@@ -345,18 +393,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const B
         }
     }
 
-    const bool active = warp < wk.count;
-    const int slot = active ? warp : wk.count - 1;       // surplus warps redo the item's last θ and skip the store
+    // Surplus warps of a partly filled item leave: the stage hand-back counts the item's own warps, and a tail item of
+    // wk.count <= 4 then runs one warp per sub-partition at the single-warp rate instead of sharing the pipe with redundant sweeps.
+    const int nact = wk.count < NW ? wk.count : NW;
+    if (warp >= nact) return;
+    const int slot = warp;
     const int th = wk.theta_begin + slot;
     const BlkLane L = make_blk_lane(lane);
-    const int RG = R;
+    const int RG = blk_phys_row(R, R);
 
-    double* amp_s = amps + warp * RPT;
-    for (int k = lane; k < RPT; k += 32) amp_s[k] = (k < R) ? args.amp[(size_t)th * amp_stride + k] : (k == RG ? 1.0 : 0.0);
+    double* amp_s = amps + warp * APW;
+    double* amp_l = amp_s + RPT;
+    for (int k = lane; k < APW; k += 32) amp_s[k] = 0.0;
     __syncwarp();
-    const int hoff = (lane < 4 * NT) ? 2 * lane : 0;
-    const double ampk0 = (2 * lane < R) ? amp_s[2 * lane] : 0.0;
-    const double ampk1 = (2 * lane + 1 < R) ? amp_s[2 * lane + 1] : 0.0;
+    for (int k = lane; k < R; k += 32) {
+        const double av = args.amp[(size_t)th * amp_stride + k];
+        amp_s[blk_phys_row(k, R)] = av;
+        amp_l[k] = av;
+    }
+    if (lane == 0) amp_s[RG] = 1.0;
+    __syncwarp();
     const double suma = args.suma[th];
     const size_t pi = (size_t)wk.par_begin + slot;
     const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
@@ -373,13 +429,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const B
 
     int sidx = 0;
     uint32_t parity = 0;
+    double cm0 = 0.0, cm1 = 0.0;
+    mbar_wait(&bars[0], 0);
+#if PIORAN_BLK_PREFETCH
+    blk_kblk<NT, NTR>(stages, amp_l, L, lane, suma, nu, 0, N, sb, cm0, cm1);
+#endif
     for (int64_t b = 0; b < nblocks; b++) {
-        mbar_wait(&bars[sidx], parity);
-        blocked_step<NT, NTR>(st, stages + sidx * BD, amp_s, L, lane, ampk0, ampk1, hoff, suma, mu, nu, b * BLK, N, yb, sb, RG);
+        // the next block's record (its K_blk is formed during this block); the last block points at itself
+        int nidx = sidx + 1;
+        uint32_t npar = parity;
+        if (nidx == BLK_NSTAGE) { nidx = 0; npar ^= 1; }
+        if (b + 1 < nblocks) mbar_wait(&bars[nidx], npar);
+        else nidx = sidx;
+        blocked_step<NT, NTR, HALF>(st, stages + sidx * BD, stages + nidx * BD, amp_s, amp_l, L, lane, suma, mu, nu, b * BLK, N,
+                                    yb, sb, RG, cm0, cm1);
         __syncwarp();
         if (lane == 0 && b + BLK_NSTAGE < nblocks) {
             __threadfence_block();
-            if (atomicAdd(&done[sidx], 1) == NW - 1) {
+            if (atomicAdd(&done[sidx], 1) == nact - 1) {
                 done[sidx] = 0;
                 fence_proxy_async();
                 mbar_arrive_expect_tx(&bars[sidx], STAGE_BYTES);
@@ -400,7 +467,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const B
     const double logdet = log(dfirst) + la;
     // celerite_solver.jl:333
     const double res = -logdet / 2 - (double)N * 1.8378770664093453 / 2 - ch / 2;
-    if (active && lane == 0) args.out[wk.out_begin + warp] = res;
+    if (lane == 0) args.out[wk.out_begin + warp] = res;
 }
 
 }  // namespace pioran
