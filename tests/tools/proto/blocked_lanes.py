@@ -2,10 +2,11 @@
 lanes, mma/shfl are emulated with the PTX fragment layouts of mma.sync.m8n8k4.f64.  Validates the index algebra."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc
-from tools.proto.blocked_math import rows_from_coeffs, blocked_logl
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from blocked_math import rows_from_coeffs, blocked_logl
 
 LANE = np.arange(32); G_ = LANE >> 2; T_ = LANE & 3
 

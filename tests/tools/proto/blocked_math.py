@@ -1,7 +1,7 @@
 """Math-level prototype of the 8-step blocked (tensor-core) celerite sweep, checked against the CPU oracle."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, ROOT)
 from oracle import oracle as orc
 

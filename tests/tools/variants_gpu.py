@@ -1,7 +1,7 @@
 """Development aid (GPU): time the headline shapes with every library in build_abl/ (one subprocess each, PIORAN_B200_LIB) and
 check each against the oracle on a few parameter vectors.  usage: python tools/variants_gpu.py [lib ...]"""
 import glob, json, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CHILD = r'''
 import json, os, sys
 sys.path.insert(0, %r)
