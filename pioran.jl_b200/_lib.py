@@ -24,6 +24,8 @@ SYMBOLS = {
     "pioran_version": (C.c_int, []),
     "pioran_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "pioran_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "pioran_ctx_create_multi": (C.c_int, [_ip, C.c_int, C.POINTER(C.c_void_p)]),
+    "pioran_ctx_device_count": (C.c_int, [C.c_void_p]),
     "pioran_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pioran_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "pioran_ctx_launch_count": (C.c_int64, [C.c_void_p]),

@@ -10,6 +10,8 @@ Batched entry for samplers that evaluate many parameter vectors at once (ultrane
     like = BatchedLikelihood(t, y, σ², psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO")
     ℓ    = like(Θ)        # Θ rows = [psd parameters…, variance, ν, μ]  (examples/ultranest/single_pl.jl:67)
 """
+import collections
+
 import numpy as np
 
 from . import backend
@@ -266,11 +268,52 @@ def log_likelihood(cov, τ, y, σ2, *, solver="celerite", ctx=None):
         raise ValueError(f"solver {solver} not recognised, use either :celerite or :celerite_matrix")
     ctx = ctx or get_context()
     a, b, c, d = celerite_coefs(cov)
-    ser = ctx.upload_series(τ, y, σ2)
-    try:
-        return float(ctx.celerite_logl(ser, a, b, c, d)[0])
-    finally:
-        ser.free()
+    τ = np.ascontiguousarray(τ, dtype=np.float64)
+    if τ.shape[0] >= _RESIDENT_MAX_N:
+        # long series: (t, y, σ²) go up together so that the library may route the call to its parallel-in-time path
+        ser = ctx.upload_series(τ, y, σ2)
+        try:
+            return float(ctx.celerite_logl(ser, a, b, c, d)[0])
+        finally:
+            ser.free()
+    ser = _resident_series(ctx, τ)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(1, -1)
+    σ2 = np.ascontiguousarray(σ2, dtype=np.float64).reshape(1, -1)
+    return float(ctx.celerite_logl(ser, a, b, c, d, y_batch=y, s2_batch=σ2)[0])
+
+
+# The time vector of a `:celerite_gpu` call stays on the device between calls (julia/b200_solver.jl: b200_resident_series): a
+# sampler passes the same t ~1e5 times while Y − mean and ν·σ² are fresh arrays, which travel with the call (16 N bytes).
+_RESIDENT_MAX_N = 2048
+_RESIDENT_CAP = 8
+_resident = collections.OrderedDict()
+
+
+def _resident_series(ctx, τ):
+    key = (id(ctx), τ.shape[0], float(τ[0]), float(τ[-1]), float(τ.sum()))
+    ser = _resident.get(key)
+    if ser is not None and ser.id is not None:
+        _resident.move_to_end(key)
+        return ser
+    ser = ctx.upload_series(τ, np.zeros_like(τ), np.ones_like(τ))
+    _resident[key] = ser
+    while len(_resident) > _RESIDENT_CAP:
+        _, old = _resident.popitem(last=False)
+        try:
+            old.free()
+        except Exception:
+            pass
+    return ser
+
+
+def release_resident_series():
+    """Frees the time vectors kept on the device by log_likelihood (b200_release!() of the Julia shim)."""
+    while _resident:
+        _, ser = _resident.popitem()
+        try:
+            ser.free()
+        except Exception:
+            pass
 
 
 def log_likelihood_direct(cov, t, y, σ2, *, ctx=None):

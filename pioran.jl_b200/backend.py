@@ -54,13 +54,24 @@ class Context:
     """pioran_ctx bound to one device."""
 
     def __init__(self, device=None):
+        """device: an int (one GPU), or a sequence of ints — a device group (pioran_ctx_create_multi): one process, the batched
+        host entries split their parameter vectors over the devices."""
         self.lib = _lib.load()
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         h = C.c_void_p()
-        check(self.lib.pioran_ctx_create(int(device), C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            check(self.lib.pioran_ctx_create_multi(devs, len(device), C.byref(h)))
+            self.device = int(device[0])
+        else:
+            check(self.lib.pioran_ctx_create(int(device), C.byref(h)))
+            self.device = int(device)
         self.h = h
-        self.device = int(device)
+
+    @property
+    def device_count(self):
+        return int(self.lib.pioran_ctx_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):

@@ -10,6 +10,7 @@
 #include <new>
 #include <exception>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -56,7 +57,7 @@ static int guard_fail() {
     } while (0)
 
 extern "C" const char* pioran_last_error(void) { return g_err.c_str(); }
-extern "C" int pioran_version(void) { return 100; }
+extern "C" int pioran_version(void) { return 200; }   // 0.2.0: device groups, sweep-kernel selector
 
 // ------------------------------------------------------------------------------------------------ context
 namespace {
@@ -113,6 +114,10 @@ struct pioran_ctx {
     int scan_chunks = 0;   // K3: chunks per parameter vector (0 = automatic)
     bool auto_scan = true; // route few-evaluation calls on long series to K3 (pioran_ctx_set_auto_scan)
     int sweep_kernel = PIORAN_SWEEP_AUTO;   // pioran_ctx_set_sweep_kernel
+    // pioran_ctx_create_multi: a group context owns one child context per device and no CUDA state of its own; the batched
+    // host-pointer entries split their parameter vectors over the children, everything else runs on children[0]
+    std::vector<pioran_ctx*> children;
+    std::vector<std::vector<int>> group_series;   // group series id -> series id on each child (empty = freed)
     uint64_t epoch = 0;    // bumped by every entry that uses the shared workspaces (a pending scan range checks it)
     uint64_t use_clock = 0;   // LRU stamp source of the per-series table caches
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
@@ -185,6 +190,67 @@ extern "C" int pioran_ctx_create(int device, pioran_ctx** out) try {
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 
+
+// ------------------------------------------------------------------------------------------------ device groups
+// Single-process multi-GPU (reference examples/ultranest/single_pl.jl:113-117 runs ONE process and one
+// callback): the parameter batch is cut into contiguous slices, one per device; each slice goes through the ordinary
+// single-device entry on its own host thread (cudaSetDevice is per thread) and writes straight into the caller's output
+// rows.  No data-path collective: the slices are independent, and host pointers need no all-gather.
+static bool is_group(const pioran_ctx* c) { return c && !c->children.empty(); }
+static int group_series_id(pioran_ctx* g, int gid, size_t child, int* out) {
+    if (gid < 0 || gid >= (int)g->group_series.size() || g->group_series[gid].empty())
+        return fail(PIORAN_EINVAL, "unknown series id %d", gid);
+    *out = g->group_series[gid][child];
+    return 0;
+}
+// Runs fn(child index, first row, row count) for every non-empty slice of B rows, one thread per slice.
+template <typename F>
+static int group_split(pioran_ctx* g, int B, F fn) {
+    const int nd = (int)g->children.size();
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::string> errs(nd);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; k++) {
+        const int beg = (int)((long long)B * k / nd), end = (int)((long long)B * (k + 1) / nd);
+        if (end <= beg) continue;
+        th.emplace_back([&, k, beg, end] {
+            rcs[k] = fn(k, beg, end - beg);
+            if (rcs[k]) errs[k] = pioran_last_error();     // the message is thread-local: carry it back
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int k = 0; k < nd; k++)
+        if (rcs[k]) return fail(rcs[k], "device %d: %s", g->children[k]->device, errs[k].c_str());
+    return 0;
+}
+
+extern "C" int pioran_ctx_create_multi(const int* devices, int ndev, pioran_ctx** out) try {
+    if (!devices || !out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (ndev < 1 || ndev > 64) return fail(PIORAN_EINVAL, "ndev must be in [1, 64] (got %d)", ndev);
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(PIORAN_EINVAL, "device %d listed twice", devices[i]);
+    pioran_ctx* g = new (std::nothrow) pioran_ctx();
+    if (!g) return fail(PIORAN_ENOMEM, "out of host memory");
+    for (int i = 0; i < ndev; i++) {
+        pioran_ctx* ch = nullptr;
+        const int rc = pioran_ctx_create(devices[i], &ch);
+        if (rc) {
+            const std::string msg = pioran_last_error();
+            for (pioran_ctx* x : g->children) pioran_ctx_destroy(x);
+            delete g;
+            return fail(rc, "%s", msg.c_str());
+        }
+        g->children.push_back(ch);
+    }
+    g->device = devices[0];
+    g->num_sms = g->children[0]->num_sms;
+    *out = g;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
+extern "C" int pioran_ctx_device_count(pioran_ctx* c) { return !c ? 0 : is_group(c) ? (int)c->children.size() : 1; }
+
 static void free_series(Series* s) {
     if (!s) return;
     cudaFree(s->t); cudaFree(s->y); cudaFree(s->s2);
@@ -195,6 +261,11 @@ static void free_series(Series* s) {
 
 extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     if (!c) return PIORAN_OK;
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) pioran_ctx_destroy(ch);
+        delete c;
+        return PIORAN_OK;
+    }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     scan_forget(c);
@@ -211,6 +282,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
 
 extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (is_group(c)) return fail(PIORAN_EUNSUPPORTED, "a device group has one stream per device; set streams on single-device contexts");
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t next = s ? reinterpret_cast<cudaStream_t>(s) : c->own;
     if (next != c->stream) {
@@ -223,17 +295,28 @@ extern "C" int pioran_ctx_set_stream(pioran_ctx* c, void* s) try {
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_synchronize(pioran_ctx* c) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_synchronize(ch); if (rc) return rc; }
+        return PIORAN_OK;
+    }
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int64_t pioran_ctx_launch_count(pioran_ctx* c) {
     if (!c) return 0;
+    if (is_group(c)) { int64_t n = 0; for (pioran_ctx* ch : c->children) n += pioran_ctx_launch_count(ch); return n; }
     std::lock_guard<std::mutex> lk(c->mu);
     return c->launches;
 }
 extern "C" int pioran_ctx_last_kernel_ms(pioran_ctx* c, double* ms) try {
     if (!c || !ms) return fail(PIORAN_EINVAL, "NULL argument");
+    if (is_group(c)) {   // the slowest device bounds the call
+        double worst = 0.0;
+        for (pioran_ctx* ch : c->children) { double v = 0.0; if (pioran_ctx_last_kernel_ms(ch, &v) == 0 && v > worst) worst = v; }
+        *ms = worst;
+        return PIORAN_OK;
+    }
     if (!c->ev_valid) return fail(PIORAN_EINVAL, "no main kernel has been launched on this context yet");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaEventSynchronize(c->ev_end));
@@ -247,6 +330,21 @@ extern "C" int pioran_series_upload(pioran_ctx* c, int64_t N, const double* t, c
                                     int* series_id) try {
     if (!c || !t || !y || !s2 || !series_id) return fail(PIORAN_EINVAL, "NULL argument");
     if (N < 1) return fail(PIORAN_EINVAL, "N must be >= 1 (got %lld)", (long long)N);
+    if (is_group(c)) {
+        std::vector<int> ids(c->children.size(), -1);
+        for (size_t k = 0; k < c->children.size(); k++) {
+            const int rc = pioran_series_upload(c->children[k], N, t, y, s2, &ids[k]);
+            if (rc) { for (size_t q = 0; q < k; q++) pioran_series_free(c->children[q], ids[q]); return rc; }
+        }
+        std::lock_guard<std::mutex> lk(c->mu);
+        int gid = -1;
+        for (size_t k = 0; k < c->group_series.size(); k++)
+            if (c->group_series[k].empty()) { gid = (int)k; break; }
+        if (gid < 0) { c->group_series.emplace_back(); gid = (int)c->group_series.size() - 1; }
+        c->group_series[gid] = ids;
+        *series_id = gid;
+        return PIORAN_OK;
+    }
     for (int64_t n = 1; n < N; n++)
         if (!(t[n] > t[n - 1])) return fail(PIORAN_EINVAL, "t must be strictly increasing (t[%lld] <= t[%lld])", (long long)n, (long long)(n - 1));
     std::lock_guard<std::mutex> lk(c->mu);
@@ -281,6 +379,13 @@ static Series* get_series(pioran_ctx* c, int id) {
 
 extern "C" int pioran_series_free(pioran_ctx* c, int id) try {
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (is_group(c)) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (id < 0 || id >= (int)c->group_series.size() || c->group_series[id].empty()) return fail(PIORAN_EINVAL, "unknown series id %d", id);
+        for (size_t k = 0; k < c->children.size(); k++) pioran_series_free(c->children[k], c->group_series[id][k]);
+        c->group_series[id].clear();
+        return PIORAN_OK;
+    }
     PIORAN_COMPUTE_LOCK(c);
     Series* s = get_series(c, id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
@@ -295,6 +400,11 @@ extern "C" int pioran_series_free(pioran_ctx* c, int id) try {
 
 extern "C" int pioran_series_length(pioran_ctx* c, int id, int64_t* N) try {
     if (!c || !N) return fail(PIORAN_EINVAL, "NULL argument");
+    if (is_group(c)) {
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, id, 0, &cid); if (rc) return rc; }
+        return pioran_series_length(c->children[0], cid, N);
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     Series* s = get_series(c, id);
     if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", id);
@@ -807,6 +917,7 @@ static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
 // ------------------------------------------------------------------------------------------------ K1 entry
 extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spec, int B, const double* theta,
                                     double* a, double* b, double* cc, double* d) try {
+    if (is_group(c)) return pioran_approx_coeffs(c->children[0], spec, B, theta, a, b, cc, d);
     if (!c || !spec || !theta || !a || !b || !cc || !d) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
     int rc = check_spec(*spec);
@@ -965,6 +1076,15 @@ extern "C" int pioran_approx_logl_logshift(pioran_ctx* c, int series_id, const p
                                            double* logl_out) try {
     if (!c || !spec || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    if (is_group(c)) {
+        const int npar_g = n_psd_par_of(spec->psd_model);
+        if (npar_g < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            return pioran_approx_logl_logshift(c->children[k], cid[k], spec, nb, theta + (size_t)beg * (npar_g + 4), logl_out + beg);
+        });
+    }
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     int rc;
@@ -999,6 +1119,7 @@ extern "C" int pioran_approx_logl_logshift(pioran_ctx* c, int series_id, const p
 
 extern "C" int pioran_approx_logl_dev(pioran_ctx* c, int S, const int* series_ids, const pioran_approx_spec* specs,
                                       int B, const double* theta_dev, int theta_per_series, double* logl_dev) try {
+    if (is_group(c)) return fail(PIORAN_EUNSUPPORTED, "device-resident entries need a single-device context (a group spans devices)");
     if (!c || !series_ids || !specs || !theta_dev || !logl_dev) return fail(PIORAN_EINVAL, "NULL argument");
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1009,6 +1130,28 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
                                   const double* theta, int theta_per_series, double* logl_out) try {
     if (!c || !series_ids || !specs || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (S < 1 || B < 1) return fail(PIORAN_EINVAL, "S and B must be >= 1");
+    if (is_group(c)) {
+        const int npar_g = n_psd_par_of(specs[0].psd_model);
+        if (npar_g < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", specs[0].psd_model);
+        const int tsg = npar_g + 3;
+        std::vector<std::vector<int>> cids(c->children.size(), std::vector<int>(S));
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            for (size_t k = 0; k < c->children.size(); k++)
+                for (int q = 0; q < S; q++) { const int rc = group_series_id(c, series_ids[q], k, &cids[k][q]); if (rc) return rc; }
+        }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            if (S == 1) return pioran_approx_logl(c->children[k], 1, cids[k].data(), specs, nb, theta + (size_t)beg * tsg, 0, logl_out + beg);
+            // several series: the slice of every series' rows is gathered, evaluated and scattered back
+            std::vector<double> th((size_t)(theta_per_series ? S : 1) * nb * tsg), out((size_t)S * nb);
+            for (int q = 0; q < (theta_per_series ? S : 1); q++)
+                std::memcpy(th.data() + (size_t)q * nb * tsg, theta + ((size_t)q * B + beg) * tsg, sizeof(double) * (size_t)nb * tsg);
+            const int rc = pioran_approx_logl(c->children[k], S, cids[k].data(), specs, nb, th.data(), theta_per_series, out.data());
+            if (rc) return rc;
+            for (int q = 0; q < S; q++) std::memcpy(logl_out + (size_t)q * B + beg, out.data() + (size_t)q * nb, sizeof(double) * nb);
+            return 0;
+        });
+    }
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     const int npar = n_psd_par_of(specs[0].psd_model);
@@ -1165,6 +1308,7 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
 
 extern "C" int pioran_approx_logl_grad_dev(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                            const double* theta_dev, double* logl_dev, double* grad_dev) try {
+    if (is_group(c)) return fail(PIORAN_EUNSUPPORTED, "device-resident entries need a single-device context (a group spans devices)");
     if (!c || !spec || !theta_dev || !grad_dev) return fail(PIORAN_EINVAL, "NULL argument");
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1175,6 +1319,17 @@ extern "C" int pioran_approx_logl_grad(pioran_ctx* c, int series_id, const piora
                                        const double* theta, double* logl_out, double* grad_out) try {
     if (!c || !spec || !theta || !grad_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    if (is_group(c)) {
+        const int npar_g = n_psd_par_of(spec->psd_model);
+        if (npar_g < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+        const int Pg = npar_g + 3;
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            return pioran_approx_logl_grad(c->children[k], cid[k], spec, nb, theta + (size_t)beg * Pg, logl_out ? logl_out + beg : nullptr,
+                                           grad_out + (size_t)beg * Pg);
+        });
+    }
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     const int npar = n_psd_par_of(spec->psd_model);
@@ -1233,6 +1388,17 @@ extern "C" int pioran_celerite_logl(pioran_ctx* c, int series_id, int B, int Jt,
                                     const double* y_batch, const double* s2_batch, double* logl_out) try {
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
+    if (is_group(c)) {
+        std::vector<int> cid(c->children.size());
+        int64_t Ng = 0;
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        if (y_batch || s2_batch) { const int rc = pioran_series_length(c->children[0], cid[0], &Ng); if (rc) return rc; }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            const size_t o = (size_t)beg * Jt;
+            return pioran_celerite_logl(c->children[k], cid[k], nb, Jt, a + o, b + o, cc + o, d + o, mu ? mu + beg : nullptr, nu ? nu + beg : nullptr,
+                                        y_batch ? y_batch + (size_t)beg * Ng : nullptr, s2_batch ? s2_batch + (size_t)beg * Ng : nullptr, logl_out + beg);
+        });
+    }
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);
@@ -1322,6 +1488,11 @@ static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* 
 extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                        const double* cc, const double* d, const double* mu, const double* nu, int64_t M,
                                        const double* tau, double* mean_out) try {
+    if (is_group(c)) {   // single-device work of a group runs on its first device
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
+        return pioran_celerite_predict(c->children[0], cid, B, Jt, a, b, cc, d, mu, nu, M, tau, mean_out);
+    }
     if (!c || !a || !b || !cc || !d || !tau || !mean_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1 || M < 1) return fail(PIORAN_EINVAL, "B, Jt and M must be >= 1");
     for (int64_t m = 1; m < M; m++)
@@ -1375,6 +1546,11 @@ extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int 
 extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                         const double* cc, const double* d, const double* nu, const double* q,
                                         double* y_out) try {
+    if (is_group(c)) {   // single-device work of a group runs on its first device
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
+        return pioran_celerite_simulate(c->children[0], cid, B, Jt, a, b, cc, d, nu, q, y_out);
+    }
     if (!c || !a || !b || !cc || !d || !q || !y_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     PIORAN_COMPUTE_LOCK(c);
@@ -1413,6 +1589,10 @@ static int make_term_rows(int B, int Jt, const double* b, const double* d, std::
 }
 
 extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_auto_scan(ch, enabled); if (rc) return rc; }
+        return PIORAN_OK;
+    }
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     c->auto_scan = enabled != 0;
@@ -1420,6 +1600,10 @@ extern "C" int pioran_ctx_set_auto_scan(pioran_ctx* c, int enabled) try {
 } catch (...) { return guard_fail(); }
 
 extern "C" int pioran_ctx_set_sweep_kernel(pioran_ctx* c, int which) try {
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_sweep_kernel(ch, which); if (rc) return rc; }
+        return PIORAN_OK;
+    }
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (which != PIORAN_SWEEP_AUTO && which != PIORAN_SWEEP_SCALAR) return fail(PIORAN_EINVAL, "unknown sweep kernel %d", which);
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1428,6 +1612,10 @@ extern "C" int pioran_ctx_set_sweep_kernel(pioran_ctx* c, int which) try {
 } catch (...) { return guard_fail(); }
 
 extern "C" int pioran_ctx_set_scan_tolerance(pioran_ctx* c, double tol) try {
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_scan_tolerance(ch, tol); if (rc) return rc; }
+        return PIORAN_OK;
+    }
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (tol != tol) return fail(PIORAN_EINVAL, "tol is NaN");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1435,6 +1623,7 @@ extern "C" int pioran_ctx_set_scan_tolerance(pioran_ctx* c, double tol) try {
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* n_fallback, int* n_refined) try {
+    if (is_group(c)) return pioran_ctx_last_scan_check(c->children[0], estimate, n_fallback, n_refined);
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     std::lock_guard<std::mutex> lk(c->mu);
     if (estimate) *estimate = c->scan_last_est;
@@ -1443,6 +1632,10 @@ extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* 
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_scan_chunks(ch, chunks); if (rc) return rc; }
+        return PIORAN_OK;
+    }
     if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
     if (chunks < 0) return fail(PIORAN_EINVAL, "chunks must be >= 0 (0 = automatic)");
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1733,6 +1926,11 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
 extern "C" int pioran_celerite_logl_scan(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                          const double* cc, const double* d, const double* mu, const double* nu,
                                          double* logl_out) try {
+    if (is_group(c)) {   // single-device work of a group runs on its first device
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
+        return pioran_celerite_logl_scan(c->children[0], cid, B, Jt, a, b, cc, d, mu, nu, logl_out);
+    }
     if (!c || !a || !b || !cc || !d || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     PIORAN_COMPUTE_LOCK(c);
@@ -1749,6 +1947,11 @@ extern "C" int pioran_scan_composite_doubles(void) { return SEL; }
 extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, int Jt, const double* a, const double* b,
                                                 const double* cc, const double* d, const double* mu, const double* nu,
                                                 int64_t n_lo, int64_t n_hi, int max_prev, double* composite_out) try {
+    if (is_group(c)) {   // single-device work of a group runs on its first device
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
+        return pioran_celerite_scan_range_begin(c->children[0], cid, Jt, a, b, cc, d, mu, nu, n_lo, n_hi, max_prev, composite_out);
+    }
     if (!c || !a || !b || !cc || !d || !composite_out) return fail(PIORAN_EINVAL, "NULL argument");
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1767,6 +1970,7 @@ extern "C" int pioran_celerite_scan_range_begin(pioran_ctx* c, int series_id, in
 } catch (...) { return guard_fail(); }
 
 extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const double* composites_prev, double* sums_out) try {
+    if (is_group(c)) return pioran_celerite_scan_range_end(c->children[0], nprev, composites_prev, sums_out);
     if (!c || !sums_out || (nprev > 0 && !composites_prev)) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1819,6 +2023,7 @@ extern "C" int pioran_celerite_scan_range_end(pioran_ctx* c, int nprev, const do
 } catch (...) { return guard_fail(); }
 
 extern "C" int pioran_celerite_scan_range_check(pioran_ctx* c, double* out8) try {
+    if (is_group(c)) return pioran_celerite_scan_range_check(c->children[0], out8);
     if (!c || !out8) return fail(PIORAN_EINVAL, "NULL argument");
     std::lock_guard<std::mutex> lk(c->mu);
     std::copy(c->scan_range_chk, c->scan_range_chk + 8, out8);
@@ -1828,6 +2033,11 @@ extern "C" int pioran_celerite_scan_range_check(pioran_ctx* c, double* out8) try
 extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                   const double* cc, const double* d, const double* mu, const double* nu,
                                   double* nll_out, int* info_out) try {
+    if (is_group(c)) {   // single-device work of a group runs on its first device
+        int cid;
+        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
+        return pioran_direct_logl(c->children[0], cid, B, Jt, a, b, cc, d, mu, nu, nll_out, info_out);
+    }
     if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
     PIORAN_COMPUTE_LOCK(c);

@@ -20,12 +20,18 @@ def rel_err(x, ref):
     return np.abs(x - ref) / np.maximum(1.0, np.abs(ref))
 
 
-def assert_parity(got, want, theta, ld_fn, tol=1e-9, slack=4.0):
+EXEMPTIONS = []   # (test id, rows checked, rows that used the conditioning exemption, worst |gpu − ref| among them)
+MAX_EXEMPT_FRACTION = 0.02
+
+
+def assert_parity(got, want, theta, ld_fn, tol=1e-9, slack=4.0, label=None):
     """Parity bar of BASELINE.json (≤ 1e-9 relative on logL, FP64) made conditioning-aware: a row may exceed `tol`
     only if the reference algorithm's own FP64 answer `want` is itself farther than tol/slack from the 80-bit
     evaluation of the same recursion (ld_fn(row) → long double twin in the oracle), and then the GPU value must lie
     within slack × that distance of the 80-bit value.  SURVEY §7 "parity on ill-conditioned θ": at steep PSD slopes
-    the cancellation D_n = Σa + σ²_n − UᵀSU (src/celerite_solver.jl:92) loses ~7 digits in any operation order."""
+    the cancellation D_n = Σa + σ²_n − UᵀSU (src/celerite_solver.jl:92) loses ~7 digits in any operation order.
+    The exemption is this repo's rule, not BASELINE's: every use is counted, capped at MAX_EXEMPT_FRACTION of the rows of the
+    call, and listed in the terminal summary of the run (pytest_terminal_summary below)."""
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     r = rel_err(got, want)
     bad = np.flatnonzero(~(r <= tol))
@@ -39,7 +45,22 @@ def assert_parity(got, want, theta, ld_fn, tol=1e-9, slack=4.0):
         report.append((int(i), float(r[i]), e_ref, e_gpu))
         assert e_ref > tol / slack and e_gpu <= slack * e_ref, (
             f"row {i}: |gpu-ref| {r[i]:.3e} > {tol:g}; vs 80-bit: ref {e_ref:.3e}, gpu {e_gpu:.3e}")
+    name = label or os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    EXEMPTIONS.append((name, int(got.size), len(report), max((x[1] for x in report), default=0.0)))
+    assert len(report) <= max(1, int(MAX_EXEMPT_FRACTION * got.size)), (
+        f"{len(report)} of {got.size} rows needed the conditioning exemption (cap {MAX_EXEMPT_FRACTION:.0%})")
     return report
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not EXEMPTIONS:
+        return
+    tr = terminalreporter
+    rows, used = sum(e[1] for e in EXEMPTIONS), sum(e[2] for e in EXEMPTIONS)
+    tr.write_line(f"parity exemptions (conftest.assert_parity): {used} of {rows} rows over {len(EXEMPTIONS)} checks")
+    for name, n, k, worst in EXEMPTIONS:
+        if k:
+            tr.write_line(f"  {name}: {k}/{n} rows beyond 1e-9 where the FP64 reference itself is off the 80-bit value; worst |gpu-ref| {worst:.2e}")
 
 
 class GoldenRun:
