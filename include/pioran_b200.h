@@ -95,6 +95,15 @@ int pioran_series_length(pioran_ctx *ctx, int series_id, int64_t *N);
 int pioran_approx_coeffs(pioran_ctx *ctx, const pioran_approx_spec *spec, int B, const double *theta,
                          double *a, double *b, double *c, double *d);
 
+/* approx() of a continuum plus narrow PSD features (src/psd.jl:15-44 convert_feature / get_covariance_from_psd, :221-243,
+ * :254-259, :277-282; test/test_psd.jl:206-285): each QPO(S0, f0, Q) becomes one more celerite term
+ * (a, b, c, d) = (S0 w0 Q/4, a/D, w0/(2Q), c D), D = sqrt(4 Q^2 - 1), w0 = 2 pi f0, divided by the continuum's PSD at the first
+ * grid point, normalised together with the continuum (its integral joins the norm when is_integrated_power = 1) and doubled.
+ * theta: [B x (n_psd_par + 1 + 3 n_features)] = psd parameters..., norm, then (S0, f0, Q) per feature.  Outputs: [B x (Jt +
+ * n_features)], the Jt continuum terms of pioran_approx_coeffs followed by the feature terms.  1 <= n_features <= 8. */
+int pioran_approx_coeffs_features(pioran_ctx *ctx, const pioran_approx_spec *spec, int n_features, int B,
+                                  const double *theta, double *a, double *b, double *c, double *d);
+
 /* ---- K2: celerite log-likelihood ------------------------------------------------------------------------ */
 /* Drop-in for  logl(a, b, c, d, τ, y, σ2)  (src/celerite_solver.jl:312-334) over a batch of B coefficient sets,
  * [B × Jt] row-major each.  mu/nu: per-set constant mean and variance scale (y−μ, ν·σ²; NULL → 0 / 1), the two
@@ -112,6 +121,12 @@ int pioran_celerite_logl(pioran_ctx *ctx, int series_id, int B, int Jt,
  * y_batch: NULL or [S × B × Nmax]-free form is not supported here (use pioran_celerite_logl).  logl_out: [S × B]. */
 int pioran_approx_logl(pioran_ctx *ctx, int S, const int *series_ids, const pioran_approx_spec *specs,
                        int B, const double *theta, int theta_per_series, double *logl_out);
+
+/* approx(continuum + QPO features) + logpdf for B parameter vectors on one resident series: theta [B x (n_psd_par + 3 +
+ * 3 n_features)] = psd parameters..., norm, nu, mu, then (S0, f0, Q) per feature.  The feature terms' decay rates and frequencies
+ * depend on theta, so the sweep is the explicit-coefficient kernel of pioran_celerite_logl (ranks up to 160). */
+int pioran_approx_features_logl(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int n_features, int B,
+                                const double *theta, double *logl_out);
 
 /* Fused path for log-normally distributed series (reference: docs/src/timeseries.md:16-21 and the likelihood of
  * docs/src/ultranest.md:197-217):  yn = log(y - c),  sigma2 = nu * sigma^2 / (y - c)^2,  logpdf(ScalableGP(mu, R)(t, sigma2), yn).

@@ -39,6 +39,11 @@ def _load():
     lib.orc_approx.restype = C.c_int
     lib.orc_approx.argtypes = [C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
                                C.c_int, C.c_int, _dp, _dp, _dp, _dp]
+    lib.orc_approx_features.restype = C.c_int
+    lib.orc_approx_features.argtypes = [C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    lib.orc_integral_celerite.restype = C.c_double
+    lib.orc_integral_celerite.argtypes = [C.c_double] * 5
     for name, rt in (("orc_celerite_logl", C.c_double), ("orc_celerite_logl_ld", C.c_longdouble)):
         fn = getattr(lib, name)
         fn.restype = rt
@@ -122,6 +127,24 @@ def approx(model, params, f_min, f_max, J=20, norm=1.0, S_low=20.0, S_high=20.0,
     if Jt < 0:
         raise RuntimeError(f"oracle approx failed rc={Jt}")
     return a[:Jt].copy(), b[:Jt].copy(), c[:Jt].copy(), d[:Jt].copy()
+
+
+def approx_features(model, params, features, f_min, f_max, J=20, norm=1.0, S_low=20.0, S_high=20.0, is_integrated_power=True,
+                    basis="SHO"):
+    """approx of continuum + QPO features [(S0, f0, Q), …] (src/psd.jl:214-289 with :15-44, :229-243) → (a, b, c, d)."""
+    par = _arr(params)
+    feat = _arr(np.asarray(features, dtype=np.float64).ravel())
+    nf = len(feat) // 3
+    a, b, c, d = (np.empty(2 * J + nf) for _ in range(4))
+    Jt = lib().orc_approx_features(PSD_MODELS[model], _p(par), f_min, f_max, J, norm, S_low, S_high, int(is_integrated_power),
+                                   BASES[basis], nf, _p(feat), _p(a), _p(b), _p(c), _p(d))
+    if Jt < 0:
+        raise RuntimeError(f"oracle approx_features failed rc={Jt}")
+    return a[:Jt].copy(), b[:Jt].copy(), c[:Jt].copy(), d[:Jt].copy()
+
+
+def integral_celerite(a, b, c, d, x):
+    return lib().orc_integral_celerite(a, b, c, d, x)
 
 
 def celerite_logl(a, b, c, d, t, y, s2, long_double=False):

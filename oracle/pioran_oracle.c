@@ -154,7 +154,7 @@ int orc_get_approx_coefficients(int model, const double *psd_par, double f0, dou
     return rc;
 }
 
-/* src/psd.jl:214-289 approx (continuum only, no QPO features — SURVEY §8c keeps features out of scope).
+/* src/psd.jl:214-289 approx, continuum only (orc_approx_features below adds the QPO feature branch).
  * Writes Jt = J (SHO) or 2J (DRWCelerite) celerite terms; returns Jt or a negative error. */
 int orc_approx(int model, const double *psd_par, double f_min, double f_max, int J, double norm,
                double S_low, double S_high, int is_integrated_power, int basis,
@@ -198,6 +198,75 @@ int orc_approx(int model, const double *psd_par, double f_min, double f_max, int
     }
     free(amp); free(fj);
     return Jt;
+}
+
+/* src/psd.jl:330-334 integral_celerite: antiderivative of the celerite PSD with coefficients (a, b, c, d) at x. */
+double orc_integral_celerite(double a, double b, double c, double d, double x)
+{
+    double num = c * c + (d + 2.0 * M_PI * x) * (d + 2.0 * M_PI * x);
+    double den = c * c + (d - 2.0 * M_PI * x) * (d - 2.0 * M_PI * x);
+    return (2.0 * a * (atan2(c, d - 2.0 * M_PI * x) - atan2(c, d + 2.0 * M_PI * x)) + b * log(num / den)) / (2.0 * M_PI);
+}
+
+/* src/psd.jl:214-289 approx with PSD features: continuum as in orc_approx plus nfeat QPO components feat[3k..] = (S0, f0, Q)
+ * (convert_feature :15-28; amplitudes divided by the continuum's normalisation :230-233; get_norm_psd with features :380-388;
+ * terms appended doubled :254-259, :277-282).  Writes Jt + nfeat terms; returns that count or a negative error. */
+int orc_approx_features(int model, const double *psd_par, double f_min, double f_max, int J, double norm,
+                        double S_low, double S_high, int is_integrated_power, int basis, int nfeat, const double *feat,
+                        double *a, double *b, double *c, double *d)
+{
+    double f0 = f_min / S_low, fM = f_max * S_high;
+    double *amp = (double *)malloc(sizeof(double) * J);
+    double *fj = (double *)malloc(sizeof(double) * J);
+    double *cf = (double *)malloc(sizeof(double) * 4 * (nfeat > 0 ? nfeat : 1));
+    if (!amp || !fj || !cf) { free(amp); free(fj); free(cf); return -2; }
+    int rc = orc_get_approx_coefficients(model, psd_par, f0, fM, J, basis, amp, fj);
+    if (rc) { free(amp); free(fj); free(cf); return rc; }
+    double psd_norm = orc_psd_eval(model, psd_par, fj[0]); /* :52-56 psd_zero */
+    for (int k = 0; k < nfeat; k++) { /* :15-28 */
+        double S0 = feat[3 * k], fq = feat[3 * k + 1], Q = feat[3 * k + 2];
+        double Delta = sqrt(4.0 * Q * Q - 1.0);
+        double w0 = 2.0 * M_PI * fq;
+        double ak = S0 * w0 * Q / 4.0;
+        double bk = ak / Delta;
+        double ck = w0 / Q / 2.0;
+        double dk = ck * Delta;
+        cf[4 * k] = ak / psd_norm; cf[4 * k + 1] = bk / psd_norm; cf[4 * k + 2] = ck; cf[4 * k + 3] = dk; /* :231-232 */
+    }
+    double integ;
+    if (is_integrated_power) { /* :376-388 */
+        integ = orc_integrate_basis(J, amp, fj, f_min, f_max, basis);
+        for (int k = 0; k < nfeat; k++)
+            integ += orc_integral_celerite(cf[4 * k], cf[4 * k + 1], cf[4 * k + 2], cf[4 * k + 3], f_max) -
+                     orc_integral_celerite(cf[4 * k], cf[4 * k + 1], cf[4 * k + 2], cf[4 * k + 3], f_min);
+    } else {
+        double s = 0.0;
+        for (int j = 0; j < J; j++) s += amp[j] * fj[j];
+        integ = (basis == ORC_BASIS_SHO) ? s * M_PI / sqrt(2.0) : s * 2.0 * M_PI / 3.0;
+    }
+    double scale = norm / integ;
+    for (int j = 0; j < J; j++) amp[j] *= scale;
+    for (int k = 0; k < nfeat; k++) { cf[4 * k] *= scale; cf[4 * k + 1] *= scale; } /* :241-242 */
+    int Jt;
+    if (basis == ORC_BASIS_SHO) {
+        for (int j = 0; j < J; j++) {
+            a[j] = amp[j] * fj[j] * M_PI / sqrt(2.0); b[j] = a[j];
+            c[j] = sqrt(2.0) * M_PI * fj[j]; d[j] = c[j];
+        }
+        Jt = J;
+    } else {
+        for (int j = 0; j < J; j++) {
+            double aj = amp[j] * fj[j] * M_PI / 3.0, cj = M_PI * fj[j];
+            a[j] = aj;     b[j] = sqrt(3.0) * aj; c[j] = cj;           d[j] = sqrt(3.0) * cj;
+            a[J + j] = aj; b[J + j] = 0.0;        c[J + j] = 2.0 * cj; d[J + j] = 0.0;
+        }
+        Jt = 2 * J;
+    }
+    for (int k = 0; k < nfeat; k++) { /* :254-259, :277-282 */
+        a[Jt + k] = 2.0 * cf[4 * k]; b[Jt + k] = 2.0 * cf[4 * k + 1]; c[Jt + k] = cf[4 * k + 2]; d[Jt + k] = cf[4 * k + 3];
+    }
+    free(amp); free(fj); free(cf);
+    return Jt + nfeat;
 }
 
 /* src/celerite_solver.jl:312-334 logl = :12-100 init_semi_separable! + :115-158 solve_prec!.

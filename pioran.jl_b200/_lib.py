@@ -34,6 +34,8 @@ SYMBOLS = {
     "pioran_series_free": (C.c_int, [C.c_void_p, C.c_int]),
     "pioran_series_length": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "pioran_approx_coeffs": (C.c_int, [C.c_void_p, C.POINTER(ApproxSpec), C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "pioran_approx_coeffs_features": (C.c_int, [C.c_void_p, C.POINTER(ApproxSpec), C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]),
+    "pioran_approx_features_logl": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ApproxSpec), C.c_int, C.c_int, _dp, _dp]),
     "pioran_celerite_logl": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "pioran_approx_logl": (C.c_int, [C.c_void_p, C.c_int, _ip, C.POINTER(ApproxSpec), C.c_int, _dp, C.c_int, _dp]),
     "pioran_approx_logl_logshift": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ApproxSpec), C.c_int, _dp, _dp]),

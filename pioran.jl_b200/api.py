@@ -49,6 +49,66 @@ class DoubleBendingPowerLaw(PowerSpectralDensity):
         return [self.α1, self.f1, self.α2, self.f2, self.α3]
 
 
+class QPO(PowerSpectralDensity):
+    """QPO(S₀, f₀, Q): Tonari.jl's Lorentzian feature (fields read by convert_feature, src/psd.jl:15-28; docs/src/adding_features.md)."""
+    model_name = "QPO"
+
+    def __init__(self, S0, f0, Q):
+        self.S0, self.f0, self.Q = float(S0), float(f0), float(Q)
+
+    def params(self):
+        return [self.S0, self.f0, self.Q]
+
+
+class SumOfPowerSpectralDensity(PowerSpectralDensity):
+    """𝓟₁ + 𝓟₂ + … (Tonari.jl): approx() splits it into ONE continuum and the narrow features (separate_psd, src/psd.jl:221)."""
+    model_name = "Sum"
+
+    def __init__(self, components):
+        self.components = list(components)
+
+    def params(self):
+        return [v for comp in self.components for v in comp.params()]
+
+
+def _psd_add(self, other):
+    if not isinstance(other, PowerSpectralDensity):
+        return NotImplemented
+    left = self.components if isinstance(self, SumOfPowerSpectralDensity) else [self]
+    right = other.components if isinstance(other, SumOfPowerSpectralDensity) else [other]
+    return SumOfPowerSpectralDensity(left + right)
+
+
+PowerSpectralDensity.__add__ = _psd_add
+
+
+def separate_psd(psd_model):
+    """(continuum, features) of a PSD model — features is None, or a list of QPO (src/psd.jl:221 uses Tonari's separate_psd)."""
+    comps = psd_model.components if isinstance(psd_model, SumOfPowerSpectralDensity) else [psd_model]
+    cont = [comp for comp in comps if not isinstance(comp, QPO)]
+    feats = [comp for comp in comps if isinstance(comp, QPO)]
+    if len(cont) > 1:
+        raise ValueError("only one continuum component can be approximated")
+    return (cont[0] if cont else None), (feats or None)
+
+
+def convert_feature(psd_feature):
+    """[a, b, c, d] of a PSD feature (src/psd.jl:15-28); only QPO is implemented, like the reference."""
+    if not isinstance(psd_feature, QPO):
+        raise ValueError(f"Feature {type(psd_feature).__name__} not implemented")
+    Δ = np.sqrt(4.0 * psd_feature.Q ** 2 - 1.0)
+    ω0 = 2.0 * np.pi * psd_feature.f0
+    a = psd_feature.S0 * ω0 * psd_feature.Q / 4.0
+    c = ω0 / psd_feature.Q / 2.0
+    return np.array([a, a / Δ, c, c * Δ])
+
+
+def get_covariance_from_psd(psd_features):
+    """4 × n matrix of the features' celerite coefficients (src/psd.jl:35-44)."""
+    feats = psd_features if isinstance(psd_features, (list, tuple)) else [psd_features]
+    return np.column_stack([convert_feature(f) for f in feats])
+
+
 # ----------------------------------------------------------------------------------------------- ACVF types
 class SemiSeparable:
     """src/acvf.jl: abstract semi-separable covariance."""
@@ -207,6 +267,16 @@ def approx(psd_model, f_min, f_max, n_components=20, norm=1.0, S_low=20.0, S_hig
     if not isinstance(psd_model, PowerSpectralDensity):
         raise TypeError("psd_model must be a PowerSpectralDensity")
     ctx = ctx or get_context()
+    continuum, features = separate_psd(psd_model)
+    if continuum is None:      # src/psd.jl:223
+        raise ValueError("The PSD model should contain at least one ContinuumPowerSpectrum component to be approximated")
+    if features is not None:
+        # continuum + QPO features (src/psd.jl:229-243, 254-259, 277-282): K1 appends one celerite term per feature
+        spec = make_spec(continuum.model_name, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
+        theta = np.array([continuum.params() + [float(norm)] + [v for f in features for v in f.params()]])
+        a, b, c, d = ctx.approx_coeffs_features(spec, len(features), theta)
+        return SumOfCelerite(a[0], b[0], c[0], d[0])
+    psd_model = continuum
     spec = make_spec(psd_model.model_name, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
     theta = np.array([psd_model.params() + [float(norm)]])
     a, b, c, d = ctx.approx_coeffs(spec, theta)
@@ -411,7 +481,12 @@ class BatchedLikelihood:
     The series (and its trig/exp table) is uploaded once; each call runs K1 + K2 on the whole batch."""
 
     def __init__(self, t, y, σ2, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
-                 f_min=None, f_max=None, S_low=20.0, S_high=20.0, is_integrated_power=True, ctx=None, log_shift=False):
+                 f_min=None, f_max=None, S_low=20.0, S_high=20.0, is_integrated_power=True, ctx=None, log_shift=False,
+                 n_features=0):
+        # n_features: Θ rows end with (S₀, f₀, Q) per QPO feature added to the continuum (docs/src/adding_features.md)
+        self.n_features = int(n_features)
+        if self.n_features and log_shift:
+            raise ValueError("PSD features and the log-shift transform cannot be combined in one fused call")
         # log_shift: Θ rows carry a 7th column c and the data enter as yn = log(y − c), σ² = ν σ²/(y − c)²
         # (docs/src/ultranest.md:197-217); t, y, σ2 are then the untransformed flux and its measurement variance
         self.log_shift = bool(log_shift)
@@ -425,10 +500,12 @@ class BatchedLikelihood:
             psd_model = psd_model.model_name
         self.spec = make_spec(psd_model, f_min, f_max, n_components, S_low, S_high, is_integrated_power, basis_function)
         self.series = self.ctx.upload_series(t, y, σ2)
-        self.n_par = backend.N_PSD_PAR[self.spec.psd_model] + 3 + int(self.log_shift)
+        self.n_par = backend.N_PSD_PAR[self.spec.psd_model] + 3 + int(self.log_shift) + 3 * self.n_features
 
     def __call__(self, theta):
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if self.n_features:
+            return self.ctx.approx_features_logl(self.series, self.spec, self.n_features, theta)
         if self.log_shift:
             return self.ctx.approx_logl_logshift(self.series, self.spec, theta)
         return self.ctx.approx_logl(self.series, self.spec, theta)[0]

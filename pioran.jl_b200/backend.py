@@ -122,6 +122,29 @@ class Context:
         check(self.lib.pioran_approx_coeffs(self.h, C.byref(spec), B, _p(theta), *[_p(o) for o in out]))
         return tuple(out)
 
+    def approx_coeffs_features(self, spec, n_features, theta):
+        """theta [B × (n_psd_par + 1 + 3·n_features)] = psd parameters…, norm, (S₀, f₀, Q)… → (a, b, c, d) each
+        [B × (Jt + n_features)]  (src/psd.jl:214-289 with separate_psd features)."""
+        theta = np.atleast_2d(_f64(theta))
+        npar = N_PSD_PAR[spec.psd_model]
+        if theta.shape[1] != npar + 1 + 3 * n_features:
+            raise ValueError(f"theta must have {npar + 1 + 3 * n_features} columns")
+        B = theta.shape[0]
+        Jt = spec.n_components * (1 if spec.basis == 0 else 2) + n_features
+        out = [np.empty((B, Jt)) for _ in range(4)]
+        check(self.lib.pioran_approx_coeffs_features(self.h, C.byref(spec), int(n_features), B, _p(theta), *[_p(o) for o in out]))
+        return tuple(out)
+
+    def approx_features_logl(self, series, spec, n_features, theta):
+        """theta rows = [psd parameters…, norm, ν, μ, (S₀, f₀, Q)…] → logL [B]."""
+        theta = np.atleast_2d(_f64(theta))
+        npar = N_PSD_PAR[spec.psd_model]
+        if theta.shape[1] != npar + 3 + 3 * n_features:
+            raise ValueError(f"theta must have {npar + 3 + 3 * n_features} columns")
+        out = np.empty(theta.shape[0])
+        check(self.lib.pioran_approx_features_logl(self.h, series.id, C.byref(spec), int(n_features), theta.shape[0], _p(theta), _p(out)))
+        return out
+
     # -- K2 generic
     def celerite_logl(self, series, a, b, c, d, mu=None, nu=None, y_batch=None, s2_batch=None):
         """Batched logl(a,b,c,d,τ,y,σ2) (src/celerite_solver.jl:312-334); coefficient arrays [B × Jt]."""

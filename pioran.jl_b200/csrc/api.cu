@@ -1449,6 +1449,82 @@ static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const do
     return PIORAN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ PSD features (QPO)
+// approx() of a continuum + QPO features (src/psd.jl:15-44, 221-243, 254-259, 277-282): K1 emits the Jt continuum terms followed
+// by one celerite term per feature; their decay rates and frequencies depend on θ, so the sweep is the generic kernel.
+static int approx_features_dev(pioran_ctx* c, const pioran_approx_spec* spec, int nf, int B, const double* theta, int ts,
+                               int feat_off, int* Jout) {
+    int rc;
+    if ((rc = check_spec(*spec))) return rc;
+    if (nf < 1 || nf > MAXFEAT) return fail(PIORAN_EINVAL, "n_features must be in [1, %d] (got %d)", MAXFEAT, nf);
+    ApproxPlan* plan;
+    if ((rc = get_plan(c, *spec, &plan))) return rc;
+    const int Jt = (spec->basis == PIORAN_BASIS_SHO ? spec->n_components : 2 * spec->n_components) + nf;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * ts))) return rc;
+    if ((rc = c->coef.ensure(sizeof(double) * (size_t)B * Jt * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * (size_t)B * ts, cudaMemcpyHostToDevice, c->stream));
+    double* da = c->coef.as<double>();
+    const size_t n = (size_t)B * Jt;
+    approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, c->theta.as<double>(), ts, da, da + n, da + 2 * n, da + 3 * n,
+                                                         nullptr, 0, nullptr, nf, feat_off);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    *Jout = Jt;
+    return 0;
+}
+
+extern "C" int pioran_approx_coeffs_features(pioran_ctx* c, const pioran_approx_spec* spec, int n_features, int B,
+                                             const double* theta, double* a, double* b, double* cc, double* d) try {
+    if (!c || !spec || !theta || !a || !b || !cc || !d) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    if (is_group(c)) return pioran_approx_coeffs_features(c->children[0], spec, n_features, B, theta, a, b, cc, d);
+    PIORAN_COMPUTE_LOCK(c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int npar = n_psd_par_of(spec->psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+    int Jt, rc;
+    if ((rc = approx_features_dev(c, spec, n_features, B, theta, npar + 1 + 3 * n_features, npar + 1, &Jt))) return rc;
+    const size_t n = (size_t)B * Jt;
+    const double* da = c->coef.as<double>();
+    CUDA_TRY(cudaMemcpyAsync(a, da, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(b, da + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(cc, da + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d, da + 3 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
+extern "C" int pioran_approx_features_logl(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int n_features, int B,
+                                           const double* theta, double* logl_out) try {
+    if (!c || !spec || !theta || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    const int npar = n_psd_par_of(spec->psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+    const int ts = npar + 3 + 3 * n_features;
+    if (is_group(c)) {
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            return pioran_approx_features_logl(c->children[k], cid[k], spec, n_features, nb, theta + (size_t)beg * ts, logl_out + beg);
+        });
+    }
+    PIORAN_COMPUTE_LOCK(c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    int Jt, rc;
+    if ((rc = approx_features_dev(c, spec, n_features, B, theta, ts, npar + 3, &Jt))) return rc;
+    // coefficients back to the host (B × Jt × 4 doubles: a few hundred KB for a sampler's batch), then the generic sweep
+    const size_t n = (size_t)B * Jt;
+    std::vector<double> co(4 * n), mu(B), nu(B);
+    CUDA_TRY(cudaMemcpyAsync(co.data(), c->coef.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < B; i++) { nu[i] = theta[(size_t)i * ts + npar + 1]; mu[i] = theta[(size_t)i * ts + npar + 2]; }
+    return generic_logl_locked(c, s, B, Jt, co.data(), co.data() + n, co.data() + 2 * n, co.data() + 3 * n, mu.data(), nu.data(),
+                               nullptr, nullptr, logl_out);
+} catch (...) { return guard_fail(); }
+
 // ------------------------------------------------------------------------------------------------ posterior mean, draws
 // Common set-up of the two widening entries: coefficient upload, row map, work items for the generic kernel.
 static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* a, const double* b, const double* cc,

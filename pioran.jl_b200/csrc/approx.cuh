@@ -57,10 +57,22 @@ __device__ __forceinline__ double basis_integral(int basis, int J, const double*
 //   a,b,c,d   : [B × Jt] celerite coefficients in the reference's order (src/psd.jl:247-275)
 //   amp_rows  : [B × RP] row amplitudes for the shared-table kernel, rows as built by make_rows()
 //   suma      : [B] Σ_terms a  (celerite_solver.jl:21)
+// PSD features (src/psd.jl:15-44, 229-243): nfeat QPO components (S₀, f₀, Q) per θ, read from theta[feat_off + 3k …]; each
+// becomes one more celerite term after the Jt continuum terms (output rows then have Jt + nfeat entries).  nfeat = 0: continuum only.
+constexpr int MAXFEAT = 8;
+
+// ∫ of the celerite PSD with coefficients (a, b, c, d) (src/psd.jl:330-334)
+__device__ __forceinline__ double integral_celerite(double a, double b, double c, double d, double x) {
+    const double TWO_PI = 6.283185307179586;
+    const double num = c * c + (d + TWO_PI * x) * (d + TWO_PI * x);
+    const double den = c * c + (d - TWO_PI * x) * (d - TWO_PI * x);
+    return (2.0 * a * (atan2(c, d - TWO_PI * x) - atan2(c, d + TWO_PI * x)) + b * log(num / den)) / TWO_PI;
+}
+
 __global__ void approx_kernel(const ApproxPlan* __restrict__ plan, int B, const double* __restrict__ theta, int tstride,
                               double* __restrict__ a, double* __restrict__ b, double* __restrict__ c,
                               double* __restrict__ d, double* __restrict__ amp_rows, int RP,
-                              double* __restrict__ suma) {
+                              double* __restrict__ suma, int nfeat = 0, int feat_off = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const ApproxPlan& P = *plan;
@@ -93,7 +105,26 @@ __global__ void approx_kernel(const ApproxPlan* __restrict__ plan, int B, const 
         for (int j = 0; j < J; j++) s += x[j] * P.fj[j];
         integ = (P.basis == 0) ? s * 3.141592653589793 / 1.4142135623730951 : s * 2.0 * 3.141592653589793 / 3.0;
     }
+    // features: convert_feature (src/psd.jl:15-28), amplitudes divided by the continuum's normalisation (:230-233), their
+    // integrals added to the norm (:380-388; only when the norm is the integrated power)
+    double fa[MAXFEAT], fb[MAXFEAT], fc[MAXFEAT], fd[MAXFEAT];
+    for (int k = 0; k < nfeat; k++) {
+        const double S0 = th[feat_off + 3 * k], f0q = th[feat_off + 3 * k + 1], Q = th[feat_off + 3 * k + 2];
+        const double dl = sqrt(4.0 * Q * Q - 1.0);
+        const double w0 = 2.0 * 3.141592653589793 * f0q;
+        const double ak = S0 * w0 * Q / 4.0;
+        fa[k] = ak / p0; fb[k] = (ak / dl) / p0;
+        fc[k] = w0 / Q / 2.0; fd[k] = fc[k] * dl;
+        if (P.is_integrated_power)
+            integ += integral_celerite(fa[k], fb[k], fc[k], fd[k], P.f_max) - integral_celerite(fa[k], fb[k], fc[k], fd[k], P.f_min);
+    }
     const double scale = th[P.n_psd_par] / integ;
+    const int Jout = (P.basis == 0 ? J : 2 * J) + nfeat;     // entries per output row
+    if (a)
+        for (int k = 0; k < nfeat; k++) {                     // src/psd.jl:254-259, 277-282
+            const size_t q = (size_t)i * Jout + (Jout - nfeat) + k;
+            a[q] = 2.0 * (fa[k] * scale); b[q] = 2.0 * (fb[k] * scale); c[q] = fc[k]; d[q] = fd[k];
+        }
     const double PI = 3.141592653589793, S2 = 1.4142135623730951, S3 = 1.7320508075688772;
     double sa = 0.0;
     if (P.basis == 0) {  // SHO: a = b = A f π/√2, c = d = √2 π f   (src/psd.jl:249-252)
@@ -101,7 +132,7 @@ __global__ void approx_kernel(const ApproxPlan* __restrict__ plan, int B, const 
             const double aj = (x[j] * scale) * P.fj[j] * PI / S2;
             sa += aj;
             if (a) {
-                const size_t k = (size_t)i * J + j;
+                const size_t k = (size_t)i * Jout + j;
                 a[k] = aj; b[k] = aj; c[k] = S2 * PI * P.fj[j]; d[k] = S2 * PI * P.fj[j];
             }
             if (amp_rows) { amp_rows[(size_t)i * RP + 2 * j] = aj; amp_rows[(size_t)i * RP + 2 * j + 1] = aj; }
@@ -112,7 +143,7 @@ __global__ void approx_kernel(const ApproxPlan* __restrict__ plan, int B, const 
             const double aj = (x[j] * scale) * P.fj[j] * PI / 3.0;
             const double cj = PI * P.fj[j];
             if (a) {
-                const size_t k = (size_t)i * 2 * J + j, k2 = k + J;
+                const size_t k = (size_t)i * Jout + j, k2 = k + J;
                 a[k] = aj;  b[k] = S3 * aj; c[k] = cj;        d[k] = S3 * cj;
                 a[k2] = aj; b[k2] = 0.0;    c[k2] = 2.0 * cj; d[k2] = 0.0;
             }
