@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--B", type=int, default=65536, help="parameter vectors per GPU per step")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (SHO headline, config C2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--single-process", action="store_true",
+                    help="ONE process drives --gpus N devices through a device-group context (pioran_ctx_create_multi): "
+                         "end-to-end host-pointer call only; not the driver's contract line (that one is torchrun, one rank per GPU)")
     return ap.parse_args()
 
 
@@ -121,9 +124,9 @@ def hbm_peak_gbs():
 
 def k2_traffic_bytes(basis, B, N):
     """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch of this shape, from the committed `ncu --set full`
-    capture (profiles/r01_k2_traffic.json, written by tools/ncu_summary.py); None when no capture matches the shape."""
+    capture (profiles/r02_k2_traffic.json, written by tools/ncu_summary.py); None when no capture matches the shape."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_k2_traffic.json")) as f:
             d = json.load(f)
         e = d.get(f"{basis}_B{B}_N{N}")
         return float(e["dram_bytes"]) if e else None
@@ -158,11 +161,37 @@ def cpu_leg(t, y, s2, f_min, f_max, J, basis, theta, target_s, steps=1, warmup=0
         orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
+        ref = orc.approx_logl_batch("SBPL", theta[:n], f_min, f_max, J, t, y, s2, basis=basis, nthreads=cores)
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "value_per_core": n * steps / dt / cores, "kind": "port",
+            "sample_evals_per_step": n,
             "sample": f"{n} of the step's parameter vectors per step x {steps} step(s), {dt:.1f} s, OpenMP over theta on "
-                      f"{cores} threads; C restatement of Pioran.jl approx+logl (Julia is not installed on this image)"}, dt / steps
+                      f"{cores} threads; C restatement of Pioran.jl approx+logl (Julia is not installed on this image)"}, dt / steps, ref
+
+
+def parity_of_sample(got, ref, theta, f_min, f_max, J, basis, t, y, s2, tol=1e-9, slack=4.0):
+    """|gpu − cpu| / max(1, |cpu|) over a whole CPU sample, with the rows beyond `tol` triaged like tests/conftest.assert_parity:
+    a row counts as a conditioning exemption when the reference-order FP64 value is itself farther than tol/slack from the
+    80-bit evaluation of the same recursion and the GPU value is within slack × that distance; anything else is a failure."""
+    from oracle import oracle as orc
+    ok = np.isfinite(ref)
+    r = np.abs(got[ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))
+    bad = np.flatnonzero(ok)[r > tol]
+    exempt = failed = 0
+    for i in bad[:256]:
+        a, b, c, d = orc.approx("SBPL", theta[i, :3], f_min, f_max, J, theta[i, 3], basis=basis)
+        ld = float(orc.celerite_logl(a, b, c, d, t, y - theta[i, 5], theta[i, 4] * s2, long_double=True))
+        e_ref = abs(ref[i] - ld) / max(1.0, abs(ld))
+        e_gpu = abs(got[i] - ld) / max(1.0, abs(ld))
+        if e_ref > tol / slack and e_gpu <= slack * e_ref:
+            exempt += 1
+        else:
+            failed += 1
+    return {"parity_rows": int(ok.sum()), "parity_max_rel": float(r.max()) if r.size else None,
+            "parity_median_rel": float(np.median(r)) if r.size else None, "rows_beyond_1e-9": int(len(bad)),
+            "rows_exempt_by_conditioning": int(exempt), "rows_failed": int(failed),
+            "parity_rule": "|gpu-cpu|/max(1,|cpu|) <= 1e-9, or (conditioning) the FP64 reference-order value is itself > 2.5e-10 from "
+                           "the 80-bit twin and the GPU value within 4x that distance"}
 
 
 def run_reference(args, rank, world):
@@ -172,11 +201,13 @@ def run_reference(args, rank, world):
     t, y, s2, f_min, f_max, theta = build_workload(args.N, args.J, args.basis, min(args.B, 8192), 1234, 42)
     # each step ≈ 60 s / (steps + warmup) of CPU work so the whole run ends within a few minutes
     target = max(1.0, 60.0 / max(1, args.steps + args.warmup))
-    cb, per_step = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, target, steps=args.steps, warmup=args.warmup)
+    cb, per_step, _ = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, target, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, R), "cpu_baseline": cb,
+            "config": dict(workload_config(args, R), reference_sample_evals_per_step=cb["sample_evals_per_step"],
+                           note="the CPU arm times a bounded sample of the step's parameter vectors (a rate, not the whole batch)"),
+            "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -327,6 +358,33 @@ def config_c1_and_sampler_call(ctx, pb, J):
                 got = like(th[:B])
                 best = min(best, time.perf_counter() - t0)
             row[name + "_wall_ms"] = best * 1e3
+        # the B = 1 drop-in a `:celerite_gpu` solver symbol makes per logpdf call (julia/b200_solver.jl: logl_b200): explicit
+        # coefficients, y − μ and ν σ² as fresh host arrays.  (a) time vector resident between calls, (b) everything uploaded
+        # and freed per call, (c) the first fused call of a run, which also builds the series' block table.
+        cov = pb.approx(pb.SingleBendingPowerLaw(*th[0, :3]), f_min, f_max, J, th[0, 3], basis_function=basis, ctx=ctx)
+        ca, cb, cc, cd = pb.celerite_coefs(cov)
+        yy, ss = y - th[0, 5], th[0, 4] * s2
+        pb.api.release_resident_series()
+        pb.log_likelihood(cov, t, yy, ss, ctx=ctx)
+        best_res = best_up = 1e30
+        for _ in range(20):
+            t0 = time.perf_counter()
+            v_res = pb.log_likelihood(cov, t, yy, ss, ctx=ctx)
+            best_res = min(best_res, time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            ser1 = ctx.upload_series(t, yy, ss)
+            v_up = ctx.celerite_logl(ser1, ca, cb, cc, cd)[0]
+            ser1.free()
+            best_up = min(best_up, time.perf_counter() - t0)
+        pb.api.release_resident_series()
+        t0 = time.perf_counter()
+        like1 = pb.BatchedLikelihood(t + 1e-9, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+        v_first = like1(th[:1])[0]
+        row["first_fused_call_incl_upload_and_table_build_ms"] = (time.perf_counter() - t0) * 1e3
+        like1.close()
+        row["dropin_B1_resident_time_vector_ms"] = best_res * 1e3
+        row["dropin_B1_upload_per_call_ms"] = best_up * 1e3
+        row["dropin_B1_agrees_with_fused"] = float(abs(v_res - got[0]) / max(1.0, abs(got[0]))) if B >= 1 else None
         t0 = time.perf_counter()
         ref = orc.approx_logl_batch("SBPL", th[:4], f_min, f_max, J, t, y, s2, basis=basis, nthreads=1)
         row["cpu_port_1thread_ms_per_eval"] = (time.perf_counter() - t0) * 1e3 / 4
@@ -480,6 +538,44 @@ def sharded_configs(torch, dist, ctx, pb, J, rank, world):
     return out
 
 
+def strong_scaling(torch, ctx, pb, J, rank, world, dist=None):
+    """Sampler-sized batches at FIXED total size, split over the ranks (what a nested sampler sees when it adds GPUs):
+    BASELINE configs[1] (4 096 live points x N = 10 000, DRWCelerite) and one 400-live-point call (N = 1 000).  Device time of
+    the slice's call plus the all-gather of logL, CUDA events on the launching stream, max over ranks, best of 5."""
+    out = {}
+    for name, N2, Btot, seed in (("C2_4096theta_N10000_DRWCelerite", 10000, 4096, 1235), ("call_400_live_points_N1000_DRWCelerite", 1000, 400, 1234)):
+        t, y, s2, f_min, f_max, theta_all = build_workload(N2, J, "DRWCelerite", Btot, seed, 42)
+        lo, hi = Btot * rank // world, Btot * (rank + 1) // world
+        theta = np.ascontiguousarray(theta_all[lo:hi])
+        spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function="DRWCelerite")
+        ser = ctx.upload_series(t, y, s2)
+        th_dev = torch.from_numpy(theta).cuda()
+        bmax = -(-Btot // world)
+        out_dev = torch.full((bmax,), float("nan"), dtype=torch.float64, device="cuda")
+        gathered = torch.empty(bmax * world, dtype=torch.float64, device="cuda") if world > 1 else None
+        best = 1e30
+        for it in range(7):
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ctx.approx_logl_dev([ser], [spec], hi - lo, th_dev.data_ptr(), out_dev.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out_dev)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                best = min(best, e0.elapsed_time(e1))
+        if world > 1:
+            tt = torch.tensor([best], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            best = float(tt.item())
+        ser.free()
+        out[name] = {"total_evals": Btot, "n_gpus": world, "ms": best, "evals_per_s": Btot / (best * 1e-3), "scaling": "strong"}
+    return out
+
+
+
 def widening_rows(ctx, pb, J):
     """SURVEY 8f #1/#2/#3 next to the hot path: gradients (4 096 θ × 6 directions), batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
@@ -534,6 +630,34 @@ def widening_rows(ctx, pb, J):
         out[f"simulate_4096theta_N1000_{basis}"] = {"draws_per_s": 4096 / (ms_s * 1e-3), "device_ms": ms_s,
                                                     "cpu_port_1thread_draws_per_s": 1.0 / cpu_s, "parity_max_rel_4": serr}
     return out
+
+
+def run_single_process(args):
+    """One process, one context over args.gpus devices (include/pioran_b200.h: pioran_ctx_create_multi): the headline batch of
+    B x gpus parameter vectors goes through the host-pointer entry, which cuts it into one slice per device.  Wall-clock time
+    around the call (the call synchronises), best-effort pinned host buffers via torch."""
+    import torch
+    import pioran_b200 as pb
+    ndev = args.gpus
+    ctx = pb.Context(list(range(ndev)))
+    R = wl.rank_of(args.basis, args.J)
+    t, y, s2, f_min, f_max, theta = build_workload(args.N, args.J, args.basis, args.B * ndev, 1234, 42)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, args.J, basis_function=args.basis)
+    ser = ctx.upload_series(t, y, s2)
+    th = torch.from_numpy(theta).pin_memory().numpy()
+    for _ in range(args.warmup):
+        ctx.approx_logl(ser, spec, th)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = ctx.approx_logl(ser, spec, th)[0]
+    dt = time.perf_counter() - t0
+    line = {"metric": METRIC, "mode": "single-process device group", "value": args.B * ndev * args.steps / dt, "unit": UNIT,
+            "n_gpus": ndev, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "dtype": "f64", "data": "synthetic", "config": workload_config(args, R),
+            "e2e": {"value": args.B * ndev * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(th.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
+            "kernel_ms_slowest_device": ctx.last_kernel_ms(), "finite_frac": float(np.isfinite(out).mean()),
+            "note": "wall clock around pioran_approx_logl on a group context; compare with the e2e of the torchrun line at the same N"}
+    emit(line)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -599,6 +723,8 @@ def run_b200(args, rank, world, local_rank):
 
     if not args.no_extra and world > 1:
         extra.update(sharded_configs(torch, dist, ctx, pb, args.J, rank, world))
+    if not args.no_extra:
+        extra["strong_scaling"] = strong_scaling(torch, ctx, pb, args.J, rank, world, dist if dist_on else None)
 
     if not args.no_extra and world == 1:
         extra["C3_512series_x_400theta_SHO"] = config_c3(torch, ctx, pb, args.J, peak)
@@ -609,12 +735,9 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, 15.0)
-        # spot parity of the timed batch against the same CPU code (full parity lives in tests/)
-        from oracle import oracle as orc
-        ref = orc.approx_logl_batch("SBPL", theta[:64], f_min, f_max, args.J, t, y, s2, basis=args.basis, nthreads=0)
-        ok = np.isfinite(ref)
-        cpu["parity_max_rel_64"] = float(np.max(np.abs(m["out"][:64][ok] - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))))
+        cpu, _, ref = cpu_leg(t, y, s2, f_min, f_max, args.J, args.basis, theta, 15.0)
+        # parity of the timed batch against the same CPU code over the WHOLE CPU sample (full parity lives in tests/)
+        cpu.update(parity_of_sample(m["out"][:len(ref)], ref, theta, f_min, f_max, args.J, args.basis, t, y, s2))
 
     traffic = k2_traffic_bytes(args.basis, args.B, args.N)
     try:
@@ -637,10 +760,12 @@ def run_b200(args, rank, world, local_rank):
                                 + (" + NCCL all-gather + D2H of the gathered vector" if dist_on else "") + " per step; series resident (uploaded once per sampler run)"},
                 "gpu_launches": int(m["launches"]),
                 "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                             "traffic": traffic, "hbm": hbm_view, "kernel": "celerite_shared_kernel (K2)", "kernel_ms": k2_ms,
+                             "traffic": traffic, "hbm": hbm_view, "kernel": "celerite_blocked_kernel (K2t, FP64 mma.sync)", "kernel_ms": k2_ms,
                              "flops_per_launch": flops_launch,
-                             "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d)", "peak_source": peak_src,
-                             "note": "FP64-pipe bound: the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},
+                             "flop_model": "B x N x (4R^2 + 13R + 40), FMA = 2 (SURVEY 8d) - the ALGORITHMIC count of the reference recursion; "
+                                           "the blocked kernel executes about 1.1x that (DESIGN.md 4, K2t)",
+                             "peak_source": peak_src,
+                             "note": "FP64 pipe bound (DMMA + DFMA share it): the path reads 24 N bytes per series shared by the whole batch; HBM traffic is negligible (see DESIGN.md)"},
                 "cpu_baseline": cpu, "clocks": clocks, "finite_frac": finite, "extra": extra}
         emit(line)
     if dist_on:
@@ -671,6 +796,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.single_process and args.impl == "b200":
+        run_single_process(args)
+        return
     if world == 1 and args.gpus > 1 and args.impl == "b200":
         # launched without torchrun: re-exec under torch.distributed.run
         port = 29500 + (os.getpid() % 2000)

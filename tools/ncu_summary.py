@@ -49,14 +49,14 @@ print("opcode mix per warp-step (executed | % of stall samples):")
 for op, n in ops.most_common(16):
     print(f"  {op:10s} {n / wsteps:7.2f} | {100 * samp[op] / tot:5.1f}")
 
-# optional third argument: key under which the DRAM traffic of this launch is recorded in profiles/r01_k2_traffic.json
+# optional third argument: key under which the DRAM traffic of this launch is recorded in profiles/r02_k2_traffic.json
 if len(sys.argv) > 3:
     import json, os
     def num(k):
         v, u = m.get(k, "0").replace(",", ""), hdr_units.get(k, "")
         f = float(v or 0)
         return f * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_k2_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_k2_traffic.json")
     try:
         d = json.load(open(path))
     except Exception:
