@@ -20,6 +20,10 @@ print(f"# {rep}")
 for k in keys:
     if k in m:
         print(f"{k}: {m[k]}")
+# FP64 mma.sync (DMMA) is counted on the tensor pipe, not on pipe_fp64; both feed the same FP64 datapath (tools/fp64_peak.cu)
+for k in hdr:
+    if ("pipe_tensor" in k or "dmma" in k) and m.get(k) not in (None, "", "0"):
+        print(f"{k}: {m[k]}")
 wf = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "0").replace(",", "") or 0)
 ld = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "0").replace(",", "") or 0)
 stw = float(m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum", "0").replace(",", "") or 0)
