@@ -25,6 +25,7 @@
 #include "table.cuh"
 #include "grad.cuh"
 #include "grad_pipe.cuh"
+#include "blocked_grad.cuh"
 #include "wide.cuh"
 
 using namespace pioran;
@@ -571,6 +572,7 @@ static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Ta
         rows[blk_phys_row(r, R)] = rd;
     }
     rows[blk_phys_row(R, R)] = RowDesc{0, 0, 0, ROW_AUG, 0};
+    if (blk_phys_row2(R) >= 0) rows[blk_phys_row2(R)] = RowDesc{0, 0, 0, ROW_AUG2, 0};   // ∂/∂μ row of the gradient kernel
     int rc = c->rows.ensure(sizeof(RowDesc) * RPT);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->rows.p, rows.data(), sizeof(RowDesc) * RPT, cudaMemcpyHostToDevice, c->stream));
@@ -1230,6 +1232,44 @@ template <int BS>
 static int launch_grad(pioran_ctx* c, const GradArgs& args, int nitems, int tpi) {
     return tpi <= SMALL_NW ? launch_grad_nw<BS, SMALL_NW>(c, args, nitems) : launch_grad_nw<BS, GRAD_NW>(c, args, nitems);
 }
+// K5t (blocked_grad.cuh): one CTA per parameter vector, value warp + one tangent warp per direction, all on the tensor pipe
+template <int NT, int NTR, bool HALF, int NTAN>
+static int launch_blocked_grad(pioran_ctx* c, const GradArgs& args, int nitems, int R, int amp_stride) {
+    auto kern = celerite_blocked_grad_kernel<NT, NTR, HALF, NTAN>;
+    const size_t smem = sizeof(double) * ((size_t)BLK_NSTAGE * blk_doubles(NT, NTR) + 2 * (size_t)blk_slot_doubles(NTR) +
+                                          (size_t)(1 + NTAN) * (8 * NTR + 8 * NT) + 2) + BLK_NSTAGE * sizeof(uint64_t) + 16;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, (1 + NTAN) * 32, smem, c->stream>>>(args, R, amp_stride);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+template <int NTAN>
+static int dispatch_blocked_grad(pioran_ctx* c, const GradArgs& a, int nitems, int R, int amp_stride) {
+    const int NT = blk_nt(R);
+    const bool xrow = blk_ntr(R) != NT, half = blk_half(R);
+#define PIORAN_BLKG_CASE(nt)                                                                                    \
+    case nt: return xrow ? launch_blocked_grad<nt, nt + 1, false, NTAN>(c, a, nitems, R, amp_stride)            \
+                  : half ? launch_blocked_grad<nt, nt, true, NTAN>(c, a, nitems, R, amp_stride)                 \
+                         : launch_blocked_grad<nt, nt, false, NTAN>(c, a, nitems, R, amp_stride);
+    switch (NT) {
+        PIORAN_BLKG_CASE(1) PIORAN_BLKG_CASE(2) PIORAN_BLKG_CASE(3) PIORAN_BLKG_CASE(4)
+        PIORAN_BLKG_CASE(5) PIORAN_BLKG_CASE(6) PIORAN_BLKG_CASE(7)
+        case 8:
+            if (xrow) break;
+            return half ? launch_blocked_grad<8, 8, true, NTAN>(c, a, nitems, R, amp_stride)
+                        : launch_blocked_grad<8, 8, false, NTAN>(c, a, nitems, R, amp_stride);
+    }
+#undef PIORAN_BLKG_CASE
+    return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the blocked gradient kernel", R);
+}
+static bool blocked_grad_enabled(const pioran_ctx* c, int R, int ND) {
+    return blocked_enabled(c, R) && blk_phys_row2(R) >= 0 && (ND == 3 || ND == 5);
+}
+
 static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                        const double* theta_dev, double* logl_dev, double* grad_dev) {
     int rc;
@@ -1243,8 +1283,9 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     const int BS = bs_for_rank(R);
     if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
     const int RP = G * BS;
+    const bool blkg = blocked_grad_enabled(c, R, ND);
     Table tab;
-    if ((rc = get_table(c, ser, *spec, &tab))) return rc;
+    if ((rc = blkg ? get_btable(c, ser, *spec, &tab) : get_table(c, ser, *spec, &tab))) return rc;
     ApproxPlan* plan;
     if ((rc = get_plan(c, *spec, &plan))) return rc;
     // workspace: amp [B×RP] | damp [B×ND×RP] | Σa [B] | dΣa [B×ND]
@@ -1259,10 +1300,10 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     // one warp per (θ, direction): the work items run over the virtual batch of B·(n_psd_par + 1) entries
-    const bool pipe = BS >= 6;   // one CTA per parameter vector: value warp + tangent-only warps (grad_pipe.cuh)
+    const bool pipe = blkg || BS >= 6;   // one CTA per parameter vector: value warp + tangent-only warps (blocked_grad.cuh, grad_pipe.cuh)
     const int PW = pipe ? 1 : ND + 1;    // work-item entries per parameter vector (warps: psd parameters…, ν; ∂/∂μ rides along,
                                          // ∂/∂norm follows from ∂/∂ν)
-    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS, (int64_t)pipe};
+    const std::vector<int64_t> key = {(int64_t)(intptr_t)tab.d, (int64_t)(intptr_t)ser->t, ser->N, (int64_t)B * PW, BS, (int64_t)pipe + 2 * (int64_t)blkg};
     if (key != c->gwork_key) {
         ItemPlan ip;
         Series* sp[1] = {ser};
@@ -1282,6 +1323,7 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     ga.theta = theta_dev; ga.pstride = ts; ga.ND = ND;
     ga.logl = logl_dev; ga.grad = grad_dev;
     const int nitems = c->gwork_items;
+    if (blkg) return ND == 3 ? dispatch_blocked_grad<4>(c, ga, nitems, R, RP) : dispatch_blocked_grad<6>(c, ga, nitems, R, RP);
     if (pipe) {
         const int nwarps = 1 + ND + 1;
         if (nwarps == 5) {

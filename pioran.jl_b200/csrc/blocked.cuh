@@ -36,6 +36,7 @@ namespace pioran {
 constexpr int BLK = 8;            // steps per block
 constexpr int BLK_NSTAGE = 3;     // TMA stages (one block each)
 constexpr int ROW_AUG = 4;        // RowKind of the augmented (data) row
+constexpr int ROW_AUG2 = 5;       // second data row, right-hand side −1 per step: its innovations are ∂z/∂μ (gradient kernel)
 
 // Rows of the blocked state: R celerite rows + the augmented row RG = R.  NT = tiles that carry celerite rows (columns of
 // the state), NTR = row tiles (NT, or NT+1 when R is a multiple of 8 and the augmented row needs a tile of its own).
@@ -57,6 +58,14 @@ __host__ __device__ constexpr int blk_phys_row(int r, int R) {          // logic
     return r == R ? base + 1 : base + 2 * (r - base);
 }
 __host__ __device__ constexpr int pair_slot(int s, int sp) { return s * (s - 1) / 2 + sp; }   // s > sp
+
+// Physical row of the second data row (blocked_grad.cuh), or −1 when the last tile has no free row left (R ≡ 7 mod 8).
+__host__ __device__ constexpr int blk_phys_row2(int R) {
+    const int base = 8 * ((R + 7) / 8 - 1);
+    if (R % 8 == 0) return R + 1;                 // the data rows have a tile of their own
+    if (blk_half(R)) return base + 3;
+    return (R % 8 == 7) ? -1 : R + 1;
+}
 
 // ------------------------------------------------------------------------------------------- K0b: block table
 // One thread per (block, physical row).  rows[] describes the 8·NTR physical rows (ROW_PAD where nothing lives, ROW_AUG at the
@@ -80,6 +89,7 @@ __global__ void blocked_table_kernel(double* __restrict__ table, const double* _
         if (rd.kind == ROW_PAD) { ph[s] = 0.0; continue; }
         if (n >= N) continue;                         // padded step: no decay, no coupling
         if (rd.kind == ROW_AUG) { vv[s] = y[n]; continue; }
+        if (rd.kind == ROW_AUG2) { vv[s] = -1.0; continue; }
         const double tn = t[n];
         ph[s] = (n >= 1) ? exp(-rd.c * (tn - t[n - 1])) : 0.0;      // celerite_solver.jl:54 (φ_0 := 0: nothing precedes step 0)
         if (rd.kind == ROW_REAL) { ut[s] = 1.0; vv[s] = 1.0; }
@@ -119,7 +129,7 @@ __global__ void blocked_table_kernel(double* __restrict__ table, const double* _
     }
 #pragma unroll
     for (int s = 0; s < BLK; s++) tab[blk_off_vh(NT, NTR) + r * 8 + s] = pe[s] * vv[s];
-    tab[blk_off_psi(NT, NTR) + r] = (rd.kind == ROW_AUG) ? 1.0 : p0[BLK - 1];
+    tab[blk_off_psi(NT, NTR) + r] = (rd.kind == ROW_AUG || rd.kind == ROW_AUG2) ? 1.0 : p0[BLK - 1];
     for (int q = r; q < 32; q += RPT) {
         const int s = q & 7, f = q >> 3;
         const int64_t n = n0 + s;
@@ -180,7 +190,7 @@ struct BlkState {
 // K_blk of one block in the accumulator layout (lane (g,t): C[g][2t], C[g][2t+1]).  Lane l < 28 sums pair slot l over all
 // celerite rows (4 accumulation chains, no cross-lane reduction); two exchanges then hand every lane its two entries.  The
 // diagonal is A_n = Σa + ν σ²_n.  amp_l: per-warp amplitudes by LOGICAL row (8·NT doubles, zero-padded).
-template <int NT, int NTR>
+template <int NT, int NTR, bool TAN = false>
 __device__ __forceinline__ void blk_kblk(const double* __restrict__ tab, const double* __restrict__ amp_l, const BlkLane& L,
                                          const int lane, const double suma, const double nu, const int64_t n0,
                                          const int64_t N, const double* __restrict__ sb, double& cm0, double& cm1) {
@@ -203,20 +213,24 @@ __device__ __forceinline__ void blk_kblk(const double* __restrict__ tab, const d
     const int64_t n = n0 + g;
     const double mk = tab[O_SC + 16 + g];
     const double s2v = sb ? (n < N ? sb[n] : 0.0) : tab[O_SC + 8 + g];
-    const double dg = fma(fma(nu, s2v, suma), mk, 1.0 - mk);
+    // TAN: (suma, nu) are the tangents of (Σa, ν); the unit pivot of a padded step has no tangent
+    const double dg = TAN ? fma(nu, s2v, suma) * mk : fma(fma(nu, s2v, suma), mk, 1.0 - mk);
     cm0 = L.cdiag0 ? dg : o0;
     cm1 = L.cdiag1 ? dg : o1;
 }
 
 // One block of 8 steps.  tab: this block's record in shared memory; amp_s: per-warp amplitudes (8·NTR doubles, amp[RG] = 1);
 // (cm0, cm1): K_blk of this block on entry, of the NEXT block (record tabn, first step n0 + 8) on exit.
-template <int NT, int NTR, bool HALF>
+// PUB (gradient kernel): the block's L⁻¹, 1/D, Bm and Q̂ are also written to `pub` (item i of lane l at pub[32·i + l]: the
+// tangent warps read them back lane for lane) and Σ 2 z ż/D of the second data row RM is added to *chimu.
+template <int NT, int NTR, bool HALF, bool PUB = false>
 __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double* __restrict__ tab,
                                              const double* __restrict__ tabn, const double* __restrict__ amp_s,
                                              const double* __restrict__ amp_l, const BlkLane& L, const int lane,
                                              const double suma, const double mu, const double nu,
                                              const int64_t n0, const int64_t N, const double* __restrict__ yb,
-                                             const double* __restrict__ sb, const int RG, double& cm0_io, double& cm1_io) {
+                                             const double* __restrict__ sb, const int RG, double& cm0_io, double& cm1_io,
+                                             double* __restrict__ pub = nullptr, const int RM = -1, double* chimu = nullptr) {
     constexpr int O_VH = blk_off_vh(NT, NTR), O_PSI = blk_off_psi(NT, NTR), O_SC = blk_off_sc(NT, NTR);
     const int g = L.g, t = L.t;
     double cm0 = cm0_io, cm1 = cm1_io;
@@ -333,6 +347,22 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
         Q[I][0] = Q[I][1] = 0.0;
         dmma(Q[I][0], Q[I][1], P0[I][0], e0);
         dmma(Q[I][0], Q[I][1], P0[I][1], e1);
+    }
+
+    if (PUB) {
+        double* p = pub + lane;
+        p[0] = e0; p[32] = e1; p[64] = rd0; p[96] = rd1;
+#pragma unroll
+        for (int I = 0; I < NTR; I++) {
+            p[(4 + 2 * I) * 32] = P0[I][0]; p[(5 + 2 * I) * 32] = P0[I][1];                      // Bm
+            p[(4 + 2 * NTR + 2 * I) * 32] = Q[I][0]; p[(5 + 2 * NTR + 2 * I) * 32] = Q[I][1];    // Q̂
+        }
+        // ∂χ²/∂μ = Σ_s 2 z_s ż_s / D_s with ż the innovations of the second data row (same tile, row RM)
+        const int srcm = ((RM & 7) << 2) | t;
+        const double zm0 = __shfl_sync(FULL, Q[NTR - 1][0], srcm), zm1 = __shfl_sync(FULL, Q[NTR - 1][1], srcm);
+        const bool isrg2 = (8 * (NTR - 1) + g == RG);
+        const double cmv = 2.0 * fma(Q[NTR - 1][0] * rd0, zm0, (Q[NTR - 1][1] * rd1) * zm1);
+        *chimu += isrg2 ? cmv : 0.0;
     }
 
     // ---- yᵀK⁻¹y += Σ_s z_s²/D_s  (celerite_solver.jl:333) on the lanes that hold the augmented row
