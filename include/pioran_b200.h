@@ -163,6 +163,14 @@ int pioran_approx_logl_grad_dev(pioran_ctx *ctx, int series_id, const pioran_app
 #define PIORAN_SWEEP_SCALAR 1
 int pioran_ctx_set_sweep_kernel(pioran_ctx *ctx, int which);
 
+/* Gradient of the log-normal likelihood of pioran_approx_logl_logshift: theta [B x (n_psd_par+4)] = psd parameters..., norm, nu, mu, c;
+ * grad_out [B x (n_psd_par+4)] in the column order of theta, d/dc included (the reference differentiates this model with
+ * ForwardDiff like any other: docs/src/ultranest.md:197-217, test/test_likelihood.jl:55).  The shift moves the data:
+ * d yn/dc = -1/(y - c), d sigma2/dc = 2 nu sigma^2/(y - c)^3, carried as one more tangent direction of the blocked gradient kernel.
+ * SingleBendingPowerLaw, ranks <= 62.  logl_out: [B] or NULL. */
+int pioran_approx_logl_logshift_grad(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int B,
+                                     const double *theta, double *logl_out, double *grad_out);
+
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
 /* pioran_celerite_logl and pioran_approx_logl hand calls with at most 4 parameter vectors on a long series (fused path: at

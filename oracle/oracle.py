@@ -53,7 +53,8 @@ def _load():
     lib.orc_approx_logl_batch.restype = None
     lib.orc_approx_logl_batch.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                           C.c_double, C.c_int, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, C.c_int]
-    for name in ("orc_approx_logl_grad_batch", "orc_approx_logl_grad_batch_ld"):
+    for name in ("orc_approx_logl_grad_batch", "orc_approx_logl_grad_batch_ld", "orc_approx_logl_logshift_grad_batch",
+                 "orc_approx_logl_logshift_grad_batch_ld"):
         fn = getattr(lib, name)
         fn.restype = None
         fn.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -188,6 +189,23 @@ def approx_logl_grad_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO",
     out = np.empty(theta.shape[0])
     grad = np.empty(theta.shape)
     fn = lib().orc_approx_logl_grad_batch_ld if long_double else lib().orc_approx_logl_grad_batch
+    fn(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high, int(is_integrated_power), BASES[basis], len(t),
+       _p(t), _p(y), _p(s2), _p(out), _p(grad), nthreads)
+    return out, grad
+
+
+def approx_logl_logshift_grad_batch(model, theta, f_min, f_max, J, t, y, s2, basis="SHO", S_low=20.0, S_high=20.0,
+                                    is_integrated_power=True, nthreads=1, long_double=False):
+    """Log-normal model: theta rows = [psd params…, norm, ν, μ, c]; y, s2 the UNtransformed flux and its variance.
+    Returns (logL[B], ∂logL/∂θ [B × (npar+4)])."""
+    m = PSD_MODELS[model]
+    theta = np.atleast_2d(_arr(theta))
+    npar = N_PSD_PAR[m]
+    assert theta.shape[1] == npar + 4
+    t, y, s2 = map(_arr, (t, y, s2))
+    out = np.empty(theta.shape[0])
+    grad = np.empty(theta.shape)
+    fn = lib().orc_approx_logl_logshift_grad_batch_ld if long_double else lib().orc_approx_logl_logshift_grad_batch
     fn(m, npar, theta.shape[0], _p(theta), f_min, f_max, J, S_low, S_high, int(is_integrated_power), BASES[basis], len(t),
        _p(t), _p(y), _p(s2), _p(out), _p(grad), nthreads)
     return out, grad

@@ -36,11 +36,13 @@ typedef long double real;
 #define RM(f) f##l
 #define R_PI 3.14159265358979323846264338327950288L
 #define ORC_GRAD_ENTRY orc_approx_logl_grad_batch_ld
+#define ORC_GRAD_LOGSHIFT_ENTRY orc_approx_logl_logshift_grad_batch_ld
 #else
 typedef double real;
 #define RM(f) f
 #define R_PI M_PI
 #define ORC_GRAD_ENTRY orc_approx_logl_grad_batch
+#define ORC_GRAD_LOGSHIFT_ENTRY orc_approx_logl_logshift_grad_batch
 #endif
 
 
@@ -305,6 +307,47 @@ void ORC_GRAD_ENTRY(int model, int n_psd_par, int B, const double *theta, double
             dual *yy = (dual *)malloc(sizeof(dual) * N);
             dual *ss = (dual *)malloc(sizeof(dual) * N);
             for (int64_t n = 0; n < N; n++) { yy[n] = dsub(dk(y[n]), mu); ss[n] = dmulc(nu, s2_base[n]); }
+            int Jt = approx_dual(model, par, f_min, f_max, J, norm, S_low, S_high, is_integrated_power, basis, ab,
+                                 ab + Jt_max, cd, cd + Jt_max);
+            dual r = dmk(NAN, NAN);
+            if (Jt > 0) r = celerite_logl_dual(Jt, ab, ab + Jt_max, cd, cd + Jt_max, N, t, yy, ss);
+            if (logl_out && k == 0) logl_out[i] = (double)r.v;
+            grad_out[(size_t)i * P + k] = (double)r.d;
+            free(ab); free(cd); free(yy); free(ss);
+        }
+    }
+}
+
+
+/* Log-normal model (docs/src/ultranest.md:197-217; docs/src/timeseries.md:16-21): θ row = [psd params…, norm, ν, μ, c],
+ * yn = log(y − c), σ² = ν σ²/(y − c)², logpdf(ScalableGP(μ, 𝓡)(t, σ²), yn) — the same dual-number sweep with y and σ² carrying
+ * the tangent of c.  grad_out [B × (n_psd_par + 4)]. */
+void ORC_GRAD_LOGSHIFT_ENTRY(int model, int n_psd_par, int B, const double *theta, double f_min, double f_max, int J,
+                             double S_low, double S_high, int is_integrated_power, int basis, int64_t N,
+                             const double *t, const double *y, const double *s2_base, double *logl_out,
+                             double *grad_out, int nthreads)
+{
+    const int P = n_psd_par + 4;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) collapse(2)
+#endif
+    for (int i = 0; i < B; i++) {
+        for (int k = 0; k < P; k++) {
+            const double *th = theta + (size_t)i * P;
+            dual par[9];
+            for (int q = 0; q < P; q++) par[q] = dmk(th[q], q == k ? 1.0 : 0.0);
+            dual norm = par[n_psd_par], nu = par[n_psd_par + 1], mu = par[n_psd_par + 2], cs = par[n_psd_par + 3];
+            int Jt_max = 2 * J;
+            dual *ab = (dual *)malloc(sizeof(dual) * 2 * Jt_max);
+            real *cd = (real *)malloc(sizeof(real) * 2 * Jt_max);
+            dual *yy = (dual *)malloc(sizeof(dual) * N);
+            dual *ss = (dual *)malloc(sizeof(dual) * N);
+            for (int64_t n = 0; n < N; n++) {
+                dual dl = dsub(dk(y[n]), cs);                         /* y − c */
+                yy[n] = dsub(dlog(dl), mu);                           /* log(y − c) − μ */
+                ss[n] = ddiv(dmulc(nu, s2_base[n]), dmul(dl, dl));    /* ν σ²/(y − c)² */
+            }
             int Jt = approx_dual(model, par, f_min, f_max, J, norm, S_low, S_high, is_integrated_power, basis, ab,
                                  ab + Jt_max, cd, cd + Jt_max);
             dual r = dmk(NAN, NAN);

@@ -514,8 +514,10 @@ class BatchedLikelihood:
         """(logL [B], ∂logL/∂Θ [B × n_par]) — what ForwardDiff.gradient gives the reference's HMC/NUTS runs
         (test/test_likelihood.jl:55, examples/turing_distributed/single_pl.jl), for a whole batch of chains at once."""
         theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        if self.n_features:
+            raise NotImplementedError("gradients with PSD features are not built")
         if self.log_shift:
-            raise NotImplementedError("gradients of the log-shift likelihood (∂/∂c moves the data) are not built")
+            return self.ctx.approx_logl_logshift_grad(self.series, self.spec, theta)
         return self.ctx.approx_logl_grad(self.series, self.spec, theta)
 
     def gradient(self, theta):

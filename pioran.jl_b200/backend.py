@@ -216,6 +216,17 @@ class Context:
         check(self.lib.pioran_approx_logl_grad(self.h, series.id, C.byref(spec), B, _p(theta), _p(out), _p(grad)))
         return out, grad
 
+    def approx_logl_logshift_grad(self, series, spec, theta):
+        """Log-normal series: theta rows = [psd parameters…, norm, ν, μ, c] → (logL [B], ∂logL/∂θ [B × (n_psd_par + 4)])."""
+        npar = N_PSD_PAR[spec.psd_model]
+        theta = np.atleast_2d(_f64(theta))
+        if theta.shape[1] != npar + 4:
+            raise ValueError(f"theta must have {npar + 4} columns (psd parameters, norm, ν, μ, c)")
+        B = theta.shape[0]
+        out, grad = np.empty(B), np.empty((B, npar + 4))
+        check(self.lib.pioran_approx_logl_logshift_grad(self.h, series.id, C.byref(spec), B, _p(theta), _p(out), _p(grad)))
+        return out, grad
+
     def approx_logl_grad_dev(self, series, spec, B, theta_ptr, logl_ptr, grad_ptr):
         """Device-resident variant: raw device pointers (ints); logl_ptr may be 0."""
         check(self.lib.pioran_approx_logl_grad_dev(self.h, series.id, C.byref(spec), int(B), C.c_void_p(theta_ptr),

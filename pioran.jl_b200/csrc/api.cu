@@ -1270,20 +1270,24 @@ static bool blocked_grad_enabled(const pioran_ctx* c, int R, int ND) {
     return blocked_enabled(c, R) && blk_phys_row2(R) >= 0 && (ND == 3 || ND == 5);
 }
 
+// logshift: θ rows carry a further column c and (y_batch, s2_batch) hold the per-θ transformed data; the gradient gains ∂/∂c.
 static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
-                                       const double* theta_dev, double* logl_dev, double* grad_dev) {
+                                       const double* theta_dev, double* logl_dev, double* grad_dev, bool logshift = false,
+                                       const double* y_batch = nullptr, const double* s2_batch = nullptr) {
     int rc;
     if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
     if ((rc = check_spec(*spec))) return rc;
     Series* ser = get_series(c, series_id);
     if (!ser) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
-    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 3, ND = npar, P = npar + 3;
+    const int npar = n_psd_par_of(spec->psd_model), ts = npar + 3 + (logshift ? 1 : 0), ND = npar, P = ts;
     if ((long long)B * P > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "B too large");
     const int R = rank_of(spec->basis, spec->n_components);
     const int BS = bs_for_rank(R);
     if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
     const int RP = G * BS;
     const bool blkg = blocked_grad_enabled(c, R, ND);
+    if (logshift && !(blkg && ND == 3))
+        return fail(PIORAN_EUNSUPPORTED, "the log-shift gradient is built for SingleBendingPowerLaw at ranks <= 62 (rank %d, %d PSD parameters)", R, ND);
     Table tab;
     if ((rc = blkg ? get_btable(c, ser, *spec, &tab) : get_table(c, ser, *spec, &tab))) return rc;
     ApproxPlan* plan;
@@ -1322,7 +1326,9 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     ga.amp = amp; ga.damp = damp; ga.suma = suma; ga.dsuma = dsuma;
     ga.theta = theta_dev; ga.pstride = ts; ga.ND = ND;
     ga.logl = logl_dev; ga.grad = grad_dev;
+    ga.y_batch = y_batch; ga.s2_batch = s2_batch; ga.ystride = ser->N; ga.cdir = logshift ? 1 : 0;
     const int nitems = c->gwork_items;
+    if (blkg && logshift) return dispatch_blocked_grad<5>(c, ga, nitems, R, RP);
     if (blkg) return ND == 3 ? dispatch_blocked_grad<4>(c, ga, nitems, R, RP) : dispatch_blocked_grad<6>(c, ga, nitems, R, RP);
     if (pipe) {
         const int nwarps = 1 + ND + 1;
@@ -1347,6 +1353,57 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     }
     return fail(PIORAN_EUNSUPPORTED, "block size %d not compiled", BS);
 }
+
+// Gradient of the log-normal likelihood (docs/src/ultranest.md:197-217 differentiated like every other model of the reference,
+// test/test_likelihood.jl:55): transform on the device, then K1 tangents + the blocked gradient kernel with per-θ data and the
+// extra direction c.
+extern "C" int pioran_approx_logl_logshift_grad(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
+                                                const double* theta, double* logl_out, double* grad_out) try {
+    if (!c || !spec || !theta || !grad_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    const int npar = n_psd_par_of(spec->psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+    const int ts = npar + 4;
+    if (is_group(c)) {
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            return pioran_approx_logl_logshift_grad(c->children[k], cid[k], spec, nb, theta + (size_t)beg * ts, logl_out ? logl_out + beg : nullptr,
+                                                    grad_out + (size_t)beg * ts);
+        });
+    }
+    PIORAN_COMPUTE_LOCK(c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = check_spec(*spec))) return rc;
+    Series* s = get_series(c, series_id);
+    if (!s) return fail(PIORAN_EINVAL, "unknown series id %d", series_id);
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * ts))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B * (ts + 1)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->theta.p, theta, sizeof(double) * (size_t)B * ts, cudaMemcpyHostToDevice, c->stream));
+    const int64_t N = s->N;
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)1 << 30) / (16 * std::max<int64_t>(N, 1))));
+    if ((rc = c->post.ensure(sizeof(double) * 2 * (size_t)chunk * N))) return rc;
+    double* yb = c->post.as<double>();
+    double* sb = yb + (size_t)chunk * N;
+    double* gl = c->out.as<double>();
+    double* gg = gl + B;
+    for (int off = 0; off < B; off += chunk) {
+        const int nb = std::min(chunk, B - off);
+        const double* th = c->theta.as<double>() + (size_t)off * ts;
+        const int64_t total = (int64_t)nb * N;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)c->num_sms * 16);
+        log_shift_kernel<<<grid, 256, 0, c->stream>>>(s->y, s->s2, N, th, ts, npar + 3, nb, yb, sb);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = approx_logl_grad_dev_locked(c, series_id, spec, nb, th, gl + off, gg + (size_t)off * ts, true, yb, sb))) return rc;
+    }
+    if (logl_out) CUDA_TRY(cudaMemcpyAsync(logl_out, gl, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(grad_out, gg, sizeof(double) * (size_t)B * ts, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
 
 extern "C" int pioran_approx_logl_grad_dev(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                            const double* theta_dev, double* logl_dev, double* grad_dev) try {

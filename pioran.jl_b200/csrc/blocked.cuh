@@ -193,7 +193,8 @@ struct BlkState {
 template <int NT, int NTR, bool TAN = false>
 __device__ __forceinline__ void blk_kblk(const double* __restrict__ tab, const double* __restrict__ amp_l, const BlkLane& L,
                                          const int lane, const double suma, const double nu, const int64_t n0,
-                                         const int64_t N, const double* __restrict__ sb, double& cm0, double& cm1) {
+                                         const int64_t N, const double* __restrict__ sb, double& cm0, double& cm1,
+                                         const bool diag_given = false, const double diag_value = 0.0) {
     constexpr int O_H = blk_off_h(NT, NTR), O_SC = blk_off_sc(NT, NTR);
     const int g = L.g;
     const double2* Hq = reinterpret_cast<const double2*>(tab + O_H) + lane;
@@ -214,7 +215,7 @@ __device__ __forceinline__ void blk_kblk(const double* __restrict__ tab, const d
     const double mk = tab[O_SC + 16 + g];
     const double s2v = sb ? (n < N ? sb[n] : 0.0) : tab[O_SC + 8 + g];
     // TAN: (suma, nu) are the tangents of (Σa, ν); the unit pivot of a padded step has no tangent
-    const double dg = TAN ? fma(nu, s2v, suma) * mk : fma(fma(nu, s2v, suma), mk, 1.0 - mk);
+    const double dg = diag_given ? diag_value * mk : TAN ? fma(nu, s2v, suma) * mk : fma(fma(nu, s2v, suma), mk, 1.0 - mk);
     cm0 = L.cdiag0 ? dg : o0;
     cm1 = L.cdiag1 ? dg : o1;
 }

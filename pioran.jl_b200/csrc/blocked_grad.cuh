@@ -22,6 +22,9 @@
 
 namespace pioran {
 
+#ifndef PIORAN_BLKG_TWO_CTA_MAX_NT
+#define PIORAN_BLKG_TWO_CTA_MAX_NT 5
+#endif
 __host__ __device__ constexpr int blk_slot_doubles(int NTR) { return (4 + 4 * NTR) * 32; }
 
 // One block of the tangent recursion.  xd: tangent state tiles (I ≥ K); slot: what the value warp published for this block.
@@ -30,13 +33,22 @@ __device__ __forceinline__ void blocked_tangent_step(double (&xd)[NTR][NT][2], c
                                                      const double* __restrict__ slot, const double* __restrict__ damp_s,
                                                      const double* __restrict__ damp_l, const BlkLane& L, const int lane,
                                                      const double dsuma, const double dnu, const int64_t n0, const int64_t N,
-                                                     const int RG, double& dlog, double& dchi) {
+                                                     const int RG, double& dlog, double& dchi,
+                                                     const double* __restrict__ yb = nullptr, const double* __restrict__ sb = nullptr,
+                                                     const bool cdir = false, const double nu = 1.0) {
     constexpr int O_VH = blk_off_vh(NT, NTR), O_PSI = blk_off_psi(NT, NTR);
     const int g = L.g, t = L.t;
 
-    // ---- K̇_blk
+    // ---- K̇_blk.  Log-shift direction c: the diagonal moves with the data, ∂(ν σ²_n)/∂c = 2 ν σ²_n e^{−yn_n}, σ² the transformed one
     double cd0, cd1;
-    blk_kblk<NT, NTR, true>(tab, damp_l, L, lane, dsuma, dnu, n0, N, nullptr, cd0, cd1);
+    {
+        double dgc = 0.0;
+        if (cdir) {
+            const int64_t n = n0 + g;
+            dgc = (n < N) ? 2.0 * nu * sb[n] * exp(-yb[n]) : 0.0;
+        }
+        blk_kblk<NT, NTR, true>(tab, damp_l, L, lane, dsuma, dnu, n0, N, sb, cd0, cd1, cdir, dgc);
+    }
 
     // ---- Ṗ0 = Ẋ·Û
     double P0[NTR][2];
@@ -86,8 +98,14 @@ __device__ __forceinline__ void blocked_tangent_step(double (&xd)[NTR][NT][2], c
 #pragma unroll
     for (int I = 0; I < NTR; I++) {
         const int row = 8 * I + g;
-        const double2 vh = *reinterpret_cast<const double2*>(tab + O_VH + row * 8 + 2 * t);
-        const double am = damp_s[row];
+        double2 vh = *reinterpret_cast<const double2*>(tab + O_VH + row * 8 + 2 * t);
+        double am = damp_s[row];
+        if (I == NTR - 1 && cdir && row == RG) {      // ∂yn/∂c = −1/(y − c) = −e^{−yn}: the data row's right-hand side moves
+            const int64_t n = n0 + 2 * t;
+            vh.x = (n < N) ? -exp(-yb[n]) : 0.0;
+            vh.y = (n + 1 < N) ? -exp(-yb[n + 1]) : 0.0;
+            am = 1.0;
+        }
         P0[I][0] = fma(-psr[I], P0[I][0], am * vh.x);
         P0[I][1] = fma(-psr[I], P0[I][1], am * vh.y);
     }
@@ -151,8 +169,9 @@ __device__ __forceinline__ void blocked_tangent_step(double (&xd)[NTR][NT][2], c
 
 // grid = work items (one parameter vector each); block = 1 + NTAN warps (NTAN = n_psd_par + 1).
 // dynamic smem: BLK_NSTAGE block records | 2 ring slots | (1 + NTAN) × (8·NTR + 8·NT) amplitudes | mbarriers | 2 result doubles
+// Up to 5 row tiles two CTAs share an SM (≤ 200 registers per thread): the value warp of one overlaps the tangent warps of the other.
 template <int NT, int NTR, bool HALF, int NTAN>
-__global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kernel(const GradArgs args, const int R, const int amp_stride) {
+__global__ void __launch_bounds__((1 + NTAN) * 32, (NT <= PIORAN_BLKG_TWO_CTA_MAX_NT && NTAN <= 4) ? 2 : 1) celerite_blocked_grad_kernel(const GradArgs args, const int R, const int amp_stride) {
     constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR, APW = RPT + 8 * NT, SLOT = blk_slot_doubles(NTR);
     constexpr uint32_t STAGE_BYTES = BD * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kern
     const int th = wk.theta_begin;
     const int64_t N = wk.N;
     const int64_t nblocks = (N + BLK - 1) / BLK;
-    const int P = args.ND + 3;
+    const int P = args.ND + 3 + args.cdir;
 
     if (threadIdx.x == 0) {
         for (int k = 0; k < BLK_NSTAGE; k++) mbar_init(&bars[k], 1);
@@ -184,6 +203,8 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kern
     const int RG = blk_phys_row(R, R), RM = blk_phys_row2(R);
     const double* trow = args.theta + (size_t)th * args.pstride;
     const double nu = trow[args.ND + 1], mu = trow[args.ND + 2];
+    const double* yb = args.y_batch ? args.y_batch + (size_t)th * args.ystride : nullptr;
+    const double* sb = args.s2_batch ? args.s2_batch + (size_t)th * args.ystride : nullptr;
 
     // amplitudes of this warp: the values (warp 0, data rows = 1) or the tangent of direction warp − 1 (zero for ν)
     double* amp_s = amps + warp * APW;
@@ -204,7 +225,8 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kern
     __syncwarp();
     const double suma = args.suma[th];
     const double dsuma = amp_dir ? args.dsuma[(size_t)th * args.ND + dir] : 0.0;
-    const double dnu = (warp >= 1 && !amp_dir) ? 1.0 : 0.0;
+    const bool c_dir = args.cdir && dir == args.ND + 1;          // directions: psd parameters…, ν, (c)
+    const double dnu = (warp >= 1 && dir == args.ND) ? 1.0 : 0.0;
 
     BlkState<NT, NTR> st;      // warp 0: X;  tangent warps: Ẋ in st.x
 #pragma unroll
@@ -222,14 +244,14 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kern
                 const int sidx = (int)(tau % BLK_NSTAGE);
                 mbar_wait(&bars[sidx], (uint32_t)((tau / BLK_NSTAGE) & 1));
                 blocked_step<NT, NTR, HALF, true>(st, stages + sidx * BD, stages + sidx * BD, amp_s, amp_l, L, lane, suma, mu, nu,
-                                                  tau * BLK, N, nullptr, nullptr, RG, cm0, cm1, ring + (tau & 1) * SLOT, RM, &chimu);
+                                                  tau * BLK, N, yb, sb, RG, cm0, cm1, ring + (tau & 1) * SLOT, RM, &chimu);
             }
         } else if (tau >= 1) {
             const int64_t b = tau - 1;
             const int sidx = (int)(b % BLK_NSTAGE);
             mbar_wait(&bars[sidx], (uint32_t)((b / BLK_NSTAGE) & 1));
             blocked_tangent_step<NT, NTR, HALF>(st.x, stages + sidx * BD, ring + (b & 1) * SLOT, amp_s, amp_l, L, lane, dsuma, dnu,
-                                                b * BLK, N, RG, dlog, dchi);
+                                                b * BLK, N, RG, dlog, dchi, yb, sb, c_dir, nu);
         }
         __syncthreads();
         // every warp has left block τ − 1: its stage takes block τ − 1 + BLK_NSTAGE
@@ -268,6 +290,8 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, 1) celerite_blocked_grad_kern
             const double gk = -dl / 2 - dc / 2;
             if (dir < args.ND) {
                 args.grad[(size_t)th * P + dir] = gk;
+            } else if (c_dir) {
+                args.grad[(size_t)th * P + args.ND + 3] = gk;
             } else {      // the ν warp also reports ∂/∂norm (homogeneity of K in (norm, ν), grad.cuh)
                 args.grad[(size_t)th * P + args.ND + 1] = gk;
                 args.grad[(size_t)th * P + args.ND] = (0.5 * res[0] - 0.5 * (double)N - nu * gk) / trow[args.ND];

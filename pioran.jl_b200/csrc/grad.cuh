@@ -287,6 +287,12 @@ struct GradArgs {
     int ND;                     // n_psd_par; ND + 1 warps (directions psd…, ν) and ND + 3 outputs per θ
     double* logl;               // [nθ] or nullptr
     double* grad;               // [nθ × P]
+    // blocked_grad.cuh only — log-normal series (docs/src/ultranest.md:197-217): per-θ data yn = log(y − c), σ² = σ²/(y − c)² and one
+    // more direction, c, after ν (its tangents ∂yn/∂c = −e^{−yn}, ∂σ²/∂c = 2 σ² e^{−yn} are formed from the transformed data)
+    const double* y_batch;      // [nθ × ystride] or nullptr
+    const double* s2_batch;
+    int64_t ystride;
+    int cdir;                   // 1: directions psd…, ν, c and ND + 4 outputs per θ (…, norm, ν, μ, c)
 };
 
 // grid = work items; block = NW warps; each warp one (θ, direction).  Shared memory: 2 TMA stages of the series table |

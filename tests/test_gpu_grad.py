@@ -107,3 +107,32 @@ def test_grad_short_series(pb, ctx, golden_single, basis, N):
     oval, ograd = orc.approx_logl_grad_batch("SBPL", theta, g.f_min, g.f_max, 20, t, y, s2, basis=basis, nthreads=0)
     assert np.abs(val - oval).max() <= 1e-9 * np.maximum(1.0, np.abs(oval)).max()
     _check(grad, ograd)
+
+
+@pytest.mark.parametrize("basis,J", [("SHO", 20), ("DRWCelerite", 20), ("SHO", 7), ("DRWCelerite", 13)])
+def test_logshift_gradient_vs_oracle(pb, ctx, golden_single, basis, J):
+    """Gradient of the log-normal likelihood (docs/src/ultranest.md:197-217 under ForwardDiff, test/test_likelihood.jl:55):
+    pioran_approx_logl_logshift_grad against the oracle's dual-number sweep with y and σ² carrying the tangent of c, on the
+    reference's simu_single flux (untransformed) and prior-like shifts below min(y)."""
+    g = golden_single
+    t, y, s2, f_min, f_max = g.t, g.y_raw, g.yerr ** 2, g.f_min, g.f_max
+    rows = np.linspace(0, len(g.theta) - 1, 40).astype(int)
+    rng = np.random.default_rng(17)
+    theta = np.column_stack([g.theta[rows], rng.uniform(-0.5, 0.9, len(rows)) * y.min()])
+    if basis == "DRWCelerite":
+        theta[:, 2] += 1.0
+    like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx, log_shift=True)
+    val, grad = like.value_and_gradient(theta)
+    oval, ograd = orc.approx_logl_logshift_grad_batch("SBPL", theta, f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+    assert grad.shape == (len(rows), 7)
+    verr = np.abs(val - oval) / np.maximum(1.0, np.abs(oval))
+    assert verr.max() <= 1e-9, f"value parity {verr.max():.3e}"
+    assert np.abs(val - like(theta)).max() <= 1e-9 * np.maximum(1.0, np.abs(val)).max()      # same value as the likelihood entry
+    _check(grad, ograd)
+    # c = 0 reduces to the plain model on log(y): the six common columns agree with the plain gradient entry
+    th0 = theta[:8].copy(); th0[:, 6] = 0.0
+    _, g0 = like.value_and_gradient(th0)
+    plain = pb.BatchedLikelihood(t, np.log(y), s2 / y ** 2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+    _, gp = plain.value_and_gradient(th0[:, :6])
+    _check(g0[:, :6], gp, 1e-9)
+    like.close(); plain.close()

@@ -201,3 +201,27 @@ def test_gradient_oracle_value_and_finite_differences(golden_single, basis):
                                                   long_double=True)
     assert np.max(np.abs(val_ld - val) / np.abs(val)) <= 1e-10
     assert np.max(np.abs(grad_ld - grad) / np.maximum(np.abs(grad), np.abs(grad).max(axis=0))) <= 1e-8
+
+
+def test_logshift_gradient_oracle_against_central_differences():
+    """The log-shift branch of the gradient oracle (pioran_oracle_grad.c: y and σ² carry the tangent of c) has no reference
+    literal; its value part is the pinned log-likelihood oracle on the transformed data and its derivative part matches
+    central differences of that same oracle."""
+    rng = np.random.default_rng(3)
+    N = 120
+    t = np.cumsum(0.1 + rng.exponential(1, N)); y = np.exp(rng.normal(0, 0.3, N)) + 0.5; s2 = (0.02 * y) ** 2
+    fm, fx = 1 / (t[-1] - t[0]), 1 / np.min(np.diff(t)) / 2
+    th = np.array([[0.6, 0.05, 3.0, 0.1, 1.3, 0.1, 0.2]])
+    for basis in ("SHO", "DRWCelerite"):
+        l, g = orc.approx_logl_logshift_grad_batch("SBPL", th, fm, fx, 12, t, y, s2, basis=basis)
+
+        def f(x):
+            c = x[6]
+            return orc.approx_logl_batch("SBPL", x[None, :6], fm, fx, 12, t, np.log(y - c), s2 / (y - c) ** 2, basis=basis)[0]
+        assert l[0] == f(th[0])
+        for k in range(7):
+            h = 1e-6 * max(1.0, abs(th[0, k]))
+            xp, xm = th[0].copy(), th[0].copy()
+            xp[k] += h; xm[k] -= h
+            fd = (f(xp) - f(xm)) / (2 * h)
+            assert abs(g[0, k] - fd) <= 2e-6 * max(1.0, abs(fd)), (basis, k, g[0, k], fd)
