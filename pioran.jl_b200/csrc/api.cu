@@ -558,12 +558,14 @@ static bool blocked_enabled(const pioran_ctx* c, int R) {
     static const int mode = [] { const char* e = getenv("PIORAN_K2"); return (e && (!strcmp(e, "scalar") || !strcmp(e, "0"))) ? 0 : 1; }();
     return mode != 0 && c->sweep_kernel != PIORAN_SWEEP_SCALAR && R >= 1 && blk_ntr(R) <= 8;
 }
-static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out) {
+static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Table* out, bool grad = false) {
     const double f0 = sp.f_min / sp.S_low, fM = sp.f_max * sp.S_high;
-    TableKey key{sp.basis, sp.n_components, f0, fM};
-    if (table_lookup(c, s->btables, key, out)) return 0;
     const int R = rank_of(sp.basis, sp.n_components);
-    const int NT = blk_nt(R), NTR = blk_ntr(R), RPT = 8 * NTR;
+    const BlkLayout lay = blk_layout(R, grad);
+    const bool own = grad && lay.NTR != blk_layout(R, false).NTR;      // R ≡ 7 mod 8: the gradient's table has its own row layout
+    TableKey key{sp.basis, own ? -sp.n_components : sp.n_components, f0, fM};
+    if (table_lookup(c, s->btables, key, out)) return 0;
+    const int NT = lay.NT, NTR = lay.NTR, RPT = 8 * NTR;
     std::vector<RowDesc> lrows, rows(RPT, RowDesc{0, 0, 0, ROW_PAD, 0});
     make_rows(sp, RPT, lrows);
     for (int r = 0; r < R; r++) {            // physical order; term = logical row index (the K_blk table is indexed by it)
@@ -571,8 +573,8 @@ static int get_btable(pioran_ctx* c, Series* s, const pioran_approx_spec& sp, Ta
         rd.term = r;
         rows[blk_phys_row(r, R)] = rd;
     }
-    rows[blk_phys_row(R, R)] = RowDesc{0, 0, 0, ROW_AUG, 0};
-    if (blk_phys_row2(R) >= 0) rows[blk_phys_row2(R)] = RowDesc{0, 0, 0, ROW_AUG2, 0};   // ∂/∂μ row of the gradient kernel
+    rows[lay.RG] = RowDesc{0, 0, 0, ROW_AUG, 0};
+    if (lay.RM >= 0) rows[lay.RM] = RowDesc{0, 0, 0, ROW_AUG2, 0};   // ∂/∂μ row of the gradient kernel
     int rc = c->rows.ensure(sizeof(RowDesc) * RPT);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->rows.p, rows.data(), sizeof(RowDesc) * RPT, cudaMemcpyHostToDevice, c->stream));
@@ -614,7 +616,7 @@ static int launch_blocked_nw(pioran_ctx* c, const BatchArgs& args, int nitems, i
                         BLK_NSTAGE * (sizeof(uint64_t) + sizeof(int)) + 16;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
-    kern<<<nitems, NW * 32, smem, c->stream>>>(args, R, amp_stride);
+    kern<<<nitems, NW * 32, smem, c->stream>>>(args, R, amp_stride, blk_layout(R, false).RG);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     c->launches++;
@@ -1240,7 +1242,7 @@ static int launch_blocked_grad(pioran_ctx* c, const GradArgs& args, int nitems, 
                                           (size_t)(1 + NTAN) * (8 * NTR + 8 * NT) + 2) + BLK_NSTAGE * sizeof(uint64_t) + 16;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
-    kern<<<nitems, (1 + NTAN) * 32, smem, c->stream>>>(args, R, amp_stride);
+    kern<<<nitems, (1 + NTAN) * 32, smem, c->stream>>>(args, R, amp_stride, blk_layout(R, true).RG, blk_layout(R, true).RM);
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     c->launches++;
@@ -1249,8 +1251,9 @@ static int launch_blocked_grad(pioran_ctx* c, const GradArgs& args, int nitems, 
 }
 template <int NTAN>
 static int dispatch_blocked_grad(pioran_ctx* c, const GradArgs& a, int nitems, int R, int amp_stride) {
-    const int NT = blk_nt(R);
-    const bool xrow = blk_ntr(R) != NT, half = blk_half(R);
+    const BlkLayout lay = blk_layout(R, true);
+    const int NT = lay.NT;
+    const bool xrow = lay.NTR != NT, half = lay.half;
 #define PIORAN_BLKG_CASE(nt)                                                                                    \
     case nt: return xrow ? launch_blocked_grad<nt, nt + 1, false, NTAN>(c, a, nitems, R, amp_stride)            \
                   : half ? launch_blocked_grad<nt, nt, true, NTAN>(c, a, nitems, R, amp_stride)                 \
@@ -1267,7 +1270,7 @@ static int dispatch_blocked_grad(pioran_ctx* c, const GradArgs& a, int nitems, i
     return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the blocked gradient kernel", R);
 }
 static bool blocked_grad_enabled(const pioran_ctx* c, int R, int ND) {
-    return blocked_enabled(c, R) && blk_phys_row2(R) >= 0 && (ND == 3 || ND == 5);
+    return blocked_enabled(c, R) && blk_layout(R, true).NTR <= 8 && (ND == 3 || ND == 5);
 }
 
 // logshift: θ rows carry a further column c and (y_batch, s2_batch) hold the per-θ transformed data; the gradient gains ∂/∂c.
@@ -1289,7 +1292,7 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     if (logshift && !(blkg && ND == 3))
         return fail(PIORAN_EUNSUPPORTED, "the log-shift gradient is built for SingleBendingPowerLaw at ranks <= 62 (rank %d, %d PSD parameters)", R, ND);
     Table tab;
-    if ((rc = blkg ? get_btable(c, ser, *spec, &tab) : get_table(c, ser, *spec, &tab))) return rc;
+    if ((rc = blkg ? get_btable(c, ser, *spec, &tab, true) : get_table(c, ser, *spec, &tab))) return rc;
     ApproxPlan* plan;
     if ((rc = get_plan(c, *spec, &plan))) return rc;
     // workspace: amp [B×RP] | damp [B×ND×RP] | Σa [B] | dΣa [B×ND]

@@ -66,6 +66,14 @@ __host__ __device__ constexpr int blk_phys_row2(int R) {
     if (blk_half(R)) return base + 3;
     return (R % 8 == 7) ? -1 : R + 1;
 }
+// Row layout of a block table.  The likelihood needs one data row (RG), the gradient two (RG, RM); when the last column tile
+// has no room for them (R ≡ 0 mod 8; for the gradient also R ≡ 7) both move to a row tile of their own.
+struct BlkLayout { int NT, NTR, RG, RM; bool half; };
+__host__ __device__ constexpr BlkLayout blk_layout(int R, bool grad) {
+    const int NT = (R + 7) / 8;
+    if (R % 8 == 0 || (grad && R % 8 == 7)) return BlkLayout{NT, NT + 1, 8 * NT, 8 * NT + 1, false};
+    return BlkLayout{NT, NT, blk_phys_row(R, R), blk_phys_row2(R), blk_half(R)};
+}
 
 // ------------------------------------------------------------------------------------------- K0b: block table
 // One thread per (block, physical row).  rows[] describes the 8·NTR physical rows (ROW_PAD where nothing lives, ROW_AUG at the
@@ -398,7 +406,7 @@ __device__ __forceinline__ void blocked_step(BlkState<NT, NTR>& st, const double
 // grid = work items; block = NW warps, one parameter vector each; dynamic smem: BLK_NSTAGE block records | NW × 8·NTR amplitudes |
 // BLK_NSTAGE mbarriers | BLK_NSTAGE stage counters.  Same stage hand-back as celerite_shared_kernel (last warp out refills).
 template <int NT, int NTR, bool HALF, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const BatchArgs args, const int R, const int amp_stride) {
+__global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const BatchArgs args, const int R, const int amp_stride, const int RG) {
     constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR, APW = RPT + 8 * NT;   // per warp: amplitudes by physical and by logical row
     constexpr uint32_t STAGE_BYTES = BD * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -431,7 +439,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) celerite_blocked_kernel(const B
     const int slot = warp;
     const int th = wk.theta_begin + slot;
     const BlkLane L = make_blk_lane(lane);
-    const int RG = blk_phys_row(R, R);
 
     double* amp_s = amps + warp * APW;
     double* amp_l = amp_s + RPT;

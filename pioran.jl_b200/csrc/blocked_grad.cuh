@@ -171,7 +171,7 @@ __device__ __forceinline__ void blocked_tangent_step(double (&xd)[NTR][NT][2], c
 // dynamic smem: BLK_NSTAGE block records | 2 ring slots | (1 + NTAN) × (8·NTR + 8·NT) amplitudes | mbarriers | 2 result doubles
 // Up to 5 row tiles two CTAs share an SM (≤ 200 registers per thread): the value warp of one overlaps the tangent warps of the other.
 template <int NT, int NTR, bool HALF, int NTAN>
-__global__ void __launch_bounds__((1 + NTAN) * 32, (NT <= PIORAN_BLKG_TWO_CTA_MAX_NT && NTAN <= 4) ? 2 : 1) celerite_blocked_grad_kernel(const GradArgs args, const int R, const int amp_stride) {
+__global__ void __launch_bounds__((1 + NTAN) * 32, (NT <= PIORAN_BLKG_TWO_CTA_MAX_NT && NTAN <= 4) ? 2 : 1) celerite_blocked_grad_kernel(const GradArgs args, const int R, const int amp_stride, const int RG, const int RM) {
     constexpr int BD = blk_doubles(NT, NTR), RPT = 8 * NTR, APW = RPT + 8 * NT, SLOT = blk_slot_doubles(NTR);
     constexpr uint32_t STAGE_BYTES = BD * sizeof(double);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -200,7 +200,6 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, (NT <= PIORAN_BLKG_TWO_CTA_MA
         }
     }
     const BlkLane L = make_blk_lane(lane);
-    const int RG = blk_phys_row(R, R), RM = blk_phys_row2(R);
     const double* trow = args.theta + (size_t)th * args.pstride;
     const double nu = trow[args.ND + 1], mu = trow[args.ND + 2];
     const double* yb = args.y_batch ? args.y_batch + (size_t)th * args.ystride : nullptr;
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__((1 + NTAN) * 32, (NT <= PIORAN_BLKG_TWO_CTA_MA
             amp_l[k] = av;
         }
     }
-    if (warp == 0 && lane == 0) { amp_s[RG] = 1.0; if (RM >= 0) amp_s[RM] = 1.0; }
+    if (warp == 0 && lane == 0) { amp_s[RG] = 1.0; amp_s[RM] = 1.0; }
     __syncwarp();
     const double suma = args.suma[th];
     const double dsuma = amp_dir ? args.dsuma[(size_t)th * args.ND + dir] : 0.0;
