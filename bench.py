@@ -629,8 +629,22 @@ def widening_rows(ctx, pb, J):
         gscale = np.maximum(np.abs(ograd), np.abs(ograd).max(axis=0, keepdims=True))
         gerr = float((np.abs(ggrad[:ng] - ograd) / gscale)[okg].max())
         out[f"gradient_4096theta_N1000_{basis}"] = {"gradients_per_s": 4096 / (ms_g * 1e-3), "device_ms": ms_g,
+                                                    "kernel": "celerite_blocked_grad_kernel (K5t: value warp + one tangent warp per direction, FP64 mma.sync)",
                                                     "cpu_port_forward_mode_gradients_per_s": 1.0 / cpu_g,
                                                     "cpu_threads": orc.max_threads(), "parity_max_rel_32": gerr}
+        # gradient of the log-normal likelihood (7 columns: …, μ, c), same batch size; the flux is exp(y) so that y − c > 0
+        flux = np.exp(y - y.min() + 0.1)
+        likel = pb.BatchedLikelihood(t, flux, s2 * flux ** 2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx, log_shift=True)
+        thl = np.column_stack([th, np.random.default_rng(5).uniform(-0.5, 0.9, len(th)) * flux.min()])
+        likel.value_and_gradient(thl)
+        lval, lgrad = likel.value_and_gradient(thl)
+        ms_l = ctx.last_kernel_ms()
+        likel.close()
+        _, olg = orc.approx_logl_logshift_grad_batch("SBPL", thl[:8], f_min, f_max, J, t, flux, s2 * flux ** 2, basis=basis, nthreads=0)
+        okl = np.isfinite(olg).all(axis=1)
+        lscale = np.maximum(np.abs(olg), np.abs(olg).max(axis=0, keepdims=True))
+        out[f"gradient_logshift_4096theta_N1000_{basis}"] = {"gradients_per_s": 4096 / (ms_l * 1e-3), "device_ms": ms_l,
+                                                             "parity_max_rel_8": float((np.abs(lgrad[:8] - olg) / lscale)[okl].max())}
         out[f"predict_512theta_N1000_M2000_{basis}"] = {"posterior_means_per_s": Bp / (ms_p * 1e-3), "device_ms": ms_p,
                                                         "cpu_port_1thread_means_per_s": 1.0 / cpu_p, "parity_max_rel_4": perr}
         out[f"simulate_4096theta_N1000_{basis}"] = {"draws_per_s": 4096 / (ms_s * 1e-3), "device_ms": ms_s,

@@ -246,3 +246,20 @@ function sim_b200(rng, a, b, c, d, τ, σ2)
     end
     return y
 end
+
+"""
+    logpdf_gradient_batch_lognormal(series, spec, Θ) -> (logℒ::Vector, ∇::Matrix)
+
+Gradient of the log-normal likelihood (docs/src/ultranest.md:197-217 under ForwardDiff): Θ rows = [psd parameters…, variance, ν, μ, c],
+∇[i, :] in the same order, ∂/∂c included.
+"""
+function logpdf_gradient_batch_lognormal(s::B200Series, spec::Ref{B200ApproxSpec}, Θ::Matrix{Float64})
+    B, P = size(Θ)
+    Θr = permutedims(Θ)
+    out = Vector{Float64}(undef, B)
+    gr = Matrix{Float64}(undef, P, B)
+    _b200_check(ccall((:pioran_approx_logl_logshift_grad, libpioran_b200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{B200ApproxSpec}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        b200_context().h, s.id, spec, B, Θr, out, gr))
+    return out, permutedims(gr)
+end
