@@ -76,36 +76,33 @@ __host__ __device__ constexpr BlkLayout blk_layout(int R, bool grad) {
 }
 
 // ------------------------------------------------------------------------------------------- K0b: block table
-// One thread per (block, physical row).  rows[] describes the 8·NTR physical rows (ROW_PAD where nothing lives, ROW_AUG at the
-// augmented row); RowDesc::term holds the logical row index of a celerite row.  The table is zero-filled before the launch.
-__global__ void blocked_table_kernel(double* __restrict__ table, const double* __restrict__ t, const double* __restrict__ y,
-                                     const double* __restrict__ s2, int64_t N, int64_t nblocks,
-                                     const RowDesc* __restrict__ rows, int NT, int NTR) {
+// Record entries of one (block, physical row).  kind: RowKind / ROW_AUG / ROW_AUG2; (cdec, dfreq): decay rate and angular frequency
+// of the row's term; (pa, pb): Ũ = pa·cos + pb·sin on the cos-row, pa·sin − pb·cos on the sin-row, pa on a real row — the
+// reference's U (celerite_solver.jl:59-60) divided by the row's amplitude; lr: logical row index (K_blk table).  The table is
+// zero-filled before the launch.
+__device__ __forceinline__ void blocked_table_fill(double* __restrict__ tab, const double* __restrict__ t,
+                                                   const double* __restrict__ y, const double* __restrict__ s2, const int64_t N,
+                                                   const int64_t n0, const int r, const int kind, const double cdec,
+                                                   const double dfreq, const double pa, const double pb, const int lr,
+                                                   const int NT, const int NTR) {
     const int RPT = 8 * NTR, RP = 8 * NT;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nblocks * RPT) return;
-    const int64_t b = gid / RPT;
-    const int r = (int)(gid - b * RPT);
-    double* tab = table + b * (int64_t)blk_doubles(NT, NTR);
-    const RowDesc rd = rows[r];
-    const int64_t n0 = b * BLK;
     double ph[BLK], ut[BLK], vv[BLK];
 #pragma unroll
     for (int s = 0; s < BLK; s++) {
         const int64_t n = n0 + s;
         ph[s] = 1.0; ut[s] = 0.0; vv[s] = 0.0;
-        if (rd.kind == ROW_PAD) { ph[s] = 0.0; continue; }
+        if (kind == ROW_PAD) { ph[s] = 0.0; continue; }
         if (n >= N) continue;                         // padded step: no decay, no coupling
-        if (rd.kind == ROW_AUG) { vv[s] = y[n]; continue; }
-        if (rd.kind == ROW_AUG2) { vv[s] = -1.0; continue; }
+        if (kind == ROW_AUG) { vv[s] = y[n]; continue; }
+        if (kind == ROW_AUG2) { vv[s] = -1.0; continue; }
         const double tn = t[n];
-        ph[s] = (n >= 1) ? exp(-rd.c * (tn - t[n - 1])) : 0.0;      // celerite_solver.jl:54 (φ_0 := 0: nothing precedes step 0)
-        if (rd.kind == ROW_REAL) { ut[s] = 1.0; vv[s] = 1.0; }
+        ph[s] = (n >= 1) ? exp(-cdec * (tn - t[n - 1])) : 0.0;      // celerite_solver.jl:54 (φ_0 := 0: nothing precedes step 0)
+        if (kind == ROW_REAL) { ut[s] = pa; vv[s] = 1.0; }
         else {
             double si, co;
-            sincos_large(rd.d * tn, &si, &co);                        // celerite_solver.jl:52-53 (absolute time)
-            if (rd.kind == ROW_COS) { ut[s] = fma(rd.ratio, si, co); vv[s] = co; }     // (a·co + b·si)/a
-            else                    { ut[s] = fma(-rd.ratio, co, si); vv[s] = si; }    // (a·si − b·co)/a
+            sincos_large(dfreq * tn, &si, &co);                       // celerite_solver.jl:52-53 (absolute time)
+            if (kind == ROW_COS) { ut[s] = fma(pb, si, pa * co); vv[s] = co; }     // (a·co + b·si)/amp
+            else                 { ut[s] = fma(-pb, co, pa * si); vv[s] = si; }    // (a·si − b·co)/amp
         }
     }
     // Ψ_{0→s} and Ψ_{s→8}
@@ -122,8 +119,7 @@ __global__ void blocked_table_kernel(double* __restrict__ table, const double* _
         for (int s = 0; s < BLK; s++) tab[K * 64 + s * 8 + rr] = p0[s] * ut[s];
     }
     // H2[logical row pair][slot][2]: coupling of steps (s, s') through this row; rows without a logical index stay zero (memset)
-    if (rd.kind == ROW_COS || rd.kind == ROW_SIN || rd.kind == ROW_REAL) {
-        const int lr = rd.term;
+    if (kind == ROW_COS || kind == ROW_SIN || kind == ROW_REAL) {
         double* H = tab + blk_off_h(NT, NTR) + (lr >> 1) * 64 + (lr & 1);
 #pragma unroll
         for (int s = 1; s < BLK; s++) {
@@ -137,13 +133,71 @@ __global__ void blocked_table_kernel(double* __restrict__ table, const double* _
     }
 #pragma unroll
     for (int s = 0; s < BLK; s++) tab[blk_off_vh(NT, NTR) + r * 8 + s] = pe[s] * vv[s];
-    tab[blk_off_psi(NT, NTR) + r] = (rd.kind == ROW_AUG || rd.kind == ROW_AUG2) ? 1.0 : p0[BLK - 1];
+    tab[blk_off_psi(NT, NTR) + r] = (kind == ROW_AUG || kind == ROW_AUG2) ? 1.0 : p0[BLK - 1];
     for (int q = r; q < 32; q += RPT) {
         const int s = q & 7, f = q >> 3;
         const int64_t n = n0 + s;
         double sc = 0.0;
         if (n < N) sc = (f == 0) ? y[n] : (f == 1) ? s2[n] : (f == 2) ? 1.0 : 0.0;
         tab[blk_off_sc(NT, NTR) + q] = sc;
+    }
+}
+
+// Shared table of the approx path: one thread per (block, physical row).  rows[] describes the 8·NTR physical rows (ROW_PAD where
+// nothing lives, ROW_AUG / ROW_AUG2 at the data rows); RowDesc::term holds the logical row index of a celerite row.
+__global__ void blocked_table_kernel(double* __restrict__ table, const double* __restrict__ t, const double* __restrict__ y,
+                                     const double* __restrict__ s2, int64_t N, int64_t nblocks,
+                                     const RowDesc* __restrict__ rows, int NT, int NTR) {
+    const int RPT = 8 * NTR;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nblocks * RPT) return;
+    const int64_t b = gid / RPT;
+    const int r = (int)(gid - b * RPT);
+    const RowDesc rd = rows[r];
+    blocked_table_fill(table + b * (int64_t)blk_doubles(NT, NTR), t, y, s2, N, b * BLK, r, rd.kind, rd.c, rd.d, 1.0, rd.ratio, rd.term,
+                       NT, NTR);
+}
+
+// Row amplitude of an explicit-coefficient term: a, or b when a = 0 (a pure sine term), or 1 for an empty term.
+__host__ __device__ inline double blk_term_scale(double a, double b) { return a != 0.0 ? a : (b != 0.0 ? b : 1.0); }
+
+// Per-θ tables for explicit coefficients (CARMA, PSD features, the `:celerite_gpu` drop-in): the decay rates and frequencies
+// depend on θ, so every parameter vector gets its own table.  One thread per (θ, block, physical row).  prow[r] = {kind, term,
+// logical row} of physical row r (the pattern of real / complex terms is the batch's, make_term_rows).
+struct BlkRowMap { int kind, term, lrow; };
+__global__ void blocked_table_theta_kernel(double* __restrict__ tables, int64_t table_stride, int B, const double* __restrict__ t,
+                                           const double* __restrict__ y, const double* __restrict__ s2, int64_t N, int64_t nblocks,
+                                           const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                           const double* __restrict__ d, int Jt, const BlkRowMap* __restrict__ prow, int NT, int NTR) {
+    const int RPT = 8 * NTR;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)B * nblocks * RPT) return;
+    const int64_t i = gid / (nblocks * RPT), rem = gid - i * nblocks * RPT;
+    const int64_t blk = rem / RPT;
+    const int r = (int)(rem - blk * RPT);
+    const BlkRowMap rm = prow[r];
+    double cdec = 0.0, dfreq = 0.0, pa = 1.0, pb = 0.0;
+    if (rm.term >= 0) {
+        const size_t k = (size_t)i * Jt + rm.term;
+        const double sc = blk_term_scale(a[k], b[k]);
+        cdec = c[k]; dfreq = d[k]; pa = a[k] / sc; pb = b[k] / sc;
+    }
+    blocked_table_fill(tables + i * table_stride + blk * (int64_t)blk_doubles(NT, NTR), t, y, s2, N, blk * BLK, r, rm.kind, cdec, dfreq,
+                       pa, pb, rm.lrow, NT, NTR);
+}
+// Row amplitudes (logical order, stride RPA) and Σa (celerite_solver.jl:21) of the same batch.  One thread per θ.
+__global__ void blocked_amp_theta_kernel(double* __restrict__ amp, double* __restrict__ suma, int B, int RPA, int R,
+                                         const double* __restrict__ a, const double* __restrict__ b, int Jt,
+                                         const int* __restrict__ lrow_term) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double sa = 0.0;
+    for (int m = 0; m < Jt; m++) sa += a[(size_t)i * Jt + m];
+    suma[i] = sa;
+    for (int k = 0; k < RPA; k++) {
+        double v = 0.0;
+        if (k < R) { const size_t q = (size_t)i * Jt + lrow_term[k]; v = blk_term_scale(a[q], b[q]); }
+        amp[(size_t)i * RPA + k] = v;
     }
 }
 
