@@ -458,6 +458,34 @@ def config_c4_c5(ctx, pb, hbm_peak):
         "algorithmic_bytes": abytes, "hbm_gbs": abytes / (k3 * 1e-3) / 1e9, "hbm_frac": abytes / (k3 * 1e-3) / 1e9 / hbm_peak,
         "fp64_tflops_sequential_model": N * wl.flops_per_step(R) / (k3 * 1e-3) / 1e12,
         "note": "latency/FP64-bound, not HBM-bound (DESIGN.md K3): three passes over 296 chunks of the time axis"}
+    # C4 as a sampler would drive it: 32 prior-drawn parameter vectors (slopes up to 6) with the DRWCelerite basis, one call each;
+    # the ill-conditioned draws go through the Newton refinement of the chunk states instead of the sequential sweep
+    nd = 32
+    thd = wl.prior_theta(nd, f_min, f_max, y.mean(), y.std(), 12, 6.0)
+    specd = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20, basis_function="DRWCelerite")
+    ad, bd, cd_, dd = ctx.approx_coeffs(specd, thd[:, :4])
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_auto_scan(False)
+    t0 = time.perf_counter()
+    seqd = ctx.celerite_logl(ser, ad, bd, cd_, dd, mu=thd[:, 5], nu=thd[:, 4])
+    seq_wall = time.perf_counter() - t0
+    ctx.set_auto_scan(True)
+    ctx.celerite_logl_scan(ser, ad[:1], bd[:1], cd_[:1], dd[:1], mu=thd[:1, 5], nu=thd[:1, 4])
+    gotd, msd, nfb, nrf = np.empty(nd), [], 0, 0
+    for i in range(nd):
+        gotd[i] = ctx.celerite_logl_scan(ser, ad[i:i + 1], bd[i:i + 1], cd_[i:i + 1], dd[i:i + 1], mu=thd[i:i + 1, 5], nu=thd[i:i + 1, 4])[0]
+        msd.append(ctx.last_kernel_ms())
+        sc = ctx.last_scan_check()
+        nfb += sc.fallback; nrf += sc.refined
+    ser.free()
+    okd = np.isfinite(seqd)
+    devd = np.abs(gotd[okd] - seqd[okd]) / np.maximum(1.0, np.abs(seqd[okd]))
+    out["C4_long_series_N1e6_DRWCelerite_J20_32_prior_draws"] = {
+        "device_ms_mean": float(np.mean(msd)), "device_ms_median": float(np.median(msd)), "device_ms_max": float(np.max(msd)),
+        "newton_refined": int(nrf), "sequential_fallback": int(nfb), "finite": int(okd.sum()),
+        "max_rel_vs_sequential_kernel": float(devd.max()) if okd.any() else None,
+        "sequential_kernel_32_side_by_side_ms": seq_wall * 1e3,
+        "note": "one call per parameter vector; refinement = Newton steps on the chunk states with the exact recursion as residual"}
     t, y, s2, f_min, f_max = wl.make_series(2000, 5)
     th = wl.prior_theta(64, f_min, f_max, y.mean(), y.std(), 7)
     spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 20)

@@ -179,21 +179,32 @@ int pioran_approx_logl_logshift_grad(pioran_ctx *ctx, int series_id, const piora
  * sequential kernels (default: enabled). */
 int pioran_ctx_set_auto_scan(pioran_ctx *ctx, int enabled);
 
-/* Self-check of the parallel-in-time path.  Its composites lose accuracy where the covariance is ill-conditioned (steep
- * PSD slopes), so every call verifies itself: at each chunk boundary the 8 steps after it are swept twice - continuing
- * the sweep of the previous chunk, and from the state the scan computed - and the difference of their contributions to
- * log L, scaled to the chunk length and summed over the boundaries, estimates the deviation from the sequential sweep.
- * Parameter vectors whose estimate exceeds tol * max(1, |log L|) are swept again with a run-up of 1, then 3 chunks in
- * front of every chunk (the filter forgets the error of the injected state; only the last pass of the path is repeated)
- * and verified the same way; what still fails is evaluated by the sequential kernel.  So pioran_celerite_logl_scan and
- * the automatically routed calls return the sequential kernel's accuracy for every input (reference:
- * src/celerite_solver.jl:312-334 has one formulation only).  Default tol = 1e-10; tol <= 0 disables refinement and
- * fallback (the estimate is still computed).  pioran_ctx_last_scan_check reports the largest relative estimate among
- * the results of the last call, how many parameter vectors went to the sequential kernel and how many were accepted
- * after a run-up pass (any pointer may be NULL); after pioran_celerite_scan_range_end it reports that range's part of
- * the estimate in log L units (no refinement across ranks: the caller decides). */
+/* Self-check and Newton refinement of the parallel-in-time path.  Its composites lose accuracy where the covariance is
+ * ill-conditioned (steep PSD slopes), so every call verifies itself: at each chunk boundary the 8 steps after it are
+ * swept twice - continuing the sweep of the previous chunk, and from the state the scan computed - and the difference
+ * of their contributions to log L, scaled to the chunk length and summed over the boundaries, estimates the deviation
+ * from the sequential sweep.  Parameter vectors whose estimate exceeds tol * max(1, |log L|) get their chunk states
+ * corrected by Newton steps whose residual is the exact recursion itself (the last pass of the path is run chunk by
+ * chunk and returns the state every chunk leaves behind; the corrections follow a linear recurrence along the chunks),
+ * each verified the same way.  A parameter vector is accepted when its estimate meets tol, or when at least two Newton
+ * steps were taken, the estimate stalls (within 4x of the previous one, below 1000 x cap) and the value itself moved
+ * by no more than cap * max(1, |log L|) between the last two steps: what is left then is the rounding noise of an FP64
+ * evaluation of that covariance - any two FP64 routes differ by it, the sequential sweep's distance from an 80-bit
+ * evaluation included.  What still fails (composites breaking down on a barely
+ * positive definite covariance) is evaluated by the sequential kernel (reference: src/celerite_solver.jl:312-334 has
+ * one formulation only).  Defaults: tol = 1e-10, floor cap = 1e-7; tol <= 0 disables refinement and fallback (the
+ * estimate is still computed); cap <= 0 never accepts a stalled iteration.  pioran_ctx_last_scan_check reports the
+ * largest relative estimate among the results of the last call, how many parameter vectors went to the sequential
+ * kernel and how many were accepted after a refinement pass (any pointer may be NULL); after
+ * pioran_celerite_scan_range_end it reports that range's part of the estimate in log L units (no refinement across
+ * ranks: the caller decides).  pioran_ctx_last_scan_history returns, for parameter vector `index` of the last call,
+ * the relative estimate and the value after every pass it went through (pass 0: the scan's states; pass 1: the same
+ * states swept chunk by chunk; pass k >= 2: after k - 1 Newton steps); *n_passes = how many there were. */
 int pioran_ctx_set_scan_tolerance(pioran_ctx *ctx, double tol);
 int pioran_ctx_last_scan_check(pioran_ctx *ctx, double *estimate, int *n_fallback, int *n_refined);
+int pioran_ctx_set_scan_floor_cap(pioran_ctx *ctx, double cap);
+int pioran_ctx_last_scan_history(pioran_ctx *ctx, int index, int max_passes, double *estimates, double *values,
+                                 int *n_passes);
 
 /* Number of time-axis chunks per parameter vector used by pioran_celerite_logl_scan (0 = automatic: two per SM, at
  * least 64 steps each).  The result does not depend on it beyond rounding; tests use it to exercise the scan on short

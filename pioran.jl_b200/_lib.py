@@ -49,6 +49,8 @@ SYMBOLS = {
     "pioran_ctx_set_scan_tolerance": (C.c_int, [C.c_void_p, C.c_double]),
     "pioran_celerite_scan_range_check": (C.c_int, [C.c_void_p, _dp]),
     "pioran_ctx_last_scan_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pioran_ctx_set_scan_floor_cap": (C.c_int, [C.c_void_p, C.c_double]),
+    "pioran_ctx_last_scan_history": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
     "pioran_celerite_logl_scan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "pioran_scan_composite_doubles": (C.c_int, []),
     "pioran_celerite_scan_range_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp]),

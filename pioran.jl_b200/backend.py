@@ -246,16 +246,27 @@ class Context:
         check(self.lib.pioran_ctx_set_scan_chunks(self.h, int(chunks)))
 
     def set_scan_tolerance(self, tol):
-        """Self-check of the scan path: parameter vectors whose deviation estimate exceeds tol·max(1, |log L|) are evaluated
-        again by the sequential sweep (default 1e-10; ≤ 0: never)."""
+        """Self-check of the scan path: parameter vectors whose deviation estimate exceeds tol·max(1, |log L|) are refined by
+        Newton steps on the chunk states, then (if that fails) evaluated by the sequential sweep (default 1e-10; ≤ 0: never)."""
         check(self.lib.pioran_ctx_set_scan_tolerance(self.h, float(tol)))
 
     def last_scan_check(self):
         """ScanCheck(estimate, fallback, refined) of the last scan call: largest relative deviation estimate among its results,
-        parameter vectors sent to the sequential sweep, parameter vectors accepted after a run-up pass."""
+        parameter vectors sent to the sequential sweep, parameter vectors accepted after a refinement pass."""
         est, nfb, nrf = C.c_double(0.0), C.c_int(0), C.c_int(0)
         check(self.lib.pioran_ctx_last_scan_check(self.h, C.byref(est), C.byref(nfb), C.byref(nrf)))
         return ScanCheck(est.value, nfb.value, nrf.value)
+
+    def set_scan_floor_cap(self, cap):
+        """Largest stalled estimate of a converged Newton iteration accepted as the rounding floor (default 1e-7; ≤ 0: never)."""
+        check(self.lib.pioran_ctx_set_scan_floor_cap(self.h, float(cap)))
+
+    def last_scan_history(self, index=0, max_passes=8):
+        """(estimates, values) of parameter vector `index` of the last scan call after every pass it went through."""
+        est, val, n = np.zeros(max_passes), np.zeros(max_passes), C.c_int(0)
+        check(self.lib.pioran_ctx_last_scan_history(self.h, int(index), int(max_passes), _p(est), _p(val), C.byref(n)))
+        k = min(n.value, max_passes)
+        return est[:k], val[:k]
 
     def celerite_logl_scan(self, series, a, b, c, d, mu=None, nu=None):
         a, b, c, d = (np.atleast_2d(_f64(x)) for x in (a, b, c, d))

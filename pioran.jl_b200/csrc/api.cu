@@ -122,6 +122,8 @@ struct pioran_ctx {
     uint64_t epoch = 0;    // bumped by every entry that uses the shared workspaces (a pending scan range checks it)
     uint64_t use_clock = 0;   // LRU stamp source of the per-series table caches
     double scan_tol = 1e-10;       // K3 self-check: tolerated deviation estimate, relative to max(1, |log L|); <= 0: no check
+    double scan_floor_cap = 1e-7;  // K3: largest stalled estimate of a converged Newton iteration that is accepted as rounding floor; <= 0: never
+    std::vector<std::vector<double>> scan_hist_est, scan_hist_val;   // per parameter vector of the last K3 call: estimate and value after every pass
     double scan_last_est = 0.0;    // largest relative estimate of the last K3 call
     int scan_last_fallback = 0;    // parameter vectors of the last K3 call that were re-evaluated by the sequential sweep
     int scan_last_refined = 0;     // … that were accepted after a run-up pass
@@ -1876,6 +1878,34 @@ extern "C" int pioran_ctx_last_scan_check(pioran_ctx* c, double* estimate, int* 
     if (n_refined) *n_refined = c->scan_last_refined;
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }
+extern "C" int pioran_ctx_set_scan_floor_cap(pioran_ctx* c, double cap) try {
+    if (is_group(c)) {
+        for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_scan_floor_cap(ch, cap); if (rc) return rc; }
+        return PIORAN_OK;
+    }
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    if (!(cap == cap)) return fail(PIORAN_EINVAL, "cap is NaN");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->scan_floor_cap = cap;
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+extern "C" int pioran_ctx_last_scan_history(pioran_ctx* c, int index, int max_passes, double* estimates, double* values,
+                                            int* n_passes) try {
+    if (is_group(c)) return pioran_ctx_last_scan_history(c->children[0], index, max_passes, estimates, values, n_passes);
+    if (!c) return fail(PIORAN_EINVAL, "ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (index < 0 || (size_t)index >= c->scan_hist_est.size())
+        return fail(PIORAN_EINVAL, "index %d outside the %zu parameter vectors of the last scan call", index, c->scan_hist_est.size());
+    const std::vector<double>& e = c->scan_hist_est[index];
+    const std::vector<double>& v = c->scan_hist_val[index];
+    const int n = (int)e.size();
+    if (n_passes) *n_passes = n;
+    for (int k = 0; k < n && k < max_passes; k++) {
+        if (estimates) estimates[k] = e[k];
+        if (values) values[k] = v[k];
+    }
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
 extern "C" int pioran_ctx_set_scan_chunks(pioran_ctx* c, int chunks) try {
     if (is_group(c)) {
         for (pioran_ctx* ch : c->children) { const int rc = pioran_ctx_set_scan_chunks(ch, chunks); if (rc) return rc; }
@@ -1903,6 +1933,8 @@ struct ScanRun {
     double *total = nullptr, *scratch = nullptr, *init = nullptr, *prev = nullptr, *sums = nullptr;
     double *subel = nullptr, *substate = nullptr, *tot0 = nullptr, *tot1 = nullptr, *tp = nullptr;
     double *chk = nullptr, *err = nullptr;   // self-check sums (4 per sub-chunk) and the per-θ deviation estimate
+    double *ksbuf = nullptr;                 // second Kogge–Stone buffer (the fold's composites in `elems` stay intact for the Newton step)
+    double *exits = nullptr, *tm = nullptr;  // Newton refinement: exit state of every chunk sweep, (T | m) of every chunk
     double check_scale = 1.0;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
@@ -1910,7 +1942,7 @@ struct ScanRun {
 static int scan_live_rank(int R) { return std::min(SR, (R + 3) & ~3); }
 // Steps of the self-check at a sub-chunk boundary: SCAN_CHECK_STEPS, or the (even part of the) sub-chunk when it is shorter.
 constexpr int SCAN_CHECK_STEPS = 8;
-constexpr int SCAN_MAX_WARM_SUBS = 3;   // refinement ladder: run-ups of 1 and 3 sub-chunks, then the sequential sweep
+constexpr int SCAN_MAX_NEWTON = 3;      // refinement ladder: up to three Newton steps on the chunk states, then the sequential sweep
 static int scan_check_steps(int64_t sub_len) { return (int)std::min<int64_t>(SCAN_CHECK_STEPS, sub_len & ~(int64_t)1); }
 static std::map<pioran_ctx*, ScanRun> g_scan;
 static std::mutex g_scan_mu;
@@ -1959,7 +1991,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE, n_gt = (size_t)B * G1 * SEL;
     const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
     const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
-    if ((rc = c->misc.ensure(sizeof(double) * (2 * n_el + n_gs + n_cs + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
+    const size_t n_tm = nch * SNEWT;
+    if ((rc = c->misc.ensure(sizeof(double) * (3 * n_el + n_gs + 2 * n_cs + n_tm + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
         return rc;
     run.elems = c->misc.as<double>();
     run.pref = run.elems + n_el;
@@ -1978,6 +2011,9 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.tot1 = run.tot0 + n_gt;
     run.chk = run.tot1 + n_gt;
     run.err = run.chk + n_chk;
+    run.ksbuf = run.err + B;
+    run.exits = run.ksbuf + n_el;
+    run.tm = run.exits + n_cs;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
@@ -2005,7 +2041,9 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
         for (int dd = 1; dd < G2 && P > 1; dd *= 2) {
             scan_ks_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(src, dst, P, G2, dd, Rr);
             c->launches++;
-            std::swap(src, dst);
+            double* const wrote = dst;
+            dst = (src == run.elems) ? run.ksbuf : src;     // never back into the fold's output
+            src = wrote;
         }
         run.pref = src;      // the buffer the last level wrote (the fold's own output when there is a single chunk per group)
     }
@@ -2099,24 +2137,98 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     return dispatch_chunked(c, run.BS, args, (int)(nitems / NW));
 }
 
+// Pass 3 chunk by chunk (Newton refinement, scan.cuh): SUB launches; launch j sweeps sub-chunk j of EVERY chunk from the state
+// the previous launch left behind (j = 0: the chunk state S̃_k) and stores the state it arrives at — in the inner-boundary slot
+// the next launch starts from, or (last sub-chunk) in run.exits.  The inner states are then those of the exact recursion
+// started from S̃_k, so only the chunk boundaries carry a self-check.
+static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
+    const int B = run.B, P = run.P, NW = CHUNK_NW, SUB = run.SUB;
+    const size_t nch = (size_t)B * P;
+    const size_t npl = (nch + NW - 1) / NW * NW;       // work items per launch
+    const int PS = P * SUB;
+    std::vector<WorkItem>& items = run.items_host;
+    items.assign(npl * SUB, WorkItem{});
+    auto bound = [&](int g) { return g >= PS ? run.bounds[P] : scan_sub_bound(run.bounds[g / SUB], run.bounds[g / SUB + 1], g % SUB, SUB); };
+    for (int j = 0; j < SUB; j++)
+        for (size_t k = 0; k < npl; k++) {
+            const bool real = k < nch;
+            const size_t e = std::min(k, nch - 1);
+            const int th = (int)(e / P), ch = (int)(e % P), g = ch * SUB + j;
+            WorkItem& w = items[(size_t)j * npl + k];
+            w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = run.N;
+            w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
+            w.n_begin = bound(g); w.n_end = bound(g + 1); w.n_warm = 0;
+            if (j == 0) w.init = ch == 0 ? nullptr : run.cstate + e * SSTATE;
+            else w.init = run.substate + (e * (SUB - 1) + (j - 1)) * SSTATE;
+            const size_t slot = real ? (size_t)th * PS + g : nch * SUB;       // padding warps write to the dummy slots
+            w.part = run.parts + 2 * slot;
+            w.chk = run.chk + 4 * slot;
+            w.n_head = (j == 0 && ch > 0) ? scan_check_steps(bound(g + 1) - bound(g)) : 0;
+            w.n_ext = (j == SUB - 1 && ch < P - 1) ? scan_check_steps(bound(g + 2) - bound(g + 1)) : 0;
+            w.exit = nullptr;
+            if (real && j < SUB - 1) w.exit = run.substate + (e * (SUB - 1) + j) * SSTATE;
+            else if (real && ch < P - 1) w.exit = run.exits + e * SSTATE;
+        }
+    run.check_scale = std::max(1.0, (double)(run.n_hi - run.n_lo) / ((double)P * SCAN_CHECK_STEPS));
+    int rc;
+    c->work_key.clear();
+    if ((rc = c->work.ensure(sizeof(WorkItem) * items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
+    BatchArgs args{};
+    args.a = run.gi.a; args.b = run.gi.b; args.c = run.gi.c; args.d = run.gi.d;
+    args.Jt = run.Jt; args.term_row = run.term_row_dev; args.R = run.R;
+    args.mu = run.gi.mu; args.nu = run.gi.nu; args.pstride = 1;
+    args.out = run.out;
+    for (int j = 0; j < SUB; j++) {
+        args.work = c->work.as<WorkItem>() + (size_t)j * npl;
+        if ((rc = dispatch_chunked(c, run.BS, args, (int)(npl / NW)))) return rc;
+    }
+    return 0;
+}
+
+// One Newton step on the chunk states: (T_k | m_k) of every chunk from its composite and current state, then the linear
+// recurrence of the corrections along the chunks (needs the exits of a scan_seq_pass over the current states).
+static int scan_newton_step(pioran_ctx* c, ScanRun& run) {
+    const int Rr = scan_live_rank(run.R);
+    CUDA_TRY(cudaFuncSetAttribute(scan_newton_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(scan_newton_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    scan_newton_T_kernel<<<dim3(run.P, run.B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.cstate, run.tm, run.P, Rr);
+    scan_newton_chain_kernel<<<dim3(1, run.B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tm, run.exits, run.cstate, run.P, Rr);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
                             const double* cc, const double* d, const double* mu, const double* nu, double* logl_out) {
     ScanRun run;
     int rc;
     cudaEventRecord(c->ev_beg, c->stream);
     if ((rc = scan_phase1(c, s, series_id, B, Jt, a, b, cc, d, mu, nu, 0, s->N, false, 0, run))) return rc;
-    // Self-check and refinement ladder (scan.cuh, scan_check_estimate).  The composites lose accuracy where the covariance is
-    // ill-conditioned (steep PSD slopes: the scan's value was seen 1e-8 … 1e-6 away from the sequential sweep's, which stays
-    // within 1e-9 of an 80-bit evaluation there).  Parameter vectors whose estimate exceeds the tolerance are swept again with a
-    // run-up of 1, then 3 sub-chunks in front of every sub-chunk (the filter forgets the error of the injected state; pass 3
-    // only, (1 + run-up)× its cost), verified the same way; what still fails goes to the sequential sweep.
+    // Self-check and refinement ladder (scan.cuh: scan_check_estimate, Newton refinement).  The composites lose accuracy where
+    // the covariance is ill-conditioned (steep PSD slopes: the scan's value was seen 1e-8 … 1e-6 away from the sequential
+    // sweep's).  When the estimate of a parameter vector exceeds the tolerance, the chunk states are corrected by Newton steps
+    // whose residual is the exact recursion itself (chunk-by-chunk sweeps that return their exit states), each verified the same
+    // way.  A parameter vector is accepted when its estimate meets the tolerance, or when the Newton iteration has converged and
+    // stalls at a level the tolerance cannot resolve: what is left then is the rounding noise of an FP64 evaluation of THIS
+    // covariance — two sweeps that reach a boundary by different routes differ by it, the sequential sweep included (its own
+    // distance from an 80-bit evaluation on such rows is of the same size) — capped (scan_floor_cap).  What still fails
+    // (breakdown of the composites on a barely positive definite covariance) goes to the sequential sweep.
     c->scan_last_est = 0.0; c->scan_last_fallback = 0; c->scan_last_refined = 0;
-    std::vector<double> est(B), val(B);
+    c->scan_hist_est.assign(B, {}); c->scan_hist_val.assign(B, {});
+    std::vector<double> est(B), val(B), prev_rel(B, 0.0), prev_val(B, 0.0);
     std::vector<char> accepted(B, 0);
     std::vector<int> redo;
     const int PS = run.P * run.SUB;
-    for (int level = 0, warm = 0;; level++, warm = 2 * warm + 1) {
-        if ((rc = scan_phase2(c, s, run, nullptr, warm, level > 0))) return rc;
+    for (int level = 0;; level++) {
+        // level 0: all sub-chunks at once from the scan's states; level 1: chunk by chunk from the same chunk states (exits for
+        // the first Newton step); level ≥ 2: chunk by chunk from the corrected states
+        if (level == 0) { if ((rc = scan_phase2(c, s, run, nullptr))) return rc; }
+        else {
+            if (level == 1) CUDA_TRY(cudaMemsetAsync(run.exits, 0, sizeof(double) * (size_t)B * run.P * SSTATE, c->stream));
+            if (level >= 2 && (rc = scan_newton_step(c, run))) return rc;
+            if ((rc = scan_seq_pass(c, s, run))) return rc;
+        }
         scan_finish_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(run.parts, run.chk, run.check_scale, PS, B, s->N, run.out, run.err);
         c->launches++;
         cudaEventRecord(c->ev_end, c->stream);
@@ -2129,7 +2241,17 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
         for (int i = 0; i < B; i++) {
             if (accepted[i]) continue;
             const double rel = est[i] / std::max(1.0, std::fabs(val[i]));
-            const bool ok = !(c->scan_tol > 0.0) || rel <= c->scan_tol;
+            c->scan_hist_est[i].push_back(rel); c->scan_hist_val[i].push_back(val[i]);
+            bool ok = !(c->scan_tol > 0.0) || rel <= c->scan_tol;
+            // converged Newton iteration at the rounding floor of this covariance (level ≥ 3: two Newton steps done): the
+            // estimate no longer moves (within 4× of the previous pass) and the value changed by no more than the floor cap
+            // between the last two Newton steps (the estimate itself is pessimistic: it extends the mismatch of 8 steps to the
+            // whole chunk; the pass-to-pass change of the value is what the iteration can still resolve)
+            const double moved = std::fabs(val[i] - prev_val[i]) / std::max(1.0, std::fabs(val[i]));
+            if (!ok && level >= 3 && c->scan_floor_cap > 0.0 && rel > 0.25 * prev_rel[i] && rel < 4.0 * prev_rel[i] &&
+                moved <= c->scan_floor_cap && rel <= 1e3 * c->scan_floor_cap)
+                ok = true;
+            prev_rel[i] = rel; prev_val[i] = val[i];
             if (ok || level == 0) logl_out[i] = val[i];
             if (ok) {
                 accepted[i] = 1;
@@ -2139,8 +2261,7 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
                 redo.push_back(i);
             }
         }
-        // a run-up pass pays while it is much shorter than the sequential sweep
-        if (redo.empty() || warm >= SCAN_MAX_WARM_SUBS || 4 * (2 * warm + 2) > PS) break;
+        if (redo.empty() || run.P < 2 || level >= 1 + SCAN_MAX_NEWTON) break;
     }
     {
         for (int i : redo) {

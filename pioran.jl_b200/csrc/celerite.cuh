@@ -885,15 +885,8 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
         }
     }
 
-    // CHUNKED: three segments — [nb, nb + n_head) | … n1) | [n1, n1 + n_ext) — with the sums taken and reset in between (every
-    // segment but the last has an even length, so the even/odd alternation of the steps runs through)
-    // (seg = −1: the run-up of a refinement pass, [n0, n0 + n_warm), sums discarded; the sub-chunk proper starts at nb)
-    const int64_t nb = CHUNKED ? n0 + wk.n_warm : n0;
-    for (int seg = (CHUNKED && wk.n_warm > 0) ? -1 : 0; seg < (CHUNKED ? 3 : 1); seg++) {
-    const int64_t sbeg = !CHUNKED ? n0 : seg < 0 ? n0 : seg == 0 ? nb : seg == 1 ? nb + wk.n_head : n1;
-    const int64_t send = !CHUNKED ? n1 : seg < 0 ? nb : seg == 0 ? nb + wk.n_head : seg == 1 ? n1 : n1 + wk.n_ext;
-    for (int64_t nbeg = sbeg; nbeg < send; nbeg += GCH) {
-        const int nsteps = (int)((send - nbeg) < GCH ? (send - nbeg) : GCH);
+    // table records of the steps [nbeg, nbeg + nsteps) in this warp's shared-memory chunk (celerite_solver.jl:51-64)
+    auto build_rows = [&](const int64_t nbeg, const int nsteps) {
         // pass 1: φ for steps nbeg-1 … nbeg+GCH  (φ_0 = 0, φ_N = 0; chunk start of K3: φ := 1 up to step n0)
         for (int idx = lane; idx < (GCH + 2) * Jt; idx += 32) {
             const int s = idx / Jt, m = idx - s * Jt;
@@ -931,6 +924,17 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
             }
         }
         __syncwarp();
+    };
+    // CHUNKED: three segments — [nb, nb + n_head) | … n1) | [n1, n1 + n_ext) — with the sums taken and reset in between (every
+    // segment but the last has an even length, so the even/odd alternation of the steps runs through)
+    // (seg = −1: the run-up of a refinement pass, [n0, n0 + n_warm), sums discarded; the sub-chunk proper starts at nb)
+    const int64_t nb = CHUNKED ? n0 + wk.n_warm : n0;
+    for (int seg = (CHUNKED && wk.n_warm > 0) ? -1 : 0; seg < (CHUNKED ? 3 : 1); seg++) {
+    const int64_t sbeg = !CHUNKED ? n0 : seg < 0 ? n0 : seg == 0 ? nb : seg == 1 ? nb + wk.n_head : n1;
+    const int64_t send = !CHUNKED ? n1 : seg < 0 ? nb : seg == 0 ? nb + wk.n_head : seg == 1 ? n1 : n1 + wk.n_ext;
+    for (int64_t nbeg = sbeg; nbeg < send; nbeg += GCH) {
+        const int nsteps = (int)((send - nbeg) < GCH ? (send - nbeg) : GCH);
+        build_rows(nbeg, nsteps);
         for (int s = 0; s < nsteps; s += 2) {
             const double* T0 = tab + s * SD;
             const int64_t n = nbeg + s;
@@ -938,6 +942,34 @@ __global__ void __launch_bounds__(NW * 32, 1) celerite_generic_kernel(const Batc
             if (s + 1 < nsteps)
                 celerite_step<BS, true, false, MODE>(st, T0 + SD, qs, ws, lm, yb[n + 1], sb[n + 1], suma, mu, nu, n + 1, lane,
                                                      nullptr, &aux);
+        }
+        __syncwarp();
+    }
+    if (CHUNKED && seg == 1 && wk.exit && n1 < N) {
+        // K3 Newton refinement: the state entering step n1.  The last step was a (local) odd one: M holds the state with its
+        // row factor pending and (φ∘q, w) of that step sit in the scratch vectors — what the even step n1 would do to its
+        // blocks, then the pending column factor φ_c(n1); the diagonal and g are kept fully decayed already.
+        build_rows(n1, 1);
+        constexpr int RL = SCAN_LD;
+        double* E = wk.exit;
+        const int rI = i * BS, cA = ((i + o) & 7) * BS, cB = (o == 0) ? ((i ^ 4) * BS) : cA;
+#pragma unroll
+        for (int r = 0; r < BS; r++)
+#pragma unroll
+            for (int c = 0; c < BS; c++) {
+                if (r == c && lm.dzero) continue;
+                const bool useA = r > c;
+                const int colp = useA ? lm.colA : lm.colB, col = useA ? cA : cB;
+                const double m = fma(tab[F_KAP * RPS + lm.rowI + r], st.M[r][c], qs[lm.rowI + r] * ws[colp + c]);
+                const double v = tab[F_PHI * RPS + colp + c] * m;
+                E[(size_t)(rI + r) * RL + col + c] = v;
+                E[(size_t)(col + c) * RL + rI + r] = v;
+            }
+        E[(size_t)(rI + o) * RL + rI + o] = st.sjj[0];
+        E[(size_t)RL * RL + rI + o] = st.g[0];
+        if (lm.valid1) {
+            E[(size_t)(rI + o + 4) * RL + rI + o + 4] = st.sjj[1];
+            E[(size_t)RL * RL + rI + o + 4] = st.g[1];
         }
         __syncwarp();
     }

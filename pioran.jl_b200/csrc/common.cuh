@@ -74,6 +74,10 @@ struct WorkItem {
     // K3 refinement: the sweep starts n_warm steps before the sub-chunk (n_begin and `init` refer to that earlier point) and
     // the sums of those steps are discarded — the filter forgets the error of the injected state while it runs up.
     int64_t n_warm;
+    // K3 Newton refinement: when non-null, the state entering step n_end (S | g, same layout as `init`; entries outside the
+    // 8·BS logical rows are not written) is stored here before the look-ahead steps — the exit state of the sweep, i.e. the
+    // exact recursion applied to `init`.  Needs an even number of steps in [n_begin, n_end) and n_end < N.
+    double* exit;
 };
 
 // sin and cos of a large FP64 argument.  The celerite rows take cos/sin(d_j·t_n) at ABSOLUTE times

@@ -550,6 +550,92 @@ __global__ void __launch_bounds__(256, 1) scan_substates_kernel(const double* su
     scan_apply(w, el, (ch == 0 && !has_init) ? nullptr : cstate + q * SSTATE, out);
 }
 
+// ------------------------------------------------------------------------------------------------ Newton refinement
+// The composites lose digits in their combines on ill-conditioned covariances, so the chunk states S̃_k the scan hands to
+// pass 3 can be ~1e-8 off — and the filter forgets such an error only algebraically on slowly decaying terms, so run-ups do
+// not remove it.  One Newton step on the boundary states does, with the EXACT recursion as the residual: pass 3, run chunk by
+// chunk, also returns the state it leaves behind, E_k = F_k(S̃_k) (WorkItem::exit); the correction δ_k of S̃_k obeys
+//     δS_{k+1} = T_k δS_k T_kᵀ + (E_k − S̃_{k+1}),      δg_{k+1} = T_k (δg_k + δS_k m_k) + (Eg_k − g̃_{k+1}),
+// T_k = 𝒜_k (I + S̃_k J_k)⁻¹ the closed-loop transition of chunk k and m_k = η_k − J_k ĝ_k, ĝ_k = (I + S̃_k J_k)⁻¹(g̃_k + S̃_k η_k)
+// (the derivative of the linear-fractional map of scan_apply).  T_k and m_k come from the composites and are needed to first
+// order only: their own 1e-8 error enters at second order.  Derivation and a numpy check: tests/tools/proto/scan_newton_math.py.
+constexpr int SNEWT = SR * SR + SR;           // doubles per chunk: T | m
+// grid = (P, B).  With X = (I + S J)⁻¹ S (the solve scan_apply does):  (I + S J)⁻¹ = I − X J,  so  T = 𝒜 − (𝒜 X) J.
+__global__ void __launch_bounds__(256, 1) scan_newton_T_kernel(const double* elems, const double* cstate, double* tm, int P,
+                                                               int Rr) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const ScanSmem w = scan_smem(raw, Rr);
+    const int th = blockIdx.y, ch = blockIdx.x, tid = threadIdx.x;
+    const size_t q = (size_t)th * P + ch;
+    const double* el = elems + q * SEL;
+    const double *Ae = el, *Je = el + 2 * SR * SR, *ete = el + 3 * SR * SR + SR;
+    double* To = tm + q * SNEWT;
+    double* mo = To + SR * SR;
+    if (ch == 0) {      // zero state: T = 𝒜, m = η (δ_0 = 0, so neither is used)
+        for (int k = tid; k < SR * SR; k += blockDim.x) To[k] = Ae[k];
+        if (tid < SR) mo[tid] = ete[tid];
+        return;
+    }
+    const double* in = cstate + q * SSTATE;
+    sm_load(w.m[0], in);
+    sm_load(w.m[1], Je);
+    if (tid < SR) { w.v[0][tid] = in[SR * SR + tid]; w.v[1][tid] = ete[tid]; }
+    __syncthreads();
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[0], w.m[1], nullptr, false, w.Rr);        // S J
+    if (tid < SR) {
+        w.m[2][tid * SLD + tid] += 1.0;
+        w.v[3][tid] = w.v[0][tid] + sm_matvec_row<false>(w.m[0], w.v[1], tid, w.Rr);       // g + S η
+    }
+    __syncthreads();
+    sm_gj_solve(w.m[2], w.m[0], nullptr, w.v[3], 1, w.Rr);   // m0 = X;  v3 = ĝ
+    sm_load(w.m[4], Ae);
+    __syncthreads();
+    sm_matmul<false, false>(w.m[2], nullptr, w.m[4], w.m[0], nullptr, false, w.Rr);        // 𝒜 X
+    sm_matmul<false, false>(w.m[3], nullptr, w.m[2], w.m[1], nullptr, false, w.Rr);        // (𝒜 X) J
+    for (int k = tid; k < SR * SR; k += blockDim.x) To[k] = Ae[k] - w.m[3][(k / SR) * SLD + (k % SR)];
+    if (tid < SR) mo[tid] = w.v[1][tid] - sm_matvec_row<false>(w.m[1], w.v[3], tid, w.Rr);
+}
+// grid = (1, B): the recurrence above along the chunks of one parameter vector; S̃_k ← S̃_k + δ_k in place (= E_{k−1} + the
+// propagated correction of the earlier boundaries).  exits[k] = E_k.
+__global__ void __launch_bounds__(256, 1) scan_newton_chain_kernel(const double* tm, const double* exits, double* cstate, int P,
+                                                                   int Rr) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const ScanSmem w = scan_smem(raw, Rr);
+    const int th = blockIdx.y, tid = threadIdx.x;
+    double* dS = w.m[0];
+    for (int k = tid; k < SMAT; k += blockDim.x) dS[k] = 0.0;
+    if (tid < SR) w.v[0][tid] = 0.0;                                                        // δg
+    __syncthreads();
+    for (int k = 1; k < P; k++) {
+        const size_t q = (size_t)th * P + k;
+        if (k >= 2) {                                                                       // δ_1 = r_1: nothing to propagate yet
+            const double* T = tm + (q - 1) * SNEWT;
+            sm_load(w.m[1], T);
+            if (tid < SR) w.v[1][tid] = T[SR * SR + tid];
+            __syncthreads();
+            if (tid < SR) w.v[2][tid] = w.v[0][tid] + sm_matvec_row<false>(dS, w.v[1], tid, w.Rr);    // δg + δS m
+            __syncthreads();
+            if (tid < SR) w.v[0][tid] = sm_matvec_row<false>(w.m[1], w.v[2], tid, w.Rr);              // T (δg + δS m)
+            sm_matmul<false, false>(w.m[2], nullptr, w.m[1], dS, nullptr, false, w.Rr);               // T δS
+            sm_matmul<false, true>(dS, nullptr, w.m[2], w.m[1], nullptr, true, w.Rr);                 // (T δS) Tᵀ, symmetrised
+        }
+        const double* E = exits + (q - 1) * SSTATE;
+        double* S = cstate + q * SSTATE;
+        for (int idx = tid; idx < SR * SR; idx += blockDim.x) {
+            const int sidx = (idx / SR) * SLD + (idx % SR);
+            const double d = dS[sidx] + (E[idx] - S[idx]);
+            dS[sidx] = d;
+            S[idx] += d;
+        }
+        if (tid < SR) {
+            const double d = w.v[0][tid] + (E[SR * SR + tid] - S[SR * SR + tid]);
+            w.v[0][tid] = d;
+            S[SR * SR + tid] += d;
+        }
+        __syncthreads();
+    }
+}
+
 // (e) state entering this range = the composites of the nprev earlier ranges applied, in order, to the zero state.
 //     elems_prev is [nprev × B × SEL] (rank-major, as gathered); grid = (1, B).
 __global__ void __launch_bounds__(256, 1) scan_chain_kernel(const double* elems_prev, int nprev, int B, double* state,

@@ -98,6 +98,48 @@ def test_config_c4_long_series_n1e6_j30(pb, ctx):
     ser.free()
 
 
+def test_config_c4_long_series_n1e6_drwcelerite_prior_draws(pb, ctx):
+    """C4 at full size over 32 PRIOR-DRAWN parameter vectors with the DRWCelerite basis (rank 60, slopes up to 6: the
+    ill-conditioned part of the prior included), one call each as a sampler on a single long series would make them: every
+    value within 1e-9 of the sequential sweep (or at the rounding floor of its covariance, triaged with the 80-bit twin),
+    the Newton refinement instead of the sequential fallback, mean device time reported."""
+    import workloads as wl
+    N, B, J = 1_000_000, 32, 20
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=4)
+    th = wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), 12, 6.0)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, J, basis_function="DRWCelerite")
+    a, b, c, d = ctx.approx_coeffs(spec, th[:, :4])
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_scan_chunks(0)
+    ctx.set_auto_scan(False)
+    t0 = time.perf_counter()
+    seq = ctx.celerite_logl(ser, a, b, c, d, mu=th[:, 5], nu=th[:, 4])       # 32 sequential sweeps side by side
+    wall_seq = time.perf_counter() - t0
+    ctx.set_auto_scan(True)
+    ctx.celerite_logl_scan(ser, a[:1], b[:1], c[:1], d[:1], mu=th[:1, 5], nu=th[:1, 4])     # warm-up (buffers)
+    got, ms, passes, nfb, nrf = np.empty(B), [], [], 0, 0
+    for i in range(B):
+        got[i] = ctx.celerite_logl_scan(ser, a[i:i + 1], b[i:i + 1], c[i:i + 1], d[i:i + 1], mu=th[i:i + 1, 5], nu=th[i:i + 1, 4])[0]
+        ms.append(ctx.last_kernel_ms())
+        sc = ctx.last_scan_check()
+        nfb += sc.fallback; nrf += sc.refined
+        passes.append(len(ctx.last_scan_history(0)[0]))
+    ser.free()
+    ok = np.isfinite(seq)
+    assert np.array_equal(np.isfinite(got), ok)
+    err = np.abs(got[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
+    ms = np.array(ms)
+    print(f"\nC4 N=1e6 DRWCelerite J={J} over {B} prior draws ({int(ok.sum())} finite): device ms mean {ms.mean():.2f}, median {np.median(ms):.2f}, "
+          f"max {ms.max():.2f} (one sequential sweep: {wall_seq * 1e3:.0f} ms for all {B} side by side); passes per call {np.bincount(passes).tolist()}; "
+          f"{nrf} accepted after Newton refinement, {nfb} to the sequential sweep; max |scan - seq| {err.max():.2e}")
+    for i in np.flatnonzero(ok)[err > TOL]:
+        ld = float(orc.celerite_logl(a[i], b[i], c[i], d[i], t, y - th[i, 5], th[i, 4] * s2, long_double=True))
+        floor = abs(seq[i] - ld) / max(1.0, abs(ld))
+        assert floor > 1e-10 and abs(got[i] - ld) / max(1.0, abs(ld)) <= 30 * floor + TOL, (i, err.max(), floor)
+    assert nfb <= 1, nfb          # the sequential sweep (2.6 s here) is the exception, not the ladder
+    assert ms.mean() < 40.0
+
+
 @pytest.mark.parametrize("world,chunks,N", [(2, 0, 6000), (3, 5, 6001), (8, 0, 5995), (4, 1, 6000)])
 def test_scan_time_axis_split_across_ranks(pb, ctx, world, chunks, N):
     """the time axis split over `world` ranks — emulated on one GPU with one context per rank, the
@@ -192,7 +234,9 @@ def test_scan_self_check_keeps_sequential_accuracy(pb, ctx, basis, J):
         got.append(ctx.celerite_logl(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]))   # auto-routed to the scan path
         sc = ctx.last_scan_check()
         nfb += sc.fallback; nrf += sc.refined
-        assert not (sc.estimate > 1e-10) or sc.fallback > 0      # what is returned from the scan path passed its check
+        # what is returned from the scan path passed its check, or went through the Newton refinement / the sequential sweep
+        assert not (sc.estimate > 1e-10) or sc.fallback > 0 or sc.refined > 0
+        assert not (sc.estimate > 1e-7) or sc.fallback > 0       # the floor cap of a stalled refinement
     got = np.concatenate(got)
     ctx.set_scan_tolerance(0.0)
     raw = np.concatenate([ctx.celerite_logl_scan(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]) for i in range(0, 64, 4)])
@@ -202,8 +246,15 @@ def test_scan_self_check_keeps_sequential_accuracy(pb, ctx, basis, J):
     ok = np.isfinite(seq)
     err = np.abs(got[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
     err_raw = np.abs(raw[ok] - seq[ok]) / np.maximum(1.0, np.abs(seq[ok]))
-    print(f"\n{basis} J={J}: checked max {np.nanmax(err):.1e} ({nrf} of 64 accepted after a run-up pass, {nfb} re-evaluated sequentially), raw scan max {np.nanmax(err_raw):.1e}")
-    assert np.all(err <= TOL), err.max()
+    print(f"\n{basis} J={J}: checked max {np.nanmax(err):.1e} ({nrf} of 64 accepted after a Newton refinement, {nfb} re-evaluated sequentially), raw scan max {np.nanmax(err_raw):.1e}")
+    # beyond 1e-9 only where the FP64 sequential sweep is itself off an 80-bit evaluation (rounding floor of the covariance: a
+    # converged Newton iteration is accepted there, and two FP64 routes differ by a multiple of what the 80-bit twin shows for
+    # one of them); never beyond the floor cap.  The J = 2 grid is barely positive definite: its floor rows scatter more.
+    assert np.all(err <= 1e-6), err.max()
+    for i in np.flatnonzero(ok)[err > TOL]:
+        ld = float(orc.celerite_logl(a[i], b[i], c[i], d[i], t, y, s2, long_double=True))
+        floor = abs(seq[i] - ld) / max(1.0, abs(ld))
+        assert floor > (1e-10 if J > 2 else 1e-11) and abs(got[i] - ld) / max(1.0, abs(ld)) <= (30 if J > 2 else 300) * floor + TOL, (i, err.max(), floor)
     if np.nanmax(err_raw) > TOL:
         assert nfb + nrf > 0
     assert np.array_equal(np.isfinite(got), ok)
