@@ -27,6 +27,7 @@
 #include "grad_pipe.cuh"
 #include "blocked_grad.cuh"
 #include "wide.cuh"
+#include "wide_grad.cuh"
 
 using namespace pioran;
 
@@ -891,6 +892,7 @@ static void plan_items(pioran_ctx* c, int S, Series* const* ser, const Table* ta
 
 // ------------------------------------------------------------------------------------------------ wide ranks (K2w)
 // Ranks above 64 (block size > 8): state in shared memory, one CTA per parameter vector (wide.cuh).
+template <int MODE = STEP_LOGL>
 static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
     if (args.R > WIDE_MAX_RANK)
         return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", args.R, WIDE_MAX_RANK);
@@ -898,10 +900,10 @@ static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
         const int TS = (args.R + 15) / 16;
         cudaEventRecord(c->ev_beg, c->stream);
         switch (TS) {
-            case 8: celerite_wide_reg_kernel<8><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
-            case 7: celerite_wide_reg_kernel<7><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
-            case 6: celerite_wide_reg_kernel<6><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
-            default: celerite_wide_reg_kernel<5><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            case 8: celerite_wide_reg_kernel<8, MODE><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            case 7: celerite_wide_reg_kernel<7, MODE><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            case 6: celerite_wide_reg_kernel<6, MODE><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
+            default: celerite_wide_reg_kernel<5, MODE><<<nitems, WIDE_THREADS, 0, c->stream>>>(args); break;
         }
         cudaEventRecord(c->ev_end, c->stream);
         c->ev_valid = true;
@@ -909,6 +911,8 @@ static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    if (MODE != STEP_LOGL)
+        return fail(PIORAN_EUNSUPPORTED, "posterior mean and draws are built for ranks up to 128 (rank %d)", args.R);
     const size_t smem = sizeof(double) * wide_smem_doubles(wide_geom(args.R));
     CUDA_TRY(cudaFuncSetAttribute(celerite_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEventRecord(c->ev_beg, c->stream);
@@ -919,6 +923,8 @@ static int launch_wide(pioran_ctx* c, const BatchArgs& args, int nitems) {
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+// leading dimension of the factor a STEP_STORE sweep leaves behind: 8·BS logical rows (warp kernel) or 16·TS (register-file CTA kernel)
+static int stored_factor_ld(int R) { const int BS = bs_for_rank(R); return BS <= 8 ? G * BS : 16 * std::max(5, (R + 15) / 16); }
 
 // ------------------------------------------------------------------------------------------------ K1 entry
 extern "C" int pioran_approx_coeffs(pioran_ctx* c, const pioran_approx_spec* spec, int B, const double* theta,
@@ -1276,6 +1282,67 @@ static bool blocked_grad_enabled(const pioran_ctx* c, int R, int ND) {
 }
 
 // logshift: θ rows carry a further column c and (y_batch, s2_batch) hold the per-θ transformed data; the gradient gains ∂/∂c.
+// Gradient at ranks 65 … 96 (wide_grad.cuh): K1 tangents in row form, then one CTA per (parameter vector, direction).
+static int wide_grad_locked(pioran_ctx* c, Series* ser, const pioran_approx_spec* spec, int B, const double* theta_dev,
+                            double* logl_dev, double* grad_dev, int R, int npar, int ts) {
+    int rc;
+    const int ND = npar, J = spec->n_components, TS = std::max(5, (R + 15) / 16), RP = 16 * TS;
+    const int Jt = spec->basis == PIORAN_BASIS_SHO ? J : 2 * J;
+    ApproxPlan* plan;
+    if ((rc = get_plan(c, *spec, &plan))) return rc;
+    // term tables (θ-independent on the approx path): src/psd.jl:250 (c = d = √2 π f, b = a) and :266-271 (c = π f, d = √3 c, b = √3 a; 2c)
+    std::vector<double> hv(3 * (size_t)Jt);
+    std::vector<int> hrow(Jt);
+    const double f0 = spec->f_min / spec->S_low, fM = spec->f_max * spec->S_high;
+    for (int j = 0; j < J; j++) {
+        const double fj = f0 * std::pow(fM / f0, (double)j / (double)(J - 1));
+        if (spec->basis == PIORAN_BASIS_SHO) {
+            hv[j] = hv[Jt + j] = std::sqrt(2.0) * M_PI * fj; hv[2 * Jt + j] = 1.0; hrow[j] = 2 * j;
+        } else {
+            const double cj = M_PI * fj;
+            hv[j] = cj; hv[Jt + j] = std::sqrt(3.0) * cj; hv[2 * Jt + j] = std::sqrt(3.0); hrow[j] = 2 * j;
+            hv[J + j] = 2.0 * cj; hv[Jt + J + j] = 0.0; hv[2 * Jt + J + j] = 0.0; hrow[J + j] = -(2 * J + j + 1);
+        }
+    }
+    // workspace: amp [B×RP] | damp [B×ND×RP] | Σa [B] | dΣa [B×ND] | c, d, ρ [3·Jt] | term rows [Jt ints]
+    const size_t n_amp = (size_t)B * RP, n_damp = (size_t)B * ND * RP;
+    if ((rc = c->gradws.ensure(sizeof(double) * (n_amp + n_damp + (size_t)B + (size_t)B * ND + 3 * (size_t)Jt) + sizeof(int) * (size_t)(Jt + 2)))) return rc;
+    double* amp = c->gradws.as<double>();
+    double* damp = amp + n_amp;
+    double* suma = damp + n_damp;
+    double* dsuma = suma + B;
+    double* tv = dsuma + (size_t)B * ND;
+    int* trow = reinterpret_cast<int*>(tv + 3 * (size_t)Jt);
+    std::vector<WorkItem> items(B, WorkItem{});
+    for (int i = 0; i < B; i++) {
+        WorkItem& w = items[i];
+        w.t = ser->t; w.y = ser->y; w.s2 = ser->s2; w.N = ser->N;
+        w.theta_begin = i; w.par_begin = i; w.count = 1; w.out_begin = i; w.n_begin = 0; w.n_end = ser->N;
+    }
+    c->gwork_key.clear();
+    if ((rc = c->gwork.ensure(sizeof(WorkItem) * items.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(c->gwork.p, items.data(), sizeof(WorkItem) * items.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(tv, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(trow, hrow.data(), sizeof(int) * hrow.size(), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));      // the sources are locals
+    const int nthr = B * ND;
+    cudaEventRecord(c->ev_beg, c->stream);
+    approx_grad_kernel<<<(nthr + 127) / 128, 128, 0, c->stream>>>(plan, B, theta_dev, ts, amp, damp, RP, suma, dsuma);
+    WideGradArgs ga{};
+    ga.work = c->gwork.as<WorkItem>();
+    ga.amp = amp; ga.damp = damp; ga.suma = suma; ga.dsuma = dsuma;
+    ga.c = tv; ga.d = tv + Jt; ga.rho = tv + 2 * Jt; ga.term_row = trow;
+    ga.Jt = Jt; ga.R = R; ga.RP = RP; ga.ND = ND;
+    ga.theta = theta_dev; ga.pstride = ts; ga.logl = logl_dev; ga.grad = grad_dev;
+    if (TS == 5) celerite_wide_grad_kernel<5><<<B * (ND + 1), WIDE_THREADS, 0, c->stream>>>(ga);
+    else celerite_wide_grad_kernel<6><<<B * (ND + 1), WIDE_THREADS, 0, c->stream>>>(ga);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int B,
                                        const double* theta_dev, double* logl_dev, double* grad_dev, bool logshift = false,
                                        const double* y_batch = nullptr, const double* s2_batch = nullptr) {
@@ -1288,7 +1355,11 @@ static int approx_logl_grad_dev_locked(pioran_ctx* c, int series_id, const piora
     if ((long long)B * P > 0x7fffffffLL / 64) return fail(PIORAN_EINVAL, "B too large");
     const int R = rank_of(spec->basis, spec->n_components);
     const int BS = bs_for_rank(R);
-    if (BS > 8) return fail(PIORAN_EUNSUPPORTED, "rank %d needs block size %d > 8", R, BS);
+    if (BS > 8) {
+        if (R > 96 || logshift || y_batch || s2_batch)
+            return fail(PIORAN_EUNSUPPORTED, "gradients are built for ranks <= 96 (log-shift model: <= 62); rank %d", R);
+        return wide_grad_locked(c, ser, spec, B, theta_dev, logl_dev, grad_dev, R, npar, ts);
+    }
     const int RP = G * BS;
     const bool blkg = blocked_grad_enabled(c, R, ND);
     if (logshift && !(blkg && ND == 3))
@@ -1704,8 +1775,8 @@ static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* 
     std::vector<int> term_row;
     const int R = make_term_rows(B, Jt, b, d, term_row);
     BS = bs_for_rank(R);
-    if (BS > 8 || Jt > 64)
-        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds this build's limit of 64", R, Jt);
+    if (R > 128 || Jt > 128)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the limit of 128 of the posterior mean and the draws", R, Jt);
     int rc;
     if ((rc = upload_generic(c, B, Jt, s->N, a, b, cc, d, mu, nu, y_batch, nullptr, gi))) return rc;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1)))) return rc;
@@ -1713,7 +1784,7 @@ static int generic_setup(pioran_ctx* c, Series* s, int B, int Jt, const double* 
     if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
     ItemPlan ip;
     Series* sp = s;
-    plan_items(c, 1, &sp, nullptr, B, nw_for_bs(BS), false, ip);
+    plan_items(c, 1, &sp, nullptr, B, BS > 8 ? 1 : nw_for_bs(BS), false, ip);      // wide ranks: one CTA per parameter vector
     c->work_key.clear();
     if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -1760,7 +1831,7 @@ extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int 
     GenericInputs gi;
     BatchArgs args;
     if ((rc = generic_setup(c, s, B, Jt, a, b, cc, d, mu, nu, nullptr, gi, args, BS, nitems))) return rc;
-    const int RPL = G * BS;
+    const int RPL = stored_factor_ld(args.R);
     // workspace: W [B·N·RPL] | D [B·N] | z [B·N] | mean [B·M] | tau [M] | n0 [M ints]
     const size_t nW = (size_t)B * N * RPL, nBN = (size_t)B * N, nBM = (size_t)B * M;
     if ((rc = c->post.ensure(sizeof(double) * (nW + 2 * nBN + nBM + M) + sizeof(int) * (M + 2)))) return rc;
@@ -1774,13 +1845,18 @@ extern "C" int pioran_celerite_predict(pioran_ctx* c, int series_id, int B, int 
     CUDA_TRY(cudaMemcpyAsync(n0_dev, n0.data(), sizeof(int) * M, cudaMemcpyHostToDevice, c->stream));
     args.W_out = W; args.D_out = D; args.zf_out = z;
     cudaEventRecord(c->ev_beg, c->stream);
-    if ((rc = dispatch_generic_mode<STEP_STORE>(c, BS, args, nitems))) return rc;
+    if ((rc = BS > 8 ? launch_wide<STEP_STORE>(c, args, nitems) : dispatch_generic_mode<STEP_STORE>(c, BS, args, nitems))) return rc;
     PostArgs pa{};
     pa.t = s->t; pa.tau = tau_dev; pa.n0 = n0_dev; pa.N = N; pa.M = M; pa.B = B; pa.Jt = Jt; pa.RPL = RPL;
     pa.a = gi.a; pa.b = gi.b; pa.c = gi.c; pa.d = gi.d; pa.term_row = c->rows.as<int>(); pa.mu = gi.mu;
     pa.W = W; pa.D = D; pa.z = z; pa.mean = mean;
-    celerite_backsolve_kernel<<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
-    celerite_predict_kernel<<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+    if (Jt <= 64) {
+        celerite_backsolve_kernel<2><<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+        celerite_predict_kernel<2><<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+    } else {
+        celerite_backsolve_kernel<4><<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+        celerite_predict_kernel<4><<<(B + 3) / 4, 128, 0, c->stream>>>(pa);
+    }
     c->launches += 2;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
@@ -1812,7 +1888,7 @@ extern "C" int pioran_celerite_simulate(pioran_ctx* c, int series_id, int B, int
     if ((rc = c->post.ensure(sizeof(double) * nBN))) return rc;
     args.ysim_out = c->post.as<double>();
     cudaEventRecord(c->ev_beg, c->stream);
-    if ((rc = dispatch_generic_mode<STEP_SIM>(c, BS, args, nitems))) return rc;
+    if ((rc = BS > 8 ? launch_wide<STEP_SIM>(c, args, nitems) : dispatch_generic_mode<STEP_SIM>(c, BS, args, nitems))) return rc;
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
     CUDA_TRY(cudaMemcpyAsync(y_out, c->post.p, sizeof(double) * nBN, cudaMemcpyDeviceToHost, c->stream));

@@ -8,7 +8,7 @@
 //      celerite_solver.jl:400-480: a forward recursion over the data points with t_n < τ_m and a backward one over the
 //      points with t_n ≥ τ_m (n₀ = searchsortedfirst(t, τ) − 1, computed once per call on the host — it does not depend
 //      on the parameter vector).
-// One warp per parameter vector; lane l owns the celerite terms l and l + 32 (Jt ≤ 64).  cos/sin are taken at absolute
+// One warp per parameter vector; lane l owns the celerite terms l, l + 32, … (PT per lane: 2 up to 64 terms, 4 up to 128).  cos/sin are taken at absolute
 // times like the reference (sincos_large, common.cuh).
 #pragma once
 #include "common.cuh"
@@ -35,17 +35,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // grid = ceil(B / 4), block = 128 (4 warps, one parameter vector each)
+template <int PT>
 __global__ void __launch_bounds__(128) celerite_backsolve_kernel(const PostArgs pa) {
     const int th = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (th >= pa.B) return;
     const int Jt = pa.Jt;
     const int64_t N = pa.N;
-    double ca[2], cb[2], cc[2], cd[2], gc[2] = {0.0, 0.0}, gs[2] = {0.0, 0.0};
-    int r0[2], r1[2];
+    double ca[PT], cb[PT], cc[PT], cd[PT], gc[PT], gs[PT];
+    int r0[PT], r1[PT];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < PT; k++) {
         const int m = lane + 32 * k;
         const bool on = m < Jt;
+        gc[k] = 0.0; gs[k] = 0.0;
         ca[k] = on ? pa.a[(size_t)th * Jt + m] : 0.0; cb[k] = on ? pa.b[(size_t)th * Jt + m] : 0.0;
         cc[k] = on ? pa.c[(size_t)th * Jt + m] : 0.0; cd[k] = on ? pa.d[(size_t)th * Jt + m] : 0.0;
         const int tr = on ? pa.term_row[m] : -1;
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(128) celerite_backsolve_kernel(const PostArgs 
         const double tn1 = pa.t[n + 1], dt = tn1 - pa.t[n];
         double part = 0.0;
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < PT; k++) {
             if (r0[k] >= 0) {
                 const double ph = exp(-cc[k] * dt);
                 if (r1[k] >= 0) {
@@ -87,15 +89,16 @@ __global__ void __launch_bounds__(128) celerite_backsolve_kernel(const PostArgs 
 }
 
 // grid = ceil(B / 4), block = 128.  mean[th][m] = μ_th + Σ_n k(|τ_m − t_n|) z_n.
+template <int PT>
 __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa) {
     const int th = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (th >= pa.B) return;
     const int Jt = pa.Jt;
     const int64_t N = pa.N, M = pa.M;
-    double ca[2], cb[2], cc[2], cd[2];
-    bool on[2];
+    double ca[PT], cb[PT], cc[PT], cd[PT];
+    bool on[PT];
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < PT; k++) {
         const int m = lane + 32 * k;
         on[k] = m < Jt;
         ca[k] = on[k] ? pa.a[(size_t)th * Jt + m] : 0.0; cb[k] = on[k] ? pa.b[(size_t)th * Jt + m] : 0.0;
@@ -106,7 +109,9 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
     const double mu = pa.mu ? pa.mu[th] : 0.0;
 
     // ---- forward sweep (celerite_solver.jl:400-435): Q_j = Σ_{n ≤ n_abs} z_n (cos, sin)(d_j t_n) e^{−c_j (t_{n_abs} − t_n)}
-    double qc[2] = {0.0, 0.0}, qs[2] = {0.0, 0.0};
+    double qc[PT], qs[PT];
+#pragma unroll
+    for (int k = 0; k < PT; k++) { qc[k] = 0.0; qs[k] = 0.0; }
     int64_t nabs = 0;                                   // data points absorbed so far; Q refers to time t[nabs − 1]
     for (int64_t m = 0; m < M; m++) {
         const int64_t n0 = pa.n0[m];
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
             const double tn = pa.t[nabs], zn = z[nabs];
             const double dt = nabs > 0 ? tn - pa.t[nabs - 1] : 0.0;
 #pragma unroll
-            for (int k = 0; k < 2; k++)
+            for (int k = 0; k < PT; k++)
                 if (on[k]) {
                     double si, co;
                     sincos_large(cd[k] * tn, &si, &co);
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
         if (n0 > 0) {
             const double tm = pa.tau[m], dt = tm - pa.t[n0 - 1];
 #pragma unroll
-            for (int k = 0; k < 2; k++)
+            for (int k = 0; k < PT; k++)
                 if (on[k]) {
                     double si, co;
                     sincos_large(cd[k] * tm, &si, &co);
@@ -141,7 +146,9 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
     }
     __syncwarp();
     // ---- backward sweep (celerite_solver.jl:439-480): P_j = Σ_{n ≥ n_abs} z_n U_j(t_n) e^{−c_j (t_n − t_{n_abs})}
-    double pc[2] = {0.0, 0.0}, ps[2] = {0.0, 0.0};
+    double pc[PT], ps[PT];
+#pragma unroll
+    for (int k = 0; k < PT; k++) { pc[k] = 0.0; ps[k] = 0.0; }
     nabs = N;                                           // points nabs … N−1 absorbed; P refers to time t[nabs]
     for (int64_t m = M - 1; m >= 0; m--) {
         const int64_t n0 = pa.n0[m];
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
             const double tn = pa.t[n], zn = z[n];
             const double dt = nabs < N ? pa.t[nabs] - tn : 0.0;
 #pragma unroll
-            for (int k = 0; k < 2; k++)
+            for (int k = 0; k < PT; k++)
                 if (on[k]) {
                     double si, co;
                     sincos_large(cd[k] * tn, &si, &co);
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(128) celerite_predict_kernel(const PostArgs pa
         if (n0 < N) {
             const double tm = pa.tau[m], dt = pa.t[n0] - tm;
 #pragma unroll
-            for (int k = 0; k < 2; k++)
+            for (int k = 0; k < PT; k++)
                 if (on[k]) {
                     double si, co;
                     sincos_large(cd[k] * tm, &si, &co);

@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1) celerite_wide_kernel(const Ba
 //   phase 2  owners form U_r p_r and U_r g_r, block reduction → D_n, z_n;   phase 3  owners form the next q, w.
 // Column-side vectors are read as 16 consecutive doubles per half-warp (conflict-free), row-side ones are broadcasts.  FP64-bound
 // at 4 issues per entry of the full square (twice the symmetric kernel's count), 3–4× faster than the shared-memory state.
-template <int TS>
+// MODE (celerite.cuh: StepMode): STEP_STORE also writes D_n, the forward z_n and W_n ([N × 16·TS] per parameter vector) for the
+// posterior mean; STEP_SIM takes standard-normal draws through y_batch and emits the realisation (celerite_solver.jl:536-546).
+template <int TS, int MODE = STEP_LOGL>
 __global__ void __launch_bounds__(WIDE_THREADS, TS <= 6 ? 2 : 1) celerite_wide_reg_kernel(const BatchArgs args) {
     constexpr int LD = 16 * TS;
     __shared__ __align__(16) double tabU[WIDE_CH][LD], tabV[WIDE_CH][LD], tabP[WIDE_CH][LD];
@@ -226,6 +228,10 @@ __global__ void __launch_bounds__(WIDE_THREADS, TS <= 6 ? 2 : 1) celerite_wide_r
         for (int j = 0; j < TS; j++) Tm[i][j] = 0.0;
     for (int k = tid; k < WIDE_CH * LD; k += WIDE_THREADS) { (&tabU[0][0])[k] = 0.0; (&tabV[0][0])[k] = 0.0; (&tabP[0][0])[k] = 0.0; }
     const bool owner = tid < LD;                  // owner of row `tid` in the vector phases
+    double* const Wst = MODE == STEP_STORE ? args.W_out + pi * (size_t)N * LD : nullptr;
+    double* const Dst = MODE == STEP_STORE ? args.D_out + pi * (size_t)N : nullptr;
+    double* const zst = MODE == STEP_STORE ? args.zf_out + pi * (size_t)N : nullptr;
+    double* const ysim = MODE == STEP_SIM ? args.ysim_out + pi * (size_t)N : nullptr;
     double g = 0.0, q = 0.0, w = 0.0, zprev = 0.0, chi2 = 0.0;
     double logacc = 0.0, dkeep = 1.0, dfirst = 1.0;   // Σ log|D_n|: the last warp keeps D_n in lane n % 32, one log per 32 steps
     const bool b3 = (tx & 8) != 0, b2 = (tx & 4) != 0, b1 = (tx & 2) != 0;
@@ -322,9 +328,17 @@ __global__ void __launch_bounds__(WIDE_THREADS, TS <= 6 ? 2 : 1) celerite_wide_r
             for (int k = 0; k < WIDE_THREADS / 32; k++) { stot += red[2 * k]; utot += red[2 * k + 1]; }
             // ---- phase 3: pivot, innovation, next q and w
             const double D = fma(nu, sb[n], suma) - stot;     // celerite_solver.jl:92
-            const double z = (yb[n] - mu) - utot;             // celerite_solver.jl:141
+            double z = (yb[n] - mu) - utot;                   // celerite_solver.jl:141
+            if (MODE == STEP_SIM) {                           // celerite_solver.jl:539-545: the draw enters where the innovation would
+                z = sqrt(D) * yb[n];
+                if (tid == 0) ysim[n] = utot + z;
+            }
             const double rD = fast_rcp(D);
             if (owner) { q = Vn[tid] - p; w = q * rD; }       // celerite_solver.jl:95-98 (W = q / D)
+            if (MODE == STEP_STORE) {
+                if (owner) Wst[n * LD + tid] = w;
+                if (tid == 0) { Dst[n] = D; zst[n] = z; }
+            }
             zprev = z;
             chi2 = fma(z * z, rD, chi2);
             if (warp == WIDE_THREADS / 32 - 1) {              // off the owners' critical path (celerite_solver.jl:126,140)

@@ -136,3 +136,32 @@ def test_logshift_gradient_vs_oracle(pb, ctx, golden_single, basis, J):
     _, gp = plain.value_and_gradient(th0[:, :6])
     _check(g0[:, :6], gp, 1e-9)
     like.close(); plain.close()
+
+
+@pytest.mark.parametrize("basis,J", [("SHO", 40), ("DRWCelerite", 30), ("DRWCelerite", 32), ("DRWCelerite", 24)])
+def test_grad_wide_ranks_vs_oracle(pb, ctx, golden_single, basis, J):
+    """Ranks 65 … 96 — the reference's benchmark grid above the warp kernels' limit (benchmark/benchmarks.jl:16-18: SHO J = 40,
+    DRWCelerite J = 30) — through the register-file CTA kernel on (value, tangent) pairs (csrc/wide_grad.cuh)."""
+    g = golden_single
+    t, y, s2, f_min, f_max = g.t, g.y, g.s2, g.f_min, g.f_max
+    rows = np.linspace(0, len(g.theta) - 1, 12).astype(int)
+    theta = g.theta[rows].copy()
+    if basis == "DRWCelerite":
+        theta[:, 2] += 1.0
+    like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+    val, grad = like.value_and_gradient(theta)
+    oval, ograd = orc.approx_logl_grad_batch("SBPL", theta, f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+    verr = np.abs(val - oval) / np.maximum(1.0, np.abs(oval))
+    assert verr.max() <= 1e-9, f"value parity {verr.max():.3e}"
+    plain = like(theta)
+    assert np.abs(val - plain).max() <= 1e-9 * np.maximum(1.0, np.abs(plain)).max()
+    _check(grad, ograd)
+    like.close()
+
+
+def test_grad_above_rank_96_is_refused(pb, ctx, golden_single):
+    g = golden_single
+    like = pb.BatchedLikelihood(g.t, g.y, g.s2, "SingleBendingPowerLaw", 50, "SHO", f_min=g.f_min, f_max=g.f_max, ctx=ctx)
+    with pytest.raises(pb.PioranError):
+        like.gradient(g.theta[:2].copy())
+    like.close()

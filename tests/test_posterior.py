@@ -154,3 +154,54 @@ def test_gpu_simulate_matches_oracle(basis):
     t2 = np.linspace(T[0], T[-1], 300)
     assert np.allclose(pb.rand(fx, q[0][:300], t2), orc.celerite_simulate(a[0], b[0], c[0], d[0], t2, np.zeros(300), q[0][:300]) + 1.5,
                        rtol=0, atol=1e-8)
+
+
+# ranks 65 … 128 (the register-file CTA kernel of csrc/wide.cuh in store / draw mode): the upper part of the reference's own
+# benchmark grid — SHO J = 40 (rank 80), DRWCelerite J = 30 (rank 90), DRWCelerite J = 40 (rank 120, 80 terms)
+WIDE_CASES = [("SHO", 40), ("DRWCelerite", 30), ("DRWCelerite", 40)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis,J", WIDE_CASES)
+def test_gpu_predict_wide_ranks(basis, J):
+    import pioran_b200 as pb
+    ctx = pb.get_context(0)
+    B = 5
+    th, rng = _theta_batch(B, 17)
+    mu, nu = rng.normal(Y.mean(), 0.3, B), rng.uniform(0.5, 2.0, B)
+    co = [orc.approx("SBPL", list(th[i]), F0, FM, J, VAR * rng.uniform(0.5, 2.0), basis=basis) for i in range(B)]
+    a, b, c, d = (np.stack([x[k] for x in co]) for k in range(4))
+    ser = ctx.upload_series(T, Y, S2)
+    try:
+        for name, tau in grids().items():
+            got = ctx.celerite_predict(ser, a, b, c, d, tau, mu=mu, nu=nu)
+            for i in range(B):
+                want = orc.celerite_predict(a[i], b[i], c[i], d[i], tau, T, Y - mu[i], nu[i] * S2) + mu[i]
+                err = np.max(np.abs(got[i] - want)) / max(1.0, np.max(np.abs(want)))
+                assert err < 1e-9, f"{basis} J={J}, {name}, theta {i}: {err:.2e}"
+    finally:
+        ser.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis,J", WIDE_CASES)
+def test_gpu_simulate_wide_ranks(basis, J):
+    import pioran_b200 as pb
+    ctx = pb.get_context(0)
+    B = 5
+    th, rng = _theta_batch(B, 23)
+    nu = rng.uniform(0.5, 2.0, B)
+    co = [orc.approx("SBPL", list(th[i]), F0, FM, J, VAR, basis=basis) for i in range(B)]
+    a, b, c, d = (np.stack([x[k] for x in co]) for k in range(4))
+    q = rng.standard_normal((B, len(T)))
+    ser = ctx.upload_series(T, np.zeros_like(T), S2)
+    try:
+        got = ctx.celerite_simulate(ser, a, b, c, d, q, nu=nu)
+    finally:
+        ser.free()
+    for i in range(B):
+        want = orc.celerite_simulate(a[i], b[i], c[i], d[i], T, nu[i] * S2, q[i])
+        ok = np.isfinite(want)
+        assert np.array_equal(ok, np.isfinite(got[i]))
+        err = np.max(np.abs(got[i][ok] - want[ok])) / max(1.0, np.max(np.abs(want[ok])))
+        assert err < 1e-9, f"{basis} J={J}, theta {i}: {err:.2e}"
