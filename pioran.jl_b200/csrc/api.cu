@@ -28,6 +28,7 @@
 #include "blocked_grad.cuh"
 #include "wide.cuh"
 #include "wide_grad.cuh"
+#include "scan_wide.cuh"
 
 using namespace pioran;
 
@@ -155,6 +156,7 @@ constexpr int AUTO_SCAN_MAX_BATCH = 4;
 static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R, bool explicit_coefficients = false) {
     int64_t min_steps = R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS;
     if (explicit_coefficients) min_steps /= 2;
+    if (R > SCAN_LD) return c->auto_scan && N >= 4096 && B <= AUTO_SCAN_MAX_BATCH && R <= SRW;   // wide ranks: 1.3 µs per sequential step
     return c->auto_scan && N >= min_steps && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
 }
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
@@ -2014,6 +2016,12 @@ struct ScanRun {
     double check_scale = 1.0;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
+    bool wide = false;                       // ranks 65 … 96: the kernels of scan_wide.cuh (leading dimension 96)
+    size_t sel() const { return wide ? (size_t)SELW : (size_t)SEL; }          // doubles per composite / state / (T | m)
+    size_t sstate() const { return wide ? (size_t)SSTATEW : (size_t)SSTATE; }
+    size_t snewt() const { return wide ? (size_t)SNEWTW : (size_t)SNEWT; }
+    int rr() const { return wide ? std::min(SRW, (R + 3) & ~3) : std::min(SR, (R + 3) & ~3); }   // live rank, rounded up to a multiple of 4
+    size_t smem() const { return wide ? scanw_smem_bytes(rr()) : SCAN_SMEM_BYTES; }
 };
 static int scan_live_rank(int R) { return std::min(SR, (R + 3) & ~3); }
 // Steps of the self-check at a sub-chunk boundary: SCAN_CHECK_STEPS, or the (even part of the) sub-chunk when it is shorter.
@@ -2033,8 +2041,11 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     std::vector<int> term_row;
     const int R = make_term_rows(B, Jt, b, d, term_row);
     const int BS = bs_for_rank(R);
-    if (BS > 8 || R > SR)
-        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SR);
+    const bool wide = R > SR;
+    if (R > SRW)
+        return fail(PIORAN_EUNSUPPORTED, "rank %d (Jt = %d) exceeds the scan path's limit of %d", R, Jt, SRW);
+    if (wide && (want_total || max_prev > 0 || n_lo != 0 || n_hi != s->N))
+        return fail(PIORAN_EUNSUPPORTED, "the time-axis split across devices is built for ranks <= %d (rank %d)", SR, R);
     const int64_t N = s->N, len = n_hi - n_lo;
     // chunking.  With log-depth scan levels the second pass costs little per extra chunk, so the optimum sits where the fold
     // runs as ONE round of CTAs: one chunk per SM for a single parameter vector (tools/scan_chunks_sweep.py: P = 148
@@ -2044,6 +2055,7 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     if (P <= 0) {
         P = std::min(c->num_sms, std::max(16, 2 * c->num_sms / std::max(1, B)));   // two fold CTAs fit an SM: B·P ≤ 2·SMs
         if (B == 1 && len / (2 * c->num_sms) >= 2048) P = 2 * c->num_sms;          // very long series: two chunks per SM (−7 % at 1e6 steps)
+        if (wide) P = std::min(c->num_sms, std::max(16, c->num_sms / std::max(1, B)));   // the 512-thread fold: one CTA per SM
     }
     P = (int)std::max<int64_t>(1, std::min<int64_t>(P, len / 64));
     const int G2 = (int)std::ceil(std::sqrt((double)P));
@@ -2053,7 +2065,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     const int SUB = (len / P >= 1024) ? 4 : 1;
     run = ScanRun{};
     run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2; run.SUB = SUB;
-    run.N = N; run.n_lo = n_lo; run.n_hi = n_hi;
+    run.N = N; run.n_lo = n_lo; run.n_hi = n_hi; run.wide = wide;
+    const size_t SELr = run.sel(), SSTATEr = run.sstate(), SNEWTr = run.snewt();
     run.bounds.resize(P + 1);
     // inner bounds at even offsets: every sub-chunk but the last has an even length (the self-check sweeps on across a bound)
     for (int k = 0; k <= P; k++) run.bounds[k] = k == P ? n_hi : n_lo + ((int64_t)((__int128)len * k / P) & ~(int64_t)1);
@@ -2062,12 +2075,12 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, run.gi))) return rc;
     const size_t nch = (size_t)B * P;
     // workspace (doubles): elems | pref | gstate | cstate | parts (+1 dummy pair) | out | total | scratch | init | prev | sums
-    const size_t n_el = nch * SEL, n_gs = (size_t)B * G1 * SSTATE, n_cs = nch * SSTATE, n_pt = 2 * (nch * SUB + 1);
+    const size_t n_el = nch * SELr, n_gs = (size_t)B * G1 * SSTATEr, n_cs = nch * SSTATEr, n_pt = 2 * (nch * SUB + 1);
     const size_t n_chk = 4 * (nch * SUB + 1);
-    const size_t n_sel = nch * (SUB - 1) * SEL, n_sst = nch * (SUB - 1) * SSTATE, n_gt = (size_t)B * G1 * SEL;
-    const size_t n_tot = (size_t)B * SEL, n_scr = 2 * (size_t)B * SEL, n_init = (size_t)B * SSTATE;
-    const size_t n_prev = (size_t)std::max(0, max_prev) * B * SEL;
-    const size_t n_tm = nch * SNEWT;
+    const size_t n_sel = nch * (SUB - 1) * SELr, n_sst = nch * (SUB - 1) * SSTATEr, n_gt = (size_t)B * G1 * SELr;
+    const size_t n_tot = (size_t)B * SELr, n_scr = 2 * (size_t)B * SELr, n_init = (size_t)B * SSTATEr;
+    const size_t n_prev = (size_t)std::max(0, max_prev) * B * SELr;
+    const size_t n_tm = nch * SNEWTr;
     if ((rc = c->misc.ensure(sizeof(double) * (3 * n_el + n_gs + 2 * n_cs + n_tm + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
         return rc;
     run.elems = c->misc.as<double>();
@@ -2102,6 +2115,42 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = run.bounds_dev;
     sa.a = run.gi.a; sa.b = run.gi.b; sa.c = run.gi.c; sa.d = run.gi.d; sa.Jt = Jt; sa.term_row = run.term_row_dev;
     sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems; sa.SUB = SUB; sa.subel = run.subel;
+    if (wide) {
+        // states handed to pass 3 are read over the full 96 rows: what the pass-2 kernels leave outside the live rank must be zero
+        CUDA_TRY(cudaMemsetAsync(run.gstate, 0, sizeof(double) * (n_gs + n_cs), c->stream));
+        if (n_sst) CUDA_TRY(cudaMemsetAsync(run.substate, 0, sizeof(double) * n_sst, c->stream));
+        CUDA_TRY(cudaFuncSetAttribute(scanw_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOLDW_SMEM_BYTES));
+        scanw_fold_kernel<<<dim3(P, B), FOLDW_THREADS, FOLDW_SMEM_BYTES, c->stream>>>(sa);
+        c->launches++;
+        const int Rw = run.rr();
+        const size_t smw = run.smem();
+        CUDA_TRY(cudaFuncSetAttribute(scanw_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        CUDA_TRY(cudaFuncSetAttribute(scanw_group_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        CUDA_TRY(cudaFuncSetAttribute(scanw_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        CUDA_TRY(cudaFuncSetAttribute(scanw_substates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        double* src = run.elems;
+        double* dst = run.pref;
+        for (int dd = 1; dd < G2 && P > 1; dd *= 2) {
+            scanw_ks_kernel<<<dim3(P, B), 256, smw, c->stream>>>(src, dst, P, G2, dd, Rw);
+            c->launches++;
+            double* const wrote = dst;
+            dst = (src == run.elems) ? run.ksbuf : src;
+            src = wrote;
+        }
+        run.pref = src;
+        scanw_gather_kernel<<<dim3(G1, B), 256, 0, c->stream>>>(run.pref, run.tot0, P, G2, G1);
+        c->launches++;
+        src = run.tot0; dst = run.tot1;
+        for (int dd = 1; dd < G1; dd *= 2) {
+            scanw_ks_kernel<<<dim3(G1, B), 256, smw, c->stream>>>(src, dst, G1, G1, dd, Rw);
+            c->launches++;
+            std::swap(src, dst);
+        }
+        run.tp = src;
+        CUDA_TRY(cudaGetLastError());
+        run.valid = true;
+        return 0;
+    }
     scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
     c->launches++;
     CUDA_TRY(cudaFuncSetAttribute(scan_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
@@ -2146,6 +2195,16 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     return 0;
 }
 
+// Pass 3 at ranks 65 … 96: one CTA per work item (scan_wide.cuh).
+static int launch_wide_chunk(pioran_ctx* c, const BatchArgs& args, int nitems) {
+    const int TS = std::max(5, (args.R + 15) / 16);
+    if (TS == 5) celerite_wide_chunk_kernel<5><<<nitems, WIDE_THREADS, 0, c->stream>>>(args);
+    else celerite_wide_chunk_kernel<6><<<nitems, WIDE_THREADS, 0, c->stream>>>(args);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // Phase 2: states entering every chunk (from `init_dev`, or from the start of the series when it is null), re-filter of
 // every chunk, partial sums in run.parts.
 static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* init_dev, int warm_subs = 0, bool states_ready = false) {
@@ -2159,8 +2218,8 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     auto state_at = [&](int th, int g) -> const double* {       // the state entering sub-chunk g of parameter vector th
         const size_t q = (size_t)th * P + g / SUB;
         const int j = g % SUB;
-        if (j == 0) return (g == 0 && !init_dev) ? nullptr : run.cstate + q * SSTATE;
-        return run.substate + (q * (SUB - 1) + (j - 1)) * SSTATE;
+        if (j == 0) return (g == 0 && !init_dev) ? nullptr : run.cstate + q * run.sstate();
+        return run.substate + (q * (SUB - 1) + (j - 1)) * run.sstate();
     };
     for (size_t k = 0; k < nitems; k++) {
         const size_t e = std::min(k, nsub - 1);
@@ -2192,6 +2251,27 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     c->work_key.clear();
     if ((rc = c->work.ensure(sizeof(WorkItem) * nitems))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->work.p, items.data(), sizeof(WorkItem) * nitems, cudaMemcpyHostToDevice, c->stream));
+    if (run.wide) {
+        const int Rw = run.rr();
+        const size_t smw = run.smem();
+        if (!states_ready && P > 1) {
+            scanw_group_states_kernel<<<dim3(run.G1, B), 256, smw, c->stream>>>(run.tp, run.gstate, run.G1, Rw);
+            scanw_states_kernel<<<dim3(P, B), 256, smw, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1, Rw);
+            c->launches += 2;
+        }
+        if (!states_ready && SUB > 1) {
+            scanw_substates_kernel<<<dim3(P * (SUB - 1), B), 256, smw, c->stream>>>(run.subel, run.cstate, run.substate, P, SUB, Rw);
+            c->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        BatchArgs wargs{};
+        wargs.work = c->work.as<WorkItem>();
+        wargs.a = run.gi.a; wargs.b = run.gi.b; wargs.c = run.gi.c; wargs.d = run.gi.d;
+        wargs.Jt = run.Jt; wargs.term_row = run.term_row_dev; wargs.R = run.R;
+        wargs.mu = run.gi.mu; wargs.nu = run.gi.nu; wargs.pstride = 1;
+        wargs.out = run.out;
+        return launch_wide_chunk(c, wargs, (int)nsub);
+    }
     if (!states_ready && (P > 1 || init_dev)) {
         scan_group_states_kernel<<<dim3(run.G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tp, run.gstate, run.G1, init_dev, scan_live_rank(run.R));
         scan_states_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.pref, run.gstate, run.cstate, P, run.G2, run.G1,
@@ -2234,16 +2314,16 @@ static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
             w.table = nullptr; w.t = s->t; w.y = s->y; w.s2 = s->s2; w.N = run.N;
             w.theta_begin = th; w.par_begin = th; w.count = 1; w.out_begin = 0;
             w.n_begin = bound(g); w.n_end = bound(g + 1); w.n_warm = 0;
-            if (j == 0) w.init = ch == 0 ? nullptr : run.cstate + e * SSTATE;
-            else w.init = run.substate + (e * (SUB - 1) + (j - 1)) * SSTATE;
+            if (j == 0) w.init = ch == 0 ? nullptr : run.cstate + e * run.sstate();
+            else w.init = run.substate + (e * (SUB - 1) + (j - 1)) * run.sstate();
             const size_t slot = real ? (size_t)th * PS + g : nch * SUB;       // padding warps write to the dummy slots
             w.part = run.parts + 2 * slot;
             w.chk = run.chk + 4 * slot;
             w.n_head = (j == 0 && ch > 0) ? scan_check_steps(bound(g + 1) - bound(g)) : 0;
             w.n_ext = (j == SUB - 1 && ch < P - 1) ? scan_check_steps(bound(g + 2) - bound(g + 1)) : 0;
             w.exit = nullptr;
-            if (real && j < SUB - 1) w.exit = run.substate + (e * (SUB - 1) + j) * SSTATE;
-            else if (real && ch < P - 1) w.exit = run.exits + e * SSTATE;
+            if (real && j < SUB - 1) w.exit = run.substate + (e * (SUB - 1) + j) * run.sstate();
+            else if (real && ch < P - 1) w.exit = run.exits + e * run.sstate();
         }
     run.check_scale = std::max(1.0, (double)(run.n_hi - run.n_lo) / ((double)P * SCAN_CHECK_STEPS));
     int rc;
@@ -2257,7 +2337,7 @@ static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
     args.out = run.out;
     for (int j = 0; j < SUB; j++) {
         args.work = c->work.as<WorkItem>() + (size_t)j * npl;
-        if ((rc = dispatch_chunked(c, run.BS, args, (int)(npl / NW)))) return rc;
+        if ((rc = run.wide ? launch_wide_chunk(c, args, (int)nch) : dispatch_chunked(c, run.BS, args, (int)(npl / NW)))) return rc;
     }
     return 0;
 }
@@ -2265,6 +2345,17 @@ static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
 // One Newton step on the chunk states: (T_k | m_k) of every chunk from its composite and current state, then the linear
 // recurrence of the corrections along the chunks (needs the exits of a scan_seq_pass over the current states).
 static int scan_newton_step(pioran_ctx* c, ScanRun& run) {
+    if (run.wide) {
+        const int Rw = run.rr();
+        const size_t smw = run.smem();
+        CUDA_TRY(cudaFuncSetAttribute(scanw_newton_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        CUDA_TRY(cudaFuncSetAttribute(scanw_newton_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        scanw_newton_T_kernel<<<dim3(run.P, run.B), 256, smw, c->stream>>>(run.elems, run.cstate, run.tm, run.P, Rw);
+        scanw_newton_chain_kernel<<<dim3(1, run.B), 256, smw, c->stream>>>(run.tm, run.exits, run.cstate, run.P, Rw);
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const int Rr = scan_live_rank(run.R);
     CUDA_TRY(cudaFuncSetAttribute(scan_newton_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_newton_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
@@ -2301,7 +2392,7 @@ static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int 
         // the first Newton step); level ≥ 2: chunk by chunk from the corrected states
         if (level == 0) { if ((rc = scan_phase2(c, s, run, nullptr))) return rc; }
         else {
-            if (level == 1) CUDA_TRY(cudaMemsetAsync(run.exits, 0, sizeof(double) * (size_t)B * run.P * SSTATE, c->stream));
+            if (level == 1) CUDA_TRY(cudaMemsetAsync(run.exits, 0, sizeof(double) * (size_t)B * run.P * run.sstate(), c->stream));
             if (level >= 2 && (rc = scan_newton_step(c, run))) return rc;
             if ((rc = scan_seq_pass(c, s, run))) return rc;
         }

@@ -26,7 +26,9 @@ def ctx(pb):
     c.set_scan_chunks(0)
 
 
-@pytest.mark.parametrize("basis,J", [("SHO", 20), ("DRWCelerite", 20), ("SHO", 30), ("SHO", 8)])
+# ranks above 64 (scan_wide.cuh): SHO J = 40 (80), DRWCelerite J = 30 (90), J = 32 (96), J = 24 (72: the 5-row tile shape)
+@pytest.mark.parametrize("basis,J", [("SHO", 20), ("DRWCelerite", 20), ("SHO", 30), ("SHO", 8), ("DRWCelerite", 30), ("SHO", 40),
+                                     ("DRWCelerite", 32), ("DRWCelerite", 24)])
 def test_scan_equals_sequential_and_oracle(pb, ctx, basis, J):
     t, y, s2, f_min, f_max = synthetic_series(3000, seed=11)
     a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, J, 1.0, basis=basis)
@@ -93,6 +95,35 @@ def test_config_c4_long_series_n1e6_j30(pb, ctx):
           f"{wall_seq * 1e3:.0f} ms, CPU restatement {wall_cpu:.1f} s; logL {got:.6f}; "
           f"rel(scan, seq) {rel_err(got, seq):.2e}, rel(scan, cpu) {rel_err(got, want):.2e}")
     assert np.isfinite(got)
+    assert rel_err(got, seq) <= TOL
+    assert rel_err(got, want) <= TOL
+    ser.free()
+
+
+def test_config_c4_long_series_n1e6_drwcelerite_j30(pb, ctx):
+    """C4 with the DRWCelerite basis at J = 30 — rank 90, the reference's own benchmark grid (benchmark/benchmarks.jl:16-18) —
+    through the wide-rank kernels of the scan path, against the sequential wide-rank sweep and the CPU restatement."""
+    import workloads as wl
+    N = 1_000_000
+    t, y, s2, f_min, f_max = wl.make_series_fast(N, seed=4)
+    a, b, c, d = orc.approx("SBPL", [0.82, 0.01, 3.3], f_min, f_max, 30, float(np.var(y)), basis="DRWCelerite")
+    ser = ctx.upload_series(t, y, s2)
+    ctx.set_scan_chunks(0)
+    got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]          # warm-up (buffers)
+    got = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
+    dev_scan = ctx.last_kernel_ms()
+    sc = ctx.last_scan_check()
+    ctx.set_auto_scan(False)
+    t0 = time.perf_counter()
+    seq = ctx.celerite_logl(ser, a, b, c, d)[0]
+    wall_seq = time.perf_counter() - t0
+    ctx.set_auto_scan(True)
+    t0 = time.perf_counter()
+    want = orc.celerite_logl(a, b, c, d, t, y, s2)
+    wall_cpu = time.perf_counter() - t0
+    print(f"\nC4 N=1e6 DRWCelerite J=30 (R=90): scan {dev_scan:.2f} ms device, sequential GPU sweep {wall_seq * 1e3:.0f} ms, "
+          f"CPU restatement {wall_cpu:.1f} s; rel(scan, seq) {rel_err(got, seq):.2e}, rel(scan, cpu) {rel_err(got, want):.2e}; {sc}")
+    assert np.isfinite(got) and sc.fallback == 0
     assert rel_err(got, seq) <= TOL
     assert rel_err(got, want) <= TOL
     ser.free()
@@ -215,7 +246,7 @@ def _steep_prior_draws(B, f_min, f_max, seed, alpha2_max):
     return np.stack([a1, f1, a2, np.ones(B)], axis=1)
 
 
-@pytest.mark.parametrize("basis,J", [("DRWCelerite", 5), ("DRWCelerite", 2), ("DRWCelerite", 20)])
+@pytest.mark.parametrize("basis,J", [("DRWCelerite", 5), ("DRWCelerite", 2), ("DRWCelerite", 20), ("DRWCelerite", 30)])
 def test_scan_self_check_keeps_sequential_accuracy(pb, ctx, basis, J):
     """The composites of the scan lose accuracy on ill-conditioned covariances (steep slopes: up to 1e-6, far more on the
     J = 2 grid).  Every call checks itself at the chunk boundaries and re-evaluates the offending parameter vectors with
