@@ -26,6 +26,7 @@
 #include "grad.cuh"
 #include "grad_pipe.cuh"
 #include "blocked_grad.cuh"
+#include "blocked_wide.cuh"
 #include "wide.cuh"
 #include "wide_grad.cuh"
 #include "scan_wide.cuh"
@@ -656,6 +657,38 @@ static int dispatch_blocked(pioran_ctx* c, const BatchArgs& a, int nitems, int t
     return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the blocked kernel", R);
 }
 
+// K2tw (blocked_wide.cuh): ranks 65 … 128 on the tensor pipe, one CTA of W warps per evaluation.
+static bool blocked_wide_enabled(const pioran_ctx* c, int R) {
+    static const int mode = [] { const char* e = getenv("PIORAN_K2W"); return (e && (!strcmp(e, "scalar") || !strcmp(e, "0"))) ? 0 : 1; }();
+    return mode != 0 && c->sweep_kernel != PIORAN_SWEEP_SCALAR && R > 64 && R <= 128;
+}
+template <int NT, int NTR, int W>
+static int launch_blocked_wide(pioran_ctx* c, const BatchArgs& args, int nitems, int R, int amp_stride) {
+    auto kern = celerite_blocked_wide_kernel<NT, NTR, W>;
+    const size_t smem = blkw_smem_bytes<NT, NTR, W>();
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEventRecord(c->ev_beg, c->stream);
+    kern<<<nitems, W * 32, smem, c->stream>>>(args, R, amp_stride, blk_layout(R, false).RG);
+    cudaEventRecord(c->ev_end, c->stream);
+    c->ev_valid = true;
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int dispatch_blocked_wide(pioran_ctx* c, const BatchArgs& a, int nitems, int R, int amp_stride) {
+    const int NT = blk_nt(R);
+    const bool xrow = blk_ntr(R) != NT;
+#define PIORAN_BLKW_CASE(nt, w)                                                                       \
+    case nt: return xrow ? launch_blocked_wide<nt, nt + 1, (nt + 1 > 12 ? 8 : w)>(c, a, nitems, R, amp_stride) \
+                         : launch_blocked_wide<nt, nt, w>(c, a, nitems, R, amp_stride);
+    switch (NT) {
+        PIORAN_BLKW_CASE(9, 4) PIORAN_BLKW_CASE(10, 4) PIORAN_BLKW_CASE(11, 4) PIORAN_BLKW_CASE(12, 4)
+        PIORAN_BLKW_CASE(13, 8) PIORAN_BLKW_CASE(14, 8) PIORAN_BLKW_CASE(15, 8) PIORAN_BLKW_CASE(16, 8)
+    }
+#undef PIORAN_BLKW_CASE
+    return fail(PIORAN_EUNSUPPORTED, "rank %d not served by the wide blocked kernel", R);
+}
+
 // ------------------------------------------------------------------------------------------------ K2 launchers
 #ifndef PIORAN_NW_SMALL
 #define PIORAN_NW_SMALL 12   // warps per CTA for block sizes <= 5 (register budget 168/thread)
@@ -983,8 +1016,46 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     const int BS = bs_for_rank(R);
     if ((y_batch || s2_batch) && (S != 1 || BS > 8))
         return fail(PIORAN_EUNSUPPORTED, "per-parameter-vector data need a single series and a rank <= 64 (rank %d, %d series)", R, S);
+    if (BS > 8 && blocked_wide_enabled(c, R)) {
+        // ranks 65 … 128: the blocked sweep with one CTA per (series, θ) (blocked_wide.cuh) on the shared block table
+        const int RPA = 8 * blk_nt(R);
+        for (int s = 0; s < S; s++)
+            if ((rc = get_btable(c, ser[s], specs[s], &tabs[s]))) return rc;
+        if ((rc = c->amp.ensure(sizeof(double) * (size_t)S * B * RPA))) return rc;
+        if ((rc = c->suma.ensure(sizeof(double) * (size_t)S * B))) return rc;
+        for (int s = 0; s < S; s++) {
+            ApproxPlan* plan;
+            if ((rc = get_plan(c, specs[s], &plan))) return rc;
+            const double* th = theta_dev + (theta_per_series ? (size_t)s * B * ts : 0);
+            approx_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(plan, B, th, ts, nullptr, nullptr, nullptr, nullptr,
+                                                                 c->amp.as<double>() + (size_t)s * B * RPA, RPA,
+                                                                 c->suma.as<double>() + (size_t)s * B);
+            c->launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+        std::vector<int64_t> key;
+        key.push_back(S); key.push_back(B); key.push_back(-1000 - R); key.push_back(theta_per_series != 0);
+        for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
+        if (key != c->work_key) {
+            ItemPlan ip;
+            plan_items(c, S, ser.data(), tabs.data(), B, 1, theta_per_series != 0, ip);
+            c->work_key.clear();
+            if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            c->work_key = key;
+            c->work_items = (int)ip.items.size();
+            c->work_tpi = ip.tpi;
+        }
+        BatchArgs args{};
+        args.work = c->work.as<WorkItem>();
+        args.amp = c->amp.as<double>(); args.suma = c->suma.as<double>();
+        args.mu = theta_dev + npar + 2; args.nu = theta_dev + npar + 1; args.pstride = ts;
+        args.out = logl_dev;
+        return dispatch_blocked_wide(c, args, c->work_items, R, RPA);
+    }
     if (BS > 8) {
-        // ranks above 64: K1 writes explicit coefficients, the shared-memory-state kernel sweeps one CTA per (series, θ)
+        // ranks above 128 (and the scalar-pipe selection): K1 writes explicit coefficients, one CTA per (series, θ) (wide.cuh)
         if (R > WIDE_MAX_RANK) return fail(PIORAN_EUNSUPPORTED, "rank %d exceeds this build's limit of %d", R, WIDE_MAX_RANK);
         const int J = specs[0].n_components;
         const int Jt = specs[0].basis == PIORAN_BASIS_SHO ? J : 2 * J;

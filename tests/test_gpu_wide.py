@@ -22,9 +22,11 @@ def ctx(pb):
 
 
 @pytest.mark.parametrize("basis,J", [("SHO", 40), ("SHO", 50), ("DRWCelerite", 30), ("DRWCelerite", 40), ("DRWCelerite", 50),
-                                     ("SHO", 33), ("DRWCelerite", 22)])
+                                     ("SHO", 33), ("DRWCelerite", 22), ("SHO", 36), ("SHO", 64), ("DRWCelerite", 35), ("SHO", 60),
+                                     ("DRWCelerite", 42), ("SHO", 44), ("DRWCelerite", 27), ("SHO", 56)])
 def test_wide_fused_vs_oracle(pb, ctx, golden_single, basis, J):
-    """approx + logpdf at ranks 66 … 150 on the reference's own series."""
+    """approx + logpdf at ranks 66 … 150 on the reference's own series (up to 128: the blocked one-CTA-per-evaluation kernel
+    of csrc/blocked_wide.cuh — every column-tile count 9 … 16, with and without a row tile of its own for the data row)."""
     g = golden_single
     rows = np.linspace(0, len(g.theta) - 1, 24).astype(int)
     theta = g.theta[rows].copy()
