@@ -157,7 +157,8 @@ constexpr int AUTO_SCAN_MAX_BATCH = 4;
 static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R, bool explicit_coefficients = false) {
     int64_t min_steps = R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS;
     if (explicit_coefficients) min_steps /= 2;
-    if (R > SCAN_LD) return c->auto_scan && N >= 4096 && B <= AUTO_SCAN_MAX_BATCH && R <= SRW;   // wide ranks: 1.3 µs per sequential step
+    // wide ranks: the one-CTA blocked sweep runs 0.49 µs per step, the wide scan costs ≈ 9.7 ms + 0.02 µs per step (profiles/r02_reference_suite_mirror.jsonl)
+    if (R > SCAN_LD) return c->auto_scan && N >= (c->sweep_kernel == PIORAN_SWEEP_SCALAR ? 4096 : 20480) && B <= AUTO_SCAN_MAX_BATCH && R <= SRW;
     return c->auto_scan && N >= min_steps && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
 }
 static int scan_logl_locked(pioran_ctx* c, Series* s, int series_id, int B, int Jt, const double* a, const double* b,
@@ -1671,14 +1672,14 @@ static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const do
     int rc;
     GenericInputs gi;
     if ((rc = upload_generic(c, B, Jt, s->N, a, b, cc, d, mu, nu, y_batch, s2_batch, gi))) return rc;
-    // Small batches at ranks <= 63 (the B = 1 call a `:celerite_gpu` solver symbol makes per logpdf, a CARMA or QPO sampler's few
+    // Small batches at ranks <= 63, and 65 … 128 with the one-CTA-per-evaluation kernel (the B = 1 call a `:celerite_gpu` solver symbol makes per logpdf, a CARMA or QPO sampler's few
     // hundred points): per-θ block tables are built by a parallel kernel and every parameter vector runs the tensor-pipe sweep as a
     // one-warp item (0.48 ms per 1 000 steps) instead of building its trig/exp chunks inside a scalar-pipe sweep (1.2–1.8 ms).
     {
         const BlkLayout lay = blk_layout(R, false);
         const int64_t nblocks = (s->N + BLK - 1) / BLK;
         const size_t tbytes = sizeof(double) * (size_t)nblocks * blk_doubles(lay.NT, lay.NTR);
-        if (blocked_enabled(c, R) && B <= 4 * c->num_sms && tbytes * (size_t)B <= ((size_t)2 << 30)) {
+        if ((blocked_enabled(c, R) || blocked_wide_enabled(c, R)) && B <= 4 * c->num_sms && tbytes * (size_t)B <= ((size_t)2 << 30)) {
             const int RPT = 8 * lay.NTR, RPA = 8 * lay.NT;
             std::vector<BlkRowMap> prow(RPT, BlkRowMap{ROW_PAD, -1, 0});
             std::vector<int> lrow_term(std::max(R, 1), 0);
@@ -1732,7 +1733,7 @@ static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const do
             args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
             args.y_batch = gi.yb; args.s2_batch = gi.sb; args.ystride = s->N;
             args.out = c->out.as<double>();
-            if ((rc = dispatch_blocked(c, args, B, 1, R, RPA))) return rc;
+            if ((rc = R > 64 ? dispatch_blocked_wide(c, args, B, R, RPA) : dispatch_blocked(c, args, B, 1, R, RPA))) return rc;
             CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             return PIORAN_OK;

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(W * 32, 1) celerite_blocked_wide_kernel(const 
     const size_t pi = (size_t)wk.par_begin;
     const double mu = args.mu ? args.mu[pi * args.pstride] : 0.0;
     const double nu = args.nu ? args.nu[pi * args.pstride] : 1.0;
+    const double* yb = args.y_batch ? args.y_batch + pi * args.ystride : nullptr;      // per-parameter-vector data (explicit coefficients)
+    const double* sb = args.s2_batch ? args.s2_batch + pi * args.ystride : nullptr;
 
     double x[MR][NT][2];
 #pragma unroll
@@ -128,7 +130,8 @@ __global__ void __launch_bounds__(W * 32, 1) celerite_blocked_wide_kernel(const 
             const double o1 = __shfl_sync(FULL, v, L.csrc1);
             // diagonal (warp 0): A_n = Σa + ν σ²_n (celerite_solver.jl:92); padded steps are unit pivots
             const double mk = tab[O_SC + 16 + g];
-            const double dg = warp == 0 ? fma(fma(nu, tab[O_SC + 8 + g], suma), mk, 1.0 - mk) : 0.0;
+            const double s2v = sb ? (n0 + g < N ? sb[n0 + g] : 0.0) : tab[O_SC + 8 + g];
+            const double dg = warp == 0 ? fma(fma(nu, s2v, suma), mk, 1.0 - mk) : 0.0;
             const double c0 = (L.cdiag0 ? dg : o0) - ca0, c1 = (L.cdiag1 ? dg : o1) - ca1;
             *reinterpret_cast<double2*>(cred + (warp * 32 + lane) * 2) = make_double2(c0, c1);
         }
@@ -162,6 +165,11 @@ __global__ void __launch_bounds__(W * 32, 1) celerite_blocked_wide_kernel(const 
                 const double am = amp_s[row];
                 if (I == NTR - 1) {
                     const double2 mk2 = *reinterpret_cast<const double2*>(tab + O_SC + 16 + 2 * t);
+                    if (yb && row == RG) {
+                        const int64_t n = n0 + 2 * t;
+                        vh.x = (n < N) ? yb[n] : 0.0;
+                        vh.y = (n + 1 < N) ? yb[n + 1] : 0.0;
+                    }
                     const double m_ = (row == RG) ? mu : 0.0;
                     vh.x = fma(-m_, mk2.x, vh.x);
                     vh.y = fma(-m_, mk2.y, vh.y);
