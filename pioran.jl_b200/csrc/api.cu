@@ -683,6 +683,7 @@ static int dispatch_blocked_wide(pioran_ctx* c, const BatchArgs& a, int nitems, 
     case nt: return xrow ? launch_blocked_wide<nt, nt + 1, (nt + 1 > 12 ? 8 : w)>(c, a, nitems, R, amp_stride) \
                          : launch_blocked_wide<nt, nt, w>(c, a, nitems, R, amp_stride);
     switch (NT) {
+        PIORAN_BLKW_CASE(4, 4) PIORAN_BLKW_CASE(5, 4) PIORAN_BLKW_CASE(6, 4) PIORAN_BLKW_CASE(7, 4) PIORAN_BLKW_CASE(8, 4)   // small batches (latency)
         PIORAN_BLKW_CASE(9, 4) PIORAN_BLKW_CASE(10, 4) PIORAN_BLKW_CASE(11, 4) PIORAN_BLKW_CASE(12, 4)
         PIORAN_BLKW_CASE(13, 8) PIORAN_BLKW_CASE(14, 8) PIORAN_BLKW_CASE(15, 8) PIORAN_BLKW_CASE(16, 8)
     }
@@ -1116,12 +1117,17 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     // K2
     std::vector<int64_t> key;
     key.reserve(4 + 3 * (size_t)S);
-    key.push_back(S); key.push_back(B); key.push_back(blocked ? -R : BS); key.push_back(theta_per_series != 0);
+    // Small batches (at most 2 evaluations per SM: a handful of chains, the B = 1 drop-in) at 4 … 8 column tiles: one CTA of four warps
+    // per evaluation (blocked_wide.cuh) — a block of 8 steps then costs a quarter of the products per warp: 0.22 instead of 0.48 ms per
+    // 1 000 steps at rank 60 (tools/small_batch.py).  Beyond two CTAs per SM the register file holds no more of them and the warp kernel wins.
+    static const bool cta_small_on = [] { const char* e = getenv("PIORAN_K2_SMALL_CTA"); return !(e && !strcmp(e, "0")); }();
+    const bool cta_per_theta = blocked && cta_small_on && blk_nt(R) >= 4 && (long long)S * B <= 2LL * c->num_sms;
+    key.push_back(S); key.push_back(B); key.push_back(blocked ? (cta_per_theta ? -2000 - R : -R) : BS); key.push_back(theta_per_series != 0);
     for (int s = 0; s < S; s++) { key.push_back((int64_t)(intptr_t)tabs[s].d); key.push_back((int64_t)(intptr_t)ser[s]->t); key.push_back(ser[s]->N); }
     if (key != c->work_key) {
         ItemPlan ip;
-        plan_items(c, S, ser.data(), tabs.data(), B, blocked ? blocked_nw(blk_nt(R)) : theta_per_item(BS), theta_per_series != 0, ip,
-                   blocked);
+        plan_items(c, S, ser.data(), tabs.data(), B, cta_per_theta ? 1 : blocked ? blocked_nw(blk_nt(R)) : theta_per_item(BS), theta_per_series != 0, ip,
+                   blocked && !cta_per_theta);
         c->work_key.clear();
         if ((rc = c->work.ensure(sizeof(WorkItem) * ip.items.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->work.p, ip.items.data(), sizeof(WorkItem) * ip.items.size(), cudaMemcpyHostToDevice,
@@ -1141,6 +1147,7 @@ static int approx_logl_dev_locked(pioran_ctx* c, int S, const int* series_ids, c
     args.pstride = ts;
     args.y_batch = y_batch; args.s2_batch = s2_batch; args.ystride = ser[0]->N;
     args.out = logl_dev;
+    if (cta_per_theta) return dispatch_blocked_wide(c, args, nitems, R, RP);
     if (blocked) return dispatch_blocked(c, args, nitems, c->work_tpi, R, RP);
     return dispatch_shared(c, BS, args, nitems, c->work_tpi);
 }
@@ -1733,7 +1740,8 @@ static int generic_logl_locked(pioran_ctx* c, Series* s, int B, int Jt, const do
             args.mu = gi.mu; args.nu = gi.nu; args.pstride = 1;
             args.y_batch = gi.yb; args.s2_batch = gi.sb; args.ystride = s->N;
             args.out = c->out.as<double>();
-            if ((rc = R > 64 ? dispatch_blocked_wide(c, args, B, R, RPA) : dispatch_blocked(c, args, B, 1, R, RPA))) return rc;
+            static const bool cta_small_on = [] { const char* e = getenv("PIORAN_K2_SMALL_CTA"); return !(e && !strcmp(e, "0")); }();
+            if ((rc = (R > 64 || (cta_small_on && blk_nt(R) >= 4)) ? dispatch_blocked_wide(c, args, B, R, RPA) : dispatch_blocked(c, args, B, 1, R, RPA))) return rc;
             CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             return PIORAN_OK;

@@ -9,7 +9,7 @@ t, y, s2, f_min, f_max = wl.make_series(1000, 1234)
 for basis in ("SHO", "DRWCelerite"):
     like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", 20, basis, f_min=f_min, f_max=f_max, ctx=ctx)
     row = {"basis": basis}
-    for B in (1, 16, 100, 400, 592, 593, 1184, 4096):
+    for B in (1, 16, 100, 148, 200, 296, 297, 400, 592, 593, 1184, 4096):
         th = wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), 3, 4.0 if basis == "SHO" else 6.0)
         like(th)
         best = 1e30
