@@ -30,6 +30,7 @@
 #include "wide.cuh"
 #include "wide_grad.cuh"
 #include "scan_wide.cuh"
+#include "scan_blocked.cuh"
 
 using namespace pioran;
 
@@ -105,7 +106,7 @@ struct pioran_ctx {
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
-    DevBuf theta, amp, suma, out, work, coef, rows, misc, post, gradws, gwork;
+    DevBuf theta, amp, suma, out, work, coef, rows, misc, post, gradws, gwork, stab;   // stab: per-θ block table of the K3 fold
     // device time of the most recent main-kernel launch (K2/K3/K4), for bench.py's roofline line
     cudaEvent_t ev_beg = nullptr, ev_end = nullptr;
     bool ev_valid = false;
@@ -280,7 +281,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     for (Series* s : c->series) free_series(s);
     for (auto& kv : c->plans) cudaFree(kv.second);
     c->theta.release(); c->amp.release(); c->suma.release(); c->out.release(); c->work.release();
-    c->coef.release(); c->rows.release(); c->misc.release(); c->post.release(); c->gradws.release(); c->gwork.release();
+    c->coef.release(); c->rows.release(); c->misc.release(); c->post.release(); c->gradws.release(); c->gwork.release(); c->stab.release();
     if (c->ev_beg) cudaEventDestroy(c->ev_beg);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
     if (c->own) cudaStreamDestroy(c->own);
@@ -2097,6 +2098,8 @@ struct ScanRun {
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
     bool wide = false;                       // ranks 65 … 96: the kernels of scan_wide.cuh (leading dimension 96)
+    bool bfold = false;                      // fold and pass 3 on the tensor pipe from the per-θ block table (scan_blocked.cuh)
+    int NTs = 0; const double* stab = nullptr; int64_t stab_stride = 0;
     size_t sel() const { return wide ? (size_t)SELW : (size_t)SEL; }          // doubles per composite / state / (T | m)
     size_t sstate() const { return wide ? (size_t)SSTATEW : (size_t)SSTATE; }
     size_t snewt() const { return wide ? (size_t)SNEWTW : (size_t)SNEWT; }
@@ -2142,14 +2145,28 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     const int G1 = (P + G2 - 1) / G2;
     // pass 3 on SUB sub-chunks per chunk (states at the inner boundaries from the fold's running composite): worth one extra
     // apply per boundary once a chunk is a thousand steps long
-    const int SUB = (len / P >= 1024) ? 4 : 1;
+    int SUB = (len / P >= 1024) ? 4 : 1;
     run = ScanRun{};
     run.series_id = series_id; run.B = B; run.Jt = Jt; run.R = R; run.BS = BS; run.P = P; run.G1 = G1; run.G2 = G2; run.SUB = SUB;
     run.N = N; run.n_lo = n_lo; run.n_hi = n_hi; run.wide = wide;
     const size_t SELr = run.sel(), SSTATEr = run.sstate(), SNEWTr = run.snewt();
     run.bounds.resize(P + 1);
     // inner bounds at even offsets: every sub-chunk but the last has an even length (the self-check sweeps on across a bound)
-    for (int k = 0; k <= P; k++) run.bounds[k] = k == P ? n_hi : n_lo + ((int64_t)((__int128)len * k / P) & ~(int64_t)1);
+    // Blocked fold (scan_blocked.cuh): whole-series calls at 4 … 13 row tiles whose per-θ block table fits a quarter of the free HBM
+    const int NTs = sblk_nt(R);
+    const int64_t nblk_series = (N + BLK - 1) / BLK;
+    const size_t stab_bytes = sizeof(double) * (size_t)nblk_series * sblk_doubles(NTs) * (size_t)B;
+    static const bool bfold_on = [] { const char* e = getenv("PIORAN_K3_BLOCKED_FOLD"); return !(e && !strcmp(e, "0")); }();
+    bool bfold = bfold_on && c->sweep_kernel != PIORAN_SWEEP_SCALAR && NTs >= 4 && NTs <= 13 && n_lo == 0 && n_hi == N && len / P >= 64;
+    if (bfold && stab_bytes > c->stab.cap) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if (stab_bytes > (free_b + c->stab.cap) / 4) bfold = false;
+    }
+    const int64_t bmask = bfold ? ~(int64_t)7 : ~(int64_t)1;     // chunk bounds on the table's block grid
+    run.bfold = bfold; run.NTs = NTs;
+    if (bfold) { SUB = 1; run.SUB = 1; }      // the blocked re-filter sweeps a whole chunk in 0.8 ms: no inner boundaries
+    for (int k = 0; k <= P; k++) run.bounds[k] = k == P ? n_hi : n_lo + ((int64_t)((__int128)len * k / P) & bmask);
 
     int rc;
     if ((rc = upload_generic(c, B, Jt, N, a, b, cc, d, mu, nu, nullptr, nullptr, run.gi))) return rc;
@@ -2183,7 +2200,7 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.ksbuf = run.err + B;
     run.exits = run.ksbuf + n_el;
     run.tm = run.exits + n_cs;
-    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2)))) return rc;
+    if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2) + sizeof(int) * 2 * (size_t)std::max(R, 1)))) return rc;   // + the fold's row tables
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
     CUDA_TRY(cudaMemcpyAsync(run.bounds_dev, run.bounds.data(), sizeof(int64_t) * (P + 1), cudaMemcpyHostToDevice, c->stream));
@@ -2195,13 +2212,49 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     sa.t = s->t; sa.y = s->y; sa.s2 = s->s2; sa.N = N; sa.P = P; sa.bounds = run.bounds_dev;
     sa.a = run.gi.a; sa.b = run.gi.b; sa.c = run.gi.c; sa.d = run.gi.d; sa.Jt = Jt; sa.term_row = run.term_row_dev;
     sa.mu = run.gi.mu; sa.nu = run.gi.nu; sa.elems = run.elems; sa.SUB = SUB; sa.subel = run.subel;
+    if (bfold) {
+        // per-θ block table (rows in logical order, the data row at R), then one CTA of NTs warps per chunk
+        if ((rc = c->stab.ensure(stab_bytes))) return rc;
+        std::vector<int> rmeta(2 * (size_t)std::max(R, 1));
+        for (int m = 0; m < Jt; m++) {
+            const int tr = term_row[m];
+            if (tr < 0) { rmeta[-tr - 1] = m; rmeta[R + (-tr - 1)] = ROW_REAL; }
+            else { rmeta[tr] = m; rmeta[R + tr] = ROW_COS; rmeta[tr + 1] = m; rmeta[R + tr + 1] = ROW_SIN; }
+        }
+        int* rmeta_dev = run.term_row_dev + Jt + 1;           // behind the chunk bounds and the term rows in c->rows
+        CUDA_TRY(cudaMemcpyAsync(rmeta_dev, rmeta.data(), sizeof(int) * rmeta.size(), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));          // rmeta is a local
+        const int64_t tstride = nblk_series * sblk_doubles(NTs);
+        run.stab = c->stab.as<double>(); run.stab_stride = tstride;
+        scan_block_table_kernel<<<dim3((unsigned)nblk_series, B), 128, 0, c->stream>>>(c->stab.as<double>(), tstride, s->t, s->y, s->s2, N, run.gi.a,
+                                                                                     run.gi.b, run.gi.c, run.gi.d, Jt, rmeta_dev, rmeta_dev + R, R,
+                                                                                     NTs, run.gi.mu, run.gi.nu);
+        // the blocked fold writes the live rank only: everything else of the composites must read as zero
+        CUDA_TRY(cudaMemsetAsync(run.elems, 0, sizeof(double) * n_el, c->stream));
+        if (n_sel) CUDA_TRY(cudaMemsetAsync(run.subel, 0, sizeof(double) * n_sel, c->stream));
+        const int LDSr = wide ? SRW : SR;
+#define PIORAN_SFB_CASE(nt)                                                                                                          \
+        case nt: {                                                                                                                   \
+            CUDA_TRY(cudaFuncSetAttribute(scan_fold_blocked_kernel<nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sfb_smem_bytes<nt>()));     \
+            scan_fold_blocked_kernel<nt><<<dim3(P, B), nt * 32, sfb_smem_bytes<nt>(), c->stream>>>(sa, c->stab.as<double>(), tstride, R, LDSr, (int)SELr); \
+        } break;
+        switch (NTs) {
+            PIORAN_SFB_CASE(4) PIORAN_SFB_CASE(5) PIORAN_SFB_CASE(6) PIORAN_SFB_CASE(7) PIORAN_SFB_CASE(8) PIORAN_SFB_CASE(9)
+            PIORAN_SFB_CASE(10) PIORAN_SFB_CASE(11) PIORAN_SFB_CASE(12) PIORAN_SFB_CASE(13)
+        }
+#undef PIORAN_SFB_CASE
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+    }
     if (wide) {
         // states handed to pass 3 are read over the full 96 rows: what the pass-2 kernels leave outside the live rank must be zero
         CUDA_TRY(cudaMemsetAsync(run.gstate, 0, sizeof(double) * (n_gs + n_cs), c->stream));
         if (n_sst) CUDA_TRY(cudaMemsetAsync(run.substate, 0, sizeof(double) * n_sst, c->stream));
-        CUDA_TRY(cudaFuncSetAttribute(scanw_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOLDW_SMEM_BYTES));
-        scanw_fold_kernel<<<dim3(P, B), FOLDW_THREADS, FOLDW_SMEM_BYTES, c->stream>>>(sa);
-        c->launches++;
+        if (!bfold) {
+            CUDA_TRY(cudaFuncSetAttribute(scanw_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOLDW_SMEM_BYTES));
+            scanw_fold_kernel<<<dim3(P, B), FOLDW_THREADS, FOLDW_SMEM_BYTES, c->stream>>>(sa);
+            c->launches++;
+        }
         const int Rw = run.rr();
         const size_t smw = run.smem();
         CUDA_TRY(cudaFuncSetAttribute(scanw_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
@@ -2231,8 +2284,10 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
         run.valid = true;
         return 0;
     }
-    scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
-    c->launches++;
+    if (!bfold) {
+        scan_fold_kernel<<<dim3(P, B), 256, 0, c->stream>>>(sa);
+        c->launches++;
+    }
     CUDA_TRY(cudaFuncSetAttribute(scan_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_group_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(scan_states_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
@@ -2272,6 +2327,25 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     }
     CUDA_TRY(cudaGetLastError());
     run.valid = true;
+    return 0;
+}
+
+// Pass 3 from the per-θ block table (scan_blocked.cuh): one CTA of four warps per work item.
+static int launch_scan_sweep_blocked(pioran_ctx* c, const ScanRun& run, const WorkItem* work, int nitems) {
+    const int LDSr = run.wide ? SRW : SR;
+#define PIORAN_SSB_CASE(nt)                                                                                                       \
+    case nt: {                                                                                                                    \
+        CUDA_TRY(cudaFuncSetAttribute(scan_sweep_blocked_kernel<nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssb_smem_bytes<nt>()));    \
+        scan_sweep_blocked_kernel<nt><<<nitems, SSB_W * 32, ssb_smem_bytes<nt>(), c->stream>>>(work, run.stab, run.stab_stride, run.R, LDSr);    \
+    } break;
+    switch (run.NTs) {
+        PIORAN_SSB_CASE(4) PIORAN_SSB_CASE(5) PIORAN_SSB_CASE(6) PIORAN_SSB_CASE(7) PIORAN_SSB_CASE(8) PIORAN_SSB_CASE(9)
+        PIORAN_SSB_CASE(10) PIORAN_SSB_CASE(11) PIORAN_SSB_CASE(12) PIORAN_SSB_CASE(13)
+        default: return fail(PIORAN_EUNSUPPORTED, "no blocked re-filter for %d row tiles", run.NTs);
+    }
+#undef PIORAN_SSB_CASE
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -2350,7 +2424,7 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
         wargs.Jt = run.Jt; wargs.term_row = run.term_row_dev; wargs.R = run.R;
         wargs.mu = run.gi.mu; wargs.nu = run.gi.nu; wargs.pstride = 1;
         wargs.out = run.out;
-        return launch_wide_chunk(c, wargs, (int)nsub);
+        return run.bfold ? launch_scan_sweep_blocked(c, run, c->work.as<WorkItem>(), (int)nsub) : launch_wide_chunk(c, wargs, (int)nsub);
     }
     if (!states_ready && (P > 1 || init_dev)) {
         scan_group_states_kernel<<<dim3(run.G1, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tp, run.gstate, run.G1, init_dev, scan_live_rank(run.R));
@@ -2370,6 +2444,7 @@ static int scan_phase2(pioran_ctx* c, Series* s, ScanRun& run, const double* ini
     args.Jt = run.Jt; args.term_row = run.term_row_dev; args.R = run.R;
     args.mu = run.gi.mu; args.nu = run.gi.nu; args.pstride = 1;
     args.out = run.out;
+    if (run.bfold) return launch_scan_sweep_blocked(c, run, c->work.as<WorkItem>(), (int)nsub);
     return dispatch_chunked(c, run.BS, args, (int)(nitems / NW));
 }
 
@@ -2417,7 +2492,8 @@ static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
     args.out = run.out;
     for (int j = 0; j < SUB; j++) {
         args.work = c->work.as<WorkItem>() + (size_t)j * npl;
-        if ((rc = run.wide ? launch_wide_chunk(c, args, (int)nch) : dispatch_chunked(c, run.BS, args, (int)(npl / NW)))) return rc;
+        if ((rc = run.bfold ? launch_scan_sweep_blocked(c, run, args.work, (int)nch)
+                  : run.wide ? launch_wide_chunk(c, args, (int)nch) : dispatch_chunked(c, run.BS, args, (int)(npl / NW)))) return rc;
     }
     return 0;
 }
