@@ -158,6 +158,9 @@ constexpr int AUTO_SCAN_MAX_BATCH = 4;
 static bool auto_scan(const pioran_ctx* c, int64_t N, int B, int R, bool explicit_coefficients = false) {
     int64_t min_steps = R <= 32 ? AUTO_SCAN_MIN_STEPS / 2 : AUTO_SCAN_MIN_STEPS;
     if (explicit_coefficients) min_steps /= 2;
+    // from 4 column tiles on, one evaluation runs as a CTA of four warps on the tensor pipe (blocked_wide.cuh) at 0.18–0.23 µs per
+    // step, and the scan's fixed cost (Kogge–Stone levels) is overtaken later: tools/scan_threshold.py, round 2
+    if (R >= 25 && R <= 63 && c->sweep_kernel != PIORAN_SWEEP_SCALAR) min_steps = R <= 32 ? 4096 : 8192;
     // wide ranks: the one-CTA blocked sweep runs 0.49 µs per step, the wide scan costs ≈ 9.7 ms + 0.02 µs per step (profiles/r02_reference_suite_mirror.jsonl)
     if (R > SCAN_LD) return c->auto_scan && N >= (c->sweep_kernel == PIORAN_SWEEP_SCALAR ? 4096 : 20480) && B <= AUTO_SCAN_MAX_BATCH && R <= SRW;
     return c->auto_scan && N >= min_steps && B <= AUTO_SCAN_MAX_BATCH && R <= SCAN_LD;
@@ -2094,6 +2097,7 @@ struct ScanRun {
     double *chk = nullptr, *err = nullptr;   // self-check sums (4 per sub-chunk) and the per-θ deviation estimate
     double *ksbuf = nullptr;                 // second Kogge–Stone buffer (the fold's composites in `elems` stay intact for the Newton step)
     double *exits = nullptr, *tm = nullptr;  // Newton refinement: exit state of every chunk sweep, (T | m) of every chunk
+    double *nel0 = nullptr, *nel1 = nullptr; // … and the two buffers of its affine scan (T | r | m | r^g per boundary)
     double check_scale = 1.0;
     int64_t* bounds_dev = nullptr;
     int* term_row_dev = nullptr;
@@ -2103,6 +2107,7 @@ struct ScanRun {
     size_t sel() const { return wide ? (size_t)SELW : (size_t)SEL; }          // doubles per composite / state / (T | m)
     size_t sstate() const { return wide ? (size_t)SSTATEW : (size_t)SSTATE; }
     size_t snewt() const { return wide ? (size_t)SNEWTW : (size_t)SNEWT; }
+    size_t snel() const { return wide ? (size_t)SNELW : (size_t)SNEL; }
     int rr() const { return wide ? std::min(SRW, (R + 3) & ~3) : std::min(SR, (R + 3) & ~3); }   // live rank, rounded up to a multiple of 4
     size_t smem() const { return wide ? scanw_smem_bytes(rr()) : SCAN_SMEM_BYTES; }
 };
@@ -2177,8 +2182,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     const size_t n_sel = nch * (SUB - 1) * SELr, n_sst = nch * (SUB - 1) * SSTATEr, n_gt = (size_t)B * G1 * SELr;
     const size_t n_tot = (size_t)B * SELr, n_scr = 2 * (size_t)B * SELr, n_init = (size_t)B * SSTATEr;
     const size_t n_prev = (size_t)std::max(0, max_prev) * B * SELr;
-    const size_t n_tm = nch * SNEWTr;
-    if ((rc = c->misc.ensure(sizeof(double) * (3 * n_el + n_gs + 2 * n_cs + n_tm + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
+    const size_t n_tm = nch * SNEWTr, n_nel = nch * run.snel();
+    if ((rc = c->misc.ensure(sizeof(double) * (3 * n_el + n_gs + 2 * n_cs + n_tm + 2 * n_nel + n_pt + B + n_tot + n_scr + n_init + n_prev + 3 * (size_t)B + n_sel + n_sst + 2 * n_gt + n_chk + B))))
         return rc;
     run.elems = c->misc.as<double>();
     run.pref = run.elems + n_el;
@@ -2200,6 +2205,8 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     run.ksbuf = run.err + B;
     run.exits = run.ksbuf + n_el;
     run.tm = run.exits + n_cs;
+    run.nel0 = run.tm + n_tm;
+    run.nel1 = run.nel0 + n_nel;
     if ((rc = c->rows.ensure(sizeof(int) * (Jt + 1) + sizeof(int64_t) * (P + 2) + sizeof(int) * 2 * (size_t)std::max(R, 1)))) return rc;   // + the fold's row tables
     run.bounds_dev = c->rows.as<int64_t>();
     run.term_row_dev = reinterpret_cast<int*>(run.bounds_dev + P + 2);
@@ -2501,23 +2508,40 @@ static int scan_seq_pass(pioran_ctx* c, Series* s, ScanRun& run) {
 // One Newton step on the chunk states: (T_k | m_k) of every chunk from its composite and current state, then the linear
 // recurrence of the corrections along the chunks (needs the exits of a scan_seq_pass over the current states).
 static int scan_newton_step(pioran_ctx* c, ScanRun& run) {
+    const int P = run.P, B = run.B;
+    double* src = run.nel0;
+    double* dst = run.nel1;
     if (run.wide) {
         const int Rw = run.rr();
         const size_t smw = run.smem();
         CUDA_TRY(cudaFuncSetAttribute(scanw_newton_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-        CUDA_TRY(cudaFuncSetAttribute(scanw_newton_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
-        scanw_newton_T_kernel<<<dim3(run.P, run.B), 256, smw, c->stream>>>(run.elems, run.cstate, run.tm, run.P, Rw);
-        scanw_newton_chain_kernel<<<dim3(1, run.B), 256, smw, c->stream>>>(run.tm, run.exits, run.cstate, run.P, Rw);
+        CUDA_TRY(cudaFuncSetAttribute(scanw_newton_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+        scanw_newton_T_kernel<<<dim3(P, B), 256, smw, c->stream>>>(run.elems, run.cstate, run.tm, P, Rw);
+        scanw_newton_prep_kernel<<<dim3(P, B), 256, 0, c->stream>>>(run.tm, run.exits, run.cstate, src, P);
         c->launches += 2;
+        for (int d = 1; d < P - 1; d *= 2) {
+            scanw_newton_ks_kernel<<<dim3(P, B), 256, smw, c->stream>>>(src, dst, P, d, Rw);
+            c->launches++;
+            std::swap(src, dst);
+        }
+        scanw_newton_apply_kernel<<<dim3(P, B), 256, 0, c->stream>>>(src, run.cstate, P);
+        c->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
     const int Rr = scan_live_rank(run.R);
     CUDA_TRY(cudaFuncSetAttribute(scan_newton_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(scan_newton_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
-    scan_newton_T_kernel<<<dim3(run.P, run.B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.cstate, run.tm, run.P, Rr);
-    scan_newton_chain_kernel<<<dim3(1, run.B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.tm, run.exits, run.cstate, run.P, Rr);
+    CUDA_TRY(cudaFuncSetAttribute(scan_newton_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
+    scan_newton_T_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(run.elems, run.cstate, run.tm, P, Rr);
+    scan_newton_prep_kernel<<<dim3(P, B), 256, 0, c->stream>>>(run.tm, run.exits, run.cstate, src, P);
     c->launches += 2;
+    for (int d = 1; d < P - 1; d *= 2) {
+        scan_newton_ks_kernel<<<dim3(P, B), 256, SCAN_SMEM_BYTES, c->stream>>>(src, dst, P, d, Rr);
+        c->launches++;
+        std::swap(src, dst);
+    }
+    scan_newton_apply_kernel<<<dim3(P, B), 256, 0, c->stream>>>(src, run.cstate, P);
+    c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -595,45 +595,67 @@ __global__ void __launch_bounds__(256, 1) scan_newton_T_kernel(const double* ele
     for (int k = tid; k < SR * SR; k += blockDim.x) To[k] = Ae[k] - w.m[3][(k / SR) * SLD + (k % SR)];
     if (tid < SR) mo[tid] = w.v[1][tid] - sm_matvec_row<false>(w.m[1], w.v[3], tid, w.Rr);
 }
-// grid = (1, B): the recurrence above along the chunks of one parameter vector; S̃_k ← S̃_k + δ_k in place (= E_{k−1} + the
-// propagated correction of the earlier boundaries).  exits[k] = E_k.
-__global__ void __launch_bounds__(256, 1) scan_newton_chain_kernel(const double* tm, const double* exits, double* cstate, int P,
-                                                                   int Rr) {
+// The recurrence is a scan over affine maps: boundary k carries e_k = (T_{k−1}, r_k, m_{k−1}, r^g_k), and two consecutive maps
+// (i earlier, j later) compose into  T = T_j T_i,  r = T_j r_i T_jᵀ + r_j,  m = m_i + T_iᵀ m_j,  r^g = T_j (r^g_i + r_i m_j) + r^g_j.
+// A Kogge–Stone sweep over k = 1 … P−1 (⌈log2⌉ launches of independent compositions — three 64³ products each, no solve) leaves
+// at boundary k the composition of the maps 1 … k; applied to δ_0 = 0 its (r, r^g) ARE the corrections (δS_k, δg_k).  A chain
+// of P−1 dependent steps in one CTA took 8.3 ms at P = 296; the sweep takes 9 levels of ≈ 60 µs.
+constexpr int SNEL = 2 * SR * SR + 2 * SR;    // doubles per affine element: T | r | m | r^g
+// grid = (P, B): element of boundary k from (T | m) of chunk k−1, the exit state of chunk k−1 and the current state of chunk k.
+__global__ void scan_newton_prep_kernel(const double* __restrict__ tm, const double* __restrict__ exits,
+                                        const double* __restrict__ cstate, double* __restrict__ nel, int P) {
+    const int th = blockIdx.y, k = blockIdx.x;
+    if (k == 0) return;
+    const size_t q = (size_t)th * P + k;
+    const double* T = tm + (q - 1) * SNEWT;
+    const double* E = exits + (q - 1) * SSTATE;
+    const double* S = cstate + q * SSTATE;
+    double* el = nel + q * SNEL;
+    for (int i = threadIdx.x; i < SR * SR; i += blockDim.x) { el[i] = T[i]; el[SR * SR + i] = E[i] - S[i]; }
+    for (int i = threadIdx.x; i < SR; i += blockDim.x) {
+        el[2 * SR * SR + i] = T[SR * SR + i];
+        el[2 * SR * SR + SR + i] = E[SR * SR + i] - S[SR * SR + i];
+    }
+}
+// One Kogge–Stone level: out[k] = in[k−d] ∘ in[k] when k − d ≥ 1, else in[k].  grid = (P, B).
+__global__ void __launch_bounds__(256, 1) scan_newton_ks_kernel(const double* in, double* out, int P, int d, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
     const ScanSmem w = scan_smem(raw, Rr);
-    const int th = blockIdx.y, tid = threadIdx.x;
-    double* dS = w.m[0];
-    for (int k = tid; k < SMAT; k += blockDim.x) dS[k] = 0.0;
-    if (tid < SR) w.v[0][tid] = 0.0;                                                        // δg
-    __syncthreads();
-    for (int k = 1; k < P; k++) {
-        const size_t q = (size_t)th * P + k;
-        if (k >= 2) {                                                                       // δ_1 = r_1: nothing to propagate yet
-            const double* T = tm + (q - 1) * SNEWT;
-            sm_load(w.m[1], T);
-            if (tid < SR) w.v[1][tid] = T[SR * SR + tid];
-            __syncthreads();
-            if (tid < SR) w.v[2][tid] = w.v[0][tid] + sm_matvec_row<false>(dS, w.v[1], tid, w.Rr);    // δg + δS m
-            __syncthreads();
-            if (tid < SR) w.v[0][tid] = sm_matvec_row<false>(w.m[1], w.v[2], tid, w.Rr);              // T (δg + δS m)
-            sm_matmul<false, false>(w.m[2], nullptr, w.m[1], dS, nullptr, false, w.Rr);               // T δS
-            sm_matmul<false, true>(dS, nullptr, w.m[2], w.m[1], nullptr, true, w.Rr);                 // (T δS) Tᵀ, symmetrised
-        }
-        const double* E = exits + (q - 1) * SSTATE;
-        double* S = cstate + q * SSTATE;
-        for (int idx = tid; idx < SR * SR; idx += blockDim.x) {
-            const int sidx = (idx / SR) * SLD + (idx % SR);
-            const double d = dS[sidx] + (E[idx] - S[idx]);
-            dS[sidx] = d;
-            S[idx] += d;
-        }
-        if (tid < SR) {
-            const double d = w.v[0][tid] + (E[SR * SR + tid] - S[SR * SR + tid]);
-            w.v[0][tid] = d;
-            S[SR * SR + tid] += d;
-        }
-        __syncthreads();
+    const int th = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+    if (k == 0) return;
+    const size_t q = (size_t)th * P + k;
+    const double* ej = in + q * SNEL;
+    double* eo = out + q * SNEL;
+    if (k - d < 1) {
+        for (int i = tid; i < SNEL; i += blockDim.x) eo[i] = ej[i];
+        return;
     }
+    const double* ei = in + (q - d) * SNEL;
+    constexpr int MM = SR * SR;
+    sm_load(w.m[0], ej);                 // T_j
+    sm_load(w.m[1], ei);                 // T_i
+    sm_load(w.m[2], ei + MM);            // r_i
+    if (tid < SR) { w.v[0][tid] = ej[2 * MM + tid]; w.v[1][tid] = ei[2 * MM + SR + tid]; }       // m_j, r^g_i
+    __syncthreads();
+    if (tid < SR) {
+        eo[2 * MM + tid] = ei[2 * MM + tid] + sm_matvec_row<true>(w.m[1], w.v[0], tid, w.Rr);     // m = m_i + T_iᵀ m_j
+        w.v[3][tid] = w.v[1][tid] + sm_matvec_row<false>(w.m[2], w.v[0], tid, w.Rr);              // r^g_i + r_i m_j
+    }
+    __syncthreads();
+    if (tid < SR) eo[2 * MM + SR + tid] = sm_matvec_row<false>(w.m[0], w.v[3], tid, w.Rr) + ej[2 * MM + SR + tid];   // r^g
+    sm_matmul<false, false>(nullptr, eo, w.m[0], w.m[1], nullptr, false, w.Rr);                   // T = T_j T_i
+    sm_matmul<false, false>(w.m[3], nullptr, w.m[0], w.m[2], nullptr, false, w.Rr);               // T_j r_i
+    sm_matmul<false, true>(w.m[4], eo + MM, w.m[3], w.m[0], ej + MM, true, w.Rr);                 // r = (T_j r_i) T_jᵀ + r_j
+}
+// S̃_k ← S̃_k + δ_k (k ≥ 1).  grid = (P, B).
+__global__ void scan_newton_apply_kernel(const double* __restrict__ nel, double* __restrict__ cstate, int P) {
+    const int th = blockIdx.y, k = blockIdx.x;
+    if (k == 0) return;
+    const size_t q = (size_t)th * P + k;
+    const double* el = nel + q * SNEL;
+    double* S = cstate + q * SSTATE;
+    for (int i = threadIdx.x; i < SR * SR; i += blockDim.x) S[i] += el[SR * SR + i];
+    for (int i = threadIdx.x; i < SR; i += blockDim.x) S[SR * SR + i] += el[2 * SR * SR + SR + i];
 }
 
 // (e) state entering this range = the composites of the nprev earlier ranges applied, in order, to the zero state.

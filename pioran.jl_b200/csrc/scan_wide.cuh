@@ -581,45 +581,62 @@ __global__ void __launch_bounds__(256, 1) scanw_newton_T_kernel(const double* el
         To[k] = (r < w.Rr && c < w.Rr) ? X[r * w.LD + c] - Y[r * w.LD + c] : 0.0;
     }
 }
-// grid = (1, B): δS_{k} = T_{k−1} δS_{k−1} T_{k−1}ᵀ + (E_{k−1} − S̃_k), δg likewise; S̃_k ← S̃_k + δ_k in place.
-__global__ void __launch_bounds__(256, 1) scanw_newton_chain_kernel(const double* tm, const double* exits, double* cstate, int P,
-                                                                    int Rr) {
+// The affine scan of scan.cuh (scan_newton_prep / _ks / _apply) on three shared buffers.
+constexpr int SNELW = 2 * SRW * SRW + 2 * SRW;
+__global__ void scanw_newton_prep_kernel(const double* __restrict__ tm, const double* __restrict__ exits,
+                                         const double* __restrict__ cstate, double* __restrict__ nel, int P) {
+    const int th = blockIdx.y, k = blockIdx.x;
+    if (k == 0) return;
+    constexpr int MM = SRW * SRW;
+    const size_t q = (size_t)th * P + k;
+    const double* T = tm + (q - 1) * SNEWTW;
+    const double* E = exits + (q - 1) * SSTATEW;
+    const double* S = cstate + q * SSTATEW;
+    double* el = nel + q * SNELW;
+    for (int i = threadIdx.x; i < MM; i += blockDim.x) { el[i] = T[i]; el[MM + i] = E[i] - S[i]; }
+    for (int i = threadIdx.x; i < SRW; i += blockDim.x) {
+        el[2 * MM + i] = T[MM + i];
+        el[2 * MM + SRW + i] = E[MM + i] - S[MM + i];
+    }
+}
+__global__ void __launch_bounds__(256, 1) scanw_newton_ks_kernel(const double* in, double* out, int P, int d, int Rr) {
     extern __shared__ __align__(16) unsigned char raw[];
     const SwSmem w = scanw_smem(raw, Rr);
+    const int th = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+    if (k == 0) return;
     constexpr int MM = SRW * SRW;
-    const int th = blockIdx.y, tid = threadIdx.x;
-    double *dS = w.m[0], *T = w.m[1], *Z = w.m[2];
-    for (int k = tid; k < w.Rr * w.LD; k += blockDim.x) dS[k] = 0.0;
-    if (tid < SRW) w.v[0][tid] = 0.0;
-    __syncthreads();
-    for (int k = 1; k < P; k++) {
-        const size_t q = (size_t)th * P + k;
-        if (k >= 2) {
-            const double* Tg = tm + (q - 1) * SNEWTW;
-            sw_load(w, T, Tg);
-            if (tid < SRW) w.v[1][tid] = tid < w.Rr ? Tg[MM + tid] : 0.0;
-            __syncthreads();
-            if (tid < w.Rr) w.v[2][tid] = w.v[0][tid] + sw_matvec_row<false>(w, dS, w.v[1], tid);     // δg + δS m
-            __syncthreads();
-            if (tid < w.Rr) w.v[0][tid] = sw_matvec_row<false>(w, T, w.v[2], tid);                    // T (δg + δS m)
-            sw_matmul<false, false>(w, Z, nullptr, T, dS, nullptr, false);                            // T δS
-            sw_matmul<false, true>(w, dS, nullptr, Z, T, nullptr, true);                              // (T δS) Tᵀ, symmetrised
-        }
-        const double* E = exits + (q - 1) * SSTATEW;
-        double* S = cstate + q * SSTATEW;
-        for (int idx = tid; idx < w.Rr * w.Rr; idx += blockDim.x) {
-            const int r = idx / w.Rr, c = idx - r * w.Rr;
-            const double d = dS[r * w.LD + c] + (E[r * SRW + c] - S[r * SRW + c]);
-            dS[r * w.LD + c] = d;
-            S[r * SRW + c] += d;
-        }
-        if (tid < w.Rr) {
-            const double d = w.v[0][tid] + (E[MM + tid] - S[MM + tid]);
-            w.v[0][tid] = d;
-            S[MM + tid] += d;
-        }
-        __syncthreads();
+    const size_t q = (size_t)th * P + k;
+    const double* ej = in + q * SNELW;
+    double* eo = out + q * SNELW;
+    if (k - d < 1) {
+        for (int i = tid; i < SNELW; i += blockDim.x) eo[i] = ej[i];
+        return;
     }
+    const double* ei = in + (q - d) * SNELW;
+    double *X = w.m[0], *Y = w.m[1], *Z = w.m[2];
+    sw_load(w, X, ej);                   // T_j
+    sw_load(w, Y, ei);                   // T_i
+    if (tid < SRW) { w.v[0][tid] = tid < w.Rr ? ej[2 * MM + tid] : 0.0; w.v[1][tid] = tid < w.Rr ? ei[2 * MM + SRW + tid] : 0.0; }   // m_j, r^g_i
+    __syncthreads();
+    if (tid < SRW) eo[2 * MM + tid] = tid < w.Rr ? ei[2 * MM + tid] + sw_matvec_row<true>(w, Y, w.v[0], tid) : 0.0;     // m = m_i + T_iᵀ m_j
+    sw_matmul<false, false>(w, nullptr, eo, X, Y, nullptr, false);                               // T = T_j T_i
+    sw_load(w, Y, ei + MM);              // r_i
+    __syncthreads();
+    if (tid < w.Rr) w.v[3][tid] = w.v[1][tid] + sw_matvec_row<false>(w, Y, w.v[0], tid);          // r^g_i + r_i m_j
+    __syncthreads();
+    if (tid < SRW) eo[2 * MM + SRW + tid] = tid < w.Rr ? sw_matvec_row<false>(w, X, w.v[3], tid) + ej[2 * MM + SRW + tid] : 0.0;   // r^g
+    sw_matmul<false, false>(w, Z, nullptr, X, Y, nullptr, false);                                // T_j r_i
+    sw_matmul<false, true>(w, Y, eo + MM, Z, X, ej + MM, true);                                  // r = (T_j r_i) T_jᵀ + r_j
+}
+__global__ void scanw_newton_apply_kernel(const double* __restrict__ nel, double* __restrict__ cstate, int P) {
+    const int th = blockIdx.y, k = blockIdx.x;
+    if (k == 0) return;
+    constexpr int MM = SRW * SRW;
+    const size_t q = (size_t)th * P + k;
+    const double* el = nel + q * SNELW;
+    double* S = cstate + q * SSTATEW;
+    for (int i = threadIdx.x; i < MM; i += blockDim.x) S[i] += el[MM + i];
+    for (int i = threadIdx.x; i < SRW; i += blockDim.x) S[MM + i] += el[2 * MM + SRW + i];
 }
 
 // ------------------------------------------------------------------------------------------------ pass 3

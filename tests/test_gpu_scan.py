@@ -262,7 +262,7 @@ def test_scan_self_check_keeps_sequential_accuracy(pb, ctx, basis, J):
     ctx.set_scan_chunks(0)
     got, nfb, nrf = [], 0, 0
     for i in range(0, 64, 4):
-        got.append(ctx.celerite_logl(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]))   # auto-routed to the scan path
+        got.append(ctx.celerite_logl_scan(ser, a[i:i + 4], b[i:i + 4], c[i:i + 4], d[i:i + 4]))   # the scan path with its ladder (4 200 steps: below the auto-routing threshold at some ranks)
         sc = ctx.last_scan_check()
         nfb += sc.fallback; nrf += sc.refined
         # what is returned from the scan path passed its check, or went through the Newton refinement / the sequential sweep
