@@ -610,6 +610,51 @@ def strong_scaling(torch, ctx, pb, J, rank, world, dist=None):
 
 
 
+def wide_rank_rows(ctx, pb, peak):
+    """The upper part of the reference's benchmark grid (benchmark/benchmarks.jl:16-18): ranks 80 … 120 through the one-CTA-per-evaluation
+    tensor-pipe kernel (blocked_wide.cuh), 4 096 parameter vectors x N = 1 024; the scalar-pipe kernel of round 1 beside it; C4 with
+    DRWCelerite J = 30 (rank 90) through the wide-rank scan; gradients at rank 90."""
+    from oracle import oracle as orc
+    out = {}
+    B, N = 4096, 1024
+    t, y, s2, f_min, f_max = wl.make_series(N, 3)
+    th = wl.prior_theta(B, f_min, f_max, y.mean(), y.std(), 1, 4.0)
+    for basis, J in (("SHO", 40), ("DRWCelerite", 30), ("DRWCelerite", 40)):
+        R = wl.rank_of(basis, J)
+        like = pb.BatchedLikelihood(t, y, s2, "SingleBendingPowerLaw", J, basis, f_min=f_min, f_max=f_max, ctx=ctx)
+        like(th); v = like(th)
+        ms_t = ctx.last_kernel_ms()
+        ctx.set_sweep_kernel("scalar")
+        like(th); vs = like(th)
+        ms_s = ctx.last_kernel_ms()
+        ctx.set_sweep_kernel("auto")
+        ref = orc.approx_logl_batch("SBPL", th[:16], f_min, f_max, J, t, y, s2, basis=basis, nthreads=0)
+        ok = np.isfinite(ref)
+        row = {"evals_per_s": B / (ms_t * 1e-3), "device_ms": ms_t, "rank": R,
+               "fp64_tflops": B * N * wl.flops_per_step(R) / (ms_t * 1e-3) / 1e12,
+               "fp64_frac": B * N * wl.flops_per_step(R) / (ms_t * 1e-3) / 1e12 / peak,
+               "scalar_pipe_kernel_evals_per_s": B / (ms_s * 1e-3),
+               "parity_max_rel_16": float((np.abs(v[:16] - ref)[ok] / np.maximum(1.0, np.abs(ref[ok]))).max())}
+        if R <= 96:
+            like.value_and_gradient(th[:1024]); like.value_and_gradient(th[:1024])
+            row["gradients_per_s_1024theta"] = 1024 / (ctx.last_kernel_ms() * 1e-3)
+        like.close()
+        out[f"wide_rank_4096theta_N1024_{basis}_J{J}"] = row
+    Nl = 1_000_000
+    t, y, s2, f_min, f_max = wl.make_series_fast(Nl, seed=4)
+    spec = pb.make_spec("SingleBendingPowerLaw", f_min, f_max, 30, basis_function="DRWCelerite")
+    a, b, c, d = ctx.approx_coeffs(spec, np.array([[0.82, 0.01, 3.3, float(np.var(y))]]))
+    ser = ctx.upload_series(t, y, s2)
+    ms = []
+    for _ in range(3):
+        v = ctx.celerite_logl_scan(ser, a, b, c, d)[0]
+        ms.append(ctx.last_kernel_ms())
+    ser.free()
+    out["C4_long_series_N1e6_DRWCelerite_J30_rank90"] = {"device_ms": float(np.mean(ms[1:])), "logL": float(v),
+                                                        "self_check": list(ctx.last_scan_check())}
+    return out
+
+
 def widening_rows(ctx, pb, J):
     """SURVEY 8f #1/#2/#3 next to the hot path: gradients (4 096 θ × 6 directions), batched posterior mean (512 θ, N = 1 000 data points, M = 2 000 prediction
     points) and batched GP draws (4 096 θ × N = 1 000), device time of the library's kernels vs the CPU restatement on a
@@ -780,6 +825,7 @@ def run_b200(args, rank, world, local_rank):
         extra.update(config_c4_c5(ctx, pb, hbm_peak_gbs()))
         extra.update(config_log_shift(ctx, pb, args.J))
         extra.update(widening_rows(ctx, pb, args.J))
+        extra.update(wide_rank_rows(ctx, pb, peak))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
