@@ -2159,10 +2159,13 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
     // inner bounds at even offsets: every sub-chunk but the last has an even length (the self-check sweeps on across a bound)
     // Blocked fold (scan_blocked.cuh): whole-series calls at 4 … 13 row tiles whose per-θ block table fits a quarter of the free HBM
     const int NTs = sblk_nt(R);
-    const int64_t nblk_series = (N + BLK - 1) / BLK;
+    const int64_t blk_lo = n_lo / BLK, blk_hi = std::min<int64_t>((N + BLK - 1) / BLK, (n_hi + BLK - 1) / BLK + 1);   // + the look-ahead block of the self-check
+    const int64_t nblk_series = blk_hi - blk_lo;
     const size_t stab_bytes = sizeof(double) * (size_t)nblk_series * sblk_doubles(NTs) * (size_t)B;
     static const bool bfold_on = [] { const char* e = getenv("PIORAN_K3_BLOCKED_FOLD"); return !(e && !strcmp(e, "0")); }();
-    bool bfold = bfold_on && c->sweep_kernel != PIORAN_SWEEP_SCALAR && NTs >= 4 && NTs <= 13 && n_lo == 0 && n_hi == N && len / P >= 64;
+    // (a range in the middle of a series — the time axis split across devices — qualifies when it sits on the block grid)
+    bool bfold = bfold_on && c->sweep_kernel != PIORAN_SWEEP_SCALAR && NTs >= 4 && NTs <= 13 && (n_lo % BLK) == 0 &&
+                 (n_hi == N || (n_hi % BLK) == 0) && len / P >= 64;
     if (bfold && stab_bytes > c->stab.cap) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -2232,10 +2235,11 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
         CUDA_TRY(cudaMemcpyAsync(rmeta_dev, rmeta.data(), sizeof(int) * rmeta.size(), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));          // rmeta is a local
         const int64_t tstride = nblk_series * sblk_doubles(NTs);
-        run.stab = c->stab.as<double>(); run.stab_stride = tstride;
+        // the kernels index the table by the ABSOLUTE block number: hand them the base shifted by the range's first block
+        run.stab = c->stab.as<double>() - (size_t)blk_lo * sblk_doubles(NTs); run.stab_stride = tstride;
         scan_block_table_kernel<<<dim3((unsigned)nblk_series, B), 128, 0, c->stream>>>(c->stab.as<double>(), tstride, s->t, s->y, s->s2, N, run.gi.a,
                                                                                      run.gi.b, run.gi.c, run.gi.d, Jt, rmeta_dev, rmeta_dev + R, R,
-                                                                                     NTs, run.gi.mu, run.gi.nu);
+                                                                                     NTs, run.gi.mu, run.gi.nu, blk_lo);
         // the blocked fold writes the live rank only: everything else of the composites must read as zero
         CUDA_TRY(cudaMemsetAsync(run.elems, 0, sizeof(double) * n_el, c->stream));
         if (n_sel) CUDA_TRY(cudaMemsetAsync(run.subel, 0, sizeof(double) * n_sel, c->stream));
@@ -2243,7 +2247,7 @@ static int scan_phase1(pioran_ctx* c, Series* s, int series_id, int B, int Jt, c
 #define PIORAN_SFB_CASE(nt)                                                                                                          \
         case nt: {                                                                                                                   \
             CUDA_TRY(cudaFuncSetAttribute(scan_fold_blocked_kernel<nt>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sfb_smem_bytes<nt>()));     \
-            scan_fold_blocked_kernel<nt><<<dim3(P, B), nt * 32, sfb_smem_bytes<nt>(), c->stream>>>(sa, c->stab.as<double>(), tstride, R, LDSr, (int)SELr); \
+            scan_fold_blocked_kernel<nt><<<dim3(P, B), nt * 32, sfb_smem_bytes<nt>(), c->stream>>>(sa, run.stab, tstride, R, LDSr, (int)SELr); \
         } break;
         switch (NTs) {
             PIORAN_SFB_CASE(4) PIORAN_SFB_CASE(5) PIORAN_SFB_CASE(6) PIORAN_SFB_CASE(7) PIORAN_SFB_CASE(8) PIORAN_SFB_CASE(9)

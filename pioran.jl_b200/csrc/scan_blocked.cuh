@@ -28,7 +28,7 @@ __host__ __device__ constexpr int sblk_off_sc(int NT) { return 136 * NT + 64; }
 __host__ __device__ constexpr int sblk_doubles(int NT) { return 136 * NT + 96; }
 __host__ __device__ constexpr int sblk_nt(int R) { return (R + 8) / 8; }       // rows 0 … R−1 and the data row RG = R
 
-// grid = (blocks of the series, B); block = 128 threads: thread r < 8·NT fills physical row r (= logical row r; the data row at R).
+// grid = (blocks of the range, B); block = 128 threads: thread r < 8·NT fills physical row r (= logical row r; the data row at R).
 // term_row as in the generic kernels.  The record is zero-filled before the launch.
 __global__ void __launch_bounds__(128) scan_block_table_kernel(double* __restrict__ tables, int64_t table_stride,
                                                                const double* __restrict__ t, const double* __restrict__ y,
@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(128) scan_block_table_kernel(double* __restric
                                                                const double* __restrict__ a, const double* __restrict__ b,
                                                                const double* __restrict__ c, const double* __restrict__ d, int Jt,
                                                                const int* __restrict__ row_term, const int* __restrict__ row_kind,
-                                                               int R, int NT, const double* __restrict__ mu, const double* __restrict__ nu) {
+                                                               int R, int NT, const double* __restrict__ mu, const double* __restrict__ nu,
+                                                               const int64_t blk_first) {
     __shared__ double kpart[4][36];
-    const int64_t blk = blockIdx.x;
+    const int64_t blk = blk_first + blockIdx.x;       // absolute block number; record blockIdx.x of the table
     const int th = blockIdx.y, r = threadIdx.x, lane = r & 31, warp = r >> 5;
-    double* tab = tables + (size_t)th * table_stride + (size_t)blk * sblk_doubles(NT);
+    double* tab = tables + (size_t)th * table_stride + (size_t)blockIdx.x * sblk_doubles(NT);
     const int64_t n0 = blk * BLK;
     const int kind = (r < R) ? row_kind[r] : (r == R ? ROW_AUG : ROW_PAD);
     double ph[BLK], ut[BLK], vv[BLK];

@@ -17,10 +17,11 @@ def shard_bounds(n, world):
 
 
 def scan_bounds(n, world):
-    """Step ranges of the time-axis split (scan_logl_sharded): the near-equal split with the inner bounds at even steps —
-    the self-check sweeps on across a hand-over, which the kernel's even/odd step alternation allows after an even count."""
+    """Step ranges of the time-axis split (scan_logl_sharded): the near-equal split with the inner bounds at multiples of 8
+    steps — the block grid of the tensor-pipe fold and re-filter (csrc/scan_blocked.cuh); an even count is what the warp
+    kernel's even/odd step alternation needs when the self-check sweeps on across a hand-over."""
     off = shard_bounds(n, world)
-    off[1:-1] &= ~np.int64(1)
+    off[1:-1] &= ~np.int64(7)
     return off
 
 
