@@ -308,47 +308,46 @@ __device__ __forceinline__ double sm_matvec_row(const double* X, const double* x
 }
 // X ← M⁻¹ X for up to two shared SR×SR right-hand sides (R1, R2; R2 may be null) and nvec shared vectors (vecs + v·SR), by
 // Gauss–Jordan elimination with partial pivoting on the augmented system [M | R1 | R2 | vecs]; M is destroyed.  One pass of
-// Rr pivot steps, three CTA barriers each (pivot search by warp 0, row interchange, rank-1 elimination of column k from every
-// other row with a 16×16 thread grid over each 64-wide matrix) — one routine instead of an LU factorisation plus two substitution
-// sweeps per right-hand side, at the same speed (the combine is bound by its barriers, not by this arithmetic).  Rows/columns
-// ≥ Rr are the identity.
+// Rr pivot steps, two CTA barriers each (pivot search by warp 0; rank-1 elimination of column k from every other row with a
+// 16×16 thread grid over each 64-wide matrix) — one routine instead of an LU factorisation plus two substitution sweeps per
+// right-hand side (the combine is bound by its barriers, not by this arithmetic).  Rows/columns ≥ Rr are the identity.
 __device__ __forceinline__ void sm_gj_solve(double* M, double* R1, double* R2, double* vecs, int nvec, int Rr) {
+    // Two barriers per pivot (round 2; five before): no physical row interchange — the pivot row of column k is remembered and the
+    // rows are put in order once at the end — no separate factor column (column k of M is never written again, so every thread
+    // reads its factors M[r][k]/pivot directly) and no per-pivot scaling of the pivot row (the rows are divided by their pivots in
+    // the final pass).  Same pivot choice as the interchange version: the largest |M[r][k]| among the rows not yet used.
     __shared__ int piv_s;
-    __shared__ double fcol_s[SR];
+    __shared__ int used_s[SR], prow_s[SR];
+    __shared__ double pinv_s[SR];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    if (tid < SR) used_s[tid] = 0;
+    __syncthreads();
     for (int k = 0; k < Rr; k++) {
         if (tid < 32) {
-            double best = -1.0; int bi = k;
-            for (int r = k + tid; r < Rr; r += 32) {
-                const double v = fabs(M[r * SLD + k]);
-                if (v > best) { best = v; bi = r; }
+            double best = -1.0; int bi = -1;
+            for (int r = tid; r < Rr; r += 32) {
+                const double v = used_s[r] ? -1.0 : fabs(M[r * SLD + k]);
+                if (v > best || (v == best && bi < 0)) { best = v; bi = r; }
             }
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
             }
-            if (tid == 0) piv_s = bi;
+            if (tid == 0) {
+                if (bi < 0)                       // a column of NaNs: any unused row keeps the bookkeeping valid, the result is NaN
+                    for (int r = 0; r < Rr; r++) if (!used_s[r]) { bi = r; break; }
+                piv_s = bi; used_s[bi] = 1; prow_s[k] = bi; pinv_s[k] = 1.0 / M[bi * SLD + k];
+            }
         }
         __syncthreads();
         const int p = piv_s;
-        if (p != k) {      // interchange rows k and p of the whole augmented system (uniform branch)
-            if (tid < 3 * SR) {
-                double* X = tid < SR ? M : (tid < 2 * SR ? R1 : R2);
-                const int c = tid & (SR - 1);
-                if (X) { const double tmp = X[k * SLD + c]; X[k * SLD + c] = X[p * SLD + c]; X[p * SLD + c] = tmp; }
-            } else if (tid < 3 * SR + nvec) {
-                double* v = vecs + (size_t)(tid - 3 * SR) * SR;
-                const double tmp = v[k]; v[k] = v[p]; v[p] = tmp;
-            }
-            __syncthreads();
-        }
-        // elimination factors of column k (the column itself is not updated: it is e_k from here on)
-        const double inv = 1.0 / M[k * SLD + k];
-        if (tid < SR) fcol_s[tid] = (tid == k || tid >= Rr) ? 0.0 : M[tid * SLD + k] * inv;
-        __syncthreads();
-        // rows r ≠ k: row_r −= f_r · row_k on M (columns > k), R1, R2; then row k is scaled by 1/pivot
+        const double inv = pinv_s[k];
+        // rows r ≠ p: row_r −= (M[r][k]/pivot) · row_p on M (columns > k), R1, R2 and the vectors
+        double f[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int r = ty + 16 * q; f[q] = (r < Rr && r != p) ? M[r * SLD + k] * inv : 0.0; }
 #pragma unroll
         for (int which = 0; which < 3; which++) {
             double* X = which == 0 ? M : (which == 1 ? R1 : R2);
@@ -356,28 +355,39 @@ __device__ __forceinline__ void sm_gj_solve(double* M, double* R1, double* R2, d
             const int c_lo = which == 0 ? k + 1 : 0;
             for (int c = tx; c < SR; c += 16) {
                 if (c < c_lo) continue;
-                const double rk = X[k * SLD + c];
-                if (rk != 0.0)
-                    for (int r = ty; r < Rr; r += 16)
-                        if (r != k) X[r * SLD + c] = fma(-fcol_s[r], rk, X[r * SLD + c]);
+                const double rk = X[p * SLD + c];
+                if (rk != 0.0) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int r = ty + 16 * q;
+                        if (r < Rr && r != p) X[r * SLD + c] = fma(-f[q], rk, X[r * SLD + c]);
+                    }
+                }
             }
         }
         if (tid < nvec * 32) {      // one warp per vector
             double* v = vecs + (size_t)(tid >> 5) * SR;
-            const double vk = v[k];
+            const double vk = v[p];
             for (int r = (tid & 31); r < Rr; r += 32)
-                if (r != k) v[r] = fma(-fcol_s[r], vk, v[r]);
+                if (r != p) v[r] = fma(-(M[r * SLD + k] * inv), vk, v[r]);
         }
         __syncthreads();
-        if (tid < 3 * SR) {
-            double* X = tid < SR ? M : (tid < 2 * SR ? R1 : R2);
-            const int c = tid & (SR - 1);
-            if (X && (X != M || c > k)) X[k * SLD + c] *= inv;
-        } else if (tid < 3 * SR + nvec) {
-            vecs[(size_t)(tid - 3 * SR) * SR + k] *= inv;
-        }
-        // the next step's pivot search reads column k+1 of rows ≥ k+1 (written above, before the last barrier) and the
-        // scaled row k is read only after the next barrier
+    }
+    // rows into pivot order, divided by their pivots: X[k] ← X[prow[k]] / pivot_k (through the spent M as scratch)
+    for (int which = 1; which < 3; which++) {
+        double* X = which == 1 ? R1 : R2;
+        if (!X) continue;
+        for (int q = tid; q < Rr * SR; q += blockDim.x) { const int k = q / SR, c = q % SR; M[k * SLD + c] = X[prow_s[k] * SLD + c] * pinv_s[k]; }
+        __syncthreads();
+        for (int q = tid; q < Rr * SR; q += blockDim.x) { const int k = q / SR, c = q % SR; X[k * SLD + c] = M[k * SLD + c]; }
+        __syncthreads();
+    }
+    for (int v = 0; v < nvec; v++) {
+        double* x = vecs + (size_t)v * SR;
+        double val = 0.0;
+        if (tid < Rr) val = x[prow_s[tid]] * pinv_s[tid];
+        __syncthreads();
+        if (tid < Rr) x[tid] = val;
     }
     __syncthreads();
 }

@@ -337,41 +337,36 @@ __device__ __forceinline__ double sw_matvec_row_g(const SwSmem& w, const double*
 // pivoting on the augmented system, as sm_gj_solve of scan.cuh.  M is destroyed.
 __device__ __forceinline__ void sw_gj_solve(const SwSmem& w, double* M, double* R1, double* R2, double* vecs, int nvec) {
     __shared__ int piv_s;
-    __shared__ double fcol_s[SRW];
+    __shared__ int used_s[SRW], prow_s[SRW];
+    __shared__ double pinv_s[SRW];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, Rr = w.Rr, LD = w.LD;
+    if (tid < SRW) used_s[tid] = 0;
+    __syncthreads();
     for (int k = 0; k < Rr; k++) {
         if (tid < 32) {
-            double best = -1.0; int bi = k;
-            for (int r = k + tid; r < Rr; r += 32) {
-                const double v = fabs(M[r * LD + k]);
-                if (v > best) { best = v; bi = r; }
+            double best = -1.0; int bi = -1;
+            for (int r = tid; r < Rr; r += 32) {
+                const double v = used_s[r] ? -1.0 : fabs(M[r * LD + k]);
+                if (v > best || (v == best && bi < 0)) { best = v; bi = r; }
             }
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) {
                 const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
             }
-            if (tid == 0) piv_s = bi;
+            if (tid == 0) {
+                if (bi < 0)
+                    for (int r = 0; r < Rr; r++) if (!used_s[r]) { bi = r; break; }
+                piv_s = bi; used_s[bi] = 1; prow_s[k] = bi; pinv_s[k] = 1.0 / M[bi * LD + k];
+            }
         }
         __syncthreads();
         const int p = piv_s;
-        if (p != k) {
-            for (int q = tid; q < 3 * Rr + nvec; q += blockDim.x) {
-                if (q < 3 * Rr) {
-                    const int which = q / Rr, c = q - which * Rr;
-                    double* X = which == 0 ? M : (which == 1 ? R1 : R2);
-                    if (X) { const double tmp = X[k * LD + c]; X[k * LD + c] = X[p * LD + c]; X[p * LD + c] = tmp; }
-                } else {
-                    double* v = vecs + (size_t)(q - 3 * Rr) * SRW;
-                    const double tmp = v[k]; v[k] = v[p]; v[p] = tmp;
-                }
-            }
-            __syncthreads();
-        }
-        const double inv = 1.0 / M[k * LD + k];
-        if (tid < Rr) fcol_s[tid] = (tid == k) ? 0.0 : M[tid * LD + k] * inv;
-        __syncthreads();
+        const double inv = pinv_s[k];
+        double f[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) { const int r = ty + 16 * q; f[q] = (r < Rr && r != p) ? M[r * LD + k] * inv : 0.0; }
 #pragma unroll
         for (int which = 0; which < 3; which++) {
             double* X = which == 0 ? M : (which == 1 ? R1 : R2);
@@ -379,28 +374,38 @@ __device__ __forceinline__ void sw_gj_solve(const SwSmem& w, double* M, double* 
             const int c_lo = which == 0 ? k + 1 : 0;
             for (int c = tx; c < Rr; c += 16) {
                 if (c < c_lo) continue;
-                const double rk = X[k * LD + c];
-                if (rk != 0.0)
-                    for (int r = ty; r < Rr; r += 16)
-                        if (r != k) X[r * LD + c] = fma(-fcol_s[r], rk, X[r * LD + c]);
+                const double rk = X[p * LD + c];
+                if (rk != 0.0) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) {
+                        const int r = ty + 16 * q;
+                        if (r < Rr && r != p) X[r * LD + c] = fma(-f[q], rk, X[r * LD + c]);
+                    }
+                }
             }
         }
         if (tid < nvec * 32) {
             double* v = vecs + (size_t)(tid >> 5) * SRW;
-            const double vk = v[k];
+            const double vk = v[p];
             for (int r = (tid & 31); r < Rr; r += 32)
-                if (r != k) v[r] = fma(-fcol_s[r], vk, v[r]);
+                if (r != p) v[r] = fma(-(M[r * LD + k] * inv), vk, v[r]);
         }
         __syncthreads();
-        for (int q = tid; q < 3 * Rr + nvec; q += blockDim.x) {
-            if (q < 3 * Rr) {
-                const int which = q / Rr, c = q - which * Rr;
-                double* X = which == 0 ? M : (which == 1 ? R1 : R2);
-                if (X && (X != M || c > k)) X[k * LD + c] *= inv;
-            } else {
-                vecs[(size_t)(q - 3 * Rr) * SRW + k] *= inv;
-            }
-        }
+    }
+    for (int which = 1; which < 3; which++) {
+        double* X = which == 1 ? R1 : R2;
+        if (!X) continue;
+        for (int q = tid; q < Rr * Rr; q += blockDim.x) { const int k = q / Rr, c = q - k * Rr; M[k * LD + c] = X[prow_s[k] * LD + c] * pinv_s[k]; }
+        __syncthreads();
+        for (int q = tid; q < Rr * Rr; q += blockDim.x) { const int k = q / Rr, c = q - k * Rr; X[k * LD + c] = M[k * LD + c]; }
+        __syncthreads();
+    }
+    for (int v = 0; v < nvec; v++) {
+        double* x = vecs + (size_t)v * SRW;
+        double val = 0.0;
+        if (tid < Rr) val = x[prow_s[tid]] * pinv_s[tid];
+        __syncthreads();
+        if (tid < Rr) x[tid] = val;
     }
     __syncthreads();
 }
