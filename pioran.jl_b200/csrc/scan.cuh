@@ -314,18 +314,22 @@ __device__ __forceinline__ double sm_matvec_row(const double* X, const double* x
 // 16×16 thread grid over each 64-wide matrix) — one routine instead of an LU factorisation plus two substitution sweeps per
 // right-hand side (the combine is bound by its barriers, not by this arithmetic).  Rows/columns ≥ Rr are the identity.
 __device__ __forceinline__ void sm_gj_solve(double* M, double* R1, double* R2, double* vecs, int nvec, int Rr) {
-    // Two barriers per pivot (round 2; five before): no physical row interchange — the pivot row of column k is remembered and the
-    // rows are put in order once at the end — no separate factor column (column k of M is never written again, so every thread
-    // reads its factors M[r][k]/pivot directly) and no per-pivot scaling of the pivot row (the rows are divided by their pivots in
-    // the final pass).  Same pivot choice as the interchange version: the largest |M[r][k]| among the rows not yet used.
-    __shared__ int piv_s;
+    // Round 2: TWO pivots per pair of barriers.  No physical row interchange — the pivot row of column k is remembered and the
+    // rows are put in order once at the end; no separate factor column (columns k, k+1 of M are never written again, so every
+    // thread forms its factors from them in place); no per-pivot scaling (the rows are divided by their pivots in the final pass).
+    // Warp 0 picks the pivot row p1 of column k (largest |M[r][k]| among the unused rows, as partial pivoting would), forms
+    // column k+1 as it stands after that elimination, m'_r = M[r][k+1] − f1_r M[p1][k+1], and picks p2 from it; then everybody
+    // applies both eliminations at once:  row_r ← row_r − f1_r row_p1 − f2_r row'_p2  with  row'_p2 = row_p2 − f1_p2 row_p1.
+    __shared__ int piv_s[2];
     __shared__ int used_s[SR], prow_s[SR];
     __shared__ double pinv_s[SR];
+    __shared__ double rowbuf_s[2][3 * SR];       // the two pivot rows (the second after the first elimination), snapshot by warp 0
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     if (tid < SR) used_s[tid] = 0;
     __syncthreads();
-    for (int k = 0; k < Rr; k++) {
+    for (int k = 0; k < Rr; k += 2) {            // Rr is a multiple of 4
         if (tid < 32) {
+            // ---- pivot of column k
             double best = -1.0; int bi = -1;
             for (int r = tid; r < Rr; r += 32) {
                 const double v = used_s[r] ? -1.0 : fabs(M[r * SLD + k]);
@@ -337,41 +341,98 @@ __device__ __forceinline__ void sm_gj_solve(double* M, double* R1, double* R2, d
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
                 if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
             }
+            if (bi < 0) {                         // a column of NaNs: any unused row keeps the bookkeeping valid, the result is NaN
+                for (int r = 0; r < Rr; r++) if (!used_s[r]) { bi = r; break; }
+            }
+            const int p1 = bi;
+            const double inv1 = 1.0 / M[p1 * SLD + k];
+            const double mp = M[p1 * SLD + k + 1];
+            // ---- column k+1 after that elimination, and its pivot among the rows still unused
+            best = -1.0; bi = -1;
+            for (int r = tid; r < Rr; r += 32) {
+                double v = -1.0;
+                if (!used_s[r] && r != p1) v = fabs(fma(-(M[r * SLD + k] * inv1), mp, M[r * SLD + k + 1]));
+                if (v > best || (v == best && bi < 0 && v >= 0.0)) { best = v; bi = r; }
+            }
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, sft);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, sft);
+                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+            }
+            if (bi < 0) {
+                for (int r = 0; r < Rr; r++) if (!used_s[r] && r != p1) { bi = r; break; }
+            }
+            const int p2 = bi;
+            const double f1p2 = M[p2 * SLD + k] * inv1;
+            // snapshot of the pivot rows over the augmented width: the elimination overwrites them while others still need them
+            for (int q = tid; q < 3 * SR; q += 32) {
+                const int which = q / SR, c = q - which * SR;
+                const double* X = which == 0 ? M : (which == 1 ? R1 : R2);
+                double a1 = 0.0, a2 = 0.0;
+                if (X) { a1 = X[p1 * SLD + c]; a2 = fma(-f1p2, a1, X[p2 * SLD + c]); }
+                rowbuf_s[0][q] = a1; rowbuf_s[1][q] = a2;
+            }
             if (tid == 0) {
-                if (bi < 0)                       // a column of NaNs: any unused row keeps the bookkeeping valid, the result is NaN
-                    for (int r = 0; r < Rr; r++) if (!used_s[r]) { bi = r; break; }
-                piv_s = bi; used_s[bi] = 1; prow_s[k] = bi; pinv_s[k] = 1.0 / M[bi * SLD + k];
+                const double m2 = fma(-f1p2, mp, M[p2 * SLD + k + 1]);
+                piv_s[0] = p1; piv_s[1] = p2;
+                used_s[p1] = 1; used_s[p2] = 1;
+                prow_s[k] = p1; prow_s[k + 1] = p2;
+                pinv_s[k] = inv1; pinv_s[k + 1] = 1.0 / m2;
             }
         }
         __syncthreads();
-        const int p = piv_s;
-        const double inv = pinv_s[k];
-        // rows r ≠ p: row_r −= (M[r][k]/pivot) · row_p on M (columns > k), R1, R2 and the vectors
-        double f[4];
+        const int p1 = piv_s[0], p2 = piv_s[1];
+        const double inv1 = pinv_s[k], inv2 = pinv_s[k + 1];
+        const double mp = M[p1 * SLD + k + 1];
+        // factors of my rows: f1_r (0 for p1), f2_r from the updated column k+1 (0 for p2)
+        double f1[4], f2[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const int r = ty + 16 * q; f[q] = (r < Rr && r != p) ? M[r * SLD + k] * inv : 0.0; }
+        for (int q = 0; q < 4; q++) {
+            const int r = ty + 16 * q;
+            f1[q] = 0.0; f2[q] = 0.0;
+            if (r < Rr) {
+                if (r != p1) f1[q] = M[r * SLD + k] * inv1;
+                if (r != p2) f2[q] = fma(-f1[q], mp, M[r * SLD + k + 1]) * inv2;
+            }
+        }
+        // my 4×4 entries of each matrix, fully unrolled (compile-time offsets: the loop overhead of the generic version was most of
+        // the combine's 40 k instructions per warp)
+        bool rok[4], isp2[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int r = ty + 16 * q; rok[q] = r < Rr; isp2[q] = r == p2; }
 #pragma unroll
         for (int which = 0; which < 3; which++) {
             double* X = which == 0 ? M : (which == 1 ? R1 : R2);
             if (!X) continue;
-            const int c_lo = which == 0 ? k + 1 : 0;
-            for (int c = tx; c < SR; c += 16) {
-                if (c < c_lo) continue;
-                const double rk = X[p * SLD + c];
-                if (rk != 0.0) {
+            double* Xt = X + ty * SLD + tx;
+            const double* rb0 = rowbuf_s[0] + which * SR + tx;
+            const double* rb1 = rowbuf_s[1] + which * SR + tx;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int r = ty + 16 * q;
-                        if (r < Rr && r != p) X[r * SLD + c] = fma(-f[q], rk, X[r * SLD + c]);
+            for (int j = 0; j < 4; j++) {
+                if (which == 0 && tx + 16 * j < k + 2) continue;      // columns ≤ k+1 of M are spent
+                const double a1 = rb0[16 * j];
+                const double a2 = rb1[16 * j];                         // row p2 after the first elimination
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (rok[q]) {
+                        double* e = Xt + 16 * q * SLD + 16 * j;
+                        const double v = fma(-f2[q], a2, fma(-f1[q], a1, *e));      // r = p1: f1 = 0
+                        *e = isp2[q] ? a2 : v;
                     }
                 }
             }
         }
         if (tid < nvec * 32) {      // one warp per vector
             double* v = vecs + (size_t)(tid >> 5) * SR;
-            const double vk = v[p];
-            for (int r = (tid & 31); r < Rr; r += 32)
-                if (r != p) v[r] = fma(-(M[r * SLD + k] * inv), vk, v[r]);
+            const double a1 = v[p1];
+            const double a2 = fma(-(M[p2 * SLD + k] * inv1), a1, v[p2]);
+            __syncwarp();
+            for (int r = (tid & 31); r < Rr; r += 32) {
+                const double g1 = (r != p1) ? M[r * SLD + k] * inv1 : 0.0;
+                const double g2 = (r != p2) ? fma(-g1, mp, M[r * SLD + k + 1]) * inv2 : 0.0;
+                v[r] = (r == p2) ? a2 : fma(-g2, a2, fma(-g1, a1, v[r]));
+            }
         }
         __syncthreads();
     }
