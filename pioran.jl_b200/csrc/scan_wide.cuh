@@ -367,21 +367,24 @@ __device__ __forceinline__ void sw_gj_solve(const SwSmem& w, double* M, double* 
         double f[6];
 #pragma unroll
         for (int q = 0; q < 6; q++) { const int r = ty + 16 * q; f[q] = (r < Rr && r != p) ? M[r * LD + k] * inv : 0.0; }
+        // my 6×6 entries of each matrix, unrolled (the index arithmetic of the generic loops was most of the instruction count)
+        bool rok[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++) { const int r = ty + 16 * q; rok[q] = r < Rr && r != p; }
 #pragma unroll
         for (int which = 0; which < 3; which++) {
             double* X = which == 0 ? M : (which == 1 ? R1 : R2);
             if (!X) continue;
-            const int c_lo = which == 0 ? k + 1 : 0;
-            for (int c = tx; c < Rr; c += 16) {
-                if (c < c_lo) continue;
-                const double rk = X[p * LD + c];
-                if (rk != 0.0) {
+            double* Xt = X + ty * LD + tx;
+            const double* Xp = X + p * LD + tx;
 #pragma unroll
-                    for (int q = 0; q < 6; q++) {
-                        const int r = ty + 16 * q;
-                        if (r < Rr && r != p) X[r * LD + c] = fma(-f[q], rk, X[r * LD + c]);
-                    }
-                }
+            for (int j = 0; j < 6; j++) {
+                const int c = tx + 16 * j;
+                if (c >= Rr || (which == 0 && c <= k)) continue;
+                const double rk = Xp[16 * j];
+#pragma unroll
+                for (int q = 0; q < 6; q++)
+                    if (rok[q]) { double* e = Xt + 16 * q * LD + 16 * j; *e = fma(-f[q], rk, *e); }
             }
         }
         if (tid < nvec * 32) {
