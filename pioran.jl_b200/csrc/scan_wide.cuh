@@ -262,60 +262,68 @@ __device__ __forceinline__ void sw_store_full(const SwSmem& w, double* __restric
 }
 // D = op(X)·op(Y) [+ addend (global, SRW-strided)] → dst_s (shared) and/or dst_g (global, SRW-strided; entries outside the live
 // rank are not written).  dst_s must not alias X or Y; with symmetrise it is needed as scratch.  Ends with a barrier.
+// 8 warps; warp w forms the row tiles w and w + 8 of D on the FP64 tensor pipe (fragments from shared memory, scan_dmma).
 template <bool TX, bool TY>
 __device__ __forceinline__ void sw_matmul(const SwSmem& w, double* dst_s, double* dst_g, const double* X, const double* Y,
                                           const double* addend, bool symmetrise) {
-    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15, Rr = w.Rr, LD = w.LD;
-    double acc[6][6];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, Rr = w.Rr, LD = w.LD;
+    constexpr int NTW = SRW / 8;
+    double acc[2][NTW][2];
 #pragma unroll
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) acc[i][j] = 0.0;
-    // rows/columns beyond the live rank read the last live one (their results are dropped)
-    int ri[6], cj[6];
+        for (int K = 0; K < NTW; K++) acc[i][K][0] = acc[i][K][1] = 0.0;
+    const int ar0 = 8 * warp + g, ar1 = 8 * (warp + 8) + g;
+    const bool r0ok = ar0 < Rr, r1ok = ar1 < Rr;
+    for (int k0 = 0; k0 < Rr; k0 += 4) {
+        const double a0 = r0ok ? (TX ? X[(k0 + t) * LD + ar0] : X[ar0 * LD + k0 + t]) : 0.0;
+        const double a1 = r1ok ? (TX ? X[(k0 + t) * LD + ar1] : X[ar1 * LD + k0 + t]) : 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) { ri[i] = min(ty + 16 * i, Rr - 1); cj[i] = min(tx + 16 * i, Rr - 1); }
-    for (int k = 0; k < Rr; k++) {
-        double xv[6], yv[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) xv[i] = TX ? X[k * LD + ri[i]] : X[ri[i] * LD + k];
-#pragma unroll
-        for (int j = 0; j < 6; j++) yv[j] = TY ? Y[cj[j] * LD + k] : Y[k * LD + cj[j]];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int j = 0; j < 6; j++) acc[i][j] = fma(xv[i], yv[j], acc[i][j]);
+        for (int K = 0; K < NTW; K++) {
+            if (8 * K < Rr) {
+                const int col = 8 * K + g;
+                const double b = col < Rr ? (TY ? Y[col * LD + k0 + t] : Y[(k0 + t) * LD + col]) : 0.0;
+                scan_dmma(acc[0][K][0], acc[0][K][1], a0, b);
+                if (8 * (warp + 8) < Rr) scan_dmma(acc[1][K][0], acc[1][K][1], a1, b);
+            }
+        }
     }
     if (symmetrise) {
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 6; j++) {
-                const int row = ty + 16 * i, col = tx + 16 * j;
-                if (row < Rr && col < Rr) dst_s[row * LD + col] = acc[i][j];
-            }
+            for (int K = 0; K < NTW; K++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int row = i ? ar1 : ar0, col = 8 * K + 2 * t + e;
+                    if (row < Rr && col < Rr) dst_s[row * LD + col] = acc[i][K][e];
+                }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 6; j++) {
-                const int row = ty + 16 * i, col = tx + 16 * j;
-                if (row < Rr && col < Rr) acc[i][j] = 0.5 * (acc[i][j] + dst_s[col * LD + row]);
-            }
+            for (int K = 0; K < NTW; K++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int row = i ? ar1 : ar0, col = 8 * K + 2 * t + e;
+                    if (row < Rr && col < Rr) acc[i][K][e] = 0.5 * (acc[i][K][e] + dst_s[col * LD + row]);
+                }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-        for (int j = 0; j < 6; j++) {
-            const int row = ty + 16 * i, col = tx + 16 * j;
-            if (row < Rr && col < Rr) {
-                double v = acc[i][j];
-                if (addend) v += addend[row * SRW + col];
-                if (dst_s) dst_s[row * LD + col] = v;
-                if (dst_g) dst_g[row * SRW + col] = v;
+        for (int K = 0; K < NTW; K++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int row = i ? ar1 : ar0, col = 8 * K + 2 * t + e;
+                if (row < Rr && col < Rr) {
+                    double v = acc[i][K][e];
+                    if (addend) v += addend[row * SRW + col];
+                    if (dst_s) dst_s[row * LD + col] = v;
+                    if (dst_g) dst_g[row * SRW + col] = v;
+                }
             }
-        }
     __syncthreads();
 }
 template <bool TX>
