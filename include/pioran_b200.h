@@ -58,6 +58,20 @@ const char *pioran_last_error(void);
 /* Library/ABI version: major*10000 + minor*100 + patch. */
 int pioran_version(void);
 
+/* One column of a prior transform (quantile(d, u) of Distributions.jl, which the reference's samplers call:
+ * examples/ultranest/single_pl.jl:96-104, docs/src/ultranest.md:165-190). */
+#define PIORAN_PRIOR_UNIFORM 0      /* Uniform(p0, p1)                                                   */
+#define PIORAN_PRIOR_UNIFORM_FROM 1 /* Uniform(theta[ref_col], p1): lower edge = an EARLIER column        */
+#define PIORAN_PRIOR_LOGUNIFORM 2   /* LogUniform(p0, p1)                                                */
+#define PIORAN_PRIOR_NORMAL 3       /* Normal(mean p0, standard deviation p1)                            */
+#define PIORAN_PRIOR_LOGNORMAL 4    /* LogNormal(p0, p1)                                                 */
+#define PIORAN_PRIOR_GAMMA 5        /* Gamma(shape p0 (integer, 1 ... 32), scale p1)                     */
+typedef struct pioran_prior_spec {
+    int32_t kind;                /* PIORAN_PRIOR_*                                                        */
+    int32_t ref_col;             /* UNIFORM_FROM only                                                     */
+    double p0, p1;
+} pioran_prior_spec;
+
 /* ---- context & resident time series -------------------------------------------------------------------- */
 /* Binds a context to CUDA device `device` (must be compute capability 10.x).  Creates one stream. */
 int pioran_ctx_create(int device, pioran_ctx **out);
@@ -172,6 +186,16 @@ int pioran_approx_logl_logshift_grad(pioran_ctx *ctx, int series_id, const piora
                                      const double *theta, double *logl_out, double *grad_out);
 
 /* ---- K3: long single series, parallel-in-time (same recursion, N ~ 1e6) --------------------------------- */
+/* Prior transform on the device (the `prior_transform(cube)` callback of examples/ultranest/single_pl.jl:96-104, batched):
+ * cube [B x ncol] unit-cube points -> theta_out [B x ncol], columns left to right.  pioran_prior_transform_logl does the
+ * transform and the fused likelihood of pioran_approx_logl (one series) in one call - the parameter vectors never leave the
+ * device unless theta_out is given (ncol must be n_psd_par + 3: psd parameters, norm, nu, mu). */
+int pioran_prior_transform(pioran_ctx *ctx, int ncol, const pioran_prior_spec *priors, int B, const double *cube,
+                           double *theta_out);
+int pioran_prior_transform_logl(pioran_ctx *ctx, int series_id, const pioran_approx_spec *spec, int ncol,
+                                const pioran_prior_spec *priors, int B, const double *cube, double *theta_out,
+                                double *logl_out);
+
 /* Same value as pioran_celerite_logl with B small, computed by the chunked associative-scan formulation. */
 /* pioran_celerite_logl and pioran_approx_logl hand calls with at most 4 parameter vectors on a long series (fused path: at
  * least 4 096 steps, 2 048 at rank <= 32; explicit coefficients: half of that; rank <= 64, no per-vector data) to the

@@ -263,3 +263,31 @@ function logpdf_gradient_batch_lognormal(s::B200Series, spec::Ref{B200ApproxSpec
         b200_context().h, s.id, spec, B, Θr, out, gr))
     return out, permutedims(gr)
 end
+
+# --------------------------------------------------------------------------------------------------- prior transform on the device
+struct B200PriorSpec   # == struct pioran_prior_spec (24 bytes)
+    kind::Int32        # 0 Uniform(p0, p1) · 1 Uniform(θ[ref_col], p1) · 2 LogUniform · 3 Normal · 4 LogNormal · 5 Gamma(shape p0 ∈ ℕ, scale p1)
+    ref_col::Int32     # 0-based column of the same point (kind 1)
+    p0::Float64
+    p1::Float64
+end
+
+"""
+    prior_transform_logl_batch(series, spec, priors, cubes) -> (logℒ::Vector, Θ::Matrix)
+
+`prior_transform` (examples/ultranest/single_pl.jl:96-104) and `logl` (:65-93) of a whole batch of unit-cube points in one call:
+row i of `cubes` is mapped through the column priors (Distributions.jl quantiles) and evaluated; Θ is returned for the sampler's
+bookkeeping.  For the priors of single_pl.jl:
+    priors = [B200PriorSpec(0, 0, 0.0, 1.5), B200PriorSpec(2, 0, f0 * 4, fM / 4), B200PriorSpec(1, 0, 0.0, 4.0),
+              B200PriorSpec(4, 0, μₙ, σₙ), B200PriorSpec(5, 0, 2.0, 0.5), B200PriorSpec(3, 0, x̄, 5 * sqrt(va))]
+"""
+function prior_transform_logl_batch(s::B200Series, spec::Ref{B200ApproxSpec}, priors::Vector{B200PriorSpec}, cubes::Matrix{Float64})
+    B, P = size(cubes)
+    cr = permutedims(cubes)
+    out = Vector{Float64}(undef, B)
+    Θr = Matrix{Float64}(undef, P, B)
+    _b200_check(ccall((:pioran_prior_transform_logl, libpioran_b200), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{B200ApproxSpec}, Cint, Ptr{B200PriorSpec}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        b200_context().h, s.id, spec, P, priors, B, cr, Θr, out))
+    return out, permutedims(Θr)
+end

@@ -18,6 +18,11 @@ class ApproxSpec(C.Structure):
                 ("S_low", C.c_double), ("S_high", C.c_double)]
 
 
+class PriorSpec(C.Structure):
+    """struct pioran_prior_spec"""
+    _fields_ = [("kind", C.c_int32), ("ref_col", C.c_int32), ("p0", C.c_double), ("p1", C.c_double)]
+
+
 # every symbol include/pioran_b200.h declares: name → (restype, argtypes)
 SYMBOLS = {
     "pioran_last_error": (C.c_char_p, []),
@@ -51,6 +56,8 @@ SYMBOLS = {
     "pioran_ctx_last_scan_check": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pioran_ctx_set_scan_floor_cap": (C.c_int, [C.c_void_p, C.c_double]),
     "pioran_ctx_last_scan_history": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
+    "pioran_prior_transform": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PriorSpec), C.c_int, _dp, _dp]),
+    "pioran_prior_transform_logl": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ApproxSpec), C.c_int, C.POINTER(PriorSpec), C.c_int, _dp, _dp, _dp]),
     "pioran_celerite_logl_scan": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
     "pioran_scan_composite_doubles": (C.c_int, []),
     "pioran_celerite_scan_range_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int64, C.c_int64, C.c_int, _dp]),

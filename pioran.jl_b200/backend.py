@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import ApproxSpec, check
+from ._lib import ApproxSpec, PriorSpec, check
 
 PSD_MODELS = {"SingleBendingPowerLaw": 0, "DoubleBendingPowerLaw": 1}
 N_PSD_PAR = {0: 3, 1: 5}
@@ -184,6 +184,33 @@ class Context:
         out = np.empty((S, B))
         check(self.lib.pioran_approx_logl(self.h, S, ids, sp, B, _p(theta), int(theta_per_series), _p(out)))
         return out
+
+    # -- device-side prior transform
+    @staticmethod
+    def _prior_array(priors):
+        """priors: sequence of (kind, ref_col, p0, p1) tuples (sampler.PriorTransform.device_spec())."""
+        arr = (PriorSpec * len(priors))()
+        for k, (kind, ref, p0, p1) in enumerate(priors):
+            arr[k] = PriorSpec(int(kind), int(ref), float(p0), float(p1))
+        return arr
+
+    def prior_transform(self, priors, cube):
+        """Unit-cube points [B × ncol] → parameter vectors [B × ncol] on the device (pioran_prior_transform)."""
+        cube = np.atleast_2d(_f64(cube))
+        B, ncol = cube.shape
+        out = np.empty((B, ncol))
+        check(self.lib.pioran_prior_transform(self.h, ncol, self._prior_array(priors), B, _p(cube), _p(out)))
+        return out
+
+    def prior_transform_logl(self, series, spec, priors, cube, return_theta=False):
+        """Prior transform + fused likelihood in one call; the parameter vectors stay on the device unless return_theta."""
+        cube = np.atleast_2d(_f64(cube))
+        B, ncol = cube.shape
+        out = np.empty(B)
+        theta = np.empty((B, ncol)) if return_theta else None
+        check(self.lib.pioran_prior_transform_logl(self.h, series.id, C.byref(spec), ncol, self._prior_array(priors), B, _p(cube),
+                                                   _p(theta), _p(out)))
+        return (out, theta) if return_theta else out
 
     def approx_logl_logshift(self, series, spec, theta):
         """Log-normal series (docs/src/timeseries.md:16-21): theta rows = [psd parameters…, norm, ν, μ, c];

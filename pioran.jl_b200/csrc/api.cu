@@ -28,6 +28,7 @@
 #include "blocked_grad.cuh"
 #include "blocked_wide.cuh"
 #include "wide.cuh"
+#include "prior.cuh"
 #include "wide_grad.cuh"
 #include "scan_wide.cuh"
 #include "scan_blocked.cuh"
@@ -1288,6 +1289,76 @@ extern "C" int pioran_approx_logl(pioran_ctx* c, int S, const int* series_ids, c
                                      c->out.as<double>())))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)S * B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+
+// ------------------------------------------------------------------------------------------------ prior transform
+static_assert(sizeof(pioran_prior_spec) == sizeof(PriorSpec), "pioran_prior_spec layout");
+static int prior_transform_dev_locked(pioran_ctx* c, int ncol, const pioran_prior_spec* priors, int B, const double* cube,
+                                      double* theta_dev, int tstride) {
+    if (ncol < 1 || ncol > PRIOR_MAX_COLS) return fail(PIORAN_EINVAL, "ncol must be in [1, %d]", PRIOR_MAX_COLS);
+    for (int k = 0; k < ncol; k++) {
+        const pioran_prior_spec& p = priors[k];
+        if (p.kind < PIORAN_PRIOR_UNIFORM || p.kind > PIORAN_PRIOR_GAMMA) return fail(PIORAN_EINVAL, "column %d: unknown prior kind %d", k, p.kind);
+        if (p.kind == PIORAN_PRIOR_UNIFORM_FROM && (p.ref_col < 0 || p.ref_col >= k))
+            return fail(PIORAN_EINVAL, "column %d: ref_col %d must be an earlier column", k, p.ref_col);
+        if (p.kind == PIORAN_PRIOR_LOGUNIFORM && !(p.p0 > 0.0 && p.p1 > 0.0)) return fail(PIORAN_EINVAL, "column %d: LogUniform needs positive bounds", k);
+        if ((p.kind == PIORAN_PRIOR_NORMAL || p.kind == PIORAN_PRIOR_LOGNORMAL) && !(p.p1 > 0.0)) return fail(PIORAN_EINVAL, "column %d: sigma must be positive", k);
+        if (p.kind == PIORAN_PRIOR_GAMMA && !(p.p0 >= 1.0 && p.p0 <= 32.0 && p.p0 == std::floor(p.p0) && p.p1 > 0.0))
+            return fail(PIORAN_EUNSUPPORTED, "column %d: Gamma needs an integer shape in [1, 32] and a positive scale (shape %g)", k, p.p0);
+    }
+    int rc;
+    const size_t ncube = (size_t)B * ncol;
+    if ((rc = c->coef.ensure(sizeof(double) * ncube + sizeof(PriorSpec) * PRIOR_MAX_COLS))) return rc;
+    double* cube_dev = c->coef.as<double>();
+    PriorSpec* pr_dev = reinterpret_cast<PriorSpec*>(cube_dev + ncube);
+    CUDA_TRY(cudaMemcpyAsync(cube_dev, cube, sizeof(double) * ncube, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(pr_dev, priors, sizeof(PriorSpec) * ncol, cudaMemcpyHostToDevice, c->stream));
+    prior_transform_kernel<<<(B + 127) / 128, 128, 0, c->stream>>>(pr_dev, ncol, B, cube_dev, theta_dev, tstride);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+extern "C" int pioran_prior_transform(pioran_ctx* c, int ncol, const pioran_prior_spec* priors, int B, const double* cube,
+                                      double* theta_out) try {
+    if (is_group(c)) return pioran_prior_transform(c->children[0], ncol, priors, B, cube, theta_out);
+    if (!c || !priors || !cube || !theta_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    PIORAN_COMPUTE_LOCK(c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * PRIOR_MAX_COLS))) return rc;
+    if ((rc = prior_transform_dev_locked(c, ncol, priors, B, cube, c->theta.as<double>(), ncol))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(theta_out, c->theta.p, sizeof(double) * (size_t)B * ncol, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return PIORAN_OK;
+} catch (...) { return guard_fail(); }
+extern "C" int pioran_prior_transform_logl(pioran_ctx* c, int series_id, const pioran_approx_spec* spec, int ncol,
+                                           const pioran_prior_spec* priors, int B, const double* cube, double* theta_out,
+                                           double* logl_out) try {
+    if (!c || !spec || !priors || !cube || !logl_out) return fail(PIORAN_EINVAL, "NULL argument");
+    if (B < 1) return fail(PIORAN_EINVAL, "B must be >= 1");
+    if (is_group(c)) {
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            return pioran_prior_transform_logl(c->children[k], cid[k], spec, ncol, priors, nb, cube + (size_t)beg * ncol,
+                                               theta_out ? theta_out + (size_t)beg * ncol : nullptr, logl_out + beg);
+        });
+    }
+    const int npar = n_psd_par_of(spec->psd_model);
+    if (npar < 0) return fail(PIORAN_EINVAL, "unknown psd_model %d", spec->psd_model);
+    if (ncol != npar + 3) return fail(PIORAN_EINVAL, "ncol must be %d (psd parameters, norm, nu, mu) for this model, got %d", npar + 3, ncol);
+    PIORAN_COMPUTE_LOCK(c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = c->theta.ensure(sizeof(double) * (size_t)B * ncol))) return rc;
+    if ((rc = c->out.ensure(sizeof(double) * (size_t)B))) return rc;
+    if ((rc = prior_transform_dev_locked(c, ncol, priors, B, cube, c->theta.as<double>(), ncol))) return rc;
+    if ((rc = approx_logl_dev_locked(c, 1, &series_id, spec, B, c->theta.as<double>(), 0, c->out.as<double>()))) return rc;
+    if (theta_out) CUDA_TRY(cudaMemcpyAsync(theta_out, c->theta.p, sizeof(double) * (size_t)B * ncol, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(logl_out, c->out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return PIORAN_OK;
 } catch (...) { return guard_fail(); }

@@ -5,9 +5,11 @@ one `logl(pars)` per point.  With the GPU backend the natural mode is `vectorize
 points of an iteration at once — `transform(cubes [B × P]) → Θ [B × P]`, `loglike(Θ [B × P]) → logL [B]` — and ONE fused call
 evaluates them (0.6–0.8 ms for 400 live points at N = 1 000, J = 20).
 
-The prior transform stays on the HOST on purpose: it is P scalar quantiles per point (≈ 40 µs for 400 × 6 with numpy/scipy),
-an order of magnitude under the call's own launch + copy overhead; moving it to the device would trade a 19 KB θ upload for a
-19 KB cube upload.  Quantiles follow Distributions.jl's definitions (`quantile(d, u)`), which the reference calls.
+The prior transform runs on the host by default: it is P scalar quantiles per point (≈ 40 µs for 400 × 6 with numpy/scipy),
+an order of magnitude under the call's own launch + copy overhead.  `PriorTransform.device_spec()` describes the same columns
+for the device-side transform (`pioran_prior_transform`, `pioran_prior_transform_logl`: cube in, logℒ out, θ never leaves the
+GPU) — `vectorized_callbacks(..., device_prior=True)`.  Quantiles follow Distributions.jl's definitions (`quantile(d, u)`),
+which the reference calls.
 """
 import numpy as np
 
@@ -18,6 +20,9 @@ class Uniform:
 
     def quantile(self, u, prev):
         return self.a + u * (self.b - self.a)
+
+    def device(self):
+        return (0, 0, self.a, self.b)
 
 
 class UniformFrom:
@@ -30,6 +35,9 @@ class UniformFrom:
         lo = prev[:, self.col]
         return lo + u * (self.b - lo)
 
+    def device(self):
+        return (1, self.col, 0.0, self.b)
+
 
 class LogUniform:
     def __init__(self, a, b):
@@ -37,6 +45,9 @@ class LogUniform:
 
     def quantile(self, u, prev):
         return np.exp(self.la + u * (self.lb - self.la))
+
+    def device(self):
+        return (2, 0, float(np.exp(self.la)), float(np.exp(self.lb)))
 
 
 class Normal:
@@ -47,10 +58,16 @@ class Normal:
         from scipy.special import ndtri
         return self.mu + self.sigma * ndtri(u)
 
+    def device(self):
+        return (3, 0, self.mu, self.sigma)
+
 
 class LogNormal(Normal):
     def quantile(self, u, prev):
         return np.exp(super().quantile(u, prev))
+
+    def device(self):
+        return (4, 0, self.mu, self.sigma)
 
 
 class Gamma:
@@ -62,6 +79,9 @@ class Gamma:
     def quantile(self, u, prev):
         from scipy.special import gammaincinv
         return self.theta * gammaincinv(self.k, u)
+
+    def device(self):
+        return (5, 0, self.k, self.theta)
 
 
 class PriorTransform:
@@ -79,6 +99,10 @@ class PriorTransform:
         for k, p in enumerate(self.priors):
             out[:, k] = p.quantile(u[:, k], out)
         return out[0] if single else out
+
+    def device_spec(self):
+        """(kind, ref_col, p0, p1) per column — struct pioran_prior_spec of include/pioran_b200.h."""
+        return [p.device() for p in self.priors]
 
 
 def single_bending_power_law_prior(f_min, f_max, xbar, va, mu_v=-1.5, sigma_v=1.0, alpha2_max=4.0, log_data=False):
@@ -122,7 +146,7 @@ def vectorized_callbacks_log_normal(t, y, yerr, psd_model="SingleBendingPowerLaw
 
 
 def vectorized_callbacks(t, y, yerr, psd_model="SingleBendingPowerLaw", n_components=20, basis_function="SHO",
-                         log_transform=True, prior=None, ctx=None, **approx_kw):
+                         log_transform=True, prior=None, ctx=None, device_prior=False, **approx_kw):
     """(loglike, transform, close) for `ultranest.ReactiveNestedSampler(paramnames, loglike, transform=transform,
     vectorized=True)`.  log_transform follows single_pl.jl:70-73 (σ² = ν σ²/y², yn = log y); the series is uploaded once."""
     from .api import BatchedLikelihood
@@ -142,4 +166,20 @@ def vectorized_callbacks(t, y, yerr, psd_model="SingleBendingPowerLaw", n_compon
         out[~np.isfinite(out)] = -1e300        # ultranest needs finite values; the reference's scripts never hit non-PD priors
         return out
 
+    if device_prior:
+        # the transform callback on the device (same columns, pioran_prior_transform); loglike_from_cube fuses both callbacks
+        spec = prior.device_spec()
+
+        def transform(cubes):
+            cubes = np.asarray(cubes, dtype=np.float64)
+            out = like.ctx.prior_transform(spec, np.atleast_2d(cubes))
+            return out[0] if cubes.ndim == 1 else out
+
+        def loglike_from_cube(cubes):
+            out = like.ctx.prior_transform_logl(like.series, like.spec, spec, np.atleast_2d(cubes))
+            out[~np.isfinite(out)] = -1e300
+            return out
+
+        loglike.from_cube = loglike_from_cube
+        return loglike, transform, like.close
     return loglike, prior, like.close

@@ -108,3 +108,36 @@ def test_nested_sampling_run_reproduces_the_shipped_evidence():
     assert abs(res["delta_logz_in_sigma"]) < 3.0, res
     assert abs(res["logz"] - res["reference_logz"]) < 1.0, res
     assert res["max_abs_mean_shift_in_reference_stdevs"] < 1.5, res
+
+
+def test_device_prior_transform_matches_host_quantiles(pb, golden_single):
+    """SURVEY §8f #4 as written: the prior transform of examples/ultranest/single_pl.jl:96-104 on the device
+    (pioran_prior_transform), column for column against the host quantiles (scipy: ndtri, gammaincinv), including the tails,
+    and the fused cube → log-likelihood call against transform-then-evaluate."""
+    g = golden_single
+    ctx = pb.get_context(0)
+    loglike, transform_dev, close = pb.sampler.vectorized_callbacks(g.t, g.y_raw, g.yerr, n_components=20, basis_function="SHO",
+                                                                    ctx=ctx, device_prior=True)
+    yn = np.log(g.y_raw)
+    host = pb.sampler.single_bending_power_law_prior(g.f_min, g.f_max, float(np.mean(yn)), float(np.var(yn, ddof=1)), alpha2_max=4.0)
+    rng = np.random.default_rng(3)
+    u = rng.uniform(size=(2000, 6))
+    u[:6] = [1e-12, 1e-6, 0.5, 1 - 1e-6, 1 - 1e-12, 0.999]          # tails of every column
+    want = host(u)
+    got = transform_dev(u)
+    rel = np.abs(got - want) / np.maximum(1e-300, np.abs(want))
+    assert rel.max() <= 1e-11, (rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+    assert np.array_equal(transform_dev(u[7]), got[7])            # one point
+    # other kinds: Uniform from an earlier column, Gamma of other integer shapes, LogNormal, Normal
+    other = pb.sampler.PriorTransform([pb.sampler.Normal(-0.3, 2.0), pb.sampler.UniformFrom(0, 9.0), pb.sampler.Gamma(5, 1.7),
+                                       pb.sampler.Gamma(1, 0.2), pb.sampler.LogNormal(0.4, 0.6), pb.sampler.LogUniform(1e-6, 3.0)])
+    w2 = other(u)
+    g2 = ctx.prior_transform(other.device_spec(), u)
+    assert (np.abs(g2 - w2) / np.maximum(1e-300, np.abs(w2))).max() <= 1e-11
+    # fused: cube in, log-likelihood out
+    fused = loglike.from_cube(u[:400])
+    sep = loglike(got[:400])
+    assert np.array_equal(fused, sep)
+    with pytest.raises(pb.PioranError):
+        ctx.prior_transform([(5, 0, 2.5, 1.0)], u[:, :1])            # non-integer Gamma shape is refused, not approximated
+    close()
