@@ -47,12 +47,15 @@ int main(int argc, char **argv) {
         printf("{\"version\": %d, \"sizeof_spec\": %zu, \"off_psd_model\": %zu, \"off_n_components\": %zu, \"off_basis\": %zu, "
                "\"off_is_integrated_power\": %zu, \"off_f_min\": %zu, \"off_f_max\": %zu, \"off_S_low\": %zu, \"off_S_high\": %zu, "
                "\"PIORAN_OK\": %d, \"PIORAN_EINVAL\": %d, \"PIORAN_ECUDA\": %d, \"PIORAN_ENOMEM\": %d, \"PIORAN_ESINGULAR\": %d, "
-               "\"PIORAN_EUNSUPPORTED\": %d}\n",
+               "\"PIORAN_EUNSUPPORTED\": %d, \"sizeof_prior\": %zu, \"off_prior_kind\": %zu, \"off_prior_ref_col\": %zu, "
+               "\"off_prior_p0\": %zu, \"off_prior_p1\": %zu}\n",
                version(), sizeof(pioran_approx_spec), offsetof(pioran_approx_spec, psd_model),
                offsetof(pioran_approx_spec, n_components), offsetof(pioran_approx_spec, basis),
                offsetof(pioran_approx_spec, is_integrated_power), offsetof(pioran_approx_spec, f_min),
                offsetof(pioran_approx_spec, f_max), offsetof(pioran_approx_spec, S_low), offsetof(pioran_approx_spec, S_high),
-               PIORAN_OK, PIORAN_EINVAL, PIORAN_ECUDA, PIORAN_ENOMEM, PIORAN_ESINGULAR, PIORAN_EUNSUPPORTED);
+               PIORAN_OK, PIORAN_EINVAL, PIORAN_ECUDA, PIORAN_ENOMEM, PIORAN_ESINGULAR, PIORAN_EUNSUPPORTED,
+               sizeof(pioran_prior_spec), offsetof(pioran_prior_spec, kind), offsetof(pioran_prior_spec, ref_col),
+               offsetof(pioran_prior_spec, p0), offsetof(pioran_prior_spec, p1));
         /* argument checking needs no device */
         if (ctx_create(0, NULL) != PIORAN_EINVAL) { fprintf(stderr, "ctx_create(NULL out) must be EINVAL\n"); return 4; }
         if (!last_error()[0]) { fprintf(stderr, "no error message after a failed call\n"); return 4; }

@@ -37,6 +37,10 @@ def test_struct_layout_and_error_codes_match_the_bindings(abi_check):
         assert out["off_" + f] == getattr(ApproxSpec, f).offset, f
     assert [out[k] for k in ("PIORAN_OK", "PIORAN_EINVAL", "PIORAN_ECUDA", "PIORAN_ENOMEM", "PIORAN_ESINGULAR", "PIORAN_EUNSUPPORTED")] \
         == [0, -1, -2, -3, -4, -5]
+    from pioran_b200._lib import PriorSpec
+    assert out["sizeof_prior"] == C.sizeof(PriorSpec) == 24
+    for f in ("kind", "ref_col", "p0", "p1"):
+        assert out["off_prior_" + f] == getattr(PriorSpec, f).offset, f
     assert out["version"] >= 200
     # the Julia struct of the shim declares the same fields in the same order
     jl = open(os.path.join(ROOT, "julia", "b200_solver.jl")).read()
