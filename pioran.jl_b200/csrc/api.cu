@@ -104,6 +104,9 @@ struct pioran_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t own = nullptr, stream = nullptr;
+    cudaStream_t side = nullptr, hi = nullptr;   // K4: the bulk trailing updates (side) run beside the panel chain (hi: highest stream priority, so its
+                                                 // small kernels take the SM slots the bulk's CTAs free); created on first use
+    cudaEvent_t ev_fact = nullptr, ev_bulk = nullptr, ev_join = nullptr;
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
@@ -288,6 +291,11 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     c->coef.release(); c->rows.release(); c->misc.release(); c->post.release(); c->gradws.release(); c->gwork.release(); c->stab.release();
     if (c->ev_beg) cudaEventDestroy(c->ev_beg);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_fact) cudaEventDestroy(c->ev_fact);
+    if (c->ev_bulk) cudaEventDestroy(c->ev_bulk);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->hi) cudaStreamDestroy(c->hi);
     if (c->own) cudaStreamDestroy(c->own);
     delete c;
     return PIORAN_OK;
@@ -2856,6 +2864,15 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     const size_t fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB + 4 * (size_t)Jt * DNB);
     if (fill_smem > 200 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
     CUDA_TRY(cudaFuncSetAttribute(dense_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    if (!c->side) {
+        int prio_least = 0, prio_greatest = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_least));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->hi, cudaStreamNonBlocking, prio_greatest));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fact, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bulk, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     cudaEventRecord(c->ev_beg, c->stream);
     for (int th0 = 0; th0 < B; th0 += chunk) {
         const int nb = std::min(chunk, B - th0);
@@ -2863,28 +2880,55 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
                                                                          gi.d, gi.mu, gi.nu, th0);
         c->launches++;
+        // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates of the NEXT pair's two block
+        // columns) stays on the main stream; the bulk of a pair's trailing update (blocks ≥ kb + 4) runs on a side stream as soon as
+        // the pair is factorised, beside the factorisation of the next pair.  A pair's narrow updates wait for the previous bulk
+        // (they read-modify-write tiles it wrote); consecutive bulks are ordered by their stream.
+        cudaStream_t S1 = c->hi, S2 = c->side;
+        bool bulk_pending = false;
+        CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain
+        CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));
         for (int kb = 0; kb < nblk;) {
-            dense_potrf_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, N, kb, acc, info);
+            dense_potrf_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, N, kb, acc, info);
             c->launches++;
             const int m = nblk - kb - 1;            // block rows below panel kb
             if (m == 0) break;
-            dense_trsm_kernel<<<dim3(m, nb), DNB, 0, c->stream>>>(A, ld, kb);
+            dense_trsm_kernel<<<dim3(m, nb), DNB, 0, S1>>>(A, ld, kb);
             c->launches++;
             if (m == 1) {                           // one block left: plain single-panel update
-                dense_syrk_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, kb, 1, kb + 1, 0);
+                dense_syrk_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, kb, 1, kb + 1, 0);
                 c->launches++;
                 kb += 1;
                 continue;
             }
-            // two panels per trailing update: panel kb onto block column kb+1 only, factorise it, then both panels onto the rest
-            dense_syrk_kernel<<<dim3(m, nb), 256, 0, c->stream>>>(A, ld, kb, 1, kb + 1, 1);
-            dense_potrf_kernel<<<dim3(1, nb), 256, 0, c->stream>>>(A, ld, N, kb + 1, acc, info);
-            dense_trsm_kernel<<<dim3(m - 1, nb), DNB, 0, c->stream>>>(A, ld, kb + 1);
+            // panel kb onto block column kb+1 only, factorise it: the pair (kb, kb+1) is complete
+            dense_syrk_kernel<<<dim3(m, nb), 256, 0, S1>>>(A, ld, kb, 1, kb + 1, 1);
+            dense_potrf_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, N, kb + 1, acc, info);
+            dense_trsm_kernel<<<dim3(m - 1, nb), DNB, 0, S1>>>(A, ld, kb + 1);
+            c->launches += 3;
             const int m2 = m - 1;                   // block rows/columns from kb+2 on
-            dense_syrk_kernel<<<dim3(m2 * (m2 + 1) / 2, nb), 256, 0, c->stream>>>(A, ld, kb, 2, kb + 2, 0);
-            c->launches += 4;
+            if (m2 > 2) {                           // bulk: both panels onto the blocks ≥ kb+4, on the side stream
+                CUDA_TRY(cudaEventRecord(c->ev_fact, S1));
+                CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fact, 0));
+                const int m4 = m2 - 2;
+                dense_syrk_kernel<<<dim3(m4 * (m4 + 1) / 2, nb), 256, 0, S2>>>(A, ld, kb, 2, kb + 4, 0);
+                c->launches++;
+            }
+            // narrow: both panels onto the next pair's block columns kb+2 (rows ≥ kb+2) and kb+3 (rows ≥ kb+3)
+            if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));      // the previous bulk wrote these tiles
+            dense_syrk_kernel<<<dim3(m2, nb), 256, 0, S1>>>(A, ld, kb, 2, kb + 2, 1);
+            c->launches++;
+            if (m2 > 1) {
+                dense_syrk_kernel<<<dim3(m2 - 1, nb), 256, 0, S1>>>(A, ld, kb, 2, kb + 3, 1);
+                c->launches++;
+            }
+            if (m2 > 2) { CUDA_TRY(cudaEventRecord(c->ev_bulk, S2)); bulk_pending = true; }
+            else bulk_pending = false;
             kb += 2;
         }
+        if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));
+        CUDA_TRY(cudaEventRecord(c->ev_join, S1));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         dense_finish_kernel<<<(nb + 127) / 128, 128, 0, c->stream>>>(acc, info, N, nb, nll);
         c->launches++;
         CUDA_TRY(cudaGetLastError());

@@ -139,9 +139,12 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
 // Diagonal block kb of every matrix.  grid = (1, B), block = 256.  acc[θ] = {Σ log L_ii, zᵀz}; info[θ] = first bad minor.
 __global__ void __launch_bounds__(256) dense_potrf_kernel(double* __restrict__ A, int64_t ld, int64_t N, int kb,
                                                           double* __restrict__ acc, int* __restrict__ info) {
+    // One barrier per pivot (round 2; three before, with the pivot's sqrt/log on one thread): column k is never written after
+    // step k, so the trailing update uses it UNSCALED with the pivot as it stands, L[r][q] −= L[r][k] L[q][k] / p_k, every thread
+    // reads p_k itself, and the scaling by 1/√p_k happens once, when the block is written back.
     __shared__ double L[DNB][DNB + 1];
-    __shared__ double piv_s;
-    const int th = blockIdx.y;
+    __shared__ double sp_s[DNB];                       // √pivot of every column
+    const int th = blockIdx.y, ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double* At = A + (size_t)th * ld * ld + ((size_t)kb * DNB) * ld + (size_t)kb * DNB;
     for (int e = threadIdx.x; e < DNB * DNB; e += blockDim.x) {
         const int r = e / DNB, q = e - r * DNB;
@@ -151,38 +154,36 @@ __global__ void __launch_bounds__(256) dense_potrf_kernel(double* __restrict__ A
     double logsum = 0.0;
     for (int k = 0; k < DNB; k++) {
         const int64_t g = (int64_t)kb * DNB + k;
-        if (threadIdx.x == 0) {
-            double p = L[k][k];
-            if (g < N) {
-                if (!(p > 0.0)) {                      // PosDefException in the reference (direct_solver.jl:14)
-                    if (info[th] == 0) info[th] = (int)(g + 1);
-                    p = 1.0;
-                }
-                p = sqrt(p);
-                logsum += log(p);
-            } else if (g == N) {
-                acc[2 * th + 1] = -p;                  // Schur complement of the augmented corner = −zᵀz
-                p = 1.0;
-            } else {
+        double p = L[k][k];
+        if (g < N) {
+            if (!(p > 0.0)) {                          // PosDefException in the reference (direct_solver.jl:14)
+                if (threadIdx.x == 0 && info[th] == 0) info[th] = (int)(g + 1);
                 p = 1.0;
             }
-            L[k][k] = p;
-            piv_s = p;
+            if (threadIdx.x == 0) { const double sp = sqrt(p); sp_s[k] = sp; logsum += log(sp); }
+        } else {
+            if (g == N && threadIdx.x == 0) acc[2 * th + 1] = -p;   // Schur complement of the augmented corner = −zᵀz
+            p = 1.0;
+            if (threadIdx.x == 0) sp_s[k] = 1.0;
         }
-        __syncthreads();
-        const double ip = 1.0 / piv_s;
-        for (int r = k + 1 + threadIdx.x; r < DNB; r += blockDim.x) L[r][k] *= ip;
-        __syncthreads();
-        const int rem = DNB - k - 1;
-        for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-            const int r = k + 1 + e / rem, q = k + 1 + e % rem;
-            if (q <= r) L[r][q] -= L[r][k] * L[q][k];
-        }
+        const double ip = 1.0 / p;
+        // thread (ty, tx) of a 16×16 grid owns the entries (ty + 16 i, tx + 16 j): no index arithmetic per entry
+        double lr[4], lq[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { lr[i] = L[ty + 16 * i][k] * ip; lq[i] = L[tx + 16 * i][k]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int r = ty + 16 * i, q = tx + 16 * j;
+                if (q > k && q <= r) L[r][q] = fma(-lr[i], lq[j], L[r][q]);
+            }
         __syncthreads();
     }
     for (int e = threadIdx.x; e < DNB * DNB; e += blockDim.x) {
         const int r = e / DNB, q = e - r * DNB;
-        if (q <= r) At[(size_t)r * ld + q] = L[r][q];
+        if (q < r) At[(size_t)r * ld + q] = L[r][q] / sp_s[q];
+        else if (q == r) At[(size_t)r * ld + q] = sp_s[q];
     }
     if (threadIdx.x == 0) acc[2 * th] += logsum;
 }
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256) dense_potrf_kernel(double* __restrict__ A
 // Row blocks i > kb: A_ik ← A_ik L_kk^{-T}.  grid = (nblk − kb − 1, B), block = 64 (one thread per row).
 __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A, int64_t ld, int kb) {
     __shared__ double L[DNB][DNB + 1];
+    __shared__ double invd[DNB];
     const int th = blockIdx.y;
     const int ib = kb + 1 + blockIdx.x;
     double* At = A + (size_t)th * ld * ld;
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A,
         const int r = e / DNB, q = e - r * DNB;      // coalesced along q
         L[r][q] = Lk[(size_t)r * ld + q];
     }
+    invd[threadIdx.x] = 1.0 / Lk[(size_t)threadIdx.x * ld + threadIdx.x];
     __syncthreads();
     double* row = Ai + (size_t)threadIdx.x * ld;     // 64 consecutive doubles, 16-byte aligned (ld, kb·64 even)
     double x[DNB];
@@ -207,12 +210,14 @@ __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A,
         const double2 v = *reinterpret_cast<const double2*>(row + j);
         x[j] = v.x; x[j + 1] = v.y;
     }
+    // right-looking substitution (round 2): x_j is final once the earlier columns are eliminated, and its elimination from the
+    // 63 − j later entries is 63 − j INDEPENDENT FMAs (the left-looking form was one dependent chain per entry, plus a division)
 #pragma unroll
     for (int j = 0; j < DNB; j++) {
-        double v = x[j];
+        const double xj = x[j] * invd[j];
+        x[j] = xj;
 #pragma unroll
-        for (int l = 0; l < j; l++) v = fma(-x[l], L[j][l], v);
-        x[j] = v / L[j][j];
+        for (int l = j + 1; l < DNB; l++) x[l] = fma(-xj, L[l][j], x[l]);
     }
 #pragma unroll
     for (int j = 0; j < DNB; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
