@@ -2843,7 +2843,10 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     const int64_t N = s->N;
     const int nblk = (int)((N + 1 + DNB - 1) / DNB);        // +1: the augmented (y − μ)ᵀ row
     const int64_t ld = (int64_t)nblk * DNB;
-    const size_t per = sizeof(double) * (size_t)ld * (size_t)ld;
+    const int nfull = (int)(N / DNB);                       // blocks without padding or the augmented row
+    const size_t tab_per = sizeof(double) * 4 * (size_t)Jt * DNB * (size_t)nfull;      // separable factors per block (dense_fill_tables_kernel)
+    const size_t mat_per = sizeof(double) * (size_t)ld * (size_t)ld;
+    const size_t per = mat_per + tab_per;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::min<size_t>(free_b / 2 + c->misc.cap, (size_t)32 << 30);
@@ -2857,11 +2860,12 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     if ((rc = c->misc.ensure(per * (size_t)chunk))) return rc;
     if ((rc = c->out.ensure(sizeof(double) * 3 * (size_t)chunk + sizeof(int) * (size_t)chunk))) return rc;
     double* A = c->misc.as<double>();
+    double* tab = A + (size_t)chunk * (size_t)ld * (size_t)ld;
     double* acc = c->out.as<double>();
     double* nll = acc + 2 * (size_t)chunk;
     int* info = reinterpret_cast<int*>(nll + chunk);
     const int ntri = nblk * (nblk + 1) / 2;
-    const size_t fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB + 4 * (size_t)Jt * DNB);
+    const size_t fill_smem = sizeof(double) * dense_fill_smem_doubles(Jt);
     if (fill_smem > 200 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
     CUDA_TRY(cudaFuncSetAttribute(dense_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     if (!c->side) {
@@ -2877,8 +2881,12 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     for (int th0 = 0; th0 < B; th0 += chunk) {
         const int nb = std::min(chunk, B - th0);
         CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)chunk + sizeof(int) * (size_t)chunk, c->stream));
+        if (nfull > 0) {
+            dense_fill_tables_kernel<<<dim3(nfull, nb), 256, 0, c->stream>>>(tab, nfull, s->t, Jt, gi.a, gi.b, gi.c, gi.d, th0);
+            c->launches++;
+        }
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
-                                                                         gi.d, gi.mu, gi.nu, th0);
+                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull);
         c->launches++;
         // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates of the NEXT pair's two block
         // columns) stays on the main stream; the bulk of a pair's trailing update (blocks ≥ kb + 4) runs on a side stream as soon as
@@ -2888,43 +2896,44 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         bool bulk_pending = false;
         CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain
         CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));
+        static const int G = [] { const char* e = getenv("PIORAN_K4_GROUP"); const int g = e ? atoi(e) : 4; return g >= 1 && g <= 8 ? g : 4; }();
+        // Groups of G panels: inside a group every panel is applied to the next block column alone (narrow update with all the
+        // group's panels so far), so that a trailing tile is read and written once per G panels.
         for (int kb = 0; kb < nblk;) {
-            dense_potrf_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, N, kb, acc, info);
-            c->launches++;
-            const int m = nblk - kb - 1;            // block rows below panel kb
-            if (m == 0) break;
-            dense_trsm_kernel<<<dim3(m, nb), DNB, 0, S1>>>(A, ld, kb);
-            c->launches++;
-            if (m == 1) {                           // one block left: plain single-panel update
-                dense_syrk_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, kb, 1, kb + 1, 0);
+            const int Gp = std::min(G, nblk - kb);
+            bool done = false;
+            for (int g = 0; g < Gp; g++) {
+                const int k = kb + g;
+                dense_potrf_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, N, k, acc, info);
                 c->launches++;
-                kb += 1;
-                continue;
+                const int m = nblk - k - 1;         // block rows below panel k
+                if (m == 0) { done = true; break; }
+                dense_trsm_kernel<<<dim3(m, nb), DNB, 0, S1>>>(A, ld, k);
+                c->launches++;
+                if (g < Gp - 1) {                   // the group's panels so far onto block column k+1 (rows ≥ k+1)
+                    dense_syrk_kernel<<<dim3(m, nb), 256, 0, S1>>>(A, ld, kb, g + 1, k + 1, 1);
+                    c->launches++;
+                }
             }
-            // panel kb onto block column kb+1 only, factorise it: the pair (kb, kb+1) is complete
-            dense_syrk_kernel<<<dim3(m, nb), 256, 0, S1>>>(A, ld, kb, 1, kb + 1, 1);
-            dense_potrf_kernel<<<dim3(1, nb), 256, 0, S1>>>(A, ld, N, kb + 1, acc, info);
-            dense_trsm_kernel<<<dim3(m - 1, nb), DNB, 0, S1>>>(A, ld, kb + 1);
-            c->launches += 3;
-            const int m2 = m - 1;                   // block rows/columns from kb+2 on
-            if (m2 > 2) {                           // bulk: both panels onto the blocks ≥ kb+4, on the side stream
+            const int rem = nblk - (kb + Gp);       // blocks behind the group
+            if (done || rem <= 0) break;
+            const int nextG = std::min(G, rem);
+            const bool bulk = rem > nextG;
+            if (bulk) {                             // all of the group's panels onto the blocks behind the NEXT group, on the side stream
                 CUDA_TRY(cudaEventRecord(c->ev_fact, S1));
                 CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fact, 0));
-                const int m4 = m2 - 2;
-                dense_syrk_kernel<<<dim3(m4 * (m4 + 1) / 2, nb), 256, 0, S2>>>(A, ld, kb, 2, kb + 4, 0);
+                const int mb = rem - nextG;
+                dense_syrk_kernel<<<dim3(mb * (mb + 1) / 2, nb), 256, 0, S2>>>(A, ld, kb, Gp, kb + Gp + nextG, 0);
                 c->launches++;
             }
-            // narrow: both panels onto the next pair's block columns kb+2 (rows ≥ kb+2) and kb+3 (rows ≥ kb+3)
-            if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));      // the previous bulk wrote these tiles
-            dense_syrk_kernel<<<dim3(m2, nb), 256, 0, S1>>>(A, ld, kb, 2, kb + 2, 1);
-            c->launches++;
-            if (m2 > 1) {
-                dense_syrk_kernel<<<dim3(m2 - 1, nb), 256, 0, S1>>>(A, ld, kb, 2, kb + 3, 1);
+            if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));      // the previous bulk wrote the tiles updated next
+            for (int cidx = 0; cidx < nextG; cidx++) {   // … and onto the next group's block columns (rows from the column's own block on)
+                dense_syrk_kernel<<<dim3(rem - cidx, nb), 256, 0, S1>>>(A, ld, kb, Gp, kb + Gp + cidx, 1);
                 c->launches++;
             }
-            if (m2 > 2) { CUDA_TRY(cudaEventRecord(c->ev_bulk, S2)); bulk_pending = true; }
-            else bulk_pending = false;
-            kb += 2;
+            if (bulk) CUDA_TRY(cudaEventRecord(c->ev_bulk, S2));
+            bulk_pending = bulk;
+            kb += Gp;
         }
         if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));
         CUDA_TRY(cudaEventRecord(c->ev_join, S1));

@@ -28,20 +28,63 @@ __device__ __forceinline__ void tri_index(int p, int& ti, int& tj) {   // p → 
     tj = p - ti * (ti + 1) / 2;
 }
 
-// A[θ] lower tiles ← covariance.  grid = (ntile·(ntile+1)/2, B), block = 256.
+// Separable factors of the kernel per FULL 64-block, for dense_fill_kernel (round 2).  With α = t_k − t_first(b) ≥ 0 (row role)
+// and γ = t_last(b) − t_k ≥ 0 (column role):
+//     P = e^{−cα}(a cos dα + b sin dα),  Q = e^{−cα}(b cos dα − a sin dα),  Gc = e^{−cγ} cos dγ,  Gs = e^{−cγ} sin dγ
+// tab[θ][b][P|Q|Gc|Gs][Jt][64].  grid = (nfull, B), block = 256.  2·64 transcendental triples per term and BLOCK — the tiles of
+// a block row/column share them (they were recomputed per tile before: 1.9 of C5's 12 ms went into the fill).
+__global__ void __launch_bounds__(256) dense_fill_tables_kernel(double* __restrict__ tab, int nfull, const double* __restrict__ t,
+                                                                int Jt, const double* __restrict__ a, const double* __restrict__ b,
+                                                                const double* __restrict__ c, const double* __restrict__ d,
+                                                                int theta0) {
+    const int th = blockIdx.y, blk = blockIdx.x;
+    const size_t JD = (size_t)Jt * DNB;
+    double* T = tab + ((size_t)th * nfull + blk) * 4 * JD;
+    const double t0 = t[(int64_t)blk * DNB], t1 = t[(int64_t)blk * DNB + DNB - 1];
+    for (int e = threadIdx.x; e < Jt * DNB; e += blockDim.x) {
+        const int m = e / DNB, k = e - m * DNB;
+        const size_t idx = (size_t)(theta0 + th) * Jt + m;
+        const double am = a[idx], bm = b[idx], cm = c[idx], dm = d[idx];
+        const double tk = t[(int64_t)blk * DNB + k];
+        double si, co;
+        const double al = tk - t0;
+        sincos(dm * al, &si, &co);
+        double ex = exp(-cm * al);
+        T[e] = ex * (am * co + bm * si);
+        T[JD + e] = ex * (bm * co - am * si);
+        const double ga = t1 - tk;
+        sincos(dm * ga, &si, &co);
+        ex = exp(-cm * ga);
+        T[2 * JD + e] = ex * co;
+        T[3 * JD + e] = ex * si;
+    }
+}
+
+constexpr int DFILL_DIAG = 8 * 36;      // entries of the 8 diagonal 8×8 sub-tiles of a diagonal tile
+__host__ __device__ inline size_t dense_fill_smem_doubles(int Jt) {
+    return 4 * (size_t)Jt + 2 * DNB + 4 * (size_t)Jt * DNB + 24 * (size_t)Jt + 4 * DFILL_DIAG;
+}
+
+// A[θ] lower tiles ← covariance.  grid = (ntile·(ntile+1)/2, B), block = 256; big tiles first.
 __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A, int64_t ld, int64_t N,
                                                          const double* __restrict__ t, const double* __restrict__ y,
                                                          const double* __restrict__ s2, int Jt,
                                                          const double* __restrict__ a, const double* __restrict__ b,
                                                          const double* __restrict__ c, const double* __restrict__ d,
                                                          const double* __restrict__ mu, const double* __restrict__ nu,
-                                                         int theta0) {
+                                                         int theta0, const double* __restrict__ tab, int nfull) {
     extern __shared__ double sm[];
     double* ca = sm; double* cb = ca + Jt; double* cc = cb + Jt; double* cd = cc + Jt;
     double* ti_s = cd + Jt; double* tj_s = ti_s + DNB;
+    double* Ps = tj_s + DNB;            // [Jt][DNB] each
+    double* Qs = Ps + (size_t)Jt * DNB;
+    double* Xs = Qs + (size_t)Jt * DNB;
+    double* Ys = Xs + (size_t)Jt * DNB;
+    double* rot = Ys + (size_t)Jt * DNB;    // [8 warps][3][Jt]: e^{−cβ}, cos dβ, sin dβ of a (row block, column block) pair
+    double* part = rot + 24 * (size_t)Jt;   // [4][DFILL_DIAG]
     const int th = blockIdx.y;
     int bi, bj;
-    tri_index(blockIdx.x, bi, bj);
+    tri_index(gridDim.x - 1 - blockIdx.x, bi, bj);
     for (int m = threadIdx.x; m < Jt; m += blockDim.x) {
         const size_t k = (size_t)(theta0 + th) * Jt + m;
         ca[m] = a[k]; cb[m] = b[k]; cc[m] = c[k]; cd[m] = d[k];
@@ -56,34 +99,46 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
     __syncthreads();
     const double m_ = mu ? mu[theta0 + th] : 0.0, v_ = nu ? nu[theta0 + th] : 1.0;
     double* At = A + (size_t)th * ld * ld;
-    // Off-diagonal tiles of covariance entries only: every row time ≥ every column time, and the kernel separates.  With
-    // α = t_i − t_r0 (r0 = first row of the tile), β = t_r0 − t_c1 (c1 = last column), γ = t_c1 − t_j, all ≥ 0 and τ = α+β+γ:
-    //     e^{−cτ}(a cos dτ + b sin dτ) = P_i X_j + Q_i Y_j,
-    //     P = e^{−cα}(a cos dα + b sin dα),  Q = e^{−cα}(b cos dα − a sin dα),  X = e^{−c(β+γ)} cos d(β+γ),  Y = e^{−c(β+γ)} sin d(β+γ)
-    // — 2·64 transcendental triples per term and tile instead of 64², then two FMAs per entry and term.  No exponent is positive,
-    // so nothing overflows (the celerite instability of separating e^{−c t_i} e^{+c t_j} globally does not arise per tile).
-    if (bi != bj && (int64_t)(bi + 1) * DNB <= N) {
-        double* Ps = tj_s + DNB;            // [Jt][DNB] each
-        double* Qs = Ps + (size_t)Jt * DNB;
-        double* Xs = Qs + (size_t)Jt * DNB;
-        double* Ys = Xs + (size_t)Jt * DNB;
-        const double tr0 = ti_s[0], tc1 = tj_s[DNB - 1];
-        const double beta = tr0 - tc1;
-        for (int e = threadIdx.x; e < 2 * Jt * DNB; e += blockDim.x) {
-            const int side = e / (Jt * DNB), f = e - side * Jt * DNB, m = f / DNB, k = f - m * DNB;
+    const int JD = Jt * DNB;
+    // Off-diagonal tiles: every row time ≥ every column time, and the kernel separates.  With α = t_i − t_r0 (r0 = first row of
+    // the tile), β = t_r0 − t_c1 (c1 = last column), γ = t_c1 − t_j, all ≥ 0 and τ = α+β+γ:
+    //     e^{−cτ}(a cos dτ + b sin dτ) = P_i X_j + Q_i Y_j,    X + iY = e^{−cβ} e^{i dβ} (Gc_j + i Gs_j)
+    // P, Q, Gc, Gs come from the block tables, the rotation by β costs one transcendental triple per term and TILE, then two FMAs
+    // per entry and term.  No exponent is positive, so nothing overflows (the celerite instability of separating
+    // e^{−c t_i} e^{+c t_j} globally does not arise per tile).  A partial last row block computes its few valid P, Q rows here.
+    if (bi != bj) {
+        const bool full = bi < nfull;
+        for (int m = threadIdx.x; m < Jt; m += blockDim.x) {
+            const double beta = fmax(ti_s[0] - tj_s[DNB - 1], 0.0);      // (an all-padding row block has no times; its rows are overwritten below)
             double si, co;
-            if (side == 0) {
-                const double al = ti_s[k] - tr0;
-                sincos(cd[m] * al, &si, &co);
-                const double ex = exp(-cc[m] * al);
-                Ps[f] = ex * (ca[m] * co + cb[m] * si);
-                Qs[f] = ex * (cb[m] * co - ca[m] * si);
-            } else {
-                const double bg = beta + (tc1 - tj_s[k]);
-                sincos(cd[m] * bg, &si, &co);
-                const double ex = exp(-cc[m] * bg);
-                Xs[f] = ex * co;
-                Ys[f] = ex * si;
+            sincos(cd[m] * beta, &si, &co);
+            rot[m] = exp(-cc[m] * beta); rot[Jt + m] = co; rot[2 * Jt + m] = si;
+        }
+        __syncthreads();
+        const double* Tj = tab + ((size_t)th * nfull + bj) * 4 * JD;
+        for (int e = threadIdx.x; e < JD; e += blockDim.x) {
+            const int m = e / DNB;
+            const double gc = Tj[2 * (size_t)JD + e], gs = Tj[3 * (size_t)JD + e], ex = rot[m], co = rot[Jt + m], si = rot[2 * Jt + m];
+            Xs[e] = ex * (co * gc - si * gs);
+            Ys[e] = ex * (si * gc + co * gs);
+        }
+        if (full) {
+            const double* Ti = tab + ((size_t)th * nfull + bi) * 4 * JD;
+            for (int e = threadIdx.x; e < JD; e += blockDim.x) { Ps[e] = Ti[e]; Qs[e] = Ti[(size_t)JD + e]; }
+        } else {
+            const double tr0 = ti_s[0];
+            for (int e = threadIdx.x; e < JD; e += blockDim.x) {
+                const int m = e / DNB, k = e - m * DNB;
+                double pv = 0.0, qv = 0.0;
+                if ((int64_t)bi * DNB + k < N) {
+                    const double al = ti_s[k] - tr0;
+                    double si, co;
+                    sincos(cd[m] * al, &si, &co);
+                    const double ex = exp(-cc[m] * al);
+                    pv = ex * (ca[m] * co + cb[m] * si);
+                    qv = ex * (cb[m] * co - ca[m] * si);
+                }
+                Ps[e] = pv; Qs[e] = qv;
             }
         }
         __syncthreads();
@@ -106,9 +161,87 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            double* dst = At + ((int64_t)bi * DNB + 4 * ty + u) * ld + (int64_t)bj * DNB + 4 * tx;
+            const int64_t gi = (int64_t)bi * DNB + 4 * ty + u;
+            if (!full && gi >= N) {                    // augmented row (y − μ)ᵀ, then identity padding (zeros off the diagonal)
+#pragma unroll
+                for (int w = 0; w < 4; w++) v[u][w] = gi == N ? y[(int64_t)bj * DNB + 4 * tx + w] - m_ : 0.0;
+            }
+            double* dst = At + gi * ld + (int64_t)bj * DNB + 4 * tx;
             *reinterpret_cast<double2*>(dst) = make_double2(v[u][0], v[u][1]);
             *reinterpret_cast<double2*>(dst + 2) = make_double2(v[u][2], v[u][3]);
+        }
+        return;
+    }
+    // Full diagonal tiles: the same separation one level down, on the 8×8 grid of 8×8 sub-tiles.  The 28 sub-tiles below the
+    // diagonal use P, Q relative to the first row of their 8-row group and Gc, Gs relative to the last column of their 8-column
+    // group, rotated by the gap β between the two groups; only the 8 diagonal sub-tiles (288 entries) are evaluated directly.
+    if (bi < nfull) {
+        for (int e = threadIdx.x; e < 2 * JD; e += blockDim.x) {
+            const int side = e / JD, f = e - side * JD, m = f / DNB, k = f - m * DNB;
+            double si, co;
+            if (side == 0) {
+                const double al = ti_s[k] - ti_s[k & ~7];
+                sincos(cd[m] * al, &si, &co);
+                const double ex = exp(-cc[m] * al);
+                Ps[f] = ex * (ca[m] * co + cb[m] * si);
+                Qs[f] = ex * (cb[m] * co - ca[m] * si);
+            } else {
+                const double ga = ti_s[k | 7] - ti_s[k];
+                sincos(cd[m] * ga, &si, &co);
+                const double ex = exp(-cc[m] * ga);
+                Xs[f] = ex * co;
+                Ys[f] = ex * si;
+            }
+        }
+        __syncthreads();
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double* wr = rot + (size_t)warp * 3 * Jt;
+        for (int p = warp; p < 28; p += 8) {
+            int I, J;
+            tri_index(p, I, J);
+            I += 1;                                     // strictly below the diagonal: I > J
+            const double beta = ti_s[8 * I] - ti_s[8 * J + 7];
+            for (int m = lane; m < Jt; m += 32) {
+                double si, co;
+                sincos(cd[m] * beta, &si, &co);
+                wr[m] = exp(-cc[m] * beta); wr[Jt + m] = co; wr[2 * Jt + m] = si;
+            }
+            __syncwarp();
+            const int r = 8 * I + (lane >> 2), q = 8 * J + 2 * (lane & 3);
+            double v0 = 0.0, v1 = 0.0;
+            for (int m = 0; m < Jt; m++) {
+                const double ex = wr[m], co = wr[Jt + m], si = wr[2 * Jt + m];
+                const double pr = Ps[m * DNB + r] * ex, qr = Qs[m * DNB + r] * ex;
+                const double2 gc = *reinterpret_cast<const double2*>(Xs + m * DNB + q);
+                const double2 gs = *reinterpret_cast<const double2*>(Ys + m * DNB + q);
+                v0 = fma(pr, co * gc.x - si * gs.x, fma(qr, si * gc.x + co * gs.x, v0));
+                v1 = fma(pr, co * gc.y - si * gs.y, fma(qr, si * gc.y + co * gs.y, v1));
+            }
+            *reinterpret_cast<double2*>(At + ((int64_t)bi * DNB + r) * ld + (int64_t)bj * DNB + q) = make_double2(v0, v1);
+            __syncwarp();
+        }
+        for (int it = threadIdx.x; it < 4 * DFILL_DIAG; it += blockDim.x) {     // (entry, quarter of the terms)
+            const int qt = it / DFILL_DIAG, ent = it - qt * DFILL_DIAG, I = ent / 36;
+            int r, q;
+            tri_index(ent - 36 * I, r, q);
+            const double tau = ti_s[8 * I + r] - ti_s[8 * I + q];
+            double k = 0.0;
+            for (int m = qt; m < Jt; m += 4) {
+                double si, co;
+                sincos(cd[m] * tau, &si, &co);
+                k += exp(-cc[m] * tau) * (ca[m] * co + cb[m] * si);
+            }
+            part[it] = k;
+        }
+        __syncthreads();
+        for (int ent = threadIdx.x; ent < DFILL_DIAG; ent += blockDim.x) {
+            const int I = ent / 36;
+            int r, q;
+            tri_index(ent - 36 * I, r, q);
+            const int64_t gi = (int64_t)bi * DNB + 8 * I + r, gj = (int64_t)bj * DNB + 8 * I + q;
+            double k = (part[ent] + part[DFILL_DIAG + ent]) + (part[2 * DFILL_DIAG + ent] + part[3 * DFILL_DIAG + ent]);
+            if (gi == gj) k += v_ * s2[gi];            // K + Diagonal(σ²)   (direct_solver.jl:12)
+            At[gi * ld + gj] = k;
         }
         return;
     }
