@@ -272,88 +272,76 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
 // Diagonal block kb of every matrix.  grid = (1, B), block = 256.  acc[θ] = {Σ log L_ii, zᵀz}; info[θ] = first bad minor.
 __global__ void __launch_bounds__(256) dense_potrf_kernel(double* __restrict__ A, int64_t ld, int64_t N, int kb,
                                                           double* __restrict__ acc, int* __restrict__ info) {
-    // One barrier per pivot (round 2; three before, with the pivot's sqrt/log on one thread): column k is never written after
-    // step k, so the trailing update uses it UNSCALED with the pivot as it stands, L[r][q] −= L[r][k] L[q][k] / p_k, every thread
-    // reads p_k itself, and the scaling by 1/√p_k happens once, when the block is written back.
-    __shared__ double L[DNB][DNB + 1];
+    // One barrier per pivot, block in REGISTERS (round 2; three barriers and a shared-memory read-modify-write of every entry
+    // before): thread (ty, tx) of a 16×16 grid owns the entries (ty + 16 i, tx + 16 j).  Column k is never written after step k,
+    // so its owners publish it UNSCALED through a double-buffered shared column, every thread reads the pivot p_k itself and
+    // updates e_rq −= L_rk L_qk / p_k; the scaling by 1/√p_k happens once, when the block is written back.
+    __shared__ double col_s[2][DNB];
     __shared__ double sp_s[DNB];                       // √pivot of every column
     const int th = blockIdx.y, ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double* At = A + (size_t)th * ld * ld + ((size_t)kb * DNB) * ld + (size_t)kb * DNB;
-    for (int e = threadIdx.x; e < DNB * DNB; e += blockDim.x) {
-        const int r = e / DNB, q = e - r * DNB;
-        L[r][q] = q <= r ? At[(size_t)r * ld + q] : 0.0;
-    }
-    __syncthreads();
-    double logsum = 0.0;
-    for (int k = 0; k < DNB; k++) {
-        const int64_t g = (int64_t)kb * DNB + k;
-        double p = L[k][k];
-        if (g < N) {
-            if (!(p > 0.0)) {                          // PosDefException in the reference (direct_solver.jl:14)
-                if (threadIdx.x == 0 && info[th] == 0) info[th] = (int)(g + 1);
+    double e[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int r = ty + 16 * i, q = tx + 16 * j;
+            e[i][j] = q <= r ? At[(size_t)r * ld + q] : 0.0;
+        }
+#pragma unroll
+    for (int j0 = 0; j0 < 4; j0++) {
+        for (int kk = 0; kk < 16; kk++) {
+            const int k = 16 * j0 + kk;
+            double* col = col_s[k & 1];
+            if (tx == kk) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) col[ty + 16 * i] = e[i][j0];
+            }
+            __syncthreads();
+            const int64_t g = (int64_t)kb * DNB + k;
+            double p = col[k];
+            if (g < N) {
+                if (!(p > 0.0)) {                      // PosDefException in the reference (direct_solver.jl:14)
+                    if (threadIdx.x == 0 && info[th] == 0) info[th] = (int)(g + 1);
+                    p = 1.0;
+                }
+            } else {
+                if (g == N && threadIdx.x == 0) acc[2 * th + 1] = -p;   // Schur complement of the augmented corner = −zᵀz
                 p = 1.0;
             }
-            if (threadIdx.x == 0) { const double sp = sqrt(p); sp_s[k] = sp; logsum += log(sp); }
-        } else {
-            if (g == N && threadIdx.x == 0) acc[2 * th + 1] = -p;   // Schur complement of the augmented corner = −zᵀz
-            p = 1.0;
-            if (threadIdx.x == 0) sp_s[k] = 1.0;
+            if (threadIdx.x == 0) sp_s[k] = p;         // pivot now; √ and log after the loop, 64 at a time, off the critical path
+            const double ip = 1.0 / p;
+            double lr[4], lq[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { lr[i] = col[ty + 16 * i] * ip; lq[i] = col[tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int r = ty + 16 * i, q = tx + 16 * j;
+                    if (q > k && q <= r) e[i][j] = fma(-lr[i], lq[j], e[i][j]);
+                }
         }
-        const double ip = 1.0 / p;
-        // thread (ty, tx) of a 16×16 grid owns the entries (ty + 16 i, tx + 16 j): no index arithmetic per entry
-        double lr[4], lq[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { lr[i] = L[ty + 16 * i][k] * ip; lq[i] = L[tx + 16 * i][k]; }
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int r = ty + 16 * i, q = tx + 16 * j;
-                if (q > k && q <= r) L[r][q] = fma(-lr[i], lq[j], L[r][q]);
-            }
-        __syncthreads();
     }
-    for (int e = threadIdx.x; e < DNB * DNB; e += blockDim.x) {
-        const int r = e / DNB, q = e - r * DNB;
-        if (q < r) At[(size_t)r * ld + q] = L[r][q] / sp_s[q];
-        else if (q == r) At[(size_t)r * ld + q] = sp_s[q];
-    }
-    if (threadIdx.x == 0) acc[2 * th] += logsum;
-}
-
-// Row blocks i > kb: A_ik ← A_ik L_kk^{-T}.  grid = (nblk − kb − 1, B), block = 64 (one thread per row).
-__global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A, int64_t ld, int kb) {
-    __shared__ double L[DNB][DNB + 1];
-    __shared__ double invd[DNB];
-    const int th = blockIdx.y;
-    const int ib = kb + 1 + blockIdx.x;
-    double* At = A + (size_t)th * ld * ld;
-    const double* Lk = At + ((size_t)kb * DNB) * ld + (size_t)kb * DNB;
-    double* Ai = At + ((size_t)ib * DNB) * ld + (size_t)kb * DNB;
-    for (int e = threadIdx.x; e < DNB * DNB; e += DNB) {
-        const int r = e / DNB, q = e - r * DNB;      // coalesced along q
-        L[r][q] = Lk[(size_t)r * ld + q];
-    }
-    invd[threadIdx.x] = 1.0 / Lk[(size_t)threadIdx.x * ld + threadIdx.x];
     __syncthreads();
-    double* row = Ai + (size_t)threadIdx.x * ld;     // 64 consecutive doubles, 16-byte aligned (ld, kb·64 even)
-    double x[DNB];
+    if (threadIdx.x < DNB) {
+        const double sp = sqrt(sp_s[threadIdx.x]);
+        sp_s[threadIdx.x] = sp;
+        double lg = log(sp);                           // Σ log L_ii of the block (padding and the augmented corner carry p = 1)
 #pragma unroll
-    for (int j = 0; j < DNB; j += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(row + j);
-        x[j] = v.x; x[j + 1] = v.y;
+        for (int o = 16; o; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+        if ((threadIdx.x & 31) == 0) col_s[0][threadIdx.x >> 5] = lg;
     }
-    // right-looking substitution (round 2): x_j is final once the earlier columns are eliminated, and its elimination from the
-    // 63 − j later entries is 63 − j INDEPENDENT FMAs (the left-looking form was one dependent chain per entry, plus a division)
+    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < DNB; j++) {
-        const double xj = x[j] * invd[j];
-        x[j] = xj;
+    for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int l = j + 1; l < DNB; l++) x[l] = fma(-xj, L[l][j], x[l]);
-    }
-#pragma unroll
-    for (int j = 0; j < DNB; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
+        for (int j = 0; j < 4; j++) {
+            const int r = ty + 16 * i, q = tx + 16 * j;
+            if (q < r) At[(size_t)r * ld + q] = e[i][j] / sp_s[q];
+            else if (q == r) At[(size_t)r * ld + q] = sp_s[q];
+        }
+    if (threadIdx.x == 0) acc[2 * th] += col_s[0][0] + col_s[0][1];
 }
 
 // FP64 tensor-core tile product: D(8×8) += A(8×4, row-major) · B(4×8, column-major).  Fragments (PTX ISA, m8n8k4.f64):
@@ -361,6 +349,81 @@ __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A,
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Row blocks i > kb: A_ik ← A_ik L_kk^{-T}.  grid = (nblk − kb − 1, B), block = 64 = 2 warps of 32 rows.
+// Blocked substitution on the tensor pipe (round 2; one thread per row with L_kk broadcast from shared memory before — bound by
+// the shared-memory pipe at 14 % of the FP64 rate): a warp holds its 32 × 64 slice as 4 × 8 DMMA accumulator tiles.  Per 8-column
+// group g: the 8 × 8 triangle L_gg is substituted inside the 4-lane groups that share a row (x_j travels by shuffle), −X_g goes
+// through a warp-private shared slice into A-fragment order, and the later groups get X_g' −= X_g L_g'gᵀ as 4 × 2 DMMAs each.
+__global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A, int64_t ld, int kb) {
+    constexpr int LS = DNB + 4, XS = 12;             // row strides (doubles): fragment loads fall on 32 distinct banks
+    __shared__ __align__(16) double L[DNB][LS];
+    __shared__ double invd[DNB];
+    __shared__ __align__(16) double Xs[2][32][XS];
+    const int th = blockIdx.y;
+    const int ib = kb + 1 + blockIdx.x;
+    double* At = A + (size_t)th * ld * ld;
+    const double* Lk = At + ((size_t)kb * DNB) * ld + (size_t)kb * DNB;
+    double* Ai = At + ((size_t)ib * DNB) * ld + (size_t)kb * DNB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gr = lane >> 2, gc = lane & 3;
+    double* rows = Ai + (size_t)(32 * warp) * ld;
+    double x[4][8][2];                               // the slice's loads are in flight while L_kk is staged
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const double2 v = *reinterpret_cast<const double2*>(rows + (size_t)(8 * u + gr) * ld + 8 * g + 2 * gc);
+            x[u][g][0] = v.x; x[u][g][1] = v.y;
+        }
+    const double dg = Lk[(size_t)threadIdx.x * ld + threadIdx.x];
+#pragma unroll 16
+    for (int e = threadIdx.x; e < DNB * DNB / 2; e += DNB) {      // 16-byte loads, 16 in flight per thread
+        const int r = e / (DNB / 2), q = 2 * (e - r * (DNB / 2));
+        *reinterpret_cast<double2*>(&L[r][q]) = *reinterpret_cast<const double2*>(Lk + (size_t)r * ld + q);
+    }
+    invd[threadIdx.x] = 1.0 / dg;
+    __syncthreads();
+    double (*xs)[XS] = Xs[warp];
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {                // x_j is final once the earlier columns are eliminated
+            const int src = (lane & ~3) | (j >> 1);
+            const double idj = invd[8 * g + j];
+            const double l0 = L[8 * g + 2 * gc][8 * g + j], l1 = L[8 * g + 2 * gc + 1][8 * g + j];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double xj = __shfl_sync(0xffffffffu, x[u][g][j & 1] * idj, src);
+                if (gc == (j >> 1)) x[u][g][j & 1] = xj;
+                if (2 * gc > j) x[u][g][0] = fma(-xj, l0, x[u][g][0]);
+                if (2 * gc + 1 > j) x[u][g][1] = fma(-xj, l1, x[u][g][1]);
+            }
+        }
+        if (g < 7) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                *reinterpret_cast<double2*>(&xs[8 * u + gr][2 * gc]) = make_double2(-x[u][g][0], -x[u][g][1]);
+            __syncwarp();
+            double af[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { af[u][0] = xs[8 * u + gr][gc]; af[u][1] = xs[8 * u + gr][4 + gc]; }
+#pragma unroll
+            for (int g2 = g + 1; g2 < 8; g2++)
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                    const double bf = L[8 * g2 + gr][8 * g + 4 * ks + gc];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dmma_8x8x4(x[u][g2][0], x[u][g2][1], af[u][ks], bf);
+                }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int g = 0; g < 8; g++)
+            *reinterpret_cast<double2*>(rows + (size_t)(8 * u + gr) * ld + 8 * g + 2 * gc) = make_double2(x[u][g][0], x[u][g][1]);
 }
 
 // Trailing update: C_ij −= A_ik A_jkᵀ for kb < j ≤ i — the one dense contraction of the path, on the FP64 tensor cores
