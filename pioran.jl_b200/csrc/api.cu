@@ -2888,10 +2888,11 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
                                                                          gi.d, gi.mu, gi.nu, th0, tab, nfull);
         c->launches++;
-        // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates of the NEXT pair's two block
-        // columns) stays on the main stream; the bulk of a pair's trailing update (blocks ≥ kb + 4) runs on a side stream as soon as
-        // the pair is factorised, beside the factorisation of the next pair.  A pair's narrow updates wait for the previous bulk
-        // (they read-modify-write tiles it wrote); consecutive bulks are ordered by their stream.
+        // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates inside a group of panels and
+        // onto the NEXT group's block columns) runs on a high-priority stream; the bulk of a group's trailing update (the blocks
+        // behind the next group) runs on a low-priority side stream as soon as the group is factorised, beside the factorisation
+        // of the next group.  The narrow updates onto the next group's columns wait for the previous bulk (they read-modify-write
+        // tiles it wrote); consecutive bulks are ordered by their stream.
         cudaStream_t S1 = c->hi, S2 = c->side;
         bool bulk_pending = false;
         CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain

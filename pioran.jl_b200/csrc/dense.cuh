@@ -9,10 +9,11 @@
 // identity padding).  Row N of the factor is zᵀ = (L⁻¹(y−μ))ᵀ and the Schur complement left on its diagonal is
 // −zᵀz, so the forward substitution of direct_solver.jl:16 comes out of the same blocked sweep:
 //        +NLL = Σ log L_ii + ½ zᵀz + ½ N log 2π            (direct_solver.jl:20)
-// Blocked right-looking Cholesky, NB = 64, three kernels per panel, all batched over θ (blockIdx.y):
-//   dense_potrf_kernel : 64×64 diagonal block in shared memory; log-pivots, first non-positive pivot → info
-//   dense_trsm_kernel  : row blocks below the diagonal block, one thread per row, L_kk broadcast from shared memory
-//   dense_syrk_kernel  : trailing update C_ij −= A_ik A_jkᵀ (i ≥ j > k), 64×64 tiles on the FP64 tensor cores (DMMA m8n8k4)
+// Blocked right-looking Cholesky, NB = 64, all kernels batched over θ (blockIdx.y):
+//   dense_potrf_kernel : 64×64 diagonal block in registers, one barrier per pivot; log-pivots, first non-positive pivot → info
+//   dense_trsm_kernel  : row blocks below the diagonal block, blocked substitution on the FP64 tensor cores
+//   dense_syrk_kernel  : trailing update C_ij −= A_ik A_jkᵀ (i ≥ j > k), 64×64 tiles on the FP64 tensor cores (DMMA m8n8k4),
+//                        panels applied in groups of four (api.cu: pioran_direct_logl)
 // Matrices stay in HBM/L2 (32 MB each at N = 2 000; the 126 MB L2 holds the working set of a few of them).
 #pragma once
 #include "common.cuh"
@@ -432,9 +433,9 @@ __global__ void __launch_bounds__(DNB) dense_trsm_kernel(double* __restrict__ A,
 // stride of 36 doubles: the 8 rows × 4 k of a fragment load then fall on 32 distinct banks per half-warp.  Per k-step of 4
 // a warp issues 6 shared loads for 8 DMMAs (2 048 FMAs) — the scalar version needed 4 128-bit loads per 512 FMAs and was
 // bound by the shared-memory pipe (profiles/r01_launches_k3_k4.csv: 20.5 of K4's 36 ms).
-// Two panels per trailing update: the panels kb … kb+kw−1 (kw = 1 or 2; 64·kw contiguous columns) are applied at once to the
-// tiles (i ≥ j ≥ j0), so a trailing tile is read and written once per TWO panels; in between, the block column kb+1 alone
-// gets panel kb (narrow = 1: tiles (i, j0), i ≥ j0) so that it can be factorised.  Halves the traffic that bounds the kernel.
+// Several panels per trailing update: the panels kb … kb+kw−1 (64·kw contiguous columns) are applied at once to the tiles
+// (i ≥ j ≥ j0), so a trailing tile is read and written once per GROUP of panels; inside a group the next block column alone gets
+// the group's panels so far (narrow = 1: tiles (i, j0), i ≥ j0) so that it can be factorised.
 __global__ void __launch_bounds__(256, 2) dense_syrk_kernel(double* __restrict__ A, int64_t ld, int kb, int kw, int j0, int narrow) {
     constexpr int KH = DNB / 2, LDSM = KH + 4;
     __shared__ __align__(16) double As[DNB][LDSM];   // [row][k], one half of a panel's width at a time
