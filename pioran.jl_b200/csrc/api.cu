@@ -2876,6 +2876,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fact, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bulk, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaFuncSetAttribute(dense_syrk_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SYRK_ASYNC_SMEM));
     }
     cudaEventRecord(c->ev_beg, c->stream);
     for (int th0 = 0; th0 < B; th0 += chunk) {
@@ -2894,6 +2895,12 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         // of the next group.  The narrow updates onto the next group's columns wait for the previous bulk (they read-modify-write
         // tiles it wrote); consecutive bulks are ordered by their stream.
         cudaStream_t S1 = c->hi, S2 = c->side;
+        static const bool syrk_async = [] { const char* e = getenv("PIORAN_K4_SYRK"); return !(e && !strcmp(e, "regs")); }();
+        auto syrk = [&](dim3 grid, cudaStream_t st, int kb_, int kw_, int j0_, int narrow_) {
+            if (syrk_async) dense_syrk_async_kernel<<<grid, 256, DENSE_SYRK_ASYNC_SMEM, st>>>(A, ld, kb_, kw_, j0_, narrow_);
+            else dense_syrk_kernel<<<grid, 256, 0, st>>>(A, ld, kb_, kw_, j0_, narrow_);
+            c->launches++;
+        };
         bool bulk_pending = false;
         CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain
         CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));
@@ -2912,8 +2919,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
                 dense_trsm_kernel<<<dim3(m, nb), DNB, 0, S1>>>(A, ld, k);
                 c->launches++;
                 if (g < Gp - 1) {                   // the group's panels so far onto block column k+1 (rows ≥ k+1)
-                    dense_syrk_kernel<<<dim3(m, nb), 256, 0, S1>>>(A, ld, kb, g + 1, k + 1, 1);
-                    c->launches++;
+                    syrk(dim3(m, nb), S1, kb, g + 1, k + 1, 1);
                 }
             }
             const int rem = nblk - (kb + Gp);       // blocks behind the group
@@ -2924,13 +2930,11 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
                 CUDA_TRY(cudaEventRecord(c->ev_fact, S1));
                 CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fact, 0));
                 const int mb = rem - nextG;
-                dense_syrk_kernel<<<dim3(mb * (mb + 1) / 2, nb), 256, 0, S2>>>(A, ld, kb, Gp, kb + Gp + nextG, 0);
-                c->launches++;
+                syrk(dim3(mb * (mb + 1) / 2, nb), S2, kb, Gp, kb + Gp + nextG, 0);
             }
             if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));      // the previous bulk wrote the tiles updated next
             for (int cidx = 0; cidx < nextG; cidx++) {   // … and onto the next group's block columns (rows from the column's own block on)
-                dense_syrk_kernel<<<dim3(rem - cidx, nb), 256, 0, S1>>>(A, ld, kb, Gp, kb + Gp + cidx, 1);
-                c->launches++;
+                syrk(dim3(rem - cidx, nb), S1, kb, Gp, kb + Gp + cidx, 1);
             }
             if (bulk) CUDA_TRY(cudaEventRecord(c->ev_bulk, S2));
             bulk_pending = bulk;

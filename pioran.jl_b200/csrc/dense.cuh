@@ -517,6 +517,90 @@ __global__ void __launch_bounds__(256, 2) dense_syrk_kernel(double* __restrict__
         }
 }
 
+// cp.async variant of the trailing update (round 2): the panel halves travel global → shared memory without passing through
+// registers (16-byte cp.async.cg, two stages), and the output tile is read in the epilogue, so the kernel fits 80 registers and
+// THREE CTAs share an SM — one CTA's prologue / barriers / epilogue are covered by the other two.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
+}
+constexpr size_t DENSE_SYRK_ASYNC_SMEM = sizeof(double) * 4 * DNB * (DNB / 2 + 4);
+__global__ void __launch_bounds__(256, 3) dense_syrk_async_kernel(double* __restrict__ A, int64_t ld, int kb, int kw, int j0, int narrow) {
+    constexpr int KH = DNB / 2, LDSM = KH + 4;
+    extern __shared__ __align__(16) double syrk_sm[];     // As[2][64][36] | Bs[2][64][36]
+    double (*As)[DNB][LDSM] = reinterpret_cast<double (*)[DNB][LDSM]>(syrk_sm);
+    double (*Bs)[DNB][LDSM] = reinterpret_cast<double (*)[DNB][LDSM]>(syrk_sm + 2 * DNB * LDSM);
+    const int th = blockIdx.y;
+    int pi, pj;
+    if (narrow) { pi = blockIdx.x; pj = 0; }
+    else tri_index(blockIdx.x, pi, pj);
+    const int ib = j0 + pi, jb = j0 + pj;
+    double* At = A + (size_t)th * ld * ld;
+    const double* Ai = At + ((size_t)ib * DNB) * ld + (size_t)kb * DNB;
+    const double* Aj = At + ((size_t)jb * DNB) * ld + (size_t)kb * DNB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wy = warp >> 2, wx = warp & 3, gr = lane >> 2, gc = lane & 3;
+    const int nhalf = 2 * kw;
+    auto issue = [&](int half) {      // 64 rows × 32 doubles of both panels: 4 + 4 chunks of 16 bytes per thread
+        const int st = half & 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = threadIdx.x + q * 256, r = e >> 4, k = 2 * (e & 15);
+            cp_async16(&As[st][r][k], Ai + (size_t)r * ld + half * KH + k);
+            cp_async16(&Bs[st][r][k], Aj + (size_t)r * ld + half * KH + k);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    double acc[4][2][2];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
+    const bool dead = ib == jb && 16 * wx > 32 * wy + 31;     // a warp wholly above the diagonal of a diagonal tile does no math
+    for (int half = 0; half < nhalf; half++) {
+        const int cur = half & 1;
+        if (half + 1 < nhalf) {
+            issue(half + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (!dead) {
+#pragma unroll
+            for (int k4 = 0; k4 < KH / 4; k4++) {
+                double a[4], b[2];
+#pragma unroll
+                for (int u = 0; u < 4; u++) a[u] = As[cur][32 * wy + 8 * u + gr][4 * k4 + gc];
+#pragma unroll
+                for (int v = 0; v < 2; v++) b[v] = Bs[cur][16 * wx + 8 * v + gr][4 * k4 + gc];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int v = 0; v < 2; v++) dmma_8x8x4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+            }
+        }
+        __syncthreads();              // the stage is refilled by the issue of the iteration after next
+    }
+    if (dead) return;
+    double* C = At + ((size_t)ib * DNB) * ld + (size_t)jb * DNB;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const int r = 32 * wy + 8 * u + gr, q = 16 * wx + 8 * v + 2 * gc;
+            double* dst = C + (size_t)r * ld + q;
+            if (ib != jb || q + 1 <= r) {
+                const double2 cvv = *reinterpret_cast<const double2*>(dst);
+                *reinterpret_cast<double2*>(dst) = make_double2(cvv.x - acc[u][v][0], cvv.y - acc[u][v][1]);
+            } else if (q <= r) {
+                dst[0] = dst[0] - acc[u][v][0];
+            }
+        }
+}
+
+
 // acc → +NLL (direct_solver.jl:20); NaN where the matrix was not positive definite.
 __global__ void dense_finish_kernel(const double* __restrict__ acc, const int* __restrict__ info, int64_t N, int B,
                                     double* __restrict__ nll) {
