@@ -57,9 +57,10 @@ def test_dense_simu_log_celerite_identity(pb, ctx, basis):
     assert abs(ll + nll) <= 1.5e-8 * abs(nll)
 
 
-@pytest.mark.parametrize("N", [1, 2, 63, 64, 65, 127, 128, 200])
+@pytest.mark.parametrize("N", [1, 2, 63, 64, 65, 127, 128, 200, 255, 256, 330, 580])
 def test_dense_block_edges_vs_oracle(pb, ctx, N):
-    """Sizes around the 64-wide panel (the augmented row lands first/last in a block), batched with μ and ν."""
+    """Sizes around the 64-wide panel (the augmented row lands first/last in a block) and around the groups of four panels
+    of the trailing update (4, 5, 6, 10 blocks), batched with μ and ν."""
     rng = np.random.default_rng(N)
     t = np.cumsum(0.1 + rng.exponential(1.0, N))
     y = rng.normal(0, 1, N)
