@@ -2878,6 +2878,9 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaFuncSetAttribute(dense_syrk_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SYRK_ASYNC_SMEM));
     }
+    // PIORAN_K4_FILL=direct: every covariance entry from the reference's formula (src/Celerite.jl:42-44) instead of the separable
+    // factors — the accuracy cross-check of the fill (tests/tools/fuzz_dense.py)
+    static const int fill_direct = [] { const char* e = getenv("PIORAN_K4_FILL"); return e && !strcmp(e, "direct") ? 1 : 0; }();
     cudaEventRecord(c->ev_beg, c->stream);
     for (int th0 = 0; th0 < B; th0 += chunk) {
         const int nb = std::min(chunk, B - th0);
@@ -2887,7 +2890,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
             c->launches++;
         }
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
-                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull);
+                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull, fill_direct);
         c->launches++;
         // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates inside a group of panels and
         // onto the NEXT group's block columns) runs on a high-priority stream; the bulk of a group's trailing update (the blocks

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
                                                          const double* __restrict__ a, const double* __restrict__ b,
                                                          const double* __restrict__ c, const double* __restrict__ d,
                                                          const double* __restrict__ mu, const double* __restrict__ nu,
-                                                         int theta0, const double* __restrict__ tab, int nfull) {
+                                                         int theta0, const double* __restrict__ tab, int nfull, int direct) {
     extern __shared__ double sm[];
     double* ca = sm; double* cb = ca + Jt; double* cc = cb + Jt; double* cd = cc + Jt;
     double* ti_s = cd + Jt; double* tj_s = ti_s + DNB;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
     // P, Q, Gc, Gs come from the block tables, the rotation by β costs one transcendental triple per term and TILE, then two FMAs
     // per entry and term.  No exponent is positive, so nothing overflows (the celerite instability of separating
     // e^{−c t_i} e^{+c t_j} globally does not arise per tile).  A partial last row block computes its few valid P, Q rows here.
-    if (bi != bj) {
+    if (bi != bj && !direct) {
         const bool full = bi < nfull;
         for (int m = threadIdx.x; m < Jt; m += blockDim.x) {
             const double beta = fmax(ti_s[0] - tj_s[DNB - 1], 0.0);      // (an all-padding row block has no times; its rows are overwritten below)
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
     // Full diagonal tiles: the same separation one level down, on the 8×8 grid of 8×8 sub-tiles.  The 28 sub-tiles below the
     // diagonal use P, Q relative to the first row of their 8-row group and Gc, Gs relative to the last column of their 8-column
     // group, rotated by the gap β between the two groups; only the 8 diagonal sub-tiles (288 entries) are evaluated directly.
-    if (bi < nfull) {
+    if (bi == bj && bi < nfull && !direct) {
         for (int e = threadIdx.x; e < 2 * JD; e += blockDim.x) {
             const int side = e / JD, f = e - side * JD, m = f / DNB, k = f - m * DNB;
             double si, co;
