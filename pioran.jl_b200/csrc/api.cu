@@ -2865,8 +2865,12 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     double* nll = acc + 2 * (size_t)chunk;
     int* info = reinterpret_cast<int*>(nll + chunk);
     const int ntri = nblk * (nblk + 1) / 2;
-    const size_t fill_smem = sizeof(double) * dense_fill_smem_doubles(Jt);
-    if (fill_smem > 200 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
+    // the separable fill keeps four Jt × 64 factor tables in shared memory (Jt ≤ 97); beyond that every entry is evaluated from
+    // the reference's formula, which needs the coefficients only
+    size_t fill_smem = sizeof(double) * dense_fill_smem_doubles(Jt);
+    const bool fill_tables = fill_smem <= 227 * 1024;
+    if (!fill_tables) fill_smem = sizeof(double) * (4 * (size_t)Jt + 2 * DNB);
+    if (fill_smem > 227 * 1024) return fail(PIORAN_EUNSUPPORTED, "Jt = %d is too large for the dense path", Jt);
     CUDA_TRY(cudaFuncSetAttribute(dense_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     if (!c->side) {
         int prio_least = 0, prio_greatest = 0;
@@ -2885,12 +2889,12 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
     for (int th0 = 0; th0 < B; th0 += chunk) {
         const int nb = std::min(chunk, B - th0);
         CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)chunk + sizeof(int) * (size_t)chunk, c->stream));
-        if (nfull > 0) {
+        if (nfull > 0 && fill_tables && !fill_direct) {
             dense_fill_tables_kernel<<<dim3(nfull, nb), 256, 0, c->stream>>>(tab, nfull, s->t, Jt, gi.a, gi.b, gi.c, gi.d, th0);
             c->launches++;
         }
         dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
-                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull, fill_direct);
+                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull, fill_direct || !fill_tables);
         c->launches++;
         // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates inside a group of panels and
         // onto the NEXT group's block columns) runs on a high-priority stream; the bulk of a group's trailing update (the blocks

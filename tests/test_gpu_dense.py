@@ -81,6 +81,26 @@ def test_dense_block_edges_vs_oracle(pb, ctx, N):
         assert rel_err(got[i], want) <= 1e-10, (N, i)
 
 
+def test_dense_many_terms_beyond_the_factor_tables(pb, ctx):
+    """Jt = 120 terms: the separable fill's shared-memory tables stop at 97 terms; beyond that every entry comes from the
+    reference's formula (src/Celerite.jl:42-44).  Same oracle, same bar."""
+    rng = np.random.default_rng(120)
+    N, B, Jt = 150, 3, 120
+    t = np.cumsum(0.1 + rng.exponential(1.0, N))
+    y = rng.normal(0, 1, N)
+    s2 = rng.uniform(0.01, 0.1, N)
+    a = rng.uniform(0.01, 0.05, (B, Jt)); b = np.zeros((B, Jt))
+    c = rng.uniform(0.05, 1.0, (B, Jt)); d = rng.uniform(0, 2.0, (B, Jt))
+    d[:, ::2] = 0                                   # real terms and pure damped cosines: positive-definite by construction
+    ser = ctx.upload_series(t, y, s2)
+    got, info = ctx.direct_logl(ser, a, b, c, d)
+    ser.free()
+    for i in range(B):
+        want, oi = orc.direct_nll(a[i], b[i], c[i], d[i], t, y, s2)
+        assert oi == 0 and info[i] == 0
+        assert rel_err(got[i], want) <= 1e-10, i
+
+
 def test_dense_not_positive_definite_reports_like_posdef_exception(pb, ctx):
     """A negative amplitude that makes K indefinite: the reference throws PosDefException (direct_solver.jl:14);
     the C ABI returns NaN + the order of the failing leading minor, the Python mirror raises."""
