@@ -79,7 +79,7 @@ int pioran_ctx_destroy(pioran_ctx *ctx);
 /* One context over several devices of the box, for a caller that is ONE process with one likelihood callback (the
  * reference's samplers: examples/ultranest/single_pl.jl:113-117; dispatch of src/scalable_GP.jl:24-40, 162-166).
  * pioran_series_upload places the series on every device; the batched host-pointer entries (pioran_approx_logl,
- * pioran_approx_logl_logshift, pioran_approx_logl_grad, pioran_celerite_logl) cut their B parameter vectors into ndev
+ * pioran_approx_logl_logshift, pioran_approx_logl_grad, pioran_celerite_logl, pioran_direct_logl) cut their B parameter vectors into ndev
  * contiguous slices, run each slice on its device concurrently and write the results straight into the caller's arrays -
  * the slices are independent, so no collective is involved.  Every other entry runs on devices[0]; the device-pointer
  * entries (_dev) and pioran_ctx_set_stream need a single-device context and return PIORAN_EUNSUPPORTED on a group. */

@@ -2829,13 +2829,17 @@ extern "C" int pioran_celerite_scan_range_check(pioran_ctx* c, double* out8) try
 extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, const double* a, const double* b,
                                   const double* cc, const double* d, const double* mu, const double* nu,
                                   double* nll_out, int* info_out) try {
-    if (is_group(c)) {   // single-device work of a group runs on its first device
-        int cid;
-        { std::lock_guard<std::mutex> lk(c->mu); const int rc = group_series_id(c, series_id, 0, &cid); if (rc) return rc; }
-        return pioran_direct_logl(c->children[0], cid, B, Jt, a, b, cc, d, mu, nu, nll_out, info_out);
-    }
     if (!c || !a || !b || !cc || !d || !nll_out) return fail(PIORAN_EINVAL, "NULL argument");
     if (B < 1 || Jt < 1) return fail(PIORAN_EINVAL, "B and Jt must be >= 1");
+    if (is_group(c)) {   // the parameter vectors are independent: contiguous slices, one per device
+        std::vector<int> cid(c->children.size());
+        { std::lock_guard<std::mutex> lk(c->mu); for (size_t k = 0; k < cid.size(); k++) { const int rc = group_series_id(c, series_id, k, &cid[k]); if (rc) return rc; } }
+        return group_split(c, B, [&](int k, int beg, int nb) -> int {
+            const size_t o = (size_t)beg * Jt;
+            return pioran_direct_logl(c->children[k], cid[k], nb, Jt, a + o, b + o, cc + o, d + o, mu ? mu + beg : nullptr,
+                                      nu ? nu + beg : nullptr, nll_out + beg, info_out ? info_out + beg : nullptr);
+        });
+    }
     PIORAN_COMPUTE_LOCK(c);
     CUDA_TRY(cudaSetDevice(c->device));
     Series* s = get_series(c, series_id);

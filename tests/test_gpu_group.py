@@ -45,6 +45,11 @@ def test_group_context_matches_single_device(devices):
             a, b, c, d = grp.approx_coeffs(spec, th[:53, :4])
             assert np.array_equal(grp.celerite_logl(sg, a, b, c, d, mu=th[:53, 5], nu=th[:53, 4]),
                                   one.celerite_logl(s1, a, b, c, d, mu=th[:53, 5], nu=th[:53, 4]))
+            # the dense cross-check splits its parameter vectors the same way
+            a9, b9, c9, d9 = grp.approx_coeffs(spec, th[:9, :4])
+            nw, iw = one.direct_logl(s1, a9, b9, c9, d9, mu=th[:9, 5], nu=th[:9, 4])
+            ng, ig = grp.direct_logl(sg, a9, b9, c9, d9, mu=th[:9, 5], nu=th[:9, 4])
+            assert np.array_equal(ng, nw) and np.array_equal(ig, iw)
             s1.free(); sg.free()
         # several series in one call
         sers1, sersg, specs = [], [], []
