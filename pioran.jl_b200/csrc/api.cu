@@ -106,7 +106,7 @@ struct pioran_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t side = nullptr, hi = nullptr;   // K4: the bulk trailing updates (side) run beside the panel chain (hi: highest stream priority, so its
                                                  // small kernels take the SM slots the bulk's CTAs free); created on first use
-    cudaEvent_t ev_fact = nullptr, ev_bulk = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fact = nullptr, ev_bulk = nullptr, ev_join = nullptr, ev_col[8] = {};
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
@@ -294,6 +294,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     if (c->ev_fact) cudaEventDestroy(c->ev_fact);
     if (c->ev_bulk) cudaEventDestroy(c->ev_bulk);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (cudaEvent_t e : c->ev_col) if (e) cudaEventDestroy(e);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->hi) cudaStreamDestroy(c->hi);
     if (c->own) cudaStreamDestroy(c->own);
@@ -2884,6 +2885,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fact, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bulk, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        for (cudaEvent_t& e : c->ev_col) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaFuncSetAttribute(dense_syrk_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SYRK_ASYNC_SMEM));
     }
     // PIORAN_K4_FILL=direct: every covariance entry from the reference's formula (src/Celerite.jl:42-44) instead of the separable
@@ -2916,10 +2918,28 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain
         CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));
         static const int G = [] { const char* e = getenv("PIORAN_K4_GROUP"); const int g = e ? atoi(e) : 4; return g >= 1 && g <= 8 ? g : 4; }();
+        // PIORAN_K4_GROUP0: size of the FIRST group (default: G).  Nothing runs beside its chain, so a shorter first group hands
+        // the side stream its first bulk earlier — measured: 8.92 (4) / 8.98 (3) / 9.02 (2) / 9.14 ms (1); the shorter bulk then
+        // ends before the second group's chain does.
+        static const int G0 = [] { const char* e = getenv("PIORAN_K4_GROUP0"); const int g = e ? atoi(e) : G; return g >= 1 && g <= G ? g : G; }();
+        // Of the updates onto the next group's block columns only the FIRST column's is on the panel chain (the next potrf needs
+        // it); the others go to the side stream ahead of the bulk, and the chain waits for column c's just before it updates
+        // that column itself (PIORAN_K4_SIDE_NARROW=0: all of them on the chain).
+        static const bool side_narrow = [] { const char* e = getenv("PIORAN_K4_SIDE_NARROW"); return !(e && !strcmp(e, "0")); }();
+        bool col_pending[8] = {false, false, false, false, false, false, false, false};   // next-group column c updated on the side stream
+        // PIORAN_K4_TRACE=1: time stamps of the group boundaries on both streams, printed to stderr (development aid)
+        static const bool trace = [] { const char* e = getenv("PIORAN_K4_TRACE"); return e && !strcmp(e, "1"); }();
+        std::vector<std::pair<std::string, cudaEvent_t>> marks;
+        auto mark = [&](const char* what, int kb_, cudaStream_t st) {
+            if (!trace) return;
+            cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+            marks.emplace_back(std::string(what) + " " + std::to_string(kb_), e);
+        };
+        mark("start (fill queued)", 0, c->stream);
         // Groups of G panels: inside a group every panel is applied to the next block column alone (narrow update with all the
         // group's panels so far), so that a trailing tile is read and written once per G panels.
         for (int kb = 0; kb < nblk;) {
-            const int Gp = std::min(G, nblk - kb);
+            const int Gp = std::min(kb == 0 ? G0 : G, nblk - kb);
             bool done = false;
             for (int g = 0; g < Gp; g++) {
                 const int k = kb + g;
@@ -2930,25 +2950,41 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
                 dense_trsm_kernel<<<dim3(m, nb), DNB, 0, S1>>>(A, ld, k);
                 c->launches++;
                 if (g < Gp - 1) {                   // the group's panels so far onto block column k+1 (rows ≥ k+1)
+                    if (col_pending[g + 1]) {       // … after the previous group's update of that column
+                        CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_col[g + 1], 0));
+                        col_pending[g + 1] = false;
+                    }
                     syrk(dim3(m, nb), S1, kb, g + 1, k + 1, 1);
                 }
             }
+            mark("chain of group done, kb =", kb, S1);
             const int rem = nblk - (kb + Gp);       // blocks behind the group
             if (done || rem <= 0) break;
             const int nextG = std::min(G, rem);
             const bool bulk = rem > nextG;
-            if (bulk) {                             // all of the group's panels onto the blocks behind the NEXT group, on the side stream
+            const int nside = side_narrow ? nextG - 1 : 0;      // next-group columns 1 … nside on the side stream
+            if (bulk || nside > 0) {
                 CUDA_TRY(cudaEventRecord(c->ev_fact, S1));
                 CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fact, 0));
+            }
+            for (int cidx = 1; cidx <= nside; cidx++) {          // (the side stream is in order: these follow the previous bulk)
+                syrk(dim3(rem - cidx, nb), S2, kb, Gp, kb + Gp + cidx, 1);
+                CUDA_TRY(cudaEventRecord(c->ev_col[cidx], S2));
+                col_pending[cidx] = true;
+            }
+            if (bulk) {                             // all of the group's panels onto the blocks behind the NEXT group, on the side stream
                 const int mb = rem - nextG;
                 syrk(dim3(mb * (mb + 1) / 2, nb), S2, kb, Gp, kb + Gp + nextG, 0);
             }
             if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));      // the previous bulk wrote the tiles updated next
             for (int cidx = 0; cidx < nextG; cidx++) {   // … and onto the next group's block columns (rows from the column's own block on)
+                if (cidx >= 1 && cidx <= nside) continue;
                 syrk(dim3(rem - cidx, nb), S1, kb, Gp, kb + Gp + cidx, 1);
             }
-            if (bulk) CUDA_TRY(cudaEventRecord(c->ev_bulk, S2));
-            bulk_pending = bulk;
+            if (bulk || nside > 0) CUDA_TRY(cudaEventRecord(c->ev_bulk, S2));
+            if (bulk || nside > 0) mark("side stream (narrow + bulk) done, kb =", kb, S2);
+            mark("first next-group column updated, kb =", kb, S1);
+            bulk_pending = bulk || nside > 0;
             kb += Gp;
         }
         if (bulk_pending) CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_bulk, 0));
@@ -2960,6 +2996,14 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaMemcpyAsync(nll_out + th0, nll, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
         if (info_out) CUDA_TRY(cudaMemcpyAsync(info_out + th0, info, sizeof(int) * nb, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));   // the workspace is reused by the next chunk
+        for (size_t i = 0; i < marks.size(); i++) {
+            float ms = 0.f;
+            cudaEventSynchronize(marks[i].second);
+            cudaEventElapsedTime(&ms, marks[0].second, marks[i].second);
+            fprintf(stderr, "[K4 trace] %8.3f ms  %s\n", ms, marks[i].first.c_str());
+            if (i) cudaEventDestroy(marks[i].second);
+        }
+        if (!marks.empty()) cudaEventDestroy(marks[0].second);
     }
     cudaEventRecord(c->ev_end, c->stream);
     c->ev_valid = true;
