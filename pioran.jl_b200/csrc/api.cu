@@ -106,7 +106,7 @@ struct pioran_ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t side = nullptr, hi = nullptr;   // K4: the bulk trailing updates (side) run beside the panel chain (hi: highest stream priority, so its
                                                  // small kernels take the SM slots the bulk's CTAs free); created on first use
-    cudaEvent_t ev_fact = nullptr, ev_bulk = nullptr, ev_join = nullptr, ev_col[8] = {};
+    cudaEvent_t ev_fact = nullptr, ev_bulk = nullptr, ev_join = nullptr, ev_fill = nullptr, ev_col[8] = {};
     int64_t launches = 0;
     std::vector<Series*> series;
     std::map<PlanKey, ApproxPlan*> plans;  // device pointers
@@ -294,6 +294,7 @@ extern "C" int pioran_ctx_destroy(pioran_ctx* c) try {
     if (c->ev_fact) cudaEventDestroy(c->ev_fact);
     if (c->ev_bulk) cudaEventDestroy(c->ev_bulk);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_fill) cudaEventDestroy(c->ev_fill);
     for (cudaEvent_t e : c->ev_col) if (e) cudaEventDestroy(e);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->hi) cudaStreamDestroy(c->hi);
@@ -2885,6 +2886,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fact, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_bulk, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fill, cudaEventDisableTiming));
         for (cudaEvent_t& e : c->ev_col) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaFuncSetAttribute(dense_syrk_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DENSE_SYRK_ASYNC_SMEM));
     }
@@ -2899,9 +2901,27 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
             dense_fill_tables_kernel<<<dim3(nfull, nb), 256, 0, c->stream>>>(tab, nfull, s->t, Jt, gi.a, gi.b, gi.c, gi.d, th0);
             c->launches++;
         }
-        dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
-                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull, fill_direct || !fill_tables);
-        c->launches++;
+        // the first group's block columns are filled first: its panel chain (nothing else could run beside it) then overlaps the
+        // fill of the rest (PIORAN_K4_FILL_SPLIT=0: one launch)
+        static const bool fill_split = [] { const char* e = getenv("PIORAN_K4_FILL_SPLIT"); return !(e && !strcmp(e, "0")); }();
+        static const int Gf = [] { const char* e = getenv("PIORAN_K4_GROUP"); const int g = e ? atoi(e) : 4; return g >= 1 && g <= 8 ? g : 4; }();
+        const bool split = fill_split && nblk > 2 * Gf;
+        const int fdir = fill_direct || !fill_tables;
+        if (split) {
+            const int mt = nblk - Gf;
+            dense_fill_kernel<<<dim3(nblk * Gf, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
+                                                                                  gi.d, gi.mu, gi.nu, th0, tab, nfull, fdir, 1, Gf);
+            CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));
+            dense_fill_kernel<<<dim3(mt * (mt + 1) / 2, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
+                                                                                         gi.d, gi.mu, gi.nu, th0, tab, nfull, fdir, 2, Gf);
+            c->launches += 2;
+        } else {
+            dense_fill_kernel<<<dim3(ntri, nb), 256, fill_smem, c->stream>>>(A, ld, N, s->t, s->y, s->s2, Jt, gi.a, gi.b, gi.c,
+                                                                             gi.d, gi.mu, gi.nu, th0, tab, nfull, fdir, 0, Gf);
+            c->launches++;
+            CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_fill, c->stream));
         // Look-ahead over two streams (round 2): the panel chain (potrf, trsm and the narrow updates inside a group of panels and
         // onto the NEXT group's block columns) runs on a high-priority stream; the bulk of a group's trailing update (the blocks
         // behind the next group) runs on a low-priority side stream as soon as the group is factorised, beside the factorisation
@@ -2915,8 +2935,7 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
             c->launches++;
         };
         bool bulk_pending = false;
-        CUDA_TRY(cudaEventRecord(c->ev_join, c->stream));      // the fill (and everything before it) precedes the chain
-        CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));
+        CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_join, 0));      // the fill of the first group's columns (and everything before it) precedes the chain
         static const int G = [] { const char* e = getenv("PIORAN_K4_GROUP"); const int g = e ? atoi(e) : 4; return g >= 1 && g <= 8 ? g : 4; }();
         // PIORAN_K4_GROUP0: size of the FIRST group (default: G).  Nothing runs beside its chain, so a shorter first group hands
         // the side stream its first bulk earlier — measured: 8.92 (4) / 8.98 (3) / 9.02 (2) / 9.14 ms (1); the shorter bulk then
@@ -2963,6 +2982,10 @@ extern "C" int pioran_direct_logl(pioran_ctx* c, int series_id, int B, int Jt, c
             const int nextG = std::min(G, rem);
             const bool bulk = rem > nextG;
             const int nside = side_narrow ? nextG - 1 : 0;      // next-group columns 1 … nside on the side stream
+            if (kb == 0 && split) {                 // everything behind the first group needs the rest of the fill
+                CUDA_TRY(cudaStreamWaitEvent(S1, c->ev_fill, 0));
+                CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fill, 0));
+            }
             if (bulk || nside > 0) {
                 CUDA_TRY(cudaEventRecord(c->ev_fact, S1));
                 CUDA_TRY(cudaStreamWaitEvent(S2, c->ev_fact, 0));

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
                                                          const double* __restrict__ a, const double* __restrict__ b,
                                                          const double* __restrict__ c, const double* __restrict__ d,
                                                          const double* __restrict__ mu, const double* __restrict__ nu,
-                                                         int theta0, const double* __restrict__ tab, int nfull, int direct) {
+                                                         int theta0, const double* __restrict__ tab, int nfull, int direct, int fpart, int G) {
     extern __shared__ double sm[];
     double* ca = sm; double* cb = ca + Jt; double* cc = cb + Jt; double* cd = cc + Jt;
     double* ti_s = cd + Jt; double* tj_s = ti_s + DNB;
@@ -85,7 +85,14 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
     double* part = rot + 24 * (size_t)Jt;   // [4][DFILL_DIAG]
     const int th = blockIdx.y;
     int bi, bj;
-    tri_index(gridDim.x - 1 - blockIdx.x, bi, bj);
+    // fpart 0: the whole lower triangle; 1: the first G block columns (grid.x = nblk·G); 2: the triangle behind them
+    if (fpart == 1) {
+        bi = blockIdx.x / G; bj = blockIdx.x - bi * G;
+        if (bj > bi) return;
+    } else {
+        tri_index(gridDim.x - 1 - blockIdx.x, bi, bj);
+        if (fpart == 2) { bi += G; bj += G; }
+    }
     for (int m = threadIdx.x; m < Jt; m += blockDim.x) {
         const size_t k = (size_t)(theta0 + th) * Jt + m;
         ca[m] = a[k]; cb[m] = b[k]; cc[m] = c[k]; cd[m] = d[k];
