@@ -150,7 +150,9 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
             }
         }
         __syncthreads();
-        const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;      // 4×4 entries per thread
+        // 4×4 entries per thread: rows 4 ty + u, columns tx + 16 w — the 16 lanes of a half-warp read 16 consecutive doubles of X / Y
+        // (one wavefront; columns 4 tx + w cost two per load and made the loop shared-memory bound: ncu LSU 80 %, FP64 34 %)
+        const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
         double v[4][4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
 #pragma unroll
             for (int u = 0; u < 4; u++) { pr[u] = Ps[m * DNB + 4 * ty + u]; qr[u] = Qs[m * DNB + 4 * ty + u]; }
 #pragma unroll
-            for (int w = 0; w < 4; w++) { xc[w] = Xs[m * DNB + 4 * tx + w]; yc[w] = Ys[m * DNB + 4 * tx + w]; }
+            for (int w = 0; w < 4; w++) { xc[w] = Xs[m * DNB + tx + 16 * w]; yc[w] = Ys[m * DNB + tx + 16 * w]; }
 #pragma unroll
             for (int u = 0; u < 4; u++)
 #pragma unroll
@@ -172,11 +174,11 @@ __global__ void __launch_bounds__(256) dense_fill_kernel(double* __restrict__ A,
             const int64_t gi = (int64_t)bi * DNB + 4 * ty + u;
             if (!full && gi >= N) {                    // augmented row (y − μ)ᵀ, then identity padding (zeros off the diagonal)
 #pragma unroll
-                for (int w = 0; w < 4; w++) v[u][w] = gi == N ? y[(int64_t)bj * DNB + 4 * tx + w] - m_ : 0.0;
+                for (int w = 0; w < 4; w++) v[u][w] = gi == N ? y[(int64_t)bj * DNB + tx + 16 * w] - m_ : 0.0;
             }
-            double* dst = At + gi * ld + (int64_t)bj * DNB + 4 * tx;
-            *reinterpret_cast<double2*>(dst) = make_double2(v[u][0], v[u][1]);
-            *reinterpret_cast<double2*>(dst + 2) = make_double2(v[u][2], v[u][3]);
+            double* dst = At + gi * ld + (int64_t)bj * DNB + tx;
+#pragma unroll
+            for (int w = 0; w < 4; w++) dst[16 * w] = v[u][w];
         }
         return;
     }
