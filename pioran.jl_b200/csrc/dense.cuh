@@ -527,8 +527,9 @@ __global__ void __launch_bounds__(256, 2) dense_syrk_kernel(double* __restrict__
 }
 
 // cp.async variant of the trailing update (round 2): the panel halves travel global → shared memory without passing through
-// registers (16-byte cp.async.cg, two stages), and the output tile is read in the epilogue, so the kernel fits 80 registers and
-// THREE CTAs share an SM — one CTA's prologue / barriers / epilogue are covered by the other two.
+// registers (16-byte cp.async.cg, two stages), and the output tile is staged into the free stage during the last half instead of
+// being held in registers, so the kernel fits 80 registers and THREE CTAs share an SM — one CTA's prologue / barriers / epilogue
+// are covered by the other two.
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
@@ -561,9 +562,10 @@ __global__ void __launch_bounds__(256, 3) dense_syrk_async_kernel(double* __rest
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     issue(0);
-    // the output tile is read in the epilogue (no registers to hold it meanwhile): ask for its lines now, so that the read-modify-
-    // write then finds them in the L2 instead of waiting on HBM (ncu: 29 % of the stall samples sat on the epilogue's first DADD;
-    // with three CTAs per SM the other two cover it — the prefetch moved the trailing updates from 6.92 to 6.89 ms)
+    // the output tile is needed at the end only (no registers to hold it meanwhile): ask for its lines now, so that the copy into
+    // shared memory during the last half finds them in the L2 (ncu before the staging: 29 % of the stall samples sat on the
+    // epilogue's first DADD, waiting on the tile; the prefetch alone moved the trailing updates from 6.92 to 6.89 ms, the staging
+    // to 6.63)
     double* C = At + ((size_t)ib * DNB) * ld + (size_t)jb * DNB;
     if (gc == 0) {
 #pragma unroll
@@ -576,15 +578,29 @@ __global__ void __launch_bounds__(256, 3) dense_syrk_async_kernel(double* __rest
 #pragma unroll
         for (int v = 0; v < 2; v++) acc[u][v][0] = acc[u][v][1] = 0.0;
     const bool dead = ib == jb && 16 * wx > 32 * wy + 31;     // a warp wholly above the diagonal of a diagonal tile does no math
+    constexpr int CS = DNB + 2;       // row stride (doubles) of the output tile staged in the free stage during the last half
     for (int half = 0; half < nhalf; half++) {
         const int cur = half & 1;
-        if (half + 1 < nhalf) {
+        const bool last = half + 1 == nhalf;
+        if (!last) {
             issue(half + 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
+        if (last) {
+            // the other stage is free now: the output tile travels into it (rows 0–31 into the A part, 32–63 into the B part) while
+            // the tensor cores work on the last half, so the epilogue's read-modify-write does not wait on global memory
+            double* c0 = &As[cur ^ 1][0][0];
+            double* c1 = &Bs[cur ^ 1][0][0];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = threadIdx.x + q * 256, r = e >> 5, k = 2 * (e & 31);
+                cp_async16((r < 32 ? c0 + r * CS : c1 + (r - 32) * CS) + k, C + (size_t)r * ld + k);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (!dead) {
 #pragma unroll
             for (int k4 = 0; k4 < KH / 4; k4++) {
@@ -599,20 +615,23 @@ __global__ void __launch_bounds__(256, 3) dense_syrk_async_kernel(double* __rest
                     for (int v = 0; v < 2; v++) dmma_8x8x4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
             }
         }
-        __syncthreads();              // the stage is refilled by the issue of the iteration after next
+        if (last) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();              // the stage is refilled by the issue of the iteration after next / the staged output tile is complete
     }
     if (dead) return;
+    const int fst = ((nhalf - 1) & 1) ^ 1;                                   // the stage that holds the output tile
+    const double* cs = wy == 0 ? &As[fst][0][0] : &Bs[fst][0][0];            // this warp's 32 rows of it
 #pragma unroll
     for (int u = 0; u < 4; u++)
 #pragma unroll
         for (int v = 0; v < 2; v++) {
             const int r = 32 * wy + 8 * u + gr, q = 16 * wx + 8 * v + 2 * gc;
             double* dst = C + (size_t)r * ld + q;
+            const double2 cvv = *reinterpret_cast<const double2*>(cs + (8 * u + gr) * CS + q);
             if (ib != jb || q + 1 <= r) {
-                const double2 cvv = *reinterpret_cast<const double2*>(dst);
                 *reinterpret_cast<double2*>(dst) = make_double2(cvv.x - acc[u][v][0], cvv.y - acc[u][v][1]);
             } else if (q <= r) {
-                dst[0] = dst[0] - acc[u][v][0];
+                dst[0] = cvv.x - acc[u][v][0];
             }
         }
 }
