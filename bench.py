@@ -273,7 +273,7 @@ def measure(torch, ctx, pb, t, y, s2, f_min, f_max, J, basis, theta, steps, warm
     step_dev()
     launches = (ctx.launch_count - n0) * steps   # library kernels per step (K1 + K2) x timed steps
     # dominant kernel alone (events inside the library around the K2 launch), a few extra launches after the timed region
-    for _ in range(3):
+    for _ in range(6):
         flush.zero_()
         ctx.approx_logl_dev([ser], [spec], B, th_dev.data_ptr(), out_dev.data_ptr())
         k2_ms.append(ctx.last_kernel_ms())
